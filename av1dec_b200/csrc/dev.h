@@ -1,0 +1,106 @@
+// dev.h -- one source, two builds.
+//
+//  * nvcc (sm_100a): the product.  Kernels run on the GPU.
+//  * g++ -DAV1B_EMU: a TEST-ONLY host emulation used to debug bit-exactness in a container
+//    without a GPU.  Every kernel is written block-size agnostic (strided loops over
+//    threadIdx/blockDim, __syncthreads between dependent phases), so running each CTA as a
+//    single sequential "thread" is a valid schedule.  The emulation library is built under
+//    tests/emu/ and is never loaded by the product path (av1dec_b200/__init__.py refuses it).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef AV1B_EMU
+// ------------------------------------------------------------------ host emulation
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+struct EmuDim3 {
+    unsigned x, y, z;
+    EmuDim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+typedef EmuDim3 dim3;
+extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
+#define __global__
+#define __device__
+#define __host__
+#define __shared__ static
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define AV1B_UNROLL
+static inline void __syncthreads() {}
+static inline void __syncwarp() {}
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline int av1b_ld_acquire(const int* p) { return *p; }
+static inline void av1b_st_release(int* p, int v) { *p = v; }
+static inline void av1b_nanosleep(unsigned) {}
+using std::max;
+using std::min;
+typedef void* av1b_stream_t;
+template <class F> static inline void emu_launch(dim3 grid, F f)
+{
+    gridDim = grid;
+    blockDim = EmuDim3(1, 1, 1);
+    threadIdx = EmuDim3(0, 0, 0);
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) {
+                blockIdx = EmuDim3(x, y, z);
+                f();
+            }
+}
+#define AV1B_LAUNCH(kern, grid, block, stream, ...) emu_launch(dim3 grid, [&] { kern(__VA_ARGS__); })
+#define AV1T_CONST static const
+#else
+// ------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+typedef cudaStream_t av1b_stream_t;
+#define AV1B_UNROLL _Pragma("unroll")
+#define AV1B_LAUNCH(kern, grid, block, stream, ...) kern<<<dim3 grid, dim3 block, 0, stream>>>(__VA_ARGS__)
+#define AV1T_CONST static __device__ const
+static __device__ __forceinline__ int av1b_ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void av1b_st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+static __device__ __forceinline__ void av1b_nanosleep(unsigned ns) { __nanosleep(ns); }
+#endif
+
+// ------------------------------------------------------------------ shared helpers
+#define AV1B_DEV static __device__ __forceinline__
+
+AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+AV1B_DEV int round2(int x, int n) { return n == 0 ? x : ((x + (1 << (n - 1))) >> n); }
+AV1B_DEV int round2s(int x, int n) { return x >= 0 ? round2(x, n) : -round2(-x, n); }
+AV1B_DEV int iabs(int v) { return v < 0 ? -v : v; }
+AV1B_DEV int floor_log2(unsigned x)
+{
+    int s = -1;
+    while (x) {
+        x >>= 1;
+        s++;
+    }
+    return s;
+}
+
+// Geometry of one device-resident plane.
+struct PlaneView {
+    uint8_t* p;  // address of sample (0,0)
+    int stride;  // bytes between rows
+};
+struct FrameView {
+    PlaneView pl[3];
+};

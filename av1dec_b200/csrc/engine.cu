@@ -1,0 +1,531 @@
+// engine.cu -- host side of the C ABI (include/av1b200.h): device frame pool, reference store,
+// pinned command ring, stream plumbing and the per-frame launch sequence
+//     H2D(command buffer) -> itx -> inter -> wavefront -> deblock(V,H) -> CDEF -> LR [-> D2H]
+// Replaces Decoder::decodeFrame / decode_frame_wrapup / updateFrameStore of the reference
+// (decoder/Av1Decoder.cpp:111-192).  No pixel is ever computed on the host here: when the
+// CUDA runtime is unavailable every entry point fails with AV1B_ECUDA.
+#include "kernels.h"
+#include "../../include/av1b200.h"
+#include "av1_tables_host.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// thin runtime layer (CUDA, or libc for the test-only emulation build)
+// ------------------------------------------------------------------------------------------
+#ifdef AV1B_EMU
+EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
+typedef int rt_event_t;
+static int rt_set_device(int) { return 0; }
+static int rt_malloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
+static void rt_free(void* p) { free(p); }
+static int rt_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static void rt_host_free(void* p) { free(p); }
+static int rt_h2d(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
+static int rt_d2h(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
+static int rt_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, av1b_stream_t, int)
+{
+    for (size_t i = 0; i < h; i++) memcpy((uint8_t*)d + i * dp, (const uint8_t*)s + i * sp, w);
+    return 0;
+}
+static int rt_memset(void* d, int v, size_t n, av1b_stream_t) { memset(d, v, n); return 0; }
+static int rt_stream_create(av1b_stream_t* s) { *s = nullptr; return 0; }
+static void rt_stream_destroy(av1b_stream_t) {}
+static int rt_stream_sync(av1b_stream_t) { return 0; }
+static int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
+static void rt_event_destroy(rt_event_t) {}
+static int rt_event_record(rt_event_t, av1b_stream_t) { return 0; }
+static int rt_event_sync(rt_event_t) { return 0; }
+static const char* rt_error() { return "emu"; }
+static int rt_check() { return 0; }
+const char* av1b_backend(void) { return "emu"; }
+#else
+typedef cudaEvent_t rt_event_t;
+static int rt_set_device(int d) { return cudaSetDevice(d) != cudaSuccess; }
+static int rt_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
+static void rt_free(void* p) { if (p) cudaFree(p); }
+static int rt_host_alloc(void** p, size_t n) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess; }
+static void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
+static int rt_h2d(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) != cudaSuccess; }
+static int rt_d2h(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st) != cudaSuccess; }
+static int rt_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, av1b_stream_t st, int to_host)
+{
+    return cudaMemcpy2DAsync(d, dp, s, sp, w, h, to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st) != cudaSuccess;
+}
+static int rt_memset(void* d, int v, size_t n, av1b_stream_t st) { return cudaMemsetAsync(d, v, n, st) != cudaSuccess; }
+static int rt_stream_create(av1b_stream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess; }
+static void rt_stream_destroy(av1b_stream_t s) { cudaStreamDestroy(s); }
+static int rt_stream_sync(av1b_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
+static int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess; }
+static void rt_event_destroy(rt_event_t e) { cudaEventDestroy(e); }
+static int rt_event_record(rt_event_t e, av1b_stream_t s) { return cudaEventRecord(e, s) != cudaSuccess; }
+static int rt_event_sync(rt_event_t e) { return cudaEventSynchronize(e) != cudaSuccess; }
+static const char* rt_error() { return cudaGetErrorString(cudaGetLastError()); }
+static int rt_check() { return cudaGetLastError() != cudaSuccess; }
+const char* av1b_backend(void) { return "cuda-sm_100a"; }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// wedge mask table (spec 7.11.3.11; reference initialise_wedge_mask_table, InterPredict.cpp:835)
+// ------------------------------------------------------------------------------------------
+void build_wedge_table(uint8_t* out)
+{
+    enum { HORZ, VERT, OB27, OB63, OB117, OB153, NDIR };
+    static uint8_t master[NDIR][64][64];
+    for (int j = 0; j < 64; j++) {
+        int shift = 16;
+        for (int i = 0; i < 64; i += 2) {
+            master[OB63][i][j] = hk_wedge_master_even[std::min(63, std::max(0, j - shift))];
+            shift -= 1;
+            master[OB63][i + 1][j] = hk_wedge_master_odd[std::min(63, std::max(0, j - shift))];
+            master[VERT][i][j] = hk_wedge_master_vert[j];
+            master[VERT][i + 1][j] = hk_wedge_master_vert[j];
+        }
+    }
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 64; j++) {
+            int m = master[OB63][i][j];
+            master[OB27][j][i] = (uint8_t)m;
+            master[OB117][i][63 - j] = (uint8_t)(64 - m);
+            master[OB153][63 - j][i] = (uint8_t)(64 - m);
+            master[HORZ][j][i] = master[VERT][i][j];
+        }
+    static const int sizes[9] = { 3, 4, 5, 6, 7, 8, 9, 18, 19 }; // BLOCK_SIZE values that have wedges
+    memset(out, 0, AV1B_WEDGE_TABLE_BYTES);
+    for (int s = 0; s < 9; s++) {
+        const int bs = sizes[s];
+        const int w = hk_block_w[bs], h = hk_block_h[bs];
+        const int shape = h > w ? 0 : (h < w ? 1 : 2);
+        for (int wedge = 0; wedge < 16; wedge++) {
+            const int dir = hk_wedge_codebook[shape][wedge][0];
+            const int xoff = 32 - ((hk_wedge_codebook[shape][wedge][1] * w) >> 3);
+            const int yoff = 32 - ((hk_wedge_codebook[shape][wedge][2] * h) >> 3);
+            int sum = 0;
+            for (int i = 0; i < w; i++) sum += master[dir][yoff][xoff + i];
+            for (int i = 1; i < h; i++) sum += master[dir][yoff + i][xoff];
+            const int avg = (sum + (w + h - 1) / 2) / (w + h - 1);
+            const int flip = avg < 32;
+            uint8_t* t0 = out + ((size_t)((s * 2 + flip) * 16 + wedge)) * 1024;
+            uint8_t* t1 = out + ((size_t)((s * 2 + !flip) * 16 + wedge)) * 1024;
+            for (int i = 0; i < h; i++)
+                for (int j = 0; j < w; j++) {
+                    const int m = master[dir][yoff + i][xoff + j];
+                    t0[i * 32 + j] = (uint8_t)m;
+                    t1[i * 32 + j] = (uint8_t)(64 - m);
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+namespace {
+enum { N_SLOTS = 3, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = 16 };
+
+struct DevFrame {
+    uint8_t* base = nullptr;
+    FrameView v;
+    int refcnt = 0;
+};
+
+struct CmdSlot {
+    uint8_t* host = nullptr;
+    uint8_t* dev = nullptr;
+    size_t cap = 0;
+    rt_event_t done;
+    bool pending = false;
+};
+}  // namespace
+
+struct av1b_ctx {
+    int device = 0;
+    av1b_stream_t stream = nullptr;
+    bool own_stream = false;
+    int max_w = 0, max_h = 0, aw = 0, ah = 0;
+    int stride_y = 0, stride_c = 0;
+    size_t frame_bytes = 0;
+    std::vector<DevFrame> frames;
+    int ref_slot[8];
+    CmdSlot slots[N_SLOTS];
+    int cur_slot = -1;
+    int16_t* res = nullptr;
+    size_t res_cap = 0;
+    int* sync = nullptr;
+    size_t sync_cap = 0;
+    uint8_t* wedge = nullptr;
+    int pending_input = -1;
+    rt_event_t fences[N_FENCES];
+    uint64_t fence_next = 1;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static int fail(av1b_ctx* c, int code, const char* what)
+{
+    if (c) {
+        c->err = what;
+        if (code == AV1B_ECUDA) {
+            c->err += ": ";
+            c->err += rt_error();
+        }
+    }
+    return code;
+}
+
+static int frame_alloc(av1b_ctx* c)
+{
+    for (size_t i = 0; i < c->frames.size(); i++)
+        if (c->frames[i].refcnt == 0) return (int)i;
+    if (c->frames.size() >= POOL_MAX) return -1;
+    DevFrame f;
+    void* p = nullptr;
+    if (rt_malloc(&p, c->frame_bytes)) return -1;
+    f.base = (uint8_t*)p;
+    const size_t luma_rows = (size_t)c->ah + 2 * PAD_Y, chroma_rows = (size_t)c->ah / 2 + 2 * PAD_Y;
+    uint8_t* y = f.base;
+    uint8_t* u = y + luma_rows * c->stride_y;
+    uint8_t* v = u + chroma_rows * c->stride_c;
+    f.v.pl[0].p = y + (size_t)PAD_Y * c->stride_y + PAD_X;
+    f.v.pl[0].stride = c->stride_y;
+    f.v.pl[1].p = u + (size_t)PAD_Y * c->stride_c + PAD_X;
+    f.v.pl[1].stride = c->stride_c;
+    f.v.pl[2].p = v + (size_t)PAD_Y * c->stride_c + PAD_X;
+    f.v.pl[2].stride = c->stride_c;
+    c->frames.push_back(f);
+    return (int)c->frames.size() - 1;
+}
+
+extern "C" {
+
+int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream)
+{
+    if (!out || max_w <= 0 || max_h <= 0 || max_w > 16384 || max_h > 16384) return AV1B_EINVAL;
+    av1b_ctx* c = new av1b_ctx;
+    *out = c;
+    c->device = device;
+    for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
+    if (rt_set_device(device)) return fail(c, AV1B_ECUDA, "cudaSetDevice");
+    if (stream) c->stream = (av1b_stream_t)stream;
+    else {
+        if (rt_stream_create(&c->stream)) return fail(c, AV1B_ECUDA, "cudaStreamCreate");
+        c->own_stream = true;
+    }
+    c->max_w = max_w;
+    c->max_h = max_h;
+    c->aw = (max_w + 127) & ~127;
+    c->ah = (max_h + 127) & ~127;
+    c->stride_y = c->aw + 2 * PAD_X;
+    c->stride_c = c->aw / 2 + 2 * PAD_X;
+    c->frame_bytes = (size_t)(c->ah + 2 * PAD_Y) * c->stride_y + 2 * (size_t)(c->ah / 2 + 2 * PAD_Y) * c->stride_c;
+    for (int i = 0; i < N_SLOTS; i++)
+        if (rt_event_create(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+    for (int i = 0; i < N_FENCES; i++)
+        if (rt_event_create(&c->fences[i])) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+    std::vector<uint8_t> wt(AV1B_WEDGE_TABLE_BYTES);
+    build_wedge_table(wt.data());
+    void* p = nullptr;
+    if (rt_malloc(&p, AV1B_WEDGE_TABLE_BYTES)) return fail(c, AV1B_ENOMEM, "wedge table alloc");
+    c->wedge = (uint8_t*)p;
+    if (rt_h2d(c->wedge, wt.data(), AV1B_WEDGE_TABLE_BYTES, c->stream) || rt_stream_sync(c->stream))
+        return fail(c, AV1B_ECUDA, "wedge table upload");
+    return AV1B_OK;
+}
+
+void av1b_ctx_destroy(av1b_ctx* c)
+{
+    if (!c) return;
+    rt_set_device(c->device);
+    if (c->stream || true) rt_stream_sync(c->stream);
+    for (auto& f : c->frames) rt_free(f.base);
+    for (int i = 0; i < N_SLOTS; i++) {
+        rt_host_free(c->slots[i].host);
+        rt_free(c->slots[i].dev);
+        rt_event_destroy(c->slots[i].done);
+    }
+    for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
+    rt_free(c->res);
+    rt_free(c->sync);
+    rt_free(c->wedge);
+    if (c->own_stream) rt_stream_destroy(c->stream);
+    delete c;
+}
+
+const char* av1b_last_error(av1b_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int av1b_cmd_acquire(av1b_ctx* c, size_t bytes, void** host_ptr)
+{
+    if (!c || !host_ptr) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    const int s = (c->cur_slot + 1) % N_SLOTS;
+    CmdSlot& sl = c->slots[s];
+    if (sl.pending) {
+        if (rt_event_sync(sl.done)) return fail(c, AV1B_ECUDA, "slot wait");
+        sl.pending = false;
+    }
+    if (sl.cap < bytes) {
+        size_t cap = bytes + bytes / 2 + 4096;
+        rt_host_free(sl.host);
+        rt_free(sl.dev);
+        sl.host = sl.dev = nullptr;
+        sl.cap = 0;
+        void *h = nullptr, *d = nullptr;
+        if (rt_host_alloc(&h, cap)) return fail(c, AV1B_ENOMEM, "pinned command slot");
+        if (rt_malloc(&d, cap)) {
+            rt_host_free(h);
+            return fail(c, AV1B_ENOMEM, "device command slot");
+        }
+        sl.host = (uint8_t*)h;
+        sl.dev = (uint8_t*)d;
+        sl.cap = cap;
+    }
+    c->cur_slot = s;
+    *host_ptr = sl.host;
+    return AV1B_OK;
+}
+
+static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* hdr, uint32_t stages, uint32_t refresh_mask,
+    int* frame_id)
+{
+    const Av1bFrameHdr& h = *hdr;
+    if (h.magic != AV1B_MAGIC || h.version != AV1B_FORMAT_VERSION) return fail(c, AV1B_EINVAL, "bad command buffer magic/version");
+    if (h.mi_cols * 4 > c->aw || h.mi_rows * 4 > c->ah || (h.sb_cols << h.sb_log2) > c->aw || (h.sb_rows << h.sb_log2) > c->ah)
+        return fail(c, AV1B_EINVAL, "frame larger than the context");
+    // scratch
+    if ((stages & AV1B_STAGE_ITX) && h.n_res > c->res_cap) {
+        rt_stream_sync(c->stream);
+        rt_free(c->res);
+        c->res = nullptr;
+        c->res_cap = 0;
+        void* p = nullptr;
+        size_t cap = (size_t)h.n_res + h.n_res / 2 + 4096;
+        if (rt_malloc(&p, cap * sizeof(int16_t))) return fail(c, AV1B_ENOMEM, "residual arena");
+        c->res = (int16_t*)p;
+        c->res_cap = cap;
+    }
+    const size_t sync_need = 1 + (size_t)h.sb_rows;
+    if (sync_need > c->sync_cap) {
+        rt_stream_sync(c->stream);
+        rt_free(c->sync);
+        void* p = nullptr;
+        if (rt_malloc(&p, (sync_need + 64) * sizeof(int))) return fail(c, AV1B_ENOMEM, "sync buffer");
+        c->sync = (int*)p;
+        c->sync_cap = sync_need + 64;
+    }
+    // frames
+    int cur = c->pending_input;
+    c->pending_input = -1;
+    if (cur < 0) cur = frame_alloc(c);
+    if (cur < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+    c->frames[cur].refcnt++;
+    ReconCtx rc;
+    memset(&rc, 0, sizeof(rc));
+    rc.cmd = dev_cmd;
+    rc.cur = c->frames[cur].v;
+    for (int i = 0; i < 8; i++)
+        if (c->ref_slot[i] >= 0) rc.ref[i] = c->frames[c->ref_slot[i]].v;
+    rc.res = c->res;
+    rc.wedge = c->wedge;
+    rc.sync = c->sync;
+    if (stages & AV1B_STAGE_ITX) {
+        launch_itx(rc, h, c->stream);
+        c->launches += h.n_itx ? 1 : 0;
+    }
+    if (stages & AV1B_STAGE_INTER) {
+        launch_inter(rc, h, c->stream);
+        c->launches += h.n_iblk ? 1 : 0;
+    }
+    if (stages & AV1B_STAGE_WAVE) {
+        if (rt_memset(c->sync, 0, sync_need * sizeof(int), c->stream)) return fail(c, AV1B_ECUDA, "memset");
+        launch_wave(rc, h, c->stream);
+        c->launches += h.n_ops ? 1 : 0;
+    }
+    PostCtx pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.cmd = dev_cmd;
+    pc.src = c->frames[cur].v;
+    int final_frame = cur, cdef = -1, lr = -1;
+    if ((stages & AV1B_STAGE_DEBLOCK) && (h.lf.level[0] || h.lf.level[1])) {
+        launch_deblock(pc, h, c->stream);
+        c->launches += 2;
+    }
+    pc.cdef = pc.src;
+    if ((stages & AV1B_STAGE_CDEF) && h.cdef.enabled) {
+        cdef = frame_alloc(c);
+        if (cdef < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+        c->frames[cdef].refcnt++;
+        pc.cdef = c->frames[cdef].v;
+        launch_cdef(pc, h, c->stream);
+        c->launches += 1;
+        final_frame = cdef;
+    }
+    if ((stages & AV1B_STAGE_LR) && h.lr.uses_lr) {
+        lr = frame_alloc(c);
+        if (lr < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+        c->frames[lr].refcnt++;
+        pc.lr = c->frames[lr].v;
+        launch_lr(pc, h, c->stream);
+        c->launches += 1;
+        final_frame = lr;
+    }
+    if (rt_check()) return fail(c, AV1B_ECUDA, "kernel launch");
+    // reference refresh (Decoder::updateFrameStore)
+    for (int i = 0; i < 8; i++) {
+        if (refresh_mask & (1u << i)) {
+            if (c->ref_slot[i] >= 0) c->frames[c->ref_slot[i]].refcnt--;
+            c->ref_slot[i] = final_frame;
+            c->frames[final_frame].refcnt++;
+        }
+    }
+    c->frames[cur].refcnt--;
+    if (cdef >= 0) c->frames[cdef].refcnt--;
+    if (lr >= 0) c->frames[lr].refcnt--;
+    if (frame_id) *frame_id = final_frame;
+    return AV1B_OK;
+}
+
+int av1b_frame_submit(av1b_ctx* c, size_t bytes, uint32_t stages, uint32_t refresh_mask, int* frame_id)
+{
+    if (!c || c->cur_slot < 0) return AV1B_ESTATE;
+    rt_set_device(c->device);
+    CmdSlot& sl = c->slots[c->cur_slot];
+    if (bytes > sl.cap || bytes < sizeof(Av1bFrameHdr)) return fail(c, AV1B_EINVAL, "command size");
+    if (rt_h2d(sl.dev, sl.host, bytes, c->stream)) return fail(c, AV1B_ECUDA, "command upload");
+    int r = submit_impl(c, sl.dev, (const Av1bFrameHdr*)sl.host, stages, refresh_mask, frame_id);
+    if (r) return r;
+    if (rt_event_record(sl.done, c->stream)) return fail(c, AV1B_ECUDA, "event record");
+    sl.pending = true;
+    return AV1B_OK;
+}
+
+int av1b_frame_submit_resident(av1b_ctx* c, const void* dev_cmd, const Av1bFrameHdr* hdr, uint32_t stages,
+    uint32_t refresh_mask, int* frame_id)
+{
+    if (!c || !dev_cmd || !hdr) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    return submit_impl(c, (const uint8_t*)dev_cmd, hdr, stages, refresh_mask, frame_id);
+}
+
+int av1b_show_existing(av1b_ctx* c, int slot, uint32_t refresh_mask, int* frame_id)
+{
+    if (!c || slot < 0 || slot > 7) return AV1B_EINVAL;
+    const int f = c->ref_slot[slot];
+    if (f < 0) return fail(c, AV1B_ESTATE, "show_existing_frame of an empty slot");
+    for (int i = 0; i < 8; i++) {
+        if (refresh_mask & (1u << i)) {
+            c->frames[f].refcnt++;
+            if (c->ref_slot[i] >= 0) c->frames[c->ref_slot[i]].refcnt--;
+            c->ref_slot[i] = f;
+        }
+    }
+    if (frame_id) *frame_id = f;
+    return AV1B_OK;
+}
+
+int av1b_frame_download(av1b_ctx* c, int frame_id, uint8_t* const dst[3], const int dst_stride[3], int w, int h)
+{
+    if (!c || frame_id < 0 || frame_id >= (int)c->frames.size()) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    const FrameView& v = c->frames[frame_id].v;
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? (w >> 1) : w, ph = p ? (h >> 1) : h;
+        if (!dst[p] || pw <= 0 || ph <= 0) continue;
+        if (rt_copy2d(dst[p], dst_stride[p], v.pl[p].p, v.pl[p].stride, pw, ph, c->stream, 1)) return fail(c, AV1B_ECUDA, "download");
+    }
+    return AV1B_OK;
+}
+
+int av1b_sync(av1b_ctx* c)
+{
+    if (!c) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
+    return AV1B_OK;
+}
+
+int av1b_fence_record(av1b_ctx* c, uint64_t* fence)
+{
+    if (!c || !fence) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    const uint64_t id = c->fence_next++;
+    if (rt_event_record(c->fences[id % N_FENCES], c->stream)) return fail(c, AV1B_ECUDA, "fence record");
+    *fence = id;
+    return AV1B_OK;
+}
+
+int av1b_fence_wait(av1b_ctx* c, uint64_t fence)
+{
+    if (!c) return AV1B_EINVAL;
+    if (fence == 0 || fence + N_FENCES <= c->fence_next) return AV1B_OK; // long retired
+    rt_set_device(c->device);
+    if (rt_event_sync(c->fences[fence % N_FENCES])) return fail(c, AV1B_ECUDA, "fence wait");
+    return AV1B_OK;
+}
+
+void* av1b_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    return rt_host_alloc(&p, bytes) ? nullptr : p;
+}
+void av1b_host_free(void* p) { rt_host_free(p); }
+void* av1b_dev_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    return rt_malloc(&p, bytes) ? nullptr : p;
+}
+void av1b_dev_free(void* p) { rt_free(p); }
+int av1b_dev_upload(av1b_ctx* c, void* dev_dst, const void* host_src, size_t bytes)
+{
+    if (!c) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (rt_h2d(dev_dst, host_src, bytes, c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "upload");
+    return AV1B_OK;
+}
+
+static int upload_planes(av1b_ctx* c, int f, const uint8_t* const src[3], const int src_stride[3], int w, int h)
+{
+    const FrameView& v = c->frames[f].v;
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? (w >> 1) : w, ph = p ? (h >> 1) : h;
+        if (rt_copy2d(v.pl[p].p, v.pl[p].stride, src[p], src_stride[p], pw, ph, c->stream, 0)) return fail(c, AV1B_ECUDA, "upload planes");
+    }
+    if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "upload planes");
+    return AV1B_OK;
+}
+
+int av1b_debug_set_input(av1b_ctx* c, const uint8_t* const src[3], const int src_stride[3], int w, int h)
+{
+    if (!c || w > c->aw || h > c->ah) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    int f = c->pending_input >= 0 ? c->pending_input : frame_alloc(c);
+    if (f < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+    c->pending_input = f;
+    return upload_planes(c, f, src, src_stride, w, h);
+}
+
+int av1b_debug_set_ref(av1b_ctx* c, int slot, const uint8_t* const src[3], const int src_stride[3], int w, int h)
+{
+    if (!c || slot < 0 || slot > 7 || w > c->aw || h > c->ah) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    int f = frame_alloc(c);
+    if (f < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+    if (c->ref_slot[slot] >= 0) c->frames[c->ref_slot[slot]].refcnt--;
+    c->ref_slot[slot] = f;
+    c->frames[f].refcnt++;
+    return upload_planes(c, f, src, src_stride, w, h);
+}
+
+int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
+{
+    if (!c || n > c->res_cap) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (rt_d2h(dst, c->res, n * sizeof(int16_t), c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "residual download");
+    return AV1B_OK;
+}
+
+uint64_t av1b_launch_count(av1b_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

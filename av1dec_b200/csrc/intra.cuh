@@ -1,0 +1,323 @@
+// intra.cuh -- AV1 intra prediction for one transform block, executed by one CTA.
+//
+// Restates decoder/IntraPredict.cpp of the reference (edge assembly :563-611, DC :485,
+// Paeth :151, smooth :526-561, directional with edge filter / upsample :269-469,
+// recursive filter-intra :112-149, chroma-from-luma :632-667) with the CTA's threads
+// striding over samples.  The prediction lands in shared memory (`pred`, pitch = w) so the
+// caller can add the residual / blend and store once.
+//
+// Reference quirks that are reproduced on purpose:
+//   * directional numPx uses maxX WITHOUT the -1 (IntraPredict.cpp:385,401)
+//   * the frame-edge clamp of the edge fetch uses ((MiCols*4)>>subX)-1 (:568-569)
+#pragma once
+#include "dev.h"
+#include "av1_tables.h"
+
+namespace intra {
+
+enum { EDGE_OFF = 32, EDGE_LEN = 320 };
+
+struct Scratch {
+    uint8_t above[EDGE_LEN]; // AboveRow[i] at above[EDGE_OFF + i]
+    uint8_t left[EDGE_LEN];
+    uint8_t tmp[EDGE_LEN];   // filter / upsample staging
+    uint8_t pred[64 * 64];
+    int16_t luma[32 * 32];   // CfL sub-sampled luma
+    int acc;                 // CfL sum
+};
+
+struct Args {
+    const uint8_t* plane; // current-frame plane, sample (0,0)
+    int stride;
+    int x, y, log2w, log2h;
+    int max_x, max_y; // ((MiCols*4)>>subX)-1, ((MiRows*4)>>subY)-1
+    int plane_idx;
+    int mode;         // PREDICTION_MODE (0..12)
+    int angle_delta;
+    bool have_left, have_above, have_above_right, have_below_left;
+    bool edge_filter_enabled; // sequence enable_intra_edge_filter
+    bool edge_smooth;         // get_filter_type()
+    bool filter_intra;
+    int fi_mode;
+};
+
+AV1B_DEV int px(const Args& a, int x, int y) { return __ldcg(a.plane + (size_t)y * a.stride + x); }
+
+AV1B_DEV int edge_filter_strength(int w, int h, bool smooth, int delta)
+{
+    int d = iabs(delta), wh = w + h, s = 0;
+    if (!smooth) {
+        if (wh <= 8) { if (d >= 56) s = 1; }
+        else if (wh <= 12) { if (d >= 40) s = 1; }
+        else if (wh <= 16) { if (d >= 40) s = 1; }
+        else if (wh <= 24) { if (d >= 8) s = 1; if (d >= 16) s = 2; if (d >= 32) s = 3; }
+        else if (wh <= 32) { s = 1; if (d >= 4) s = 2; if (d >= 32) s = 3; }
+        else s = 3;
+    } else {
+        if (wh <= 8) { if (d >= 40) s = 1; if (d >= 64) s = 2; }
+        else if (wh <= 16) { if (d >= 20) s = 1; if (d >= 48) s = 2; }
+        else if (wh <= 24) { if (d >= 4) s = 3; }
+        else s = 3;
+    }
+    return s;
+}
+
+AV1B_DEV int edge_upsample(int w, int h, bool smooth, int delta)
+{
+    int d = iabs(delta), wh = w + h;
+    if (d <= 0 || d >= 40) return 0;
+    return smooth ? (wh <= 8) : (wh <= 16);
+}
+
+// In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter)
+AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int tid, int nt)
+{
+    if (!strength) return;
+    for (int k = tid; k < sz; k += nt) tmp[k] = edge[k - 1];
+    __syncthreads();
+    for (int i = 1 + tid; i < sz; i += nt) {
+        int s = 0;
+        AV1B_UNROLL
+        for (int j = 0; j < 5; j++) s += k_intra_edge_kernel[strength - 1][j] * tmp[clip3(0, sz - 1, i - 2 + j)];
+        edge[i - 1] = (uint8_t)((s + 8) >> 4);
+    }
+    __syncthreads();
+}
+
+// 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample)
+AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt)
+{
+    // tmp[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
+    for (int k = tid; k < n + 3; k += nt) tmp[k] = edge[clip3(-1, n - 1, k - 2)];
+    __syncthreads();
+    if (tid == 0) edge[-2] = tmp[0];
+    for (int i = tid; i < n; i += nt) {
+        int s = -tmp[i] + 9 * tmp[i + 1] + 9 * tmp[i + 2] - tmp[i + 3];
+        edge[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
+        edge[2 * i] = tmp[i + 2];
+    }
+    __syncthreads();
+}
+
+// Predict one block into S.pred (pitch w).  All threads of the CTA must call it.
+AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
+{
+    const int w = 1 << a.log2w, h = 1 << a.log2h;
+    uint8_t* A = S.above + EDGE_OFF;
+    uint8_t* L = S.left + EDGE_OFF;
+    const int x = a.x, y = a.y;
+    // ---- edge assembly (IntraPredict.cpp:579-611)
+    {
+        const bool hl = a.have_left, ha = a.have_above;
+        int above_const = -1, left_const = -1;
+        if (!ha && hl) above_const = px(a, x - 1, y);
+        else if (!ha && !hl) above_const = 127;
+        if (!hl && ha) left_const = px(a, x, y - 1);
+        else if (!ha && !hl) left_const = 129;
+        const int above_limit = min(a.max_x, x + (a.have_above_right ? 2 * w : w) - 1);
+        const int left_limit = min(a.max_y, y + (a.have_below_left ? 2 * h : h) - 1);
+        for (int i = tid; i < w + h; i += nt) {
+            A[i] = (uint8_t)(above_const >= 0 ? above_const : px(a, min(above_limit, x + i), y - 1));
+            L[i] = (uint8_t)(left_const >= 0 ? left_const : px(a, x - 1, min(left_limit, y + i)));
+        }
+        if (tid == 0) {
+            int c;
+            if (ha && hl) c = px(a, x - 1, y - 1);
+            else if (ha) c = px(a, x, y - 1);
+            else if (hl) c = px(a, x - 1, y);
+            else c = 128;
+            A[-1] = (uint8_t)c;
+            L[-1] = (uint8_t)c;
+        }
+        __syncthreads();
+    }
+    uint8_t* P = S.pred;
+    if (a.plane_idx == 0 && a.filter_intra) {
+        // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront
+        const int w4 = w >> 2, h2 = h >> 1;
+        for (int d = 0; d < w4 + h2 - 1; d++) {
+            int j_lo = max(0, d - (h2 - 1)), j_hi = min(w4 - 1, d);
+            int nsb = j_hi - j_lo + 1;
+            for (int e = tid; e < nsb * 8; e += nt) {
+                int j4 = j_lo + (e >> 3), i2 = d - j4, k = e & 7;
+                int i1 = k >> 2, j1 = k & 3;
+                int p[7];
+                AV1B_UNROLL
+                for (int i = 0; i < 5; i++) {
+                    if (!i2) p[i] = A[(j4 << 2) + i - 1];
+                    else if (!j4 && !i) p[i] = L[(i2 << 1) - 1];
+                    else p[i] = P[((i2 << 1) - 1) * w + (j4 << 2) + i - 1];
+                }
+                AV1B_UNROLL
+                for (int i = 5; i < 7; i++) {
+                    if (!j4) p[i] = L[(i2 << 1) + i - 5];
+                    else p[i] = P[((i2 << 1) + i - 5) * w + (j4 << 2) - 1];
+                }
+                int pr = 0;
+                AV1B_UNROLL
+                for (int i = 0; i < 7; i++) pr += k_intra_filter_taps[a.fi_mode][k][i] * p[i];
+                P[((i2 << 1) + i1) * w + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    const int mode = a.mode;
+    if (mode >= 1 && mode <= 8) {
+        // ---- directional (IntraPredict.cpp:379-469)
+        const int p_angle = k_mode_to_angle[mode] + a.angle_delta * 3;
+        int up_above = 0, up_left = 0;
+        if (a.edge_filter_enabled && p_angle != 90 && p_angle != 180) {
+            if (p_angle > 90 && p_angle < 180 && (w + h) >= 24) {
+                if (tid == 0) {
+                    int s = (L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4;
+                    L[-1] = (uint8_t)s;
+                    A[-1] = (uint8_t)s;
+                }
+                __syncthreads();
+            }
+            const int maxx_q = a.max_x + 1, maxy_q = a.max_y + 1; // quirk: no -1
+            if (a.have_above) {
+                int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
+                int num = min(w, maxx_q - x + 1) + (p_angle < 90 ? h : 0) + 1;
+                filter_edge(A, S.tmp, num, strength, tid, nt);
+            }
+            if (a.have_left) {
+                int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
+                int num = min(h, maxy_q - y + 1) + (p_angle > 180 ? w : 0) + 1;
+                filter_edge(L, S.tmp, num, strength, tid, nt);
+            }
+            up_above = edge_upsample(w, h, a.edge_smooth, p_angle - 90);
+            if (up_above) upsample_edge(A, S.tmp, w + (p_angle < 90 ? h : 0), tid, nt);
+            up_left = edge_upsample(w, h, a.edge_smooth, p_angle - 180);
+            if (up_left) upsample_edge(L, S.tmp, h + (p_angle > 180 ? w : 0), tid, nt);
+        }
+        if (p_angle < 90) {
+            const int dx = k_dr_intra_derivative[p_angle];
+            const int max_base = (w + h - 1) << up_above;
+            for (int e = tid; e < w * h; e += nt) {
+                int i = e >> a.log2w, j = e & (w - 1);
+                int idx = (i + 1) * dx;
+                int base = (idx >> (6 - up_above)) + (j << up_above);
+                int shift = ((idx << up_above) >> 1) & 31;
+                P[e] = (uint8_t)(base < max_base ? ((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base]);
+            }
+        } else if (p_angle > 90 && p_angle < 180) {
+            const int dx = k_dr_intra_derivative[180 - p_angle];
+            const int dy = k_dr_intra_derivative[p_angle - 90];
+            for (int e = tid; e < w * h; e += nt) {
+                int i = e >> a.log2w, j = e & (w - 1);
+                int idx = (j << 6) - (i + 1) * dx;
+                int base = idx >> (6 - up_above);
+                int v;
+                if (base >= -(1 << up_above)) {
+                    int shift = ((idx << up_above) >> 1) & 31;
+                    v = (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5;
+                } else {
+                    idx = (i << 6) - (j + 1) * dy;
+                    base = idx >> (6 - up_left);
+                    int shift = ((idx << up_left) >> 1) & 31;
+                    v = (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+                }
+                P[e] = (uint8_t)v;
+            }
+        } else if (p_angle > 180) {
+            const int dy = k_dr_intra_derivative[270 - p_angle];
+            for (int e = tid; e < w * h; e += nt) {
+                int i = e >> a.log2w, j = e & (w - 1);
+                int idx = (j + 1) * dy;
+                int base = (idx >> (6 - up_left)) + (i << up_left);
+                int shift = ((idx << up_left) >> 1) & 31;
+                P[e] = (uint8_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+            }
+        } else if (p_angle == 90) {
+            for (int e = tid; e < w * h; e += nt) P[e] = A[e & (w - 1)];
+        } else {
+            for (int e = tid; e < w * h; e += nt) P[e] = L[e >> a.log2w];
+        }
+    } else if (mode == 12) {
+        // ---- Paeth
+        const int tl = A[-1];
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> a.log2w, j = e & (w - 1);
+            int base = A[j] + L[i] - tl;
+            int pl = iabs(base - L[i]), pt = iabs(base - A[j]), ptl = iabs(base - tl);
+            P[e] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
+        }
+    } else if (mode == 0) {
+        // ---- DC
+        int avg;
+        if (a.have_left && a.have_above) {
+            int sum = 0;
+            for (int k = 0; k < h; k++) sum += L[k];
+            for (int k = 0; k < w; k++) sum += A[k];
+            avg = (sum + ((w + h) >> 1)) / (w + h);
+        } else if (a.have_left) {
+            int sum = 0;
+            for (int k = 0; k < h; k++) sum += L[k];
+            avg = clip_u8((sum + (h >> 1)) >> a.log2h);
+        } else if (a.have_above) {
+            int sum = 0;
+            for (int k = 0; k < w; k++) sum += A[k];
+            avg = clip_u8((sum + (w >> 1)) >> a.log2w);
+        } else {
+            avg = 128;
+        }
+        for (int e = tid; e < w * h; e += nt) P[e] = (uint8_t)avg;
+    } else if (mode == 9) {
+        const uint8_t* wx = k_sm_weights + (w - 4);
+        const uint8_t* wy = k_sm_weights + (h - 4);
+        const int bl = L[h - 1], tr = A[w - 1];
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> a.log2w, j = e & (w - 1);
+            int v = wy[i] * A[j] + (256 - wy[i]) * bl + wx[j] * L[i] + (256 - wx[j]) * tr;
+            P[e] = (uint8_t)((v + 256) >> 9);
+        }
+    } else if (mode == 10) {
+        const uint8_t* wy = k_sm_weights + (h - 4);
+        const int bl = L[h - 1];
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> a.log2w, j = e & (w - 1);
+            P[e] = (uint8_t)((wy[i] * A[j] + (256 - wy[i]) * bl + 128) >> 8);
+        }
+    } else { // mode == 11, SMOOTH_H
+        const uint8_t* wx = k_sm_weights + (w - 4);
+        const int tr = A[w - 1];
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> a.log2w, j = e & (w - 1);
+            P[e] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
+        }
+    }
+    __syncthreads();
+}
+
+// Chroma-from-luma on top of the DC prediction already in S.pred (IntraPredict.cpp:632-667).
+// `luma` is plane 0 of the current frame (already reconstructed for this block).
+AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int alpha, int max_luma_w, int max_luma_h,
+    Scratch& S, int tid, int nt)
+{
+    const int w = 1 << a.log2w, h = 1 << a.log2h;
+    if (tid == 0) S.acc = 0;
+    __syncthreads();
+    int local = 0;
+    for (int e = tid; e < w * h; e += nt) {
+        int i = e >> a.log2w, j = e & (w - 1);
+        int ly = min((a.y + i) << 1, max_luma_h - 2);
+        int lx = min((a.x + j) << 1, max_luma_w - 2);
+        const uint8_t* q = luma + (size_t)ly * luma_stride + lx;
+        int t = __ldcg(q) + __ldcg(q + 1) + __ldcg(q + luma_stride) + __ldcg(q + luma_stride + 1);
+        int v = t << 1;
+        S.luma[e] = (int16_t)v;
+        local += v;
+    }
+    atomicAdd(&S.acc, local);
+    __syncthreads();
+    const int avg = round2(S.acc, a.log2w + a.log2h);
+    for (int e = tid; e < w * h; e += nt) {
+        int scaled = round2s(alpha * (S.luma[e] - avg), 6);
+        S.pred[e] = (uint8_t)clip_u8(S.pred[e] + scaled);
+    }
+    __syncthreads();
+}
+
+}  // namespace intra

@@ -1,0 +1,34 @@
+// kernels.h -- internal interface between the engine (engine.cu) and the kernel files.
+#pragma once
+#include "dev.h"
+#include "../../include/av1b200_format.h"
+
+// Everything the reconstruction kernels need, passed by value as a kernel argument.
+struct ReconCtx {
+    const uint8_t* cmd;   // device copy of the frame command buffer
+    FrameView cur;        // frame being reconstructed
+    FrameView ref[8];     // reference frames by frame-store slot
+    int16_t* res;         // residual arena (written by itx_kernel)
+    const uint8_t* wedge; // wedge mask table [9][2][16][32*32]
+    int* sync;            // [0] = SB ticket counter, [1 + r] = finished SBs of SB row r
+};
+
+// In-loop filter context.
+struct PostCtx {
+    const uint8_t* cmd;
+    FrameView src;  // reconstructed frame; deblocked in place
+    FrameView cdef; // CDEF output
+    FrameView lr;   // loop-restoration output
+};
+
+void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+
+void launch_deblock(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+void launch_cdef(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+void launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+
+// Builds the wedge mask table (host memory, 9*2*16*1024 bytes).
+void build_wedge_table(uint8_t* out);
+#define AV1B_WEDGE_TABLE_BYTES (9 * 2 * 16 * 1024)

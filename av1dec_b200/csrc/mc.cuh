@@ -1,0 +1,231 @@
+// mc.cuh -- motion compensation: 8-tap sub-pel convolve, warped motion, compound / masked /
+// distance-weighted blending and OBMC strips, for one "inter prediction unit" (Av1bIpu).
+//
+// Restates the arithmetic of the reference's InterPredict (decoder/InterPredict.cpp):
+//   motionVectorScaling :66-83 (unscaled references only, as the reference asserts :395)
+//   blockPixelPredict :319-331, blockSubPixelPredict :333-383, getFilterIdx :85-97
+//   blockWarp :507-553, maskBlend :584-609, predict_overlap :611-628
+//   wedgeMask :888-899, differenceWeightMask :901-915, final writers :1023-1045
+// but is organised for a CTA: the unit is cut into <=32x32 tiles, each tile's horizontal pass
+// lands in shared memory (int16), the vertical pass and the blend run one thread per sample.
+#pragma once
+#include "dev.h"
+#include "av1_tables.h"
+#include "../../include/av1b200_format.h"
+
+namespace mc {
+
+enum { TILE = 32, INTER_ELEMS = 16 * 15 * 8 /* >= (TILE+7)*TILE */ };
+
+struct Scratch {
+    int16_t inter[INTER_ELEMS];   // horizontal-pass intermediates
+    int16_t pred[2][TILE * TILE]; // per-list predictions of the current tile
+};
+
+struct RefPlane {
+    const uint8_t* p;
+    int stride;
+    int last_x, last_y;
+    bool coherent; // true: read through L2 (current frame, intrabc)
+};
+
+AV1B_DEV int ref_px(const RefPlane& r, int x, int y)
+{
+    x = clip3(0, r.last_x, x);
+    y = clip3(0, r.last_y, y);
+    const uint8_t* q = r.p + (size_t)y * r.stride + x;
+    return r.coherent ? (int)__ldcg(q) : (int)__ldg(q);
+}
+
+// InterpFilter -> row of k_subpel_filters (reference getFilterIdx)
+AV1B_DEV int filter_row(int size, int interp)
+{
+    if (size <= 4) {
+        if (interp == 0 || interp == 2) return 4;
+        if (interp == 1) return 5;
+    }
+    return interp;
+}
+
+// Wedge mask table: [9 block sizes][2 signs][16 wedges][32*32], built by the engine at start-up.
+AV1B_DEV int wedge_size_index(int mi_size)
+{
+    // BLOCK_8X8=3 8X16=4 16X8=5 16X16=6 16X32=7 32X16=8 32X32=9 8X32=18 32X8=19
+    if (mi_size >= 3 && mi_size <= 9) return mi_size - 3;
+    if (mi_size == 18) return 7;
+    if (mi_size == 19) return 8;
+    return -1;
+}
+AV1B_DEV const uint8_t* wedge_mask_ptr(const uint8_t* table, int mi_size, int sign, int index)
+{
+    return table + ((size_t)((wedge_size_index(mi_size) * 2 + sign) * 16 + index)) * 1024;
+}
+
+struct Params {
+    const Av1bFrameHdr* hdr;
+    const Av1bBlkAux* aux;   // may be null when the unit needs none
+    const uint8_t* wedge;    // wedge table
+    uint8_t* mask;           // luma-resolution mask scratch (128 x 128), diff-weighted compound
+    PlaneView dst;           // destination plane of the current frame
+    RefPlane ref[2];
+};
+
+// Prediction of list `l` for the tile at (tx,ty) size (tw,th) into s.pred[l].
+AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int ty, int tw, int th,
+    Scratch& s, int tid, int nt)
+{
+    const int subx = u.plane ? 1 : 0, suby = u.plane ? 1 : 0;
+    const bool compound = (u.flags & AV1B_IPUF_COMPOUND) != 0;
+    const int round1 = compound ? 7 : 11;
+    const RefPlane& R = P.ref[l];
+    int use_warp = u.warp[l];
+    if (u.w < 8 || u.h < 8) use_warp = 0;
+    int16_t* pred = s.pred[l];
+    if (use_warp) {
+        const int32_t* wp = (use_warp == 1) ? P.aux->warp_params : P.hdr->gm_params[u.ref_frame[l]];
+        const int16_t* ab = (use_warp == 1) ? P.aux->warp_abgd : P.hdr->gm_abgd[u.ref_frame[l]];
+        const int alpha = ab[0], beta = ab[1], gamma = ab[2], delta = ab[3];
+        const int nux = tw >> 3, nuy = th >> 3, nu = nux * nuy;
+        // horizontal pass: 15 x 8 per 8x8 unit
+        for (int e = tid; e < nu * 120; e += nt) {
+            int unit = e / 120, k = e - unit * 120;
+            int i1 = k / 8 - 7, i2 = (k & 7) - 4;
+            int uy = unit / nux, ux = unit - uy * nux;
+            int srcx = (u.x + tx + ux * 8 + 4) << subx;
+            int srcy = (u.y + ty + uy * 8 + 4) << suby;
+            int dstx = wp[2] * srcx + wp[3] * srcy + wp[0];
+            int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
+            int x4 = dstx >> subx, y4 = dsty >> suby;
+            int ix4 = x4 >> 16, sx4 = x4 & 0xFFFF, iy4 = y4 >> 16;
+            int sx = sx4 + alpha * i2 + beta * i1;
+            int offs = ((sx + 512) >> 10) + 64;
+            const int16_t* f = k_warped_filters[offs];
+            int sum = 0;
+            AV1B_UNROLL
+            for (int t = 0; t < 8; t++) sum += f[t] * ref_px(R, ix4 + i2 - 3 + t, iy4 + i1);
+            s.inter[e] = (int16_t)((sum + 4) >> 3);
+        }
+        __syncthreads();
+        for (int e = tid; e < nu * 64; e += nt) {
+            int unit = e >> 6, k = e & 63;
+            int i1 = (k >> 3) - 4, i2 = (k & 7) - 4;
+            int uy = unit / nux, ux = unit - uy * nux;
+            int srcx = (u.x + tx + ux * 8 + 4) << subx;
+            int srcy = (u.y + ty + uy * 8 + 4) << suby;
+            int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
+            int y4 = dsty >> suby;
+            int sy4 = y4 & 0xFFFF;
+            int sy = sy4 + gamma * i2 + delta * i1;
+            int offs = ((sy + 512) >> 10) + 64;
+            const int16_t* f = k_warped_filters[offs];
+            const int16_t* in = s.inter + unit * 120 + (i2 + 4);
+            int sum = 0;
+            AV1B_UNROLL
+            for (int t = 0; t < 8; t++) sum += f[t] * in[(i1 + t + 4) * 8];
+            pred[(uy * 8 + i1 + 4) * TILE + ux * 8 + i2 + 4] = (int16_t)round2(sum, round1);
+        }
+        __syncthreads();
+        return;
+    }
+    // translational prediction
+    const int mvx = (2 * u.mv[l][1]) >> subx; // 1/16 sample
+    const int mvy = (2 * u.mv[l][0]) >> suby;
+    const int fx = mvx & 15, fy = mvy & 15;
+    const int px0 = u.x + tx + (mvx >> 4), py0 = u.y + ty + (mvy >> 4);
+    if (!fx && !fy) {
+        const int sh = 14 - 3 - round1;
+        for (int e = tid; e < tw * th; e += nt) {
+            int r = e / tw, c = e - r * tw;
+            pred[r * TILE + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
+        }
+        __syncthreads();
+        return;
+    }
+    const int16_t* fh = k_subpel_filters[filter_row(u.w, u.filt[1])][fx];
+    const int16_t* fv = k_subpel_filters[filter_row(u.h, u.filt[0])][fy];
+    const int ih = th + 7;
+    for (int e = tid; e < ih * tw; e += nt) {
+        int r = e / tw, c = e - r * tw;
+        int y = py0 + r - 3, x = px0 + c - 3;
+        int sum = 0;
+        AV1B_UNROLL
+        for (int t = 0; t < 8; t++) sum += fh[t] * ref_px(R, x + t, y);
+        s.inter[r * TILE + c] = (int16_t)((sum + 4) >> 3);
+    }
+    __syncthreads();
+    for (int e = tid; e < tw * th; e += nt) {
+        int r = e / tw, c = e - r * tw;
+        int sum = 0;
+        AV1B_UNROLL
+        for (int t = 0; t < 8; t++) sum += fv[t] * s.inter[(r + t) * TILE + c];
+        pred[r * TILE + c] = (int16_t)round2(sum, round1);
+    }
+    __syncthreads();
+}
+
+// Execute one unit: predict every tile and write / blend it into the destination plane.
+AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, int nt)
+{
+    const bool compound = (u.flags & AV1B_IPUF_COMPOUND) != 0;
+    const int plane = u.plane;
+    for (int ty = 0; ty < u.h; ty += TILE) {
+        const int th = min((int)TILE, u.h - ty);
+        for (int tx = 0; tx < u.w; tx += TILE) {
+            const int tw = min((int)TILE, u.w - tx);
+            predict_tile(P, u, 0, tx, ty, tw, th, s, tid, nt);
+            if (compound) predict_tile(P, u, 1, tx, ty, tw, th, s, tid, nt);
+            for (int e = tid; e < tw * th; e += nt) {
+                int r = e / tw, c = e - r * tw;
+                int i = ty + r, j = tx + c; // position inside the unit
+                uint8_t* d = P.dst.p + (size_t)(u.y + i) * P.dst.stride + (u.x + j);
+                int p0 = s.pred[0][r * TILE + c];
+                int out;
+                if (u.kind != AV1B_IPU_PRED) {
+                    // OBMC strip (reference predict_overlap): mask runs along rows for the
+                    // above pass, along columns for the left pass.
+                    int len = (u.kind == AV1B_IPU_OBMC_ABOVE) ? u.h : u.w;
+                    int m = k_obmc_mask[len - 2 + ((u.kind == AV1B_IPU_OBMC_ABOVE) ? i : j)];
+                    int cur = *d;
+                    out = clip_u8(round2(m * cur + (64 - m) * clip_u8(p0), 6));
+                } else if (!compound) {
+                    out = clip_u8(p0);
+                } else {
+                    int p1 = s.pred[1][r * TILE + c];
+                    if (u.comp_type == AV1B_COMP_AVERAGE) {
+                        out = clip_u8(round2(p0 + p1, 5));
+                    } else if (u.comp_type == AV1B_COMP_DISTANCE) {
+                        out = clip_u8(round2(u.fwd_w * p0 + u.bck_w * p1, 8));
+                    } else {
+                        int m;
+                        if (u.comp_type == AV1B_COMP_WEDGE) {
+                            const uint8_t* W = wedge_mask_ptr(P.wedge, P.aux->mi_size, P.aux->wedge_sign, P.aux->wedge_index);
+                            if (!plane) m = W[i * 32 + j];
+                            else
+                                m = (W[(2 * i) * 32 + 2 * j] + W[(2 * i) * 32 + 2 * j + 1] + W[(2 * i + 1) * 32 + 2 * j]
+                                        + W[(2 * i + 1) * 32 + 2 * j + 1] + 2)
+                                    >> 2;
+                        } else { // DIFFWTD
+                            if (!plane) {
+                                int diff = iabs(p0 - p1);
+                                diff = (diff + 8) >> 4;
+                                m = clip3(0, 64, 38 + diff / 16);
+                                if (P.aux->mask_type) m = 64 - m;
+                                P.mask[i * 128 + j] = (uint8_t)m;
+                            } else {
+                                const uint8_t* M = P.mask;
+                                m = (M[(2 * i) * 128 + 2 * j] + M[(2 * i) * 128 + 2 * j + 1] + M[(2 * i + 1) * 128 + 2 * j]
+                                        + M[(2 * i + 1) * 128 + 2 * j + 1] + 2)
+                                    >> 2;
+                            }
+                        }
+                        out = clip_u8(round2(m * p0 + (64 - m) * p1, 10));
+                    }
+                }
+                *d = (uint8_t)out;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace mc

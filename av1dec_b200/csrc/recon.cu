@@ -1,0 +1,341 @@
+// recon.cu -- block reconstruction kernels for sm_100a.
+//
+//   itx_kernel    batched inverse transform: dequantised int16 coefficients -> int16 residual
+//                 arena, one warp per transform block (independent, fully parallel).
+//   inter_kernel  motion compensation for every inter block of the frame (independent of the
+//                 current frame's pixels; one CTA per block).
+//   wave_kernel   the dependent pass: intra prediction (+CfL, filter-intra, palette), inter-intra
+//                 blend, intrabc and residual add, scheduled as a superblock wavefront with the
+//                 classic 2-SB lag.  CTAs take superblocks from an atomic ticket counter in
+//                 raster order, so a CTA only ever waits for CTAs that are already running.
+//
+// Reference for the behaviour: decoder/TransformBlock.cpp:2376-2456 (TransformBlock::decode),
+// decoder/Block.cpp:100-174,1600-1608 (compute_prediction / Block::decode),
+// decoder/Tile.cpp:172-181 (SB raster order).
+#include "dev.h"
+#include "av1_tables.h"
+#include "itx.cuh"
+#include "intra.cuh"
+#include "mc.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------
+// inverse transform
+// ------------------------------------------------------------------------------------------
+namespace {
+
+enum { ITX_WARPS = 4, ITX_TMP_STRIDE = 66, ITX_TMP_ROWS = 32 };
+
+template <int n>
+AV1B_DEV void itx_rows(const int16_t* coef, int tw, int nz_rows, int16_t* tmp, int kind, bool rect, int row_shift,
+    int lane, int nl)
+{
+    for (int i = lane; i < nz_rows; i += nl)
+        itx::row_pass<n>(coef + i * tw, tw, tmp + i * ITX_TMP_STRIDE, kind, rect, row_shift);
+}
+
+template <int n>
+AV1B_DEV void itx_cols(const int16_t* tmp, int nz_rows, int16_t* out, int w, bool fud, bool flr, int kind, int col_shift,
+    int lane, int nl)
+{
+    for (int j = lane; j < w; j += nl) {
+        int jo = flr ? (w - 1 - j) : j;
+        itx::col_pass<n>(tmp + j, ITX_TMP_STRIDE, nz_rows, out + jo, w, fud, kind, col_shift);
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(ITX_WARPS * 32)
+    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, int n_list,
+        const int16_t* __restrict__ coef, int16_t* __restrict__ res)
+{
+    __shared__ int16_t tmp_all[ITX_WARPS][ITX_TMP_ROWS * ITX_TMP_STRIDE];
+    const int nl = min(32u, blockDim.x);
+    const int nw = max(1u, blockDim.x / 32);
+    const int lane = threadIdx.x % nl;
+    const int warp = threadIdx.x / nl;
+    int16_t* tmp = tmp_all[warp];
+    for (int t = blockIdx.x * nw + warp; t < n_list; t += gridDim.x * nw) {
+        const Av1bOp op = ops[list[t]];
+        const int txs = op.tx_size;
+        const int lw = k_tx_wlog2[txs], lh = k_tx_hlog2[txs];
+        const int w = 1 << lw, h = 1 << lh;
+        const int tw = min(w, 32);
+        const bool lossless = op.lossless != 0;
+        const int rk = lossless ? itx::K_WHT : itx::row_kind(op.tx_type);
+        const int ck = lossless ? itx::K_WHT : itx::col_kind(op.tx_type);
+        const bool rect = (lw - lh == 1) || (lh - lw == 1);
+        const int row_shift = lossless ? 0 : k_tx_row_shift[txs];
+        const int col_shift = lossless ? 0 : 4;
+        const int nz_rows = min((int)op.nz_rows, min(h, 32));
+        const int16_t* c = coef + op.coef_off;
+        int16_t* out = res + op.res_off;
+        switch (lw) {
+        case 2: itx_rows<2>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
+        case 3: itx_rows<3>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
+        case 4: itx_rows<4>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
+        case 5: itx_rows<5>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
+        default: itx_rows<6>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
+        }
+        __syncwarp();
+        const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
+        switch (lh) {
+        case 2: itx_cols<2>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 3: itx_cols<3>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 4: itx_cols<4>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 5: itx_cols<5>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        default: itx_cols<6>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// inter prediction (independent pass)
+// ------------------------------------------------------------------------------------------
+AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bIpu& u, uint8_t* mask, mc::Params& P)
+{
+    const int plane = u.plane, sub = plane ? 1 : 0;
+    P.hdr = hdr;
+    P.aux = (u.aux != 0xFFFFFFFFu) ? ((const Av1bBlkAux*)(c.cmd + hdr->off_aux) + u.aux) : nullptr;
+    P.wedge = c.wedge;
+    P.mask = mask;
+    P.dst = c.cur.pl[plane];
+    const int nl = (u.flags & AV1B_IPUF_COMPOUND) ? 2 : 1;
+    for (int l = 0; l < nl; l++) {
+        mc::RefPlane& R = P.ref[l];
+        if (u.flags & AV1B_IPUF_INTRABC) {
+            R.p = c.cur.pl[plane].p;
+            R.stride = c.cur.pl[plane].stride;
+            R.last_x = ((hdr->ref_w[0] + sub) >> sub) - 1;
+            R.last_y = ((hdr->ref_h[0] + sub) >> sub) - 1;
+            R.coherent = true;
+        } else {
+            const PlaneView& pv = c.ref[u.ref_slot[l]].pl[plane];
+            R.p = pv.p;
+            R.stride = pv.stride;
+            R.last_x = ((hdr->ref_w[u.ref_frame[l]] + sub) >> sub) - 1;
+            R.last_y = ((hdr->ref_h[u.ref_frame[l]] + sub) >> sub) - 1;
+            R.coherent = false;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) inter_kernel(ReconCtx c)
+{
+    __shared__ mc::Scratch M;
+    __shared__ uint8_t mask[128 * 128];
+    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const Av1bInterBlk* blks = (const Av1bInterBlk*)(c.cmd + hdr->off_iblk);
+    const Av1bIpu* ipus = (const Av1bIpu*)(c.cmd + hdr->off_ipu);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (unsigned b = blockIdx.x; b < hdr->n_iblk; b += gridDim.x) {
+        const Av1bInterBlk blk = blks[b];
+        for (unsigned k = 0; k < blk.n_ipu; k++) {
+            const Av1bIpu u = ipus[blk.first_ipu + k];
+            mc::Params P;
+            setup_mc_params(c, hdr, u, mask, P);
+            mc::run_ipu(P, u, M, tid, nt);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dependent pass (superblock wavefront)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct WaveShared {
+    intra::Scratch I;
+    mc::Scratch M;
+    int sb;
+};
+
+AV1B_DEV void store_with_residual(const PlaneView& dst, int x, int y, int w, int h, const uint8_t* pred,
+    const int16_t* res, int tid, int nt)
+{
+    for (int e = tid; e < w * h; e += nt) {
+        int i = e / w, j = e - i * w;
+        int v = pred[e];
+        if (res) v = clip_u8(v + res[e]);
+        dst.p[(size_t)(y + i) * dst.stride + x + j] = (uint8_t)v;
+    }
+}
+
+AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, WaveShared& S, int tid, int nt)
+{
+    const int plane = op.plane, sub = plane ? 1 : 0;
+    const PlaneView dst = c.cur.pl[plane];
+    const int16_t* res = (op.flags & AV1B_OPF_HAS_RESID) ? (c.res + op.res_off) : nullptr;
+    int lw, lh;
+    if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
+        lw = op.tx_size & 15;
+        lh = op.tx_size >> 4;
+    } else {
+        lw = k_tx_wlog2[op.tx_size];
+        lh = k_tx_hlog2[op.tx_size];
+    }
+    const int w = 1 << lw, h = 1 << lh;
+    switch (op.kind) {
+    case AV1B_OP_INTER_RES: {
+        if (!res) break;
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> lw, j = e & (w - 1);
+            uint8_t* d = dst.p + (size_t)(op.y + i) * dst.stride + op.x + j;
+            *d = (uint8_t)clip_u8((int)__ldcg(d) + res[e]);
+        }
+        break;
+    }
+    case AV1B_OP_INTRA:
+    case AV1B_OP_INTERINTRA: {
+        intra::Args a;
+        a.plane = dst.p;
+        a.stride = dst.stride;
+        a.x = op.x;
+        a.y = op.y;
+        a.log2w = lw;
+        a.log2h = lh;
+        a.max_x = ((hdr->mi_cols * 4) >> sub) - 1;
+        a.max_y = ((hdr->mi_rows * 4) >> sub) - 1;
+        a.plane_idx = plane;
+        a.mode = op.mode;
+        a.angle_delta = op.angle_delta;
+        a.have_left = (op.flags & AV1B_OPF_HAVE_LEFT) != 0;
+        a.have_above = (op.flags & AV1B_OPF_HAVE_ABOVE) != 0;
+        a.have_above_right = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) != 0;
+        a.have_below_left = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) != 0;
+        a.edge_filter_enabled = hdr->enable_intra_edge_filter != 0;
+        a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
+        a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
+        a.fi_mode = op.fi_mode;
+        intra::predict(a, S.I, tid, nt);
+        if (op.kind == AV1B_OP_INTRA) {
+            if (op.flags & AV1B_OPF_CFL)
+                intra::apply_cfl(a, c.cur.pl[0].p, c.cur.pl[0].stride, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, tid, nt);
+            store_with_residual(dst, op.x, op.y, w, h, S.I.pred, res, tid, nt);
+        } else {
+            // inter-intra blend over the inter prediction already in the frame
+            // (reference maskBlend, InterPredict.cpp:584-609; masks :555-582, :888-899)
+            const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
+            const uint8_t* W = aux->wedge_interintra ? mc::wedge_mask_ptr(c.wedge, aux->mi_size, aux->wedge_sign, aux->wedge_index) : nullptr;
+            const int scale = 128 / max(w, h);
+            const int iim = aux->interintra_mode;
+            for (int e = tid; e < w * h; e += nt) {
+                int i = e >> lw, j = e & (w - 1);
+                int m;
+                if (W) {
+                    if (!plane) m = W[i * 32 + j];
+                    else
+                        m = (W[(2 * i) * 32 + 2 * j] + W[(2 * i) * 32 + 2 * j + 1] + W[(2 * i + 1) * 32 + 2 * j]
+                                + W[(2 * i + 1) * 32 + 2 * j + 1] + 2)
+                            >> 2;
+                } else if (iim == 1) m = k_ii_weights_1d[i * scale];
+                else if (iim == 2) m = k_ii_weights_1d[j * scale];
+                else if (iim == 3) m = k_ii_weights_1d[min(i, j) * scale];
+                else m = 32;
+                uint8_t* d = dst.p + (size_t)(op.y + i) * dst.stride + op.x + j;
+                int inter = __ldcg(d);
+                *d = (uint8_t)clip_u8(round2(m * S.I.pred[e] + (64 - m) * inter, 6));
+            }
+        }
+        break;
+    }
+    case AV1B_OP_PALETTE: {
+        const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
+        const int pi = plane ? 1 : 0;
+        const uint8_t* map = c.cmd + hdr->off_pal + aux->pal_map_off[pi];
+        const int ms = aux->pal_map_stride[pi];
+        const int ox = op.x - aux->base_x[pi], oy = op.y - aux->base_y[pi];
+        const uint8_t* colors = aux->pal_colors[plane];
+        for (int e = tid; e < w * h; e += nt) {
+            int i = e >> lw, j = e & (w - 1);
+            int v = colors[map[(oy + i) * ms + ox + j]];
+            if (res) v = clip_u8(v + res[e]);
+            dst.p[(size_t)(op.y + i) * dst.stride + op.x + j] = (uint8_t)v;
+        }
+        break;
+    }
+    case AV1B_OP_INTRABC: {
+        const Av1bIpu u = ((const Av1bIpu*)(c.cmd + hdr->off_ipu))[op.aux];
+        mc::Params P;
+        setup_mc_params(c, hdr, u, nullptr, P);
+        mc::run_ipu(P, u, S.M, tid, nt);
+        break;
+    }
+    }
+    __syncthreads();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) wave_kernel(ReconCtx c)
+{
+    __shared__ WaveShared S;
+    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
+    const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
+    int* ticket = c.sync;
+    int* progress = c.sync + 1;
+    for (;;) {
+        if (tid == 0) S.sb = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int sb = S.sb;
+        if (sb >= n_sb) break;
+        const int r = sb / sb_cols, col = sb - r * sb_cols;
+        if (tid == 0) {
+            if (r > 0) {
+                const int need = min(col + 2, sb_cols);
+                while (av1b_ld_acquire(progress + r - 1) < need) av1b_nanosleep(100);
+            }
+            if (col > 0) {
+                while (av1b_ld_acquire(progress + r) < col) av1b_nanosleep(100);
+            }
+        }
+        __syncthreads();
+        const Av1bSb e = sbs[sb];
+        for (unsigned k = 0; k < e.n_ops; k++) {
+            const Av1bOp op = ops[e.first_op + k];
+            exec_op(c, hdr, op, S, tid, nt);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            av1b_st_release(progress + r, col + 1);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------
+void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
+{
+    if (!h.n_itx) return;
+    const Av1bOp* ops = (const Av1bOp*)(c.cmd + h.off_ops);
+    const uint32_t* list = (const uint32_t*)(c.cmd + h.off_itx);
+    const int16_t* coef = (const int16_t*)(c.cmd + h.off_coef);
+    int grid = (int)((h.n_itx + ITX_WARPS - 1) / ITX_WARPS);
+    if (grid > 148 * 16) grid = 148 * 16;
+    AV1B_LAUNCH(itx_kernel, (grid), (ITX_WARPS * 32), st, ops, list, (int)h.n_itx, coef, c.res);
+}
+
+void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
+{
+    if (!h.n_iblk) return;
+    int grid = (int)h.n_iblk;
+    if (grid > 148 * 8) grid = 148 * 8;
+    AV1B_LAUNCH(inter_kernel, (grid), (256), st, c);
+}
+
+void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
+{
+    if (!h.n_ops) return;
+    int grid = (int)h.n_sb;
+    if (grid > 148 * 2) grid = 148 * 2;
+    AV1B_LAUNCH(wave_kernel, (grid), (256), st, c);
+}

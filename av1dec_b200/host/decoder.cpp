@@ -1,0 +1,273 @@
+// decoder.cpp -- YamiAv1::Decoder on top of the B200 engine.
+//
+// Frame lifecycle of the reference (decoder/Av1Decoder.cpp):
+//     decode() OBU loop :49-109  -> kept on the host, drives the reference's own Parser
+//     decodeFrame() :128-156     -> emit commands, av1b_frame_submit() (recon + filters on GPU)
+//     showExistingFrame() :158   -> av1b_show_existing()
+//     updateFrameStore() :111    -> refresh mask handed to the engine (device-resident refs)
+//     getOutput() :203           -> async D2H into pooled pinned I420 frames
+// There is no host pixel path: if the engine reports an error, decode() returns false.
+#include "ref_access.h"
+#include "Av1Decoder.h"
+#include "decoder_impl.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace Yami;
+
+namespace YamiAv1 {
+
+namespace {
+
+// Pinned host frame handed to the caller; same field layout as the reference's YuvFrame.
+struct HostFrame : public YuvFrame {
+    void* buf = nullptr;
+    size_t cap = 0;
+};
+
+struct HostPool {
+    std::vector<HostFrame*> free_list;
+    ~HostPool()
+    {
+        for (HostFrame* f : free_list) {
+            av1b_host_free(f->buf);
+            delete f;
+        }
+    }
+};
+
+std::shared_ptr<YuvFrame> acquireHostFrame(const std::shared_ptr<HostPool>& pool, int w, int h)
+{
+    const int sy = (w + 63) & ~63, sc = ((w >> 1) + 63) & ~63;
+    const size_t need = (size_t)sy * h + 2 * (size_t)sc * (h >> 1);
+    HostFrame* f = nullptr;
+    for (size_t i = 0; i < pool->free_list.size(); i++) {
+        if (pool->free_list[i]->cap >= need) {
+            f = pool->free_list[i];
+            pool->free_list.erase(pool->free_list.begin() + i);
+            break;
+        }
+    }
+    if (!f) {
+        f = new HostFrame;
+        f->buf = av1b_host_alloc(need);
+        f->cap = need;
+        if (!f->buf) {
+            delete f;
+            return nullptr;
+        }
+    }
+    uint8_t* p = (uint8_t*)f->buf;
+    f->pts = 0;
+    f->width = w;
+    f->height = h;
+    f->data[0] = p;
+    f->data[1] = p + (size_t)sy * h;
+    f->data[2] = f->data[1] + (size_t)sc * (h >> 1);
+    f->strides[0] = sy;
+    f->strides[1] = f->strides[2] = sc;
+    f->widths[0] = w;
+    f->heights[0] = h;
+    f->widths[1] = f->widths[2] = w / 2;
+    f->heights[1] = f->heights[2] = h / 2;
+    std::shared_ptr<HostPool> keep = pool;
+    return std::shared_ptr<YuvFrame>(static_cast<YuvFrame*>(f), [keep](YuvFrame* y) { keep->free_list.push_back(static_cast<HostFrame*>(y)); });
+}
+
+}  // namespace
+
+struct Decoder::Impl {
+    std::unique_ptr<Parser> parser;
+    FramePtr frame;
+    TileGroup tiles;
+    av1b_ctx* ctx = nullptr;
+    av1b200::FrameEmitter emitter;
+    std::shared_ptr<HostPool> pool = std::make_shared<HostPool>();
+    struct Pending {
+        std::shared_ptr<YuvFrame> frame;
+        uint64_t fence;
+    };
+    std::deque<Pending> output;
+    int frame_w[32], frame_h[32]; // visible size of each device frame id
+    av1b200::DecoderOptions opt;
+    std::string error;
+
+    bool fail(const char* what)
+    {
+        error = what;
+        if (ctx) {
+            error += ": ";
+            error += av1b_last_error(ctx);
+        }
+        fprintf(stderr, "av1b200: %s\n", error.c_str());
+        return false;
+    }
+
+    bool ensureCtx()
+    {
+        if (ctx) return true;
+        const SequenceHeader& s = *parser->m_sequence;
+        const int mw = s.max_frame_width_minus_1 + 1, mh = s.max_frame_height_minus_1 + 1;
+        if (s.BitDepth != 8 || !s.subsampling_x || !s.subsampling_y || s.mono_chrome) return fail("only 8-bit 4:2:0 streams are supported (same envelope as the reference)");
+        if (av1b_ctx_create(&ctx, opt.device, mw, mh, nullptr) != AV1B_OK) return fail("av1b_ctx_create");
+        return true;
+    }
+
+    bool queueOutput(int fid)
+    {
+        const int w = frame_w[fid], h = frame_h[fid];
+        std::shared_ptr<YuvFrame> hf = acquireHostFrame(pool, w, h);
+        if (!hf) return fail("pinned output allocation");
+        uint8_t* dst[3] = { hf->data[0], hf->data[1], hf->data[2] };
+        int st[3] = { hf->strides[0], hf->strides[1], hf->strides[2] };
+        if (av1b_frame_download(ctx, fid, dst, st, w, h) != AV1B_OK) return fail("av1b_frame_download");
+        uint64_t fence = 0;
+        if (av1b_fence_record(ctx, &fence) != AV1B_OK) return fail("av1b_fence_record");
+        output.push_back(Pending{ hf, fence });
+        return true;
+    }
+
+    bool decodeFrame(TileGroup& ts)
+    {
+        FrameHeader& h = *frame;
+        if (!ensureCtx()) return false;
+        emitter.begin(h, *parser->m_sequence);
+        for (auto& t : ts) {
+            emitter.emitTile(*t);
+            t->m_sbs.clear(); // the block tree is no longer needed (Tile::decode pops as it goes)
+        }
+        for (auto& t : ts) t->frame_end_update_cdf();
+        emitter.finish();
+        const size_t bytes = emitter.bytes();
+        void* slot = nullptr;
+        if (av1b_cmd_acquire(ctx, bytes, &slot) != AV1B_OK) return fail("av1b_cmd_acquire");
+        emitter.write((uint8_t*)slot);
+        if (opt.sink) opt.sink(opt.sink_user, (const uint8_t*)slot, bytes, h.refresh_frame_flags, h.show_frame);
+        int fid = -1;
+        if (av1b_frame_submit(ctx, bytes, opt.stages, h.refresh_frame_flags, &fid) != AV1B_OK) return fail("av1b_frame_submit");
+        frame_w[fid] = h.FrameWidth;
+        frame_h[fid] = h.FrameHeight;
+        if (h.show_frame && !queueOutput(fid)) return false;
+        h.motionVectorStorage();
+        parser->finishFrame();
+        return true;
+    }
+
+    bool showExisting()
+    {
+        FrameHeader& h = *frame;
+        if (!ctx) return fail("show_existing_frame before any frame");
+        int fid = -1;
+        if (av1b_show_existing(ctx, h.frame_to_show_map_idx, h.refresh_frame_flags, &fid) != AV1B_OK) return fail("av1b_show_existing");
+        if (opt.sink) opt.sink(opt.sink_user, nullptr, (size_t)h.frame_to_show_map_idx, h.refresh_frame_flags, 1);
+        if (!queueOutput(fid)) return false;
+        h.referenceFrameLoading();
+        h.motionVectorStorage();
+        parser->finishFrame();
+        return true;
+    }
+};
+
+Decoder::Decoder()
+    : m_impl(new Impl)
+{
+    m_impl->parser.reset(new Parser);
+    const char* dev = getenv("AV1B200_DEVICE");
+    if (dev) m_impl->opt.device = atoi(dev);
+}
+
+Decoder::~Decoder()
+{
+    if (m_impl->ctx) {
+        av1b_sync(m_impl->ctx);
+        m_impl->output.clear();
+        av1b_ctx_destroy(m_impl->ctx);
+    }
+}
+
+bool Decoder::decode(uint8_t* data, size_t size)
+{
+    Impl& d = *m_impl;
+    Parser& parser = *d.parser;
+    BitReader reader(data, size);
+    while (reader.getRemainingBitsCount() > 0) {
+        obu_header hdr;
+        if (!hdr.parse(reader)) return false;
+        const uint64_t payload = hdr.obu_size;
+        BitReader br(data + (reader.getPos() >> 3), payload);
+        bool ok = true;
+        switch (hdr.obu_type) {
+        case OBU_SEQUENCE_HEADER: ok = parser.parseSequenceHeader(br); break;
+        case OBU_TD: ok = parser.parseTemporalDelimiter(br); break;
+        case OBU_FRAME_HEADER:
+            d.frame = parser.parseFrameHeader(br);
+            ok = bool(d.frame);
+            if (ok && d.frame->show_existing_frame) ok = d.showExisting();
+            break;
+        case OBU_TILE_GROUP: {
+            if (!d.frame) return false;
+            TileGroup group;
+            ok = parser.parseTileGroup(br, d.frame, group);
+            if (ok) {
+                d.tiles.insert(d.tiles.end(), group.begin(), group.end());
+                if (d.tiles.size() == parser.m_frame->NumTiles) {
+                    ok = d.decodeFrame(d.tiles);
+                    d.tiles.clear();
+                }
+            }
+            break;
+        }
+        case OBU_FRAME: {
+            TileGroup group;
+            d.frame = parser.parseFrame(br, group);
+            ok = d.frame ? d.decodeFrame(group) : false;
+            d.tiles.clear();
+            break;
+        }
+        case OBU_METADATA: ok = parser.parseMetadata(br); break;
+        case OBU_PADDING: ok = parser.parsePadding(br); break;
+        default: ok = parser.praseReserved(br); break;
+        }
+        if (!ok) return false;
+        reader.skip(payload << 3);
+    }
+    return true;
+}
+
+std::shared_ptr<YuvFrame> Decoder::getOutput()
+{
+    Impl& d = *m_impl;
+    if (d.output.empty()) return nullptr;
+    Impl::Pending p = d.output.front();
+    d.output.pop_front();
+    if (av1b_fence_wait(d.ctx, p.fence) != AV1B_OK) {
+        d.fail("av1b_fence_wait");
+        return nullptr;
+    }
+    return p.frame;
+}
+
+}  // namespace YamiAv1
+
+// ---- helpers for the C API / adapter ---------------------------------------------------------
+namespace av1b200 {
+static YamiAv1::Decoder::Impl* implOf(YamiAv1::Decoder& d) { return d.impl(); }
+DecoderOptions& decoderOptions(YamiAv1::Decoder& d) { return implOf(d)->opt; }
+const char* decoderError(YamiAv1::Decoder& d) { return implOf(d)->error.c_str(); }
+av1b_ctx* decoderCtx(YamiAv1::Decoder& d) { return implOf(d)->ctx; }
+bool decoderFormat(YamiAv1::Decoder& d, int& w, int& h)
+{
+    auto* i = implOf(d);
+    if (!i->parser->m_sequence) return false;
+    w = i->parser->m_sequence->max_frame_width_minus_1 + 1;
+    h = i->parser->m_sequence->max_frame_height_minus_1 + 1;
+    return true;
+}
+void decoderFlush(YamiAv1::Decoder& d)
+{
+    auto* i = implOf(d);
+    if (i->ctx) av1b_sync(i->ctx);
+    i->output.clear();
+}
+}  // namespace av1b200

@@ -1,0 +1,660 @@
+// emitter.cpp -- see emitter.h.  Every function cites the reference code whose *reads* it
+// replays; nothing here computes a pixel.
+#include "ref_access.h"
+#include "emitter.h"
+#include "../csrc/av1_tables_host.h"
+
+#include <cstdlib>
+
+using namespace YamiAv1;
+
+namespace av1b200 {
+
+static const uint32_t kNoAux = 0xFFFFFFFFu;
+
+template <class T> static inline T clip3(T lo, T hi, T v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
+{
+    m_frame = &frame;
+    m_seq = &seq;
+    memset(&m_hdr, 0, sizeof(m_hdr));
+    Av1bFrameHdr& h = m_hdr;
+    h.magic = AV1B_MAGIC;
+    h.version = AV1B_FORMAT_VERSION;
+    h.frame_w = (uint16_t)frame.FrameWidth;
+    h.frame_h = (uint16_t)frame.FrameHeight;
+    h.mi_cols = (uint16_t)frame.MiCols;
+    h.mi_rows = (uint16_t)frame.MiRows;
+    h.sb_log2 = seq.use_128x128_superblock ? 7 : 6;
+    const int sb4 = 1 << (h.sb_log2 - 2);
+    h.sb_cols = (uint16_t)((frame.MiCols + sb4 - 1) / sb4);
+    h.sb_rows = (uint16_t)((frame.MiRows + sb4 - 1) / sb4);
+    h.enable_intra_edge_filter = seq.enable_intra_edge_filter;
+    h.frame_is_intra = frame.FrameIsIntra;
+    h.allow_intrabc = frame.allow_intrabc;
+    // reference slots and dimensions (InterPredict.cpp:389-394,982)
+    for (int i = 0; i < 8; i++) h.ref_slot[i] = -1;
+    h.ref_w[0] = (uint16_t)(frame.MiCols * MI_SIZE); // intrabc "reference" (InterPredict.cpp:990-995)
+    h.ref_h[0] = (uint16_t)(frame.MiRows * MI_SIZE);
+    if (!frame.FrameIsIntra) {
+        for (int rf = LAST_FRAME; rf <= ALTREF_FRAME; rf++) {
+            const int slot = frame.ref_frame_idx[rf - LAST_FRAME];
+            const RefFrame& r = frame.m_refInfo.m_refs[slot];
+            h.ref_slot[rf] = (int8_t)slot;
+            h.ref_w[rf] = (uint16_t)r.RefUpscaledWidth;
+            h.ref_h[rf] = (uint16_t)r.RefFrameHeight;
+            for (int k = 0; k < 6; k++) h.gm_params[rf][k] = frame.gm_params[rf][k];
+        }
+    }
+    m_gmReady = false;
+    m_sbs.assign((size_t)h.sb_cols * h.sb_rows, Av1bSb{ 0, 0 });
+    m_ops.clear();
+    m_itx.clear();
+    m_iblk.clear();
+    m_ipu.clear();
+    m_aux.clear();
+    m_coef.clear();
+    m_pal.clear();
+    m_lru.clear();
+    m_lftx.assign((size_t)3 * frame.MiRows * frame.MiCols, 0);
+    m_nRes = 0;
+    m_total = 0;
+}
+
+void FrameEmitter::emitTile(Tile& tile)
+{
+    const int sb4 = 1 << (m_hdr.sb_log2 - 2);
+    for (auto& sbp : tile.m_sbs) {
+        SuperBlock& sb = *sbp;
+        // SuperBlock::decode (SuperBlock.cpp:46-51)
+        tile.m_decoded.clear_block_decoded_flags(sb.m_r, sb.m_c, sb4);
+        const size_t idx = (size_t)(sb.m_r / sb4) * m_hdr.sb_cols + (sb.m_c / sb4);
+        const uint32_t first = (uint32_t)m_ops.size();
+        walk(sb);
+        m_sbs[idx].first_op = first;
+        m_sbs[idx].n_ops = (uint32_t)m_ops.size() - first;
+    }
+}
+
+void FrameEmitter::walk(Partition& p)
+{
+    // Partition::decode (Partition.cpp:207-214): children in parse order
+    for (auto& bt : p.m_blocks) {
+        if (Block* b = dynamic_cast<Block*>(bt.get())) emitBlock(*b);
+        else walk(*static_cast<Partition*>(bt.get()));
+    }
+}
+
+void FrameEmitter::emitBlock(Block& b)
+{
+    // Block::decode (Block.cpp:1600-1608): prediction, then the transform blocks in order
+    m_blockAux = kNoAux;
+    if (b.is_inter) emitInter(b);
+    for (auto& t : b.m_transformBlocks) emitTb(b, *t);
+}
+
+uint32_t FrameEmitter::auxFor(Block& b)
+{
+    if (m_blockAux != kNoAux) return m_blockAux;
+    Av1bBlkAux a;
+    memset(&a, 0, sizeof(a));
+    a.mi_size = (uint8_t)b.MiSize;
+    if (b.is_inter) {
+        a.interintra_mode = (uint8_t)b.interintra_mode;
+        a.wedge_interintra = b.interintra ? b.wedge_interintra : 0;
+        a.wedge_index = b.wedge_index;
+        a.wedge_sign = b.wedge_sign;
+        a.mask_type = b.mask_type;
+        if (b.motion_mode == LOCALWARP && b.m_localWarp.LocalValid) {
+            int al, be, ga, de;
+            b.m_localWarp.setupShear(b.m_localWarp.LocalWarpParams, al, be, ga, de);
+            for (int k = 0; k < 6; k++) a.warp_params[k] = b.m_localWarp.LocalWarpParams[k];
+            a.warp_abgd[0] = (int16_t)al;
+            a.warp_abgd[1] = (int16_t)be;
+            a.warp_abgd[2] = (int16_t)ga;
+            a.warp_abgd[3] = (int16_t)de;
+        }
+    } else {
+        // Palette::predict_palette inputs (Block.cpp:2279-2297)
+        const auto& pal = b.m_palette;
+        a.pal_size_y = b.PaletteSizeY;
+        a.pal_size_uv = b.PaletteSizeUV;
+        for (int i = 0; i < b.PaletteSizeY && i < 8; i++) a.pal_colors[0][i] = pal.palette_colors_y[i];
+        for (int i = 0; i < b.PaletteSizeUV && i < 8; i++) {
+            a.pal_colors[1][i] = pal.palette_colors_u[i];
+            a.pal_colors[2][i] = pal.palette_colors_v[i];
+        }
+        const std::vector<std::vector<uint8_t>>* maps[2] = { &pal.ColorMapY, &pal.ColorMapUV };
+        const int sizes[2] = { b.PaletteSizeY, b.PaletteSizeUV };
+        for (int k = 0; k < 2; k++) {
+            if (!sizes[k] || maps[k]->empty()) continue;
+            const size_t rows = maps[k]->size(), cols = (*maps[k])[0].size();
+            a.pal_map_off[k] = (uint32_t)m_pal.size();
+            a.pal_map_stride[k] = (uint16_t)cols;
+            for (size_t r = 0; r < rows; r++) m_pal.insert(m_pal.end(), (*maps[k])[r].begin(), (*maps[k])[r].end());
+        }
+        a.base_x[0] = (uint16_t)(b.MiCol * MI_SIZE);
+        a.base_y[0] = (uint16_t)(b.MiRow * MI_SIZE);
+        a.base_x[1] = (uint16_t)((b.MiCol >> b.subsampling_x) * MI_SIZE);
+        a.base_y[1] = (uint16_t)((b.MiRow >> b.subsampling_y) * MI_SIZE);
+    }
+    m_aux.push_back(a);
+    m_blockAux = (uint32_t)m_aux.size() - 1;
+    return m_blockAux;
+}
+
+// get_filter_type (IntraPredict.cpp:211-267): does the left or above neighbour use a SMOOTH mode
+bool FrameEmitter::edgeSmooth(const Block& b, int plane) const
+{
+    auto smooth = [&](int r, int c) -> bool {
+        const ModeInfoBlock& info = m_frame->getModeInfo(r, c);
+        int mode;
+        if (!plane) mode = info.YMode;
+        else {
+            if (info.RefFrames[0] > INTRA_FRAME) return false;
+            mode = info.UVMode;
+        }
+        return mode == SMOOTH_PRED || mode == SMOOTH_V_PRED || mode == SMOOTH_H_PRED;
+    };
+    bool above = false, left = false;
+    if (plane ? b.AvailUChroma : b.AvailU) {
+        int r = b.MiRow - 1, c = b.MiCol;
+        if (plane > 0) {
+            if (b.subsampling_x && !(b.MiCol & 1)) c++;
+            if (b.subsampling_y && (b.MiRow & 1)) r--;
+        }
+        above = smooth(r, c);
+    }
+    if (plane ? b.AvailLChroma : b.AvailL) {
+        int r = b.MiRow, c = b.MiCol - 1;
+        if (plane > 0) {
+            if (b.subsampling_x && (b.MiCol & 1)) c--;
+            if (b.subsampling_y && !(b.MiRow & 1)) r++;
+        }
+        left = smooth(r, c);
+    }
+    return above || left;
+}
+
+// getDistanceWeights (InterPredict.cpp:917-960)
+void FrameEmitter::distanceWeights(int candRow, int candCol, int& fwd, int& bck) const
+{
+    int dist[2];
+    for (int l = 0; l < 2; l++) {
+        const uint8_t ref = (uint8_t)m_frame->getModeInfo(candRow, candCol).RefFrames[l];
+        dist[l] = clip3(0, (int)MAX_FRAME_DISTANCE, std::abs((int)m_frame->get_relative_dist(ref)));
+    }
+    const int d0 = dist[1], d1 = dist[0];
+    const int order = d0 <= d1;
+    int i = 3;
+    if (d0 != 0 && d1 != 0) {
+        for (i = 0; i < 3; i++) {
+            const int c0 = hk_quant_dist_weight[i][order], c1 = hk_quant_dist_weight[i][1 - order];
+            if (order ? (d0 * c0 > d1 * c1) : (d0 * c0 < d1 * c1)) break;
+        }
+    }
+    fwd = hk_quant_dist_lookup[i][order];
+    bck = hk_quant_dist_lookup[i][1 - order];
+}
+
+void FrameEmitter::emitInter(Block& b)
+{
+    FrameHeader& f = *m_frame;
+    const SequenceHeader& seq = *m_seq;
+    // Global-motion shear parameters once per frame (InterPredict.cpp:974-977); needs any block's
+    // LocalWarp object to reach the reference's setupShear().
+    if (!m_gmReady) {
+        for (int rf = LAST_FRAME; rf <= ALTREF_FRAME; rf++) {
+            m_hdr.gm_warp_ok[rf] = 0;
+            if (!f.FrameIsIntra && f.GmType[rf] > TRANSLATION && !f.is_scaled(rf)) {
+                int al, be, ga, de;
+                const bool ok = b.m_localWarp.setupShear(f.gm_params[rf], al, be, ga, de);
+                m_hdr.gm_abgd[rf][0] = (int16_t)al;
+                m_hdr.gm_abgd[rf][1] = (int16_t)be;
+                m_hdr.gm_abgd[rf][2] = (int16_t)ga;
+                m_hdr.gm_abgd[rf][3] = (int16_t)de;
+                m_hdr.gm_warp_ok[rf] = ok;
+            }
+        }
+        m_gmReady = true;
+    }
+    const bool interintra = b.RefFrame[1] == INTRA_FRAME;
+    const bool intrabc = b.use_intrabc;
+    if (b.motion_mode == LOCALWARP) {
+        // predict_inter, plane 0 (InterPredict.cpp:967-970)
+        b.m_localWarp.warpEstimation();
+        b.m_localWarp.setupShear();
+    }
+    Av1bInterBlk ib;
+    memset(&ib, 0, sizeof(ib));
+    ib.first_ipu = (uint32_t)m_ipu.size();
+    ib.bw = (uint16_t)b.bw;
+    ib.bh = (uint16_t)b.bh;
+    const int subBlockMiRow = b.MiRow & b.sbMask, subBlockMiCol = b.MiCol & b.sbMask;
+    // Block::compute_prediction (Block.cpp:100-174)
+    for (int plane = 0; plane < 1 + b.HasChroma * 2; plane++) {
+        const int planeSz = seq.get_plane_residual_size(b.MiSize, plane);
+        const int num4x4W = Num_4x4_Blocks_Wide[planeSz], num4x4H = Num_4x4_Blocks_High[planeSz];
+        const int subX = plane ? b.subsampling_x : 0, subY = plane ? b.subsampling_y : 0;
+        const int baseX = (b.MiCol >> subX) * MI_SIZE, baseY = (b.MiRow >> subY) * MI_SIZE;
+        int candRow = (b.MiRow >> subY) << subY, candCol = (b.MiCol >> subX) << subX;
+        if (interintra) {
+            Av1bOp op;
+            memset(&op, 0, sizeof(op));
+            op.x = (uint16_t)baseX;
+            op.y = (uint16_t)baseY;
+            op.plane = (uint8_t)plane;
+            op.kind = AV1B_OP_INTERINTRA;
+            const int log2W = MI_SIZE_LOG2 + Mi_Width_Log2[planeSz], log2H = MI_SIZE_LOG2 + Mi_Height_Log2[planeSz];
+            op.tx_size = (uint8_t)(log2W | (log2H << 4));
+            switch (b.interintra_mode) {
+            case II_DC_PRED: op.mode = DC_PRED; break;
+            case II_V_PRED: op.mode = V_PRED; break;
+            case II_H_PRED: op.mode = H_PRED; break;
+            default: op.mode = SMOOTH_PRED; break;
+            }
+            uint8_t fl = 0;
+            if (plane == 0 ? b.AvailL : b.AvailLChroma) fl |= AV1B_OPF_HAVE_LEFT;
+            if (plane == 0 ? b.AvailU : b.AvailUChroma) fl |= AV1B_OPF_HAVE_ABOVE;
+            if (b.m_decoded.getFlag(plane, (subBlockMiRow >> subY) - 1, (subBlockMiCol >> subX) + num4x4W)) fl |= AV1B_OPF_HAVE_ABOVE_RIGHT;
+            if (b.m_decoded.getFlag(plane, (subBlockMiRow >> subY) + num4x4H, (subBlockMiCol >> subX) - 1)) fl |= AV1B_OPF_HAVE_BELOW_LEFT;
+            op.flags = fl;
+            op.aux = auxFor(b);
+            m_ops.push_back(op);
+        }
+        int predW = b.bw >> subX, predH = b.bh >> subY;
+        bool someUseIntra = false;
+        for (int r = 0; r < (num4x4H << subY); r++)
+            for (int c = 0; c < (num4x4W << subX); c++)
+                if (f.getModeInfo(candRow + r, candCol + c).RefFrames[0] == INTRA_FRAME) someUseIntra = true;
+        if (someUseIntra) {
+            predH = num4x4H * 4;
+            predW = num4x4W * 4;
+            candRow = b.MiRow;
+            candCol = b.MiCol;
+        }
+        int r = 0;
+        for (int y = 0; y < num4x4H * 4; y += predH) {
+            int c = 0;
+            for (int x = 0; x < num4x4W * 4; x += predW) {
+                // InterPredict::predict_inter(baseX + x, baseY + y, predW, predH, candRow + r, candCol + c)
+                const ModeInfoBlock& info = f.getModeInfo(candRow + r, candCol + c);
+                const bool isCompound = info.RefFrames[1] > INTRA_FRAME;
+                Av1bIpu u;
+                memset(&u, 0, sizeof(u));
+                u.x = (uint16_t)(baseX + x);
+                u.y = (uint16_t)(baseY + y);
+                u.w = (uint8_t)predW;
+                u.h = (uint8_t)predH;
+                u.plane = (uint8_t)plane;
+                u.kind = AV1B_IPU_PRED;
+                u.aux = kNoAux;
+                u.ref_slot[0] = u.ref_slot[1] = -1;
+                bool needAux = false;
+                for (int l = 0; l < 1 + isCompound; l++) {
+                    const int refFrame = info.RefFrames[l];
+                    u.mv[l][0] = info.Mvs[l].mv[0];
+                    u.mv[l][1] = info.Mvs[l].mv[1];
+                    if (!intrabc) {
+                        u.ref_slot[l] = (int8_t)f.ref_frame_idx[refFrame - LAST_FRAME];
+                        u.ref_frame[l] = (uint8_t)refFrame;
+                        // getUseWarp (InterPredict.cpp:50-64); the w/h >= 8 test runs on the device
+                        if (!f.force_integer_mv) {
+                            if (b.motion_mode == LOCALWARP && b.m_localWarp.LocalValid) {
+                                u.warp[l] = 1;
+                                needAux = true;
+                            } else if ((b.YMode == GLOBALMV || b.YMode == GLOBAL_GLOBALMV) && m_hdr.gm_warp_ok[refFrame]) {
+                                u.warp[l] = 2;
+                            }
+                        }
+                    }
+                }
+                u.filt[0] = (uint8_t)info.InterpFilters[0];
+                u.filt[1] = (uint8_t)info.InterpFilters[1];
+                u.flags = (isCompound ? AV1B_IPUF_COMPOUND : 0) | (interintra ? AV1B_IPUF_INTERINTRA : 0) | (intrabc ? AV1B_IPUF_INTRABC : 0);
+                u.comp_type = (uint8_t)b.compound_type;
+                if (isCompound) {
+                    if (b.compound_type == COMPOUND_DISTANCE) {
+                        int fw, bk;
+                        distanceWeights(candRow + r, candCol + c, fw, bk);
+                        u.fwd_w = (uint8_t)fw;
+                        u.bck_w = (uint8_t)bk;
+                    } else if (b.compound_type == COMPOUND_WEDGE || b.compound_type == COMPOUND_DIFFWTD) {
+                        needAux = true;
+                    }
+                }
+                if (needAux) u.aux = auxFor(b);
+                m_ipu.push_back(u);
+                if (intrabc) {
+                    Av1bOp op;
+                    memset(&op, 0, sizeof(op));
+                    op.x = u.x;
+                    op.y = u.y;
+                    op.plane = (uint8_t)plane;
+                    op.kind = AV1B_OP_INTRABC;
+                    op.aux = (uint32_t)m_ipu.size() - 1;
+                    m_ops.push_back(op);
+                }
+                c++;
+            }
+            r++;
+        }
+        if (b.motion_mode == OBMC_CAUSAL) emitObmc(b, plane, predW, predH);
+    }
+    ib.n_ipu = (uint32_t)m_ipu.size() - ib.first_ipu;
+    if (!intrabc && ib.n_ipu) m_iblk.push_back(ib);
+}
+
+// overlappedMotionCompensation (InterPredict.cpp:658-709): which neighbours contribute strips
+void FrameEmitter::emitObmc(Block& b, int plane, int w, int h)
+{
+    FrameHeader& f = *m_frame;
+    const int subX = plane ? b.subsampling_x : 0, subY = plane ? b.subsampling_y : 0;
+    auto strip = [&](int kind, int candRow, int candCol, int x4, int y4, int predW, int predH) {
+        const ModeInfoBlock& info = f.getModeInfo(candRow, candCol);
+        Av1bIpu u;
+        memset(&u, 0, sizeof(u));
+        u.x = (uint16_t)((x4 * 4) >> subX);
+        u.y = (uint16_t)((y4 * 4) >> subY);
+        u.w = (uint8_t)predW;
+        u.h = (uint8_t)predH;
+        u.plane = (uint8_t)plane;
+        u.kind = (uint8_t)kind;
+        u.mv[0][0] = info.Mvs[0].mv[0];
+        u.mv[0][1] = info.Mvs[0].mv[1];
+        u.ref_slot[0] = (int8_t)f.ref_frame_idx[info.RefFrames[0] - LAST_FRAME];
+        u.ref_slot[1] = -1;
+        u.ref_frame[0] = (uint8_t)info.RefFrames[0];
+        u.filt[0] = (uint8_t)info.InterpFilters[0];
+        u.filt[1] = (uint8_t)info.InterpFilters[1];
+        u.aux = kNoAux;
+        m_ipu.push_back(u);
+    };
+    if (b.AvailU && m_seq->get_plane_residual_size(b.MiSize, plane) >= BLOCK_8X8) {
+        const int w4 = Num_4x4_Blocks_Wide[b.MiSize];
+        int x4 = b.MiCol, nCount = 0;
+        const int nLimit = std::min(4, (int)Mi_Width_Log2[b.MiSize]);
+        while (nCount < nLimit && x4 < std::min(f.MiCols, b.MiCol + w4)) {
+            const int candRow = b.MiRow - 1, candCol = x4 | 1;
+            const ModeInfoBlock& info = f.getModeInfo(candRow, candCol);
+            const int step4 = clip3(2, 16, Num_4x4_Blocks_Wide[info.MiSize]);
+            if (info.RefFrames[0] > INTRA_FRAME) {
+                nCount++;
+                strip(AV1B_IPU_OBMC_ABOVE, candRow, candCol, x4, b.MiRow, std::min(w, (step4 * MI_SIZE) >> subX), std::min(h >> 1, 32 >> subY));
+            }
+            x4 += step4;
+        }
+    }
+    if (b.AvailL) {
+        const int h4 = Num_4x4_Blocks_High[b.MiSize];
+        int y4 = b.MiRow, nCount = 0;
+        const int nLimit = std::min(4, (int)Mi_Height_Log2[b.MiSize]);
+        while (nCount < nLimit && y4 < std::min(f.MiRows, b.MiRow + h4)) {
+            const int candCol = b.MiCol - 1, candRow = y4 | 1;
+            const ModeInfoBlock& info = f.getModeInfo(candRow, candCol);
+            const int step4 = clip3(2, 16, Num_4x4_Blocks_High[info.MiSize]);
+            if (info.RefFrames[0] > INTRA_FRAME) {
+                nCount++;
+                strip(AV1B_IPU_OBMC_LEFT, candRow, candCol, b.MiCol, y4, std::min(w >> 1, 32 >> subX), std::min(h, (step4 * MI_SIZE) >> subY));
+            }
+            y4 += step4;
+        }
+    }
+}
+
+// TransformBlock::decode (TransformBlock.cpp:2376-2456) and reconstruct()'s dequantisation (:2255-2276)
+void FrameEmitter::emitTb(Block& b, TransformBlock& t)
+{
+    FrameHeader& f = *m_frame;
+    const int plane = t.plane;
+    const int subX = plane ? b.subsampling_x : 0, subY = plane ? b.subsampling_y : 0;
+    const int x = t.x, y = t.y;
+    const TX_SIZE txSz = t.txSz;
+    const int row = (y << subY) >> MI_SIZE_LOG2, col = (x << subX) >> MI_SIZE_LOG2;
+    const int subBlockMiRow = row & b.sbMask, subBlockMiCol = col & b.sbMask;
+    const int stepX = Tx_Width[txSz] >> MI_SIZE_LOG2, stepY = Tx_Height[txSz] >> MI_SIZE_LOG2;
+    Av1bOp op;
+    memset(&op, 0, sizeof(op));
+    op.x = (uint16_t)x;
+    op.y = (uint16_t)y;
+    op.plane = (uint8_t)plane;
+    op.tx_size = (uint8_t)txSz;
+    if (!b.is_inter) {
+        if (b.m_palette.isPalettePredict(plane)) {
+            op.kind = AV1B_OP_PALETTE;
+            op.aux = auxFor(b);
+        } else {
+            op.kind = AV1B_OP_INTRA;
+            const bool isCfl = plane > 0 && b.UVMode == UV_CFL_PRED;
+            const int mode = plane == 0 ? (int)b.YMode : (isCfl ? (int)DC_PRED : (int)b.UVMode);
+            op.mode = (uint8_t)mode;
+            op.angle_delta = plane == 0 ? b.AngleDeltaY : b.AngleDeltaUV;
+            uint8_t fl = 0;
+            if ((plane == 0 ? b.AvailL : b.AvailLChroma) || x > t.m_baseX) fl |= AV1B_OPF_HAVE_LEFT;
+            if ((plane == 0 ? b.AvailU : b.AvailUChroma) || y > t.m_baseY) fl |= AV1B_OPF_HAVE_ABOVE;
+            if (b.m_decoded.getFlag(plane, (subBlockMiRow >> subY) - 1, (subBlockMiCol >> subX) + stepX)) fl |= AV1B_OPF_HAVE_ABOVE_RIGHT;
+            if (b.m_decoded.getFlag(plane, (subBlockMiRow >> subY) + stepY, (subBlockMiCol >> subX) - 1)) fl |= AV1B_OPF_HAVE_BELOW_LEFT;
+            if (plane == 0 && b.use_filter_intra) {
+                fl |= AV1B_OPF_FILTER_INTRA;
+                op.fi_mode = (uint8_t)b.filter_intra_mode;
+            } else if (is_directional_mode(mode) && m_seq->enable_intra_edge_filter) {
+                if (edgeSmooth(b, plane)) fl |= AV1B_OPF_EDGE_SMOOTH;
+            }
+            if (isCfl) {
+                fl |= AV1B_OPF_CFL;
+                op.cfl_alpha = plane == 1 ? b.CflAlphaU : b.CflAlphaV;
+                op.max_luma_w = (uint16_t)m_maxLumaW;
+                op.max_luma_h = (uint16_t)m_maxLumaH;
+            }
+            op.flags = fl;
+        }
+        if (plane == 0) {
+            m_maxLumaW = x + stepX * 4;
+            m_maxLumaH = y + stepY * 4;
+        }
+    } else {
+        op.kind = AV1B_OP_INTER_RES;
+    }
+    if (t.m_eob > 0) {
+        const int tw = t.tw, th = t.th;
+        const int dcq = t.get_dc_quant(), acq = t.get_ac_quant();
+        const int denom = t.dqDenom;
+        const size_t off = m_coef.size();
+        m_coef.resize(off + (size_t)tw * th);
+        int16_t* out = &m_coef[off];
+        int nzr = 0, nzc = 0;
+        for (int i = 0; i < th; i++) {
+            for (int j = 0; j < tw; j++) {
+                const int q = t.Quant[i * tw + j];
+                int v = 0;
+                if (q) {
+                    const int dq = (int)((unsigned)q * (unsigned)((i | j) ? acq : dcq));
+                    const int mag = (int)(((dq < 0) ? (0u - (unsigned)dq) : (unsigned)dq) & 0xffffffu) / denom;
+                    v = clip3(-32768, 32767, dq < 0 ? -mag : mag);
+                    if (i + 1 > nzr) nzr = i + 1;
+                    if (j + 1 > nzc) nzc = j + 1;
+                }
+                out[i * tw + j] = (int16_t)v;
+            }
+        }
+        op.flags |= AV1B_OPF_HAS_RESID;
+        op.tx_type = (uint8_t)t.PlaneTxType;
+        op.lossless = b.Lossless;
+        op.nz_rows = (uint8_t)nzr;
+        op.nz_cols = (uint8_t)nzc;
+        op.coef_off = (uint32_t)off;
+        op.res_off = m_nRes;
+        m_nRes += (uint32_t)(Tx_Width[txSz] * Tx_Height[txSz]);
+        m_itx.push_back((uint32_t)m_ops.size());
+    }
+    if (op.kind != AV1B_OP_INTER_RES || (op.flags & AV1B_OPF_HAS_RESID)) m_ops.push_back(op);
+    else if (t.m_eob > 0) m_itx.pop_back();
+    // LoopfilterTxSizes + BlockDecoded bookkeeping (TransformBlock.cpp:2444-2454)
+    const int miRows = f.MiRows, miCols = f.MiCols;
+    uint8_t* lftx = &m_lftx[(size_t)plane * miRows * miCols];
+    for (int i = 0; i < stepY; i++) {
+        for (int j = 0; j < stepX; j++) {
+            for (int xx = 0; xx < subX + 1; xx++)
+                for (int yy = 0; yy < subY + 1; yy++) {
+                    const int rr = row + (i << subY) + yy, cc = col + (j << subX) + xx;
+                    if (rr < miRows && cc < miCols) lftx[(size_t)rr * miCols + cc] = (uint8_t)txSz;
+                }
+            b.m_decoded.setFlag(plane, (subBlockMiRow >> subY) + i, (subBlockMiCol >> subX) + j);
+        }
+    }
+}
+
+static int countUnits(int unitSize, int frameSize) { return std::max((frameSize + (unitSize >> 1)) / unitSize, 1); }
+
+void FrameEmitter::finish()
+{
+    FrameHeader& f = *m_frame;
+    Av1bFrameHdr& h = m_hdr;
+    const int miRows = f.MiRows, miCols = f.MiCols;
+    // ---- deblocking inputs (LoopFilter.cpp:40-58,301-359)
+    const LoopFilterParams& lf = f.m_loopFilter;
+    for (int i = 0; i < 4; i++) h.lf.level[i] = lf.loop_filter_level[i];
+    if (m_seq->NumPlanes == 1 || !(lf.loop_filter_level[0] || lf.loop_filter_level[1])) h.lf.level[2] = h.lf.level[3] = 0;
+    h.lf.sharpness = lf.loop_filter_sharpness;
+    h.lf.delta_enabled = lf.loop_filter_delta_enabled;
+    h.lf.delta_lf_multi = f.m_deltaLf.delta_lf_multi;
+    for (int i = 0; i < 8; i++) h.lf.ref_deltas[i] = lf.loop_filter_ref_deltas[i];
+    for (int i = 0; i < 2; i++) h.lf.mode_deltas[i] = lf.loop_filter_mode_deltas[i];
+    m_lfmi.resize((size_t)miRows * miCols);
+    const uint8_t* txY = &m_lftx[0];
+    const uint8_t* txU = &m_lftx[(size_t)miRows * miCols];
+    const uint8_t* txV = &m_lftx[(size_t)2 * miRows * miCols];
+    for (int r = 0; r < miRows; r++) {
+        for (int c = 0; c < miCols; c++) {
+            const ModeInfoBlock& info = f.getModeInfo(r, c);
+            Av1bLfMi& m = m_lfmi[(size_t)r * miCols + c];
+            const size_t k = (size_t)r * miCols + c;
+            m.mi_size = (uint8_t)info.MiSize;
+            const int mode = info.YMode;
+            const int modeType = mode >= NEARESTMV && mode != GLOBALMV && mode != GLOBAL_GLOBALMV;
+            const int ref = std::max(0, (int)info.RefFrames[0]);
+            m.flags = (uint8_t)((info.Skip ? 1 : 0) | (modeType << 1) | ((ref & 7) << 2));
+            m.tx = (uint16_t)(txY[k] | (txU[k] << 5) | (txV[k] << 10));
+            for (int i = 0; i < 4; i++) m.delta_lf[i] = info.DeltaLFs[i];
+        }
+    }
+    // ---- CDEF inputs (Cdef.cpp:41-101)
+    const CdefParams& cd = f.m_cdef;
+    const int r8n = miRows >> 1, c8n = miCols >> 1;
+    m_cdef8.assign((size_t)r8n * c8n, 0xFF);
+    bool anyCdef = false;
+    const bool cdefOff = f.CodedLossless || f.allow_intrabc || !m_seq->enable_cdef;
+    if (!cdefOff) {
+        for (int r8 = 0; r8 < r8n; r8++) {
+            for (int c8 = 0; c8 < c8n; c8++) {
+                const int r = r8 * 2, c = c8 * 2;
+                const int idx = cd.cdef_idx[r & ~15][c & ~15];
+                if (idx == -1) continue;
+                const bool skip = f.getModeInfo(r, c).Skip && f.getModeInfo(r + 1, c).Skip && f.getModeInfo(r, c + 1).Skip
+                    && f.getModeInfo(r + 1, c + 1).Skip;
+                if (skip) continue;
+                m_cdef8[(size_t)r8 * c8n + c8] = (uint8_t)idx;
+                anyCdef = true;
+            }
+        }
+    }
+    h.cdef.enabled = anyCdef;
+    h.cdef.damping = cd.CdefDamping;
+    for (int i = 0; i < 8; i++) {
+        h.cdef.y_pri[i] = cd.cdef_y_pri_strength[i];
+        h.cdef.y_sec[i] = cd.cdef_y_sec_strength[i];
+        h.cdef.uv_pri[i] = cd.cdef_uv_pri_strength[i];
+        h.cdef.uv_sec[i] = cd.cdef_uv_sec_strength[i];
+    }
+    // ---- loop-restoration inputs (LoopRestoration.cpp:49-134,191-219)
+    const LoopRestorationpParams& lr = f.m_loopRestoration;
+    h.lr.uses_lr = lr.UsesLr;
+    if (lr.UsesLr) {
+        for (int p = 0; p < m_seq->NumPlanes && p < 3; p++) {
+            h.lr.frame_type[p] = (uint8_t)lr.FrameRestorationType[p];
+            if (lr.FrameRestorationType[p] == RESTORE_NONE) continue;
+            const int sub = p ? 1 : 0;
+            const int us = lr.LoopRestorationSize[p];
+            const int rows = countUnits(us, (f.FrameHeight + sub) >> sub), cols = countUnits(us, (f.UpscaledWidth + sub) >> sub);
+            h.lr.unit_size[p] = (uint16_t)us;
+            h.lr.unit_rows[p] = (uint16_t)rows;
+            h.lr.unit_cols[p] = (uint16_t)cols;
+            h.lr.unit_first[p] = (uint32_t)m_lru.size();
+            for (int r = 0; r < rows; r++) {
+                for (int c = 0; c < cols; c++) {
+                    Av1bLrUnit u;
+                    memset(&u, 0, sizeof(u));
+                    u.type = (uint8_t)lr.LrType[p][r][c];
+                    if (u.type == RESTORE_WIENER) {
+                        for (int pass = 0; pass < 2; pass++)
+                            for (int k = 0; k < 3; k++) u.wiener[pass][k] = lr.LrWiener[p][r][c][pass][k];
+                    } else if (u.type == RESTORE_SGRPROJ) {
+                        u.sgr_set = lr.LrSgrSet[p][r][c];
+                        u.sgr_xqd[0] = lr.LrSgrXqd[p][r][c][0];
+                        u.sgr_xqd[1] = lr.LrSgrXqd[p][r][c][1];
+                    }
+                    m_lru.push_back(u);
+                }
+            }
+        }
+    }
+    layout();
+}
+
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+void FrameEmitter::layout()
+{
+    Av1bFrameHdr& h = m_hdr;
+    size_t off = align16(sizeof(Av1bFrameHdr));
+    auto place = [&](uint32_t& o, size_t bytes) {
+        o = (uint32_t)off;
+        off = align16(off + bytes);
+    };
+    h.n_sb = (uint32_t)m_sbs.size();
+    place(h.off_sb, m_sbs.size() * sizeof(Av1bSb));
+    h.n_ops = (uint32_t)m_ops.size();
+    place(h.off_ops, m_ops.size() * sizeof(Av1bOp));
+    h.n_itx = (uint32_t)m_itx.size();
+    place(h.off_itx, m_itx.size() * sizeof(uint32_t));
+    h.n_iblk = (uint32_t)m_iblk.size();
+    place(h.off_iblk, m_iblk.size() * sizeof(Av1bInterBlk));
+    h.n_ipu = (uint32_t)m_ipu.size();
+    place(h.off_ipu, m_ipu.size() * sizeof(Av1bIpu));
+    h.n_aux = (uint32_t)m_aux.size();
+    place(h.off_aux, m_aux.size() * sizeof(Av1bBlkAux));
+    h.n_coef = (uint32_t)m_coef.size();
+    place(h.off_coef, m_coef.size() * sizeof(int16_t));
+    h.n_res = m_nRes;
+    h.n_pal = (uint32_t)m_pal.size();
+    place(h.off_pal, m_pal.size());
+    place(h.off_lfmi, m_lfmi.size() * sizeof(Av1bLfMi));
+    place(h.off_cdef8, m_cdef8.size());
+    h.n_lru = (uint32_t)m_lru.size();
+    place(h.off_lru, m_lru.size() * sizeof(Av1bLrUnit));
+    h.total_bytes = (uint32_t)off;
+    m_total = off;
+}
+
+void FrameEmitter::write(uint8_t* dst) const
+{
+    const Av1bFrameHdr& h = m_hdr;
+    memcpy(dst, &h, sizeof(h));
+    auto put = [&](uint32_t o, const void* p, size_t bytes) {
+        if (bytes) memcpy(dst + o, p, bytes);
+    };
+    put(h.off_sb, m_sbs.data(), m_sbs.size() * sizeof(Av1bSb));
+    put(h.off_ops, m_ops.data(), m_ops.size() * sizeof(Av1bOp));
+    put(h.off_itx, m_itx.data(), m_itx.size() * sizeof(uint32_t));
+    put(h.off_iblk, m_iblk.data(), m_iblk.size() * sizeof(Av1bInterBlk));
+    put(h.off_ipu, m_ipu.data(), m_ipu.size() * sizeof(Av1bIpu));
+    put(h.off_aux, m_aux.data(), m_aux.size() * sizeof(Av1bBlkAux));
+    put(h.off_coef, m_coef.data(), m_coef.size() * sizeof(int16_t));
+    put(h.off_pal, m_pal.data(), m_pal.size());
+    put(h.off_lfmi, m_lfmi.data(), m_lfmi.size() * sizeof(Av1bLfMi));
+    put(h.off_cdef8, m_cdef8.data(), m_cdef8.size());
+    put(h.off_lru, m_lru.data(), m_lru.size() * sizeof(Av1bLrUnit));
+}
+
+}  // namespace av1b200

@@ -1,0 +1,110 @@
+/*
+ * av1b200.h -- C ABI of the B200 (sm_100a) AV1 reconstruction + in-loop-filter engine.
+ *
+ * This is the drop-in boundary for the reference's pixel path.  The reference (oddstone/av1dec)
+ * runs, per frame,
+ *     Tile::decode()                 decoder/Tile.cpp:172        block reconstruction
+ *     Decoder::decode_frame_wrapup() decoder/Av1Decoder.cpp:171  deblock -> CDEF -> loop restoration
+ *     Decoder::updateFrameStore()    decoder/Av1Decoder.cpp:111  reference refresh
+ *     Decoder::getOutput()           decoder/Av1Decoder.cpp:203  shown-frame hand-off
+ * on host memory.  Here the host front end (the reference's own parser / entropy decoder)
+ * serialises what those calls read into one command buffer per frame (av1b200_format.h)
+ * and the functions below replace them; frames and reference frames stay in HBM.
+ *
+ * Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
+ * Every function returns 0 on success or a negative AV1B_E* code; av1b_last_error() gives text.
+ * A context is single-threaded (like the reference's Decoder); contexts are independent and
+ * many may share one GPU.
+ */
+#ifndef AV1B200_H_
+#define AV1B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include "av1b200_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AV1B_OK 0
+#define AV1B_EINVAL (-1)
+#define AV1B_ECUDA (-2)
+#define AV1B_ENOMEM (-3)
+#define AV1B_ESTATE (-4)
+
+/* stage bits for av1b_frame_submit() */
+#define AV1B_STAGE_ITX 1u     /* TransformBlock::inverseTransform (TransformBlock.cpp:2173)   */
+#define AV1B_STAGE_INTER 2u   /* InterPredict::predict_inter (InterPredict.cpp:962)           */
+#define AV1B_STAGE_WAVE 4u    /* intra predict + residual add (TransformBlock.cpp:2376)       */
+#define AV1B_STAGE_DEBLOCK 8u /* LoopFilter::filter (LoopFilter.cpp:40)                       */
+#define AV1B_STAGE_CDEF 16u   /* Cdef::filter (Cdef.cpp:41)                                   */
+#define AV1B_STAGE_LR 32u     /* LoopRestoration::filter (LoopRestoration.cpp:191)            */
+#define AV1B_STAGE_RECON (AV1B_STAGE_ITX | AV1B_STAGE_INTER | AV1B_STAGE_WAVE)
+#define AV1B_STAGE_POST (AV1B_STAGE_DEBLOCK | AV1B_STAGE_CDEF | AV1B_STAGE_LR)
+#define AV1B_STAGE_ALL (AV1B_STAGE_RECON | AV1B_STAGE_POST)
+
+typedef struct av1b_ctx av1b_ctx;
+
+/* Library identity: "cuda-sm_100a" for the product, "emu" for the test-only host emulation. */
+const char* av1b_backend(void);
+
+/* Create an engine for frames up to max_w x max_h luma samples on CUDA device `device`.
+ * `stream` is a cudaStream_t to enqueue on, or NULL to let the engine create its own.
+ * Replaces the YuvFrame allocations of Decoder::decodeFrame (Av1Decoder.cpp:131). */
+int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream);
+void av1b_ctx_destroy(av1b_ctx* ctx);
+const char* av1b_last_error(av1b_ctx* ctx);
+
+/* Pinned command ring.  Returns a host pointer with room for `bytes`; blocks until the slot's
+ * previous frame has been consumed by the device. */
+int av1b_cmd_acquire(av1b_ctx* ctx, size_t bytes, void** host_ptr);
+
+/* Reconstruct + filter the frame whose command buffer was written into the pointer returned
+ * by the last av1b_cmd_acquire().  Asynchronous.  `stages` is a mask of AV1B_STAGE_*.
+ * On return *frame_id names the device-resident output frame (valid until released by the
+ * reference store).  refresh_mask: FrameHeader::refresh_frame_flags (Av1Decoder.cpp:115). */
+int av1b_frame_submit(av1b_ctx* ctx, size_t bytes, uint32_t stages, uint32_t refresh_mask, int* frame_id);
+
+/* Same, but the command buffer already lives in device memory (`dev_cmd`), `hdr` is a host
+ * copy of its header.  Used to time the kernels with inputs resident in HBM. */
+int av1b_frame_submit_resident(av1b_ctx* ctx, const void* dev_cmd, const Av1bFrameHdr* hdr, uint32_t stages,
+    uint32_t refresh_mask, int* frame_id);
+
+/* show_existing_frame (Decoder::showExistingFrame, Av1Decoder.cpp:158): returns the frame in
+ * store slot `slot` and applies refresh_mask. */
+int av1b_show_existing(av1b_ctx* ctx, int slot, uint32_t refresh_mask, int* frame_id);
+
+/* Asynchronous copy of the visible w x h (and chroma) area of a device frame to host planes
+ * (pinned memory from av1b_host_alloc gives a true async copy).  Decoder::getOutput(). */
+int av1b_frame_download(av1b_ctx* ctx, int frame_id, uint8_t* const dst[3], const int dst_stride[3], int w, int h);
+/* Block until everything enqueued so far (kernels and copies) has finished. */
+int av1b_sync(av1b_ctx* ctx);
+/* Mark a fence after the work enqueued so far / wait for it: lets a caller overlap parsing of
+ * the next frame with this frame's device work. */
+int av1b_fence_record(av1b_ctx* ctx, uint64_t* fence);
+int av1b_fence_wait(av1b_ctx* ctx, uint64_t fence);
+
+void* av1b_host_alloc(size_t bytes); /* pinned host memory */
+void av1b_host_free(void* p);
+/* raw device memory helpers for the resident-command benchmark path */
+void* av1b_dev_alloc(size_t bytes);
+void av1b_dev_free(void* p);
+int av1b_dev_upload(av1b_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+
+/* Test / stage-level entry points --------------------------------------------------------- */
+/* Load host planes (MI-aligned area: w x h luma samples given) into the frame that the next
+ * av1b_frame_submit() will treat as "current" -- lets a test or benchmark run the post-filter
+ * stages (or a residual-only pass) on arbitrary input without a bitstream. */
+int av1b_debug_set_input(av1b_ctx* ctx, const uint8_t* const src[3], const int src_stride[3], int w, int h);
+/* Load host planes into reference store slot `slot`. */
+int av1b_debug_set_ref(av1b_ctx* ctx, int slot, const uint8_t* const src[3], const int src_stride[3], int w, int h);
+/* Copy the int16 residual arena of the last submitted frame to host (n values). */
+int av1b_debug_get_residual(av1b_ctx* ctx, int16_t* dst, size_t n);
+/* Number of kernel launches issued by this context so far. */
+uint64_t av1b_launch_count(av1b_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AV1B200_H_ */
