@@ -47,7 +47,7 @@ $(LIB)/obj/%.o: $(CSRC)/%.cu $(KHDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB)/libav1b200.so: $(patsubst %,$(LIB)/obj/%.o,$(KERNELS))
-	$(NVCC) -shared -o $@ $^ -lcudart
+	$(NVCC) -shared -cudart static -o $@ $^
 
 ifneq ($(HAVE_REF),)
 # ---------------------------------------------------------------- reference front end
