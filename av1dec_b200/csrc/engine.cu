@@ -528,4 +528,19 @@ int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
 
 uint64_t av1b_launch_count(av1b_ctx* c) { return c ? c->launches : 0; }
 
+size_t av1b_struct_size(int which)
+{
+    switch (which) {
+    case 0: return sizeof(Av1bFrameHdr);
+    case 1: return sizeof(Av1bOp);
+    case 2: return sizeof(Av1bSb);
+    case 3: return sizeof(Av1bIpu);
+    case 4: return sizeof(Av1bInterBlk);
+    case 5: return sizeof(Av1bBlkAux);
+    case 6: return sizeof(Av1bLfMi);
+    case 7: return sizeof(Av1bLrUnit);
+    default: return 0;
+    }
+}
+
 }  // extern "C"

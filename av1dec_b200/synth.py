@@ -1,0 +1,259 @@
+"""Synthetic frames and frame parameters for the per-kernel configurations (BASELINE.json
+config 4): random partitions / transform sizes / skip / reference classes,
+deblock levels, CDEF presets and loop-restoration units, plus pixel planes in the distributions
+
+    'U'  uniform [0,255] per sample
+    'B'  blocky-smooth: per-8x8 DC ~ clip(N(128,40)) + per-sample U[-3,3]
+
+PRNG: splitmix64, seed 20261018 (+ frame index), as BASELINE.md fixes it.  The output is a
+command buffer in the engine's own format (av1dec_b200.format) -- the same bytes feed the GPU
+stage entry points and, through oracle/oracle_shim.cpp, the reference's C++ filter classes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import format as F
+
+SEED = 20261018
+_MASK = (1 << 64) - 1
+
+
+class SplitMix64:
+    """Vectorised splitmix64."""
+
+    def __init__(self, seed):
+        self.state = np.uint64(seed & _MASK)
+
+    def u64(self, n):
+        with np.errstate(over="ignore"):
+            idx = np.arange(1, n + 1, dtype=np.uint64)
+            z = self.state + idx * np.uint64(0x9E3779B97F4A7C15)
+            self.state = z[-1] if n else self.state
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def randint(self, lo, hi, shape):
+        """Uniform integers in [lo, hi]."""
+        n = int(np.prod(shape))
+        return (((self.u64(n) >> np.uint64(11)) % np.uint64(hi - lo + 1)).astype(np.int64) + lo).reshape(shape)
+
+    def uniform(self, shape):
+        n = int(np.prod(shape))
+        return ((self.u64(n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)).reshape(shape)
+
+    def normal(self, shape):
+        u1 = np.maximum(self.uniform(shape), 1e-12)
+        u2 = self.uniform(shape)
+        return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def _up(a, cell, rows, cols):
+    return np.repeat(np.repeat(a, cell, axis=0), cell, axis=1)[:rows, :cols]
+
+
+def make_planes(rng, w, h, dist="B"):
+    """Planes covering the MI-aligned area of a w x h frame."""
+    aw, ah = 8 * ((w + 7) // 8), 8 * ((h + 7) // 8)
+    planes = []
+    for sub in (0, 1, 1):
+        pw, ph = aw >> sub, ah >> sub
+        if dist == "U":
+            p = rng.randint(0, 255, (ph, pw))
+        else:
+            bs = 8 >> sub
+            dc = np.clip(128 + 40 * rng.normal(((ph + bs - 1) // bs, (pw + bs - 1) // bs)), 0, 255)
+            p = np.clip(np.rint(_up(dc, bs, ph, pw)) + rng.randint(-3, 3, (ph, pw)), 0, 255)
+        planes.append(p.astype(np.uint8))
+    return planes
+
+
+class SynthFrame:
+    pass
+
+
+def make_postfilter_frame(w, h, seed=SEED, dist="B", delta_lf=False, lr_unit=64, sb128=False, levels=None,
+                          lr_types=(0, 1, 2)):
+    """Random but structurally valid inputs for deblock + CDEF + loop restoration."""
+    rng = SplitMix64(seed)
+    mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
+    s = SynthFrame()
+    s.w, s.h, s.mi_cols, s.mi_rows, s.sb128 = w, h, mi_cols, mi_rows, sb128
+    s.planes = make_planes(rng, w, h, dist)
+    # ---- random partition: leaf level per MI (0: 64x64 ... 4: 4x4), optional 2:1 split of the leaf
+    level = np.zeros((mi_rows, mi_cols), np.int64)
+    props = []
+    for l in range(5):
+        cell = 16 >> l
+        r, c = (mi_rows + cell - 1) // cell, (mi_cols + cell - 1) // cell
+        split = _up(rng.uniform((r, c)) < (0.75, 0.6, 0.5, 0.35, 0.0)[l], cell, mi_rows, mi_cols)
+        if l < 4:
+            level = np.where((level == l) & split, l + 1, level)
+        props.append({
+            "shape": _up(rng.randint(0, 3, (r, c)) % 3 if l < 4 else np.zeros((r, c), np.int64), cell, mi_rows, mi_cols),
+            "skip": _up((rng.uniform((r, c)) < 0.25).astype(np.int64), cell, mi_rows, mi_cols),
+            "ref": _up(np.where(rng.uniform((r, c)) < 0.3, 0, rng.randint(1, 7, (r, c))), cell, mi_rows, mi_cols),
+            "mode": _up(rng.randint(0, 1, (r, c)), cell, mi_rows, mi_cols),
+        })
+    pick = lambda key: np.choose(level, [p[key] for p in props])
+    shape, skip, ref, mode = pick("shape"), pick("skip"), pick("ref"), pick("mode")
+    sq_bs = np.array([12, 9, 6, 3, 0])[level]
+    s.mi_size = (sq_bs - shape).astype(np.uint8)  # shape 1: S x S/2 (enum-1), 2: S/2 x S (enum-2)
+    tx_y = np.choose(shape, [np.array([4, 3, 2, 1, 0])[level], np.array([12, 10, 8, 6, 0])[level],
+                             np.array([11, 9, 7, 5, 0])[level]])
+    tx_uv = np.choose(shape, [np.array([3, 2, 1, 0, 0])[level], np.array([10, 8, 6, 0, 0])[level],
+                              np.array([9, 7, 5, 0, 0])[level]])
+    s.tx = (tx_y | (tx_uv << 5) | (tx_uv << 10)).astype(np.uint16)
+    s.flags = (skip | (mode << 1) | (ref << 2)).astype(np.uint8)
+    s.delta_lf = np.zeros((mi_rows, mi_cols, 4), np.int8)
+    if delta_lf:
+        r, c = (mi_rows + 15) // 16, (mi_cols + 15) // 16
+        for i in range(4):
+            s.delta_lf[:, :, i] = _up(rng.randint(-8, 8, (r, c)), 16, mi_rows, mi_cols)
+    lfmi = np.zeros((mi_rows, mi_cols), dtype=[("mi_size", "u1"), ("flags", "u1"), ("tx", "<u2"), ("dlf", "i1", 4)])
+    lfmi["mi_size"], lfmi["flags"], lfmi["tx"], lfmi["dlf"] = s.mi_size, s.flags, s.tx, s.delta_lf
+    # ---- frame-level parameters
+    hdr = F.FrameHdr()
+    hdr.frame_w, hdr.frame_h, hdr.mi_cols, hdr.mi_rows = w, h, mi_cols, mi_rows
+    hdr.sb_log2 = 7 if sb128 else 6
+    sb4 = 1 << (hdr.sb_log2 - 2)
+    hdr.sb_cols, hdr.sb_rows = (mi_cols + sb4 - 1) // sb4, (mi_rows + sb4 - 1) // sb4
+    lv = levels if levels is not None else [int(v) for v in rng.randint(0, 63, (4,))]
+    if levels is None and lv[0] == 0 and lv[1] == 0:
+        lv[0] = 17
+    for i in range(4):
+        hdr.lf.level[i] = lv[i]
+    hdr.lf.sharpness = int(rng.randint(0, 7, (1,))[0])
+    hdr.lf.delta_enabled = 1
+    for i, v in enumerate((1, 0, 0, 0, -1, 0, -1, -1)):  # default ref deltas (Parser.cpp:1920-1930)
+        hdr.lf.ref_deltas[i] = v
+    hdr.lf.delta_lf_multi = 1 if delta_lf else 0
+    hdr.cdef.enabled = 1
+    hdr.cdef.damping = int(rng.randint(3, 6, (1,))[0])
+    for i in range(8):
+        hdr.cdef.y_pri[i] = int(rng.randint(0, 15, (1,))[0])
+        hdr.cdef.uv_pri[i] = int(rng.randint(0, 15, (1,))[0])
+        hdr.cdef.y_sec[i] = (0, 1, 2, 4)[int(rng.randint(0, 3, (1,))[0])]
+        hdr.cdef.uv_sec[i] = (0, 1, 2, 4)[int(rng.randint(0, 3, (1,))[0])]
+    r64, c64 = (mi_rows + 15) // 16, (mi_cols + 15) // 16
+    idx64 = rng.randint(0, 7, (r64, c64))
+    idx64 = np.where(rng.uniform((r64, c64)) < 0.05, -1, idx64).astype(np.int8)
+    s.cdef_idx64 = idx64
+    # cdef8: preset per 8x8, 0xFF where idx == -1 or all four MIs skip (Cdef.cpp:76-82)
+    sk = skip.astype(bool)
+    allskip = sk[0::2, 0::2] & sk[1::2, 0::2] & sk[0::2, 1::2] & sk[1::2, 1::2]
+    idx8 = _up(idx64.astype(np.int64), 8, mi_rows // 2, mi_cols // 2)
+    s.cdef8 = np.where((idx8 < 0) | allskip, 0xFF, idx8).astype(np.uint8)
+    # ---- loop restoration units (LoopRestoration.cpp:35-38 count_units_in_frame)
+    units = []
+    hdr.lr.uses_lr = 1
+    for p in range(3):
+        sub = 1 if p else 0
+        us = lr_unit if p == 0 else max(32, lr_unit >> 1)
+        rows = max((((h + sub) >> sub) + (us >> 1)) // us, 1)
+        cols = max((((w + sub) >> sub) + (us >> 1)) // us, 1)
+        hdr.lr.frame_type[p] = 3  # RESTORE_SWITCHABLE: per-unit type
+        hdr.lr.unit_size[p], hdr.lr.unit_rows[p], hdr.lr.unit_cols[p] = us, rows, cols
+        hdr.lr.unit_first[p] = len(units)
+        types = np.array(lr_types)[rng.randint(0, len(lr_types) - 1, (rows * cols,))]
+        c0 = rng.randint(-5, 10, (rows * cols, 2)) if p == 0 else np.zeros((rows * cols, 2), np.int64)
+        c1 = rng.randint(-23, 8, (rows * cols, 2))
+        c2 = rng.randint(-17, 46, (rows * cols, 2))
+        sets = rng.randint(0, 15, (rows * cols,))
+        x0 = rng.randint(-96, 31, (rows * cols,))
+        x1 = rng.randint(-32, 95, (rows * cols,))
+        for k in range(rows * cols):
+            u = F.LrUnit()
+            u.type = int(types[k])
+            u.sgr_set = int(sets[k])
+            # r == 0 rules of read_lr_unit (Parser.cpp:2198-2206)
+            st = int(sets[k])
+            q0, q1 = int(x0[k]), int(x1[k])
+            if st >= 10 and st <= 13:  # r0 == 0
+                q0 = 0
+            if st >= 14:  # r1 == 0
+                q1 = int(np.clip(128 - q0, -32, 95))
+            u.sgr_xqd[0], u.sgr_xqd[1] = q0, q1
+            for ps in range(2):
+                u.wiener[ps][0], u.wiener[ps][1], u.wiener[ps][2] = int(c0[k, ps]), int(c1[k, ps]), int(c2[k, ps])
+            units.append(bytes(u))
+    hdr.n_lru = len(units)
+    s.cmd = F.build(hdr, {"off_lfmi": lfmi.tobytes(), "off_cdef8": s.cdef8.tobytes(), "off_lru": b"".join(units)})
+    s.hdr = F.FrameHdr.from_buffer_copy(s.cmd[:C.sizeof(F.FrameHdr)])
+    return s
+
+
+# legal (tx_size, tx_type) pairs: 64-point -> DCT only, 32-point -> DCT / IDTX, else all 16
+TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
+TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
+
+
+def legal_tx_types(tx_size):
+    m = max(TX_W[tx_size], TX_H[tx_size])
+    if m == 64:
+        return [0]
+    if m == 32:
+        return [0, 9]
+    return list(range(16))
+
+
+def make_itx_batch(n, seed=SEED, lossless_frac=0.05, sizes=None):
+    """n random transform blocks: (tx_size, tx_type, lossless, coef(int16 list), nz_rows, nz_cols)."""
+    rng = SplitMix64(seed)
+    out = []
+    szs = rng.randint(0, 18, (n,)) if sizes is None else np.array(sizes)[rng.randint(0, len(sizes) - 1, (n,))]
+    tys = rng.randint(0, 15, (n,))
+    ll = rng.uniform((n,))
+    for i in range(n):
+        ts = int(szs[i])
+        lossless = ts == 0 and ll[i] < lossless_frac
+        legal = legal_tx_types(ts)
+        tt = 0 if lossless else legal[int(tys[i]) % len(legal)]
+        tw, th = min(TX_W[ts], 32), min(TX_H[ts], 32)
+        area = tw * th
+        eob = int(min(area, max(1, rng.randint(1, max(1, area // 4), (1,))[0])))
+        coef = np.zeros(area, np.int64)
+        # low-frequency-biased positions, Laplacian-ish magnitudes, ~1% at the +-2^15 clip
+        pos = np.unique((rng.uniform((eob,)) ** 2 * area).astype(np.int64))
+        mag = (-np.log(np.maximum(rng.uniform((len(pos),)), 1e-9)) * (200 if not lossless else 20)).astype(np.int64)
+        sign = np.where(rng.uniform((len(pos),)) < 0.5, -1, 1)
+        val = np.clip(mag * sign, -32768, 32767)
+        clipsel = rng.uniform((len(pos),)) < 0.01
+        val = np.where(clipsel, np.where(sign < 0, -32768, 32767), val)
+        if lossless:
+            val = np.clip(val, -2000, 2000)
+        rows, cols = pos // tw, pos % tw
+        coef[rows * tw + cols] = val
+        nz = np.nonzero(coef)[0]
+        if len(nz) == 0:
+            coef[0] = 64
+            nz = np.array([0])
+        out.append((ts, tt, int(lossless), coef.astype(np.int16), int((nz // tw).max()) + 1, int((nz % tw).max()) + 1))
+    return out
+
+
+def make_itx_cmd(batch):
+    """Command buffer holding only inverse-transform work (ops + itx list + coefficient arena)."""
+    ops, coefs, itx = [], [], []
+    coef_off = res_off = 0
+    for i, (ts, tt, lossless, coef, nzr, nzc) in enumerate(batch):
+        op = F.Op()
+        op.tx_size, op.tx_type, op.lossless = ts, tt, lossless
+        op.flags = F.OPF_HAS_RESID
+        op.nz_rows, op.nz_cols = nzr, nzc
+        op.coef_off, op.res_off = coef_off, res_off
+        coef_off += len(coef)
+        res_off += TX_W[ts] * TX_H[ts]
+        ops.append(bytes(op))
+        coefs.append(coef.tobytes())
+        itx.append(i)
+    hdr = F.FrameHdr()
+    hdr.frame_w = hdr.frame_h = 64
+    hdr.mi_cols = hdr.mi_rows = 16
+    hdr.sb_cols = hdr.sb_rows = 1
+    hdr.sb_log2 = 6
+    hdr.n_ops, hdr.n_itx, hdr.n_coef, hdr.n_res = len(ops), len(itx), coef_off, res_off
+    cmd = F.build(hdr, {"off_ops": b"".join(ops), "off_itx": np.array(itx, np.uint32).tobytes(),
+                        "off_coef": b"".join(coefs)})
+    return cmd, res_off

@@ -103,6 +103,9 @@ int av1b_debug_set_ref(av1b_ctx* ctx, int slot, const uint8_t* const src[3], con
 int av1b_debug_get_residual(av1b_ctx* ctx, int16_t* dst, size_t n);
 /* Number of kernel launches issued by this context so far. */
 uint64_t av1b_launch_count(av1b_ctx* ctx);
+/* sizeof() of the command-format structs (0 FrameHdr, 1 Op, 2 Sb, 3 Ipu, 4 InterBlk, 5 BlkAux,
+ * 6 LfMi, 7 LrUnit): lets a foreign-language binding verify its mirror of av1b200_format.h. */
+size_t av1b_struct_size(int which);
 
 #ifdef __cplusplus
 }

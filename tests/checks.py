@@ -1,0 +1,105 @@
+"""Parity checks shared by the GPU tests (product CUDA library) and the CPU tests (the test-only
+emulation build of the same kernel sources, tests/emu/).  Every check compares the engine with
+the reference's own C++ code through oracle.py, bit-exactly."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+
+import av1dec_b200 as pkg
+import oracle
+from av1dec_b200 import synth
+from av1dec_b200.engine import Engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_ENGINE = os.path.join(ROOT, "tests", "emu", "libav1b200_emu.so")
+EMU_DECODER = os.path.join(ROOT, "tests", "emu", "libav1b200dec_emu.so")
+
+
+def emu_available():
+    return os.path.exists(EMU_ENGINE) and os.path.exists(EMU_DECODER)
+
+
+def emu_engine():
+    return pkg.load_engine(EMU_ENGINE)
+
+
+def emu_decoder():
+    emu_engine()
+    return pkg.load_decoder(EMU_DECODER)
+
+
+def flip_residual(res, tx_type):
+    ud = tx_type in (4, 8, 14, 6)
+    lr = tx_type in (5, 7, 15, 6)
+    if ud:
+        res = res[::-1, :]
+    if lr:
+        res = res[:, ::-1]
+    return res
+
+
+def check_itx(lib, n=400, seed=synth.SEED, sizes=None):
+    batch = synth.make_itx_batch(n, seed=seed, sizes=sizes)
+    cmd, n_res = synth.make_itx_cmd(batch)
+    eng = Engine(64, 64, lib=lib)
+    eng.submit(cmd, stages=pkg.STAGE_ITX)
+    got = eng.residual(n_res)
+    eng.close()
+    want = oracle.inverse_transform(batch)
+    off = 0
+    for i, b in enumerate(batch):
+        w, h = synth.TX_W[b[0]], synth.TX_H[b[0]]
+        ref = np.clip(flip_residual(want[i], b[1]), -32768, 32767).astype(np.int16)
+        mine = got[off:off + w * h].reshape(h, w)
+        assert np.array_equal(ref, mine), f"itx mismatch block {i}: tx_size={b[0]} tx_type={b[1]} lossless={b[2]}"
+        off += w * h
+    return len(batch)
+
+
+POST_STAGE_BITS = {1: pkg.STAGE_DEBLOCK, 2: pkg.STAGE_CDEF, 4: pkg.STAGE_LR}
+
+
+def run_postfilter(lib, s, stages):
+    """stages: oracle bit mask (1 deblock, 2 cdef, 4 lr).  Returns engine planes (MI-aligned)."""
+    aw, ah = s.mi_cols * 4, s.mi_rows * 4
+    eng = Engine(aw, ah, lib=lib)
+    eng.set_input(s.planes, aw, ah)
+    mask = 0
+    for bit, st in POST_STAGE_BITS.items():
+        if stages & bit:
+            mask |= st
+    fid = eng.submit(s.cmd, stages=mask)
+    out = eng.download(fid, aw, ah)
+    eng.close()
+    return out
+
+
+def check_postfilter(lib, w, h, stages, **kw):
+    s = synth.make_postfilter_frame(w, h, **kw)
+    got = run_postfilter(lib, s, stages)
+    want = oracle.postfilter(s, stages)
+    visible = bool(stages & 6)
+    for p in range(3):
+        cw, ch = (w, h) if visible else (s.mi_cols * 4, s.mi_rows * 4)
+        if p:
+            cw, ch = cw >> 1, ch >> 1
+        a, b = got[p][:ch, :cw], want[p][:ch, :cw]
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError(f"postfilter stages={stages} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
+                                 f"got {a[tuple(bad[0])]} want {b[tuple(bad[0])]}")
+    return s
+
+
+def stream_md5(dec_lib, path, device=0):
+    data = open(path, "rb").read()
+    yuv, frames, pixels = pkg.decode_ivf(data, device=device, lib=dec_lib)
+    return hashlib.md5(yuv).hexdigest(), frames, pixels
+
+
+def stage_frames(dec_lib, data, stages):
+    """Shown frames (visible area, concatenated) from the engine with a restricted stage mask."""
+    yuv, frames, _ = pkg.decode_ivf(data, stages=stages, lib=dec_lib)
+    return yuv, frames
