@@ -41,6 +41,9 @@ static int rt_event_record(rt_event_t, av1b_stream_t) { return 0; }
 static int rt_event_sync(rt_event_t) { return 0; }
 static const char* rt_error() { return "emu"; }
 static int rt_check() { return 0; }
+static int rt_tevent_create(rt_event_t* e) { *e = 0; return 0; }
+static float rt_event_ms(rt_event_t, rt_event_t) { return 0.f; }
+static int rt_d2d(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
 const char* av1b_backend(void) { return "emu"; }
 #else
 typedef cudaEvent_t rt_event_t;
@@ -65,6 +68,14 @@ static int rt_event_record(rt_event_t e, av1b_stream_t s) { return cudaEventReco
 static int rt_event_sync(rt_event_t e) { return cudaEventSynchronize(e) != cudaSuccess; }
 static const char* rt_error() { return cudaGetErrorString(cudaGetLastError()); }
 static int rt_check() { return cudaGetLastError() != cudaSuccess; }
+static int rt_tevent_create(rt_event_t* e) { return cudaEventCreate(e) != cudaSuccess; }
+static float rt_event_ms(rt_event_t a, rt_event_t b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+static int rt_d2d(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess; }
 const char* av1b_backend(void) { return "cuda-sm_100a"; }
 #endif
 
@@ -162,7 +173,51 @@ struct av1b_ctx {
     uint64_t fence_next = 1;
     uint64_t launches = 0;
     std::string err;
+    // optional per-stage device timing (CUDA events around each launch group)
+    bool profiling = false;
+    struct Span {
+        int stage;
+        rt_event_t a, b;
+    };
+    std::vector<Span> spans;            // recorded, not yet resolved
+    std::vector<rt_event_t> event_pool; // reusable timing events
+    double stage_ms[AV1B_N_STAGES] = { 0 };
+    uint64_t stage_calls[AV1B_N_STAGES] = { 0 };
 };
+
+namespace {
+struct StageTimer {
+    av1b_ctx* c;
+    int stage;
+    rt_event_t a, b;
+    bool on;
+    static rt_event_t get(av1b_ctx* c)
+    {
+        if (!c->event_pool.empty()) {
+            rt_event_t e = c->event_pool.back();
+            c->event_pool.pop_back();
+            return e;
+        }
+        rt_event_t e;
+        rt_tevent_create(&e);
+        return e;
+    }
+    StageTimer(av1b_ctx* ctx, int st, bool active)
+        : c(ctx), stage(st), on(active && ctx->profiling)
+    {
+        if (!on) return;
+        a = get(c);
+        b = get(c);
+        rt_event_record(a, c->stream);
+    }
+    ~StageTimer()
+    {
+        if (!on) return;
+        rt_event_record(b, c->stream);
+        c->spans.push_back(av1b_ctx::Span{ stage, a, b });
+    }
+};
+}  // namespace
 
 static int fail(av1b_ctx* c, int code, const char* what)
 {
@@ -331,15 +386,18 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     rc.wedge = c->wedge;
     rc.sync = c->sync;
     if (stages & AV1B_STAGE_ITX) {
+        StageTimer t(c, 0, h.n_itx != 0);
         launch_itx(rc, h, c->stream);
         c->launches += h.n_itx ? 1 : 0;
     }
     if (stages & AV1B_STAGE_INTER) {
+        StageTimer t(c, 1, h.n_iblk != 0);
         launch_inter(rc, h, c->stream);
         c->launches += h.n_iblk ? 1 : 0;
     }
     if (stages & AV1B_STAGE_WAVE) {
         if (rt_memset(c->sync, 0, sync_need * sizeof(int), c->stream)) return fail(c, AV1B_ECUDA, "memset");
+        StageTimer t(c, 2, h.n_ops != 0);
         launch_wave(rc, h, c->stream);
         c->launches += h.n_ops ? 1 : 0;
     }
@@ -349,6 +407,7 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     pc.src = c->frames[cur].v;
     int final_frame = cur, cdef = -1, lr = -1;
     if ((stages & AV1B_STAGE_DEBLOCK) && (h.lf.level[0] || h.lf.level[1])) {
+        StageTimer t(c, 3, true);
         launch_deblock(pc, h, c->stream);
         c->launches += 2;
     }
@@ -358,6 +417,7 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
         if (cdef < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
         c->frames[cdef].refcnt++;
         pc.cdef = c->frames[cdef].v;
+        StageTimer t(c, 4, true);
         launch_cdef(pc, h, c->stream);
         c->launches += 1;
         final_frame = cdef;
@@ -367,6 +427,7 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
         if (lr < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
         c->frames[lr].refcnt++;
         pc.lr = c->frames[lr].v;
+        StageTimer t(c, 5, true);
         launch_lr(pc, h, c->stream);
         c->launches += 1;
         final_frame = lr;
@@ -527,6 +588,47 @@ int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
 }
 
 uint64_t av1b_launch_count(av1b_ctx* c) { return c ? c->launches : 0; }
+
+int av1b_set_profiling(av1b_ctx* c, int on)
+{
+    if (!c) return AV1B_EINVAL;
+    c->profiling = on != 0;
+    return AV1B_OK;
+}
+
+int av1b_get_stage_times(av1b_ctx* c, double ms[AV1B_N_STAGES], uint64_t calls[AV1B_N_STAGES], int reset)
+{
+    if (!c) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
+    for (auto& sp : c->spans) {
+        c->stage_ms[sp.stage] += rt_event_ms(sp.a, sp.b);
+        c->stage_calls[sp.stage]++;
+        c->event_pool.push_back(sp.a);
+        c->event_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < AV1B_N_STAGES; i++) {
+        if (ms) ms[i] = c->stage_ms[i];
+        if (calls) calls[i] = c->stage_calls[i];
+        if (reset) {
+            c->stage_ms[i] = 0;
+            c->stage_calls[i] = 0;
+        }
+    }
+    return AV1B_OK;
+}
+
+int av1b_debug_input_from_slot(av1b_ctx* c, int slot)
+{
+    if (!c || slot < 0 || slot > 7 || c->ref_slot[slot] < 0) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    int f = c->pending_input >= 0 ? c->pending_input : frame_alloc(c);
+    if (f < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+    c->pending_input = f;
+    if (rt_d2d(c->frames[f].base, c->frames[c->ref_slot[slot]].base, c->frame_bytes, c->stream)) return fail(c, AV1B_ECUDA, "d2d copy");
+    return AV1B_OK;
+}
 
 size_t av1b_struct_size(int which)
 {

@@ -84,6 +84,20 @@ class Engine:
     def sync(self):
         self._check(self.lib.av1b_sync(self.ctx), "av1b_sync")
 
+    def set_profiling(self, on=True):
+        self._check(self.lib.av1b_set_profiling(self.ctx, 1 if on else 0), "av1b_set_profiling")
+
+    def stage_times(self, reset=True):
+        """({stage: ms}, {stage: calls}) accumulated since the last reset (synchronises)."""
+        from . import STAGE_NAMES
+        ms = (C.c_double * 6)()
+        calls = (C.c_uint64 * 6)()
+        self._check(self.lib.av1b_get_stage_times(self.ctx, ms, calls, 1 if reset else 0), "av1b_get_stage_times")
+        return ({n: ms[i] for i, n in enumerate(STAGE_NAMES)}, {n: int(calls[i]) for i, n in enumerate(STAGE_NAMES)})
+
+    def input_from_slot(self, slot):
+        self._check(self.lib.av1b_debug_input_from_slot(self.ctx, slot), "av1b_debug_input_from_slot")
+
     def launches(self):
         return int(self.lib.av1b_launch_count(self.ctx))
 

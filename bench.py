@@ -1,0 +1,470 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 AV1 reconstruction + in-loop-filter engine.
+
+Metric (BASELINE.json): decoded Mpix/s (shown luma pixels per second) on the reference's
+conformance set, and post-filter GB/s against the HBM roofline.
+
+  step      = one pass over the job: every bits/ conformance stream (172 streams, 23.3 Mpix of
+              shown luma, BASELINE.json configs[1]) decoded once per GPU.  Weak scaling: every
+              rank owns a full copy of the set (independent streams, one decoder per stream,
+              no data-path collective -- SURVEY.md section 8e "replicas only").
+  value     = Mpix/s with inputs RESIDENT IN HBM: the per-frame command buffers the host front
+              end emits are recorded once (untimed, MD5-checked against bits.md5), uploaded, and
+              the timed region replays them -- inverse transform, inter prediction, intra
+              wavefront, deblock, CDEF, LR for every frame -- on concurrent CUDA streams.  Timed
+              with CUDA events joined across those streams; max over ranks.
+  e2e       = the same job through the public decoder call with HOST buffers:
+              av1b_decode_ivf(ivf bytes) -> I420 bytes, i.e. bitstream parse + command emit + H2D
+              + kernels + D2H, one decoder per stream on all host cores (wall clock).
+  roofline  = the dominant in-loop-filter kernel on synthetic 3840x2160 4:2:0 frames
+              (BASELINE.json configs[3]): algorithmic bytes / CUDA-event duration measured live
+              by the engine around each launch, against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference = the unmodified reference decoder (oracle/_ref/av1dec) on all
+              host cores, one single-threaded instance per core, same streams.
+"""
+import argparse
+import concurrent.futures as cf
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+BITS = os.path.join(ROOT, "tests", "golden", "bits")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "av1dec")
+
+METRIC = "decoded_mpix_per_s"
+UNIT = "Mpix/s"
+WORKLOAD = ("configs[1]: full bits/ conformance set (172 AV1 streams, 8-bit 4:2:0, 23.3 Mpix shown luma) "
+            "decoded once per GPU, every stream MD5-checked against bits.md5")
+
+
+# ------------------------------------------------------------------------------------------
+# helpers shared with tests/test_sharding.py
+# ------------------------------------------------------------------------------------------
+def shard_streams(streams, rank, world):
+    """Deal the job's streams to ranks round-robin (independent units, no exchange step)."""
+    return [s for i, s in enumerate(streams) if i % world == rank]
+
+
+def reduce_result(units, seconds, device):
+    """(sum of units over ranks, max of seconds over ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return units, seconds
+    t = torch.tensor([units, seconds], dtype=torch.float64, device=device)
+    s = t.clone()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    m = t.clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return float(s[0].item()), float(m[1].item())
+
+
+def load_streams():
+    md5 = {}
+    for line in open(os.path.join(BITS, "bits.md5")):
+        p = line.split()
+        if len(p) == 2:
+            md5[p[1]] = p[0]
+    names = sorted(f for f in os.listdir(BITS) if f.endswith(".ivf"))
+    return [(n, open(os.path.join(BITS, n), "rb").read(), md5[n]) for n in names]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference CLI, one instance per core
+# ------------------------------------------------------------------------------------------
+def _ref_decode_one(path, core):
+    cmd = [REF_CLI, "-i", path, "-md5"]
+    if core is not None and os.path.exists("/usr/bin/taskset"):
+        cmd = ["taskset", "-c", str(core)] + cmd
+    subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+
+
+def reference_pass(streams, cores):
+    """Decode every stream once with the reference CLI on `cores` cores.  Returns seconds."""
+    # longest first so the tail is short
+    order = sorted(streams, key=lambda s: -len(s[1]))
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(cores) as ex:
+        free = list(range(cores))
+        lock = threading.Lock()
+
+        def job(s):
+            with lock:
+                core = free.pop()
+            try:
+                _ref_decode_one(os.path.join(BITS, s[0]), core)
+            finally:
+                with lock:
+                    free.append(core)
+        list(ex.map(job, order))
+    return time.perf_counter() - t0
+
+
+def shown_pixels(streams):
+    """Shown luma pixels per stream from the IVF headers x frame count is wrong for hidden frames,
+    so use the recorded table produced by the decoders; fall back to the oracle when needed."""
+    table = os.path.join(ROOT, "tests", "golden", "shown_pixels.json")
+    return json.load(open(table))
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    streams = load_streams()
+    cores = os.cpu_count() or 1
+    pixels = sum(shown_pixels(streams)[n] for n, _, _ in streams)
+    if not os.path.exists(REF_CLI):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/av1dec was not built (needs /root/reference at build time)"}))
+        return 0
+    for _ in range(args.warmup):
+        reference_pass(streams[:16], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += reference_pass(streams, cores)
+    # `world` replicas of the job share the same host cores: the CPU arm does not scale with GPUs
+    value = pixels * args.steps / t / 1e6
+    sample = f"{args.steps} x full 172-stream set, one single-threaded reference process per core (taskset), -md5 output"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "bits/ conformance streams (committed fixtures)",
+        "config": {"workload": WORKLOAD, "impl": "unmodified oddstone/av1dec CPU decoder, -O3 -fno-aggressive-loop-optimizations"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class RecordedStream:
+    """Command buffers of one stream, resident in HBM, plus what is needed to replay them."""
+
+    def __init__(self, name, max_w, max_h):
+        self.name, self.max_w, self.max_h = name, max_w, max_h
+        self.frames = []  # (dev_ptr or None, hdr_bytes, refresh, slot)
+        self.pixels = 0
+        self.cmd_bytes = 0
+        self.yuv_bytes = 0
+
+
+def record_stream(pkg, eng_mod, name, data, want_md5, device):
+    """Decode once through the public Decoder (MD5 gate) while tapping the command buffers."""
+    frames = []
+
+    def sink(buf, n, refresh, show):
+        frames.append((buf, n, refresh, show))
+    dec = pkg.Decoder(device=device)
+    dec.set_cmd_sink(sink)
+    md5 = hashlib.md5()
+    pixels = yuv = 0
+    mw = mh = 0
+    for unit in pkg.iter_ivf(data):
+        if not dec.decode(unit):
+            raise RuntimeError(f"{name}: decode failed: {dec.error()}")
+        while True:
+            o = dec.get_output()
+            if o is None:
+                break
+            w, h, planes = o
+            mw, mh = max(mw, w), max(mh, h)
+            pixels += w * h
+            for p in planes:
+                md5.update(p)
+                yuv += len(p)
+    dec.close()
+    if md5.hexdigest() != want_md5:
+        raise RuntimeError(f"{name}: MD5 mismatch through the GPU path")
+    rs = RecordedStream(name, mw, mh)
+    rs.pixels, rs.yuv_bytes = pixels, yuv
+    rs.host_frames = frames
+    return rs
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import av1dec_b200 as pkg
+    from av1dec_b200 import format as F
+    from av1dec_b200 import synth
+    from av1dec_b200.engine import Engine
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the reconstruction / filter stages")
+    device = local_rank
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    lib = pkg.load_engine()
+    pkg.load_decoder()
+    streams_all = load_streams()
+    # weak scaling: the global job is `world` copies of the set, dealt round-robin -> one full set per rank
+    global_job = [s for _ in range(world) for s in streams_all]
+    mine = shard_streams(global_job, rank, world)
+    hdr_size = C.sizeof(F.FrameHdr)
+    cores = os.cpu_count() or 1
+    host_threads = max(1, cores // world)
+
+    # ---------------- record (untimed): MD5 gate + command capture, then upload to HBM
+    side_streams = [torch.cuda.Stream(device=dev) for _ in range(args.cuda_streams)]
+    recs = []
+    for i, (name, data, want) in enumerate(mine):
+        rs = record_stream(pkg, None, name, data, want, device)
+        rs.engine = Engine(max(rs.max_w, 16), max(rs.max_h, 16), device=device, stream=side_streams[i % len(side_streams)].cuda_stream)
+        rs.side = side_streams[i % len(side_streams)]
+        for buf, n, refresh, show in rs.host_frames:
+            if buf is None:
+                rs.frames.append((None, None, refresh, n))
+            else:
+                rs.frames.append((rs.engine.upload(buf), buf[:hdr_size], refresh, -1))
+                rs.cmd_bytes += n
+        del rs.host_frames
+        recs.append(rs)
+    pixels_step = sum(r.pixels for r in recs)
+    h2d_step = sum(r.cmd_bytes for r in recs)
+    d2h_step = sum(r.yuv_bytes for r in recs)
+    max_frames = max(len(r.frames) for r in recs)
+
+    def replay_once():
+        # interleave streams frame by frame so the GPU always has independent work queued
+        for f in range(max_frames):
+            for r in recs:
+                if f < len(r.frames):
+                    ptr, hdr, refresh, slot = r.frames[f]
+                    if ptr is None:
+                        r.engine.show_existing(slot, refresh)
+                    else:
+                        r.engine.submit_resident(ptr, hdr, pkg.STAGE_ALL, refresh)
+
+    main = torch.cuda.current_stream(dev)
+
+    def timed_replay(steps):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for s in side_streams:
+            s.wait_event(start)
+        for _ in range(steps):
+            replay_once()
+        for s in side_streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+        end.record(main)
+        end.synchronize()
+        return start.elapsed_time(end) / 1e3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        timed_replay(1)
+    launches0 = sum(r.engine.launches() for r in recs)
+    sampler = ClockSampler(device)
+    barrier()
+    sampler.start()
+    secs = timed_replay(args.steps)
+    barrier()
+    launches = sum(r.engine.launches() for r in recs) - launches0
+    total_px, tmax = reduce_result(float(pixels_step * args.steps), secs, dev)
+    value = total_px / tmax / 1e6
+
+    # per-stage share of device time for the stream workload (one extra profiled pass)
+    for r in recs:
+        r.engine.set_profiling(True)
+    replay_once()
+    share = {n: 0.0 for n in pkg.STAGE_NAMES}
+    for r in recs:
+        ms, _ = r.engine.stage_times()
+        for k, v in ms.items():
+            share[k] += v
+        r.engine.set_profiling(False)
+
+    # ---------------- e2e: public decoder call, host buffers in and out, all host cores
+    def e2e_pass():
+        def one(s):
+            yuv, frames, px = pkg.decode_ivf(s[1], device=device)
+            return px, len(yuv)
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(host_threads) as ex:
+            res = list(ex.map(one, sorted(mine, key=lambda s: -len(s[1]))))
+        return time.perf_counter() - t0, sum(p for p, _ in res)
+    e2e_pass()
+    barrier()
+    e2e_t = 0.0
+    e2e_px = 0
+    for _ in range(args.steps):
+        t, px = e2e_pass()
+        e2e_t += t
+        e2e_px += px
+    barrier()
+    clocks = sampler.stop()
+    e2e_total, e2e_tmax = reduce_result(float(e2e_px), e2e_t, dev)
+    e2e_value = e2e_total / e2e_tmax / 1e6
+    for r in recs:
+        for ptr, _, _, _ in r.frames:
+            if ptr is not None:
+                r.engine.free(ptr)
+        r.engine.close()
+
+    # ---------------- roofline leg: post-filter chain on synthetic 4K frames (rank 0's GPU, every rank runs it)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    W4, H4 = 3840, 2160
+    S = W4 * H4 * 3 // 2
+    eng = Engine(W4, H4, device=device, stream=None)
+    frames4k = []
+    n_in = 8
+    for i in range(n_in):
+        sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist="B", lr_unit=64)
+        eng.set_ref(i, sf.planes, sf.mi_cols * 4, sf.mi_rows * 4)
+        frames4k.append((eng.upload(sf.cmd), sf.cmd[:hdr_size]))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def post_pass(n):
+        for k in range(n):
+            i = k % n_in
+            eng.input_from_slot(i)
+            eng.submit_resident(frames4k[i][0], frames4k[i][1], pkg.STAGE_POST, 0)
+    post_pass(n_in)
+    eng.sync()
+    eng.set_profiling(True)
+    reps = 3
+    for _ in range(reps):
+        flush.zero_()  # L2 flush between timed iterations (a 256 MiB write, larger than the 126 MB L2)
+        torch.cuda.synchronize()
+        post_pass(n_in)
+    ms, calls = eng.stage_times()
+    eng.close()
+    alg = {"deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S + S // 16}
+    post = {}
+    for k in ("deblock", "cdef", "lr"):
+        per = ms[k] / max(calls[k], 1) * 1e-3
+        post[k] = {"us_per_frame": per * 1e6, "algorithmic_bytes": alg[k], "gbs": alg[k] / per / 1e9 if per > 0 else None}
+    chain_s = sum(ms[k] / max(calls[k], 1) for k in alg) * 1e-3
+    post["chain"] = {"us_per_frame": chain_s * 1e6, "algorithmic_bytes": sum(alg.values()),
+                     "gbs": sum(alg.values()) / chain_s / 1e9, "frac_of_peak": sum(alg.values()) / chain_s / 1e9 / peak,
+                     "mpix_per_s": W4 * H4 / chain_s / 1e6}
+    dom = max(alg, key=lambda k: post[k]["us_per_frame"])
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(dom)
+    roofline = {"bound": "hbm", "kernel": {"deblock": "deblock_kernel (V+H passes)", "cdef": "cdef_kernel", "lr": "lr_kernel"}[dom],
+                "achieved": post[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": post[dom]["gbs"] / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "workload": "synthetic 3840x2160 4:2:0 8-bit, blocky-smooth pixels, random partition/levels/CDEF presets/LR units (configs[3])"}
+
+    if rank != 0:
+        return 0
+    # ---------------- CPU baseline on rank 0 at N=1: bounded sample of the same workload
+    cpu = None
+    if world == 1 and os.path.exists(REF_CLI):
+        t = reference_pass(streams_all, cores)
+        px = sum(shown_pixels(streams_all)[n] for n, _, _ in streams_all)
+        cpu = {"value": px / t / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "1 x full 172-stream set with oracle/_ref/av1dec, one single-threaded process per core"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "bits/ conformance streams (committed fixtures); synthetic 4K frames for the roofline leg",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams),
+                   "host_threads_per_gpu": host_threads, "host_cores": cores,
+                   "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
+                   "stage_share_ms": share},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step * world, "d2h_bytes_per_step": d2h_step * world,
+                "ms_per_step": 1e3 * e2e_tmax / args.steps, "api": "av1b_decode_ivf (include/av1b200_decoder.h)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "postfilter_4k": post,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cuda-streams", type=int, default=32)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        return run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

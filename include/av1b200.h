@@ -103,6 +103,15 @@ int av1b_debug_set_ref(av1b_ctx* ctx, int slot, const uint8_t* const src[3], con
 int av1b_debug_get_residual(av1b_ctx* ctx, int16_t* dst, size_t n);
 /* Number of kernel launches issued by this context so far. */
 uint64_t av1b_launch_count(av1b_ctx* ctx);
+/* Per-stage device timing.  With profiling on, the engine brackets every launch group with CUDA
+ * events on its stream; av1b_get_stage_times() synchronises and returns accumulated milliseconds
+ * and call counts per stage (index: 0 itx, 1 inter, 2 wavefront, 3 deblock, 4 cdef, 5 lr). */
+#define AV1B_N_STAGES 6
+int av1b_set_profiling(av1b_ctx* ctx, int on);
+int av1b_get_stage_times(av1b_ctx* ctx, double ms[AV1B_N_STAGES], uint64_t calls[AV1B_N_STAGES], int reset);
+/* Device-to-device: make a copy of reference slot `slot` the "current" frame of the next submit
+ * (benchmark: re-run the in-place post-filter chain on pristine, HBM-resident input). */
+int av1b_debug_input_from_slot(av1b_ctx* ctx, int slot);
 /* sizeof() of the command-format structs (0 FrameHdr, 1 Op, 2 Sb, 3 Ipu, 4 InterBlk, 5 BlkAux,
  * 6 LfMi, 7 LrUnit): lets a foreign-language binding verify its mirror of av1b200_format.h. */
 size_t av1b_struct_size(int which);
