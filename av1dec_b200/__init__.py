@@ -26,7 +26,7 @@ CMD_SINK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_u
 ENGINE_SYMBOLS = [
     "av1b_backend", "av1b_ctx_create", "av1b_ctx_destroy", "av1b_last_error", "av1b_cmd_acquire",
     "av1b_frame_submit", "av1b_frame_submit_resident", "av1b_show_existing", "av1b_frame_download",
-    "av1b_sync", "av1b_fence_record", "av1b_fence_wait", "av1b_host_alloc", "av1b_host_free",
+    "av1b_sync", "av1b_fence_record", "av1b_fence_wait", "av1b_fence_done", "av1b_pool_purge", "av1b_host_alloc", "av1b_host_free",
     "av1b_dev_alloc", "av1b_dev_free", "av1b_dev_upload", "av1b_debug_set_input", "av1b_debug_set_ref",
     "av1b_debug_get_residual", "av1b_launch_count", "av1b_set_profiling", "av1b_get_stage_times",
     "av1b_debug_input_from_slot", "av1b_struct_size",
@@ -150,7 +150,10 @@ def decode_ivf(data, device=0, stages=STAGE_ALL, want_yuv=True, lib=None):
     The yuv layout is the reference CLI's output file (tests/DecodeOutput.cpp:48-69)."""
     lib = lib or load_decoder()
     out_bytes, n_frames, pixels = C.c_size_t(0), C.c_int(0), C.c_uint64(0)
-    cap = 1 << 20
+    # size the output from the IVF header (width, height, frame count) so one decode suffices
+    w, h = int.from_bytes(data[12:14], "little"), int.from_bytes(data[14:16], "little")
+    n = int.from_bytes(data[24:28], "little")
+    cap = max(w * h * 3 // 2 * max(n, 1) + (64 << 10), 1 << 16)
     while True:
         buf = C.create_string_buffer(cap) if want_yuv else None
         rc = lib.av1b_decode_ivf(data, len(data), device, stages, buf, cap if want_yuv else 0,

@@ -10,6 +10,8 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,6 +41,7 @@ static int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
 static void rt_event_destroy(rt_event_t) {}
 static int rt_event_record(rt_event_t, av1b_stream_t) { return 0; }
 static int rt_event_sync(rt_event_t) { return 0; }
+static int rt_event_done(rt_event_t) { return 1; }
 static const char* rt_error() { return "emu"; }
 static int rt_check() { return 0; }
 static int rt_tevent_create(rt_event_t* e) { *e = 0; return 0; }
@@ -66,6 +69,7 @@ static int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, c
 static void rt_event_destroy(rt_event_t e) { cudaEventDestroy(e); }
 static int rt_event_record(rt_event_t e, av1b_stream_t s) { return cudaEventRecord(e, s) != cudaSuccess; }
 static int rt_event_sync(rt_event_t e) { return cudaEventSynchronize(e) != cudaSuccess; }
+static int rt_event_done(rt_event_t e) { return cudaEventQuery(e) == cudaSuccess; }
 static const char* rt_error() { return cudaGetErrorString(cudaGetLastError()); }
 static int rt_check() { return cudaGetLastError() != cudaSuccess; }
 static int rt_tevent_create(rt_event_t* e) { return cudaEventCreate(e) != cudaSuccess; }
@@ -256,9 +260,50 @@ static int frame_alloc(av1b_ctx* c)
 
 extern "C" {
 
+// ---- process-wide caches -------------------------------------------------------------------
+// Creating a context costs a stream, ~70 events, several cudaMalloc / cudaHostAlloc calls and a
+// table upload; cudaFree synchronises the whole device.  A multi-stream decode service opens and
+// closes one decoder per stream, so contexts (with their frame pools and pinned rings), the wedge
+// table and pinned output buffers are recycled instead of being freed.
+static std::mutex g_mu;
+static std::vector<av1b_ctx*> g_ctx_pool;
+static std::map<int, uint8_t*> g_wedge;           // per device
+static std::map<void*, size_t> g_pinned_size;     // every live pinned block -> its bucket size
+static std::map<size_t, std::vector<void*>> g_pinned_free;
+
+static void ctx_free(av1b_ctx* c)
+{
+    rt_set_device(c->device);
+    rt_stream_sync(c->stream);
+    for (auto& f : c->frames) rt_free(f.base);
+    for (int i = 0; i < N_SLOTS; i++) {
+        rt_host_free(c->slots[i].host);
+        rt_free(c->slots[i].dev);
+        rt_event_destroy(c->slots[i].done);
+    }
+    for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
+    for (auto e : c->event_pool) rt_event_destroy(e);
+    rt_free(c->res);
+    rt_free(c->sync);
+    if (c->own_stream) rt_stream_destroy(c->stream);
+    delete c;
+}
+
 int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream)
 {
     if (!out || max_w <= 0 || max_h <= 0 || max_w > 16384 || max_h > 16384) return AV1B_EINVAL;
+    const int aw = (max_w + 127) & ~127, ah = (max_h + 127) & ~127;
+    if (!stream) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < g_ctx_pool.size(); i++) {
+            av1b_ctx* c = g_ctx_pool[i];
+            if (c->device == device && c->aw >= aw && c->ah >= ah && (size_t)c->aw * c->ah <= 2 * (size_t)aw * ah) {
+                g_ctx_pool.erase(g_ctx_pool.begin() + i);
+                *out = c;
+                return AV1B_OK;
+            }
+        }
+    }
     av1b_ctx* c = new av1b_ctx;
     *out = c;
     c->device = device;
@@ -271,8 +316,8 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
     }
     c->max_w = max_w;
     c->max_h = max_h;
-    c->aw = (max_w + 127) & ~127;
-    c->ah = (max_h + 127) & ~127;
+    c->aw = aw;
+    c->ah = ah;
     c->stride_y = c->aw + 2 * PAD_X;
     c->stride_c = c->aw / 2 + 2 * PAD_X;
     c->frame_bytes = (size_t)(c->ah + 2 * PAD_Y) * c->stride_y + 2 * (size_t)(c->ah / 2 + 2 * PAD_Y) * c->stride_c;
@@ -280,13 +325,20 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
         if (rt_event_create(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     for (int i = 0; i < N_FENCES; i++)
         if (rt_event_create(&c->fences[i])) return fail(c, AV1B_ECUDA, "cudaEventCreate");
-    std::vector<uint8_t> wt(AV1B_WEDGE_TABLE_BYTES);
-    build_wedge_table(wt.data());
-    void* p = nullptr;
-    if (rt_malloc(&p, AV1B_WEDGE_TABLE_BYTES)) return fail(c, AV1B_ENOMEM, "wedge table alloc");
-    c->wedge = (uint8_t*)p;
-    if (rt_h2d(c->wedge, wt.data(), AV1B_WEDGE_TABLE_BYTES, c->stream) || rt_stream_sync(c->stream))
-        return fail(c, AV1B_ECUDA, "wedge table upload");
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_wedge.find(device);
+        if (it == g_wedge.end()) {
+            std::vector<uint8_t> wt(AV1B_WEDGE_TABLE_BYTES);
+            build_wedge_table(wt.data());
+            void* p = nullptr;
+            if (rt_malloc(&p, AV1B_WEDGE_TABLE_BYTES)) return fail(c, AV1B_ENOMEM, "wedge table alloc");
+            if (rt_h2d(p, wt.data(), AV1B_WEDGE_TABLE_BYTES, c->stream) || rt_stream_sync(c->stream))
+                return fail(c, AV1B_ECUDA, "wedge table upload");
+            it = g_wedge.emplace(device, (uint8_t*)p).first;
+        }
+        c->wedge = it->second;
+    }
     return AV1B_OK;
 }
 
@@ -294,19 +346,48 @@ void av1b_ctx_destroy(av1b_ctx* c)
 {
     if (!c) return;
     rt_set_device(c->device);
-    if (c->stream || true) rt_stream_sync(c->stream);
-    for (auto& f : c->frames) rt_free(f.base);
-    for (int i = 0; i < N_SLOTS; i++) {
-        rt_host_free(c->slots[i].host);
-        rt_free(c->slots[i].dev);
-        rt_event_destroy(c->slots[i].done);
+    rt_stream_sync(c->stream);
+    if (c->own_stream && c->wedge) {
+        // recycle: reset the decode state, keep every allocation
+        for (auto& f : c->frames) f.refcnt = 0;
+        for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
+        for (int i = 0; i < N_SLOTS; i++) c->slots[i].pending = false;
+        c->pending_input = -1;
+        c->profiling = false;
+        for (auto& sp : c->spans) {
+            c->event_pool.push_back(sp.a);
+            c->event_pool.push_back(sp.b);
+        }
+        c->spans.clear();
+        for (int i = 0; i < AV1B_N_STAGES; i++) {
+            c->stage_ms[i] = 0;
+            c->stage_calls[i] = 0;
+        }
+        c->err.clear();
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_ctx_pool.size() < 512) {
+            g_ctx_pool.push_back(c);
+            return;
+        }
     }
-    for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
-    rt_free(c->res);
-    rt_free(c->sync);
-    rt_free(c->wedge);
-    if (c->own_stream) rt_stream_destroy(c->stream);
-    delete c;
+    ctx_free(c);
+}
+
+void av1b_pool_purge(void)
+{
+    std::vector<av1b_ctx*> pool;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        pool.swap(g_ctx_pool);
+    }
+    for (av1b_ctx* c : pool) ctx_free(c);
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_pinned_free)
+        for (void* p : kv.second) {
+            g_pinned_size.erase(p);
+            rt_host_free(p);
+        }
+    g_pinned_free.clear();
 }
 
 const char* av1b_last_error(av1b_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -517,6 +598,14 @@ int av1b_fence_record(av1b_ctx* c, uint64_t* fence)
     return AV1B_OK;
 }
 
+int av1b_fence_done(av1b_ctx* c, uint64_t fence)
+{
+    if (!c) return 1;
+    if (fence == 0 || fence + N_FENCES <= c->fence_next) return 1;
+    rt_set_device(c->device);
+    return rt_event_done(c->fences[fence % N_FENCES]);
+}
+
 int av1b_fence_wait(av1b_ctx* c, uint64_t fence)
 {
     if (!c) return AV1B_EINVAL;
@@ -528,10 +617,31 @@ int av1b_fence_wait(av1b_ctx* c, uint64_t fence)
 
 void* av1b_host_alloc(size_t bytes)
 {
+    size_t bucket = 64 << 10;
+    while (bucket < bytes) bucket <<= 1;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto& fl = g_pinned_free[bucket];
+        if (!fl.empty()) {
+            void* p = fl.back();
+            fl.pop_back();
+            return p;
+        }
+    }
     void* p = nullptr;
-    return rt_host_alloc(&p, bytes) ? nullptr : p;
+    if (rt_host_alloc(&p, bucket)) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_pinned_size[p] = bucket;
+    return p;
 }
-void av1b_host_free(void* p) { rt_host_free(p); }
+void av1b_host_free(void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_pinned_size.find(p);
+    if (it == g_pinned_size.end()) return;
+    g_pinned_free[it->second].push_back(p);
+}
 void* av1b_dev_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -70,9 +70,10 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
     YamiAv1::Decoder dec;
     av1b200::decoderOptions(dec).device = device;
     av1b200::decoderOptions(dec).stages = stages;
-    auto drain = [&]() {
+    // keepInFlight frames may still be on the device while the next temporal unit is parsed
+    auto drain = [&](size_t keepInFlight) {
         std::shared_ptr<Yami::YuvFrame> f;
-        while ((f = dec.getOutput())) {
+        while ((f = keepInFlight ? av1b200::decoderPollOutput(dec, keepInFlight) : dec.getOutput())) {
             frames++;
             pixels += (uint64_t)f->width * f->height;
             for (int p = 0; p < 3; p++) {
@@ -95,8 +96,9 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
             break;
         }
         pos += sz;
-        drain();
+        drain(2);
     }
+    if (rc != -1) drain(0);
     if (out_bytes) *out_bytes = out;
     if (n_frames) *n_frames = frames;
     if (luma_pixels) *luma_pixels = pixels;

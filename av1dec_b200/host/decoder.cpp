@@ -264,6 +264,14 @@ bool decoderFormat(YamiAv1::Decoder& d, int& w, int& h)
     h = i->parser->m_sequence->max_frame_height_minus_1 + 1;
     return true;
 }
+std::shared_ptr<Yami::YuvFrame> decoderPollOutput(YamiAv1::Decoder& d, size_t keepInFlight)
+{
+    auto* i = implOf(d);
+    if (i->output.empty()) return nullptr;
+    auto& p = i->output.front();
+    if (i->output.size() <= keepInFlight && !av1b_fence_done(i->ctx, p.fence)) return nullptr;
+    return d.getOutput();
+}
 void decoderFlush(YamiAv1::Decoder& d)
 {
     auto* i = implOf(d);

@@ -2,7 +2,12 @@
 #pragma once
 #include "../../include/av1b200.h"
 #include "emitter.h"
+#include <memory>
 #include <string>
+
+namespace Yami {
+struct YuvFrame;
+}
 
 namespace YamiAv1 {
 class Decoder;
@@ -26,5 +31,8 @@ const char* decoderError(YamiAv1::Decoder& d);
 av1b_ctx* decoderCtx(YamiAv1::Decoder& d);
 bool decoderFormat(YamiAv1::Decoder& d, int& w, int& h);
 void decoderFlush(YamiAv1::Decoder& d);
+// Next output frame if it is already complete, or if more than keepInFlight frames are queued
+// (then it blocks); null otherwise.  Lets a whole-stream loop parse ahead of the device.
+std::shared_ptr<Yami::YuvFrame> decoderPollOutput(YamiAv1::Decoder& d, size_t keepInFlight);
 
 }  // namespace av1b200

@@ -53,7 +53,10 @@ const char* av1b_backend(void);
  * `stream` is a cudaStream_t to enqueue on, or NULL to let the engine create its own.
  * Replaces the YuvFrame allocations of Decoder::decodeFrame (Av1Decoder.cpp:131). */
 int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream);
+/* Destroying a context that owns its stream returns it (frame pool, pinned ring and all) to a
+ * process-wide cache that av1b_ctx_create() draws from; av1b_pool_purge() really frees. */
 void av1b_ctx_destroy(av1b_ctx* ctx);
+void av1b_pool_purge(void);
 const char* av1b_last_error(av1b_ctx* ctx);
 
 /* Pinned command ring.  Returns a host pointer with room for `bytes`; blocks until the slot's
@@ -84,6 +87,7 @@ int av1b_sync(av1b_ctx* ctx);
  * the next frame with this frame's device work. */
 int av1b_fence_record(av1b_ctx* ctx, uint64_t* fence);
 int av1b_fence_wait(av1b_ctx* ctx, uint64_t fence);
+int av1b_fence_done(av1b_ctx* ctx, uint64_t fence); /* 1 if the fence has been reached (non-blocking) */
 
 void* av1b_host_alloc(size_t bytes); /* pinned host memory */
 void av1b_host_free(void* p);
