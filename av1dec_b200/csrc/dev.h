@@ -43,6 +43,16 @@ static inline void av1b_st_release(int* p, int v) { *p = v; }
 static inline void av1b_nanosleep(unsigned) {}
 using std::max;
 using std::min;
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
+{
+    uint32_t lo = std::max(a & 0xFFFFu, b & 0xFFFFu), hi = std::max(a >> 16, b >> 16);
+    return lo | (hi << 16);
+}
+static inline uint32_t __vminu2(uint32_t a, uint32_t b)
+{
+    uint32_t lo = std::min(a & 0xFFFFu, b & 0xFFFFu), hi = std::min(a >> 16, b >> 16);
+    return lo | (hi << 16);
+}
 typedef void* av1b_stream_t;
 template <class F> static inline void emu_launch(dim3 grid, F f)
 {

@@ -190,156 +190,266 @@ __global__ void __launch_bounds__(256) deblock_kernel(PostCtx c, int pass)
 // ==========================================================================================
 // CDEF
 // ==========================================================================================
+// One CTA filters a 64x64 luma area (8x8 CDEF blocks) and the matching 32x32 chroma areas.
+//   1. the tile + 2-sample halo of each plane is staged in shared memory as 16-bit samples;
+//      samples outside the MI-aligned frame become CDEF_LARGE so that their constrained
+//      difference is 0 and they never win the min/max (they are "unavailable", Cdef.cpp:140-156)
+//   2. direction search: one thread per (block, direction), bins in registers
+//   3. filter: one warp per 8x8 block, one lane per horizontal sample PAIR, all arithmetic on
+//      packed 16x2 lanes (VIMNMX.U16x2 / VIADD) -- the stage is issue-bound, not HBM-bound
 namespace {
 
-AV1B_DEV int cdef_constrain(int diff, int threshold, int damping)
+enum {
+    CDEF_LARGE = 0x4000,
+    CY_PITCH = 72,  // halfwords per luma tile row (36 words: conflict-free for 8 rows x 4 words)
+    CY_ROWS = 68,
+    CC_PITCH = 48,  // halfwords per chroma tile row
+    CC_ROWS = 36,
+};
+
+struct CdefBlk {
+    uint8_t idx;      // preset or 0xFF
+    uint8_t pri[2];   // [0] luma (variance adjusted), [1] chroma
+    uint8_t sec[2];
+    uint8_t adjp[2];  // damping adjustment shifts
+    uint8_t adjs[2];
+    uint8_t dir[2];
+    uint8_t pad;
+};
+
+struct CdefShared {
+    uint16_t ya[CY_ROWS * CY_PITCH];      // luma tile, ya[r*P + c] = sample (x0 - 2 + c, y0 - 2 + r)
+    uint16_t yb[CY_ROWS * CY_PITCH];      // same, shifted left by one sample (odd tap offsets stay word aligned)
+    uint16_t ca[2][CC_ROWS * CC_PITCH];
+    uint16_t cb[2][CC_ROWS * CC_PITCH];
+    int cost[64][8];
+    CdefBlk blk[64];
+};
+
+template <int D> AV1B_DEV constexpr int cdef_bin(int i, int j)
 {
-    if (!threshold) return 0;
-    const int adj = max(0, damping - floor_log2((unsigned)threshold));
-    const int ad = iabs(diff);
-    const int v = clip3(0, ad, threshold - (ad >> adj));
-    return diff < 0 ? -v : v;
+    return D == 0 ? i + j : D == 1 ? i + j / 2 : D == 2 ? i : D == 3 ? 3 + i - j / 2 : D == 4 ? 7 + i - j : D == 5 ? 3 - i / 2 + j
+        : D == 6 ? j : i / 2 + j;
 }
 
-// Direction search for the 8x8 luma block at (x0,y0). (reference cdefDirection)
-AV1B_DEV void cdef_direction(const PlaneView& y, int x0, int y0, int& dir, int& var)
+// cost of direction D for the 8x8 block whose top-left sample is at `blk` (reference cdefDirection)
+template <int D> AV1B_DEV int cdef_cost(const uint16_t* blk)
 {
-    int partial[8][15];
-    for (int i = 0; i < 8; i++)
-        for (int j = 0; j < 15; j++) partial[i][j] = 0;
+    int part[15];
+    AV1B_UNROLL
+    for (int k = 0; k < 15; k++) part[k] = 0;
+    AV1B_UNROLL
     for (int i = 0; i < 8; i++) {
-        for (int j = 0; j < 8; j++) {
-            const int x = (int)__ldg(y.p + (size_t)(y0 + i) * y.stride + x0 + j) - 128;
-            partial[0][i + j] += x;
-            partial[1][i + j / 2] += x;
-            partial[2][i] += x;
-            partial[3][3 + i - j / 2] += x;
-            partial[4][7 + i - j] += x;
-            partial[5][3 - i / 2 + j] += x;
-            partial[6][j] += x;
-            partial[7][i / 2 + j] += x;
+        AV1B_UNROLL
+        for (int j = 0; j < 8; j++) part[cdef_bin<D>(i, j)] += (int)blk[i * CY_PITCH + j] - 128;
+    }
+    int cost = 0;
+    if (D == 2 || D == 6) {
+        AV1B_UNROLL
+        for (int k = 0; k < 8; k++) cost += part[k] * part[k];
+        cost *= 105;
+    } else if (D == 0 || D == 4) {
+        AV1B_UNROLL
+        for (int k = 0; k < 7; k++) cost += (part[k] * part[k] + part[14 - k] * part[14 - k]) * k_cdef_div_table[k + 1];
+        cost += part[7] * part[7] * 105;
+    } else {
+        AV1B_UNROLL
+        for (int k = 0; k < 5; k++) cost += part[3 + k] * part[3 + k];
+        cost *= 105;
+        AV1B_UNROLL
+        for (int k = 0; k < 3; k++) cost += (part[k] * part[k] + part[10 - k] * part[10 - k]) * k_cdef_div_table[2 * k + 2];
+    }
+    return cost;
+}
+
+AV1B_DEV int cdef_cost_dyn(int d, const uint16_t* blk)
+{
+    switch (d) {
+    case 0: return cdef_cost<0>(blk);
+    case 1: return cdef_cost<1>(blk);
+    case 2: return cdef_cost<2>(blk);
+    case 3: return cdef_cost<3>(blk);
+    case 4: return cdef_cost<4>(blk);
+    case 5: return cdef_cost<5>(blk);
+    case 6: return cdef_cost<6>(blk);
+    default: return cdef_cost<7>(blk);
+    }
+}
+
+// Aligned 32-bit load of the sample pair starting at halfword index `idx` (any parity): even
+// indices come from the tile, odd ones from the copy shifted by one sample.
+AV1B_DEV uint32_t cdef_pair(const uint16_t* a, const uint16_t* b, int idx)
+{
+    const uint16_t* base = (idx & 1) ? (b + idx - 1) : (a + idx);
+    return *(const uint32_t*)base;
+}
+
+// One constrained tap on two samples at once.  x2/p2: centre / tap sample pairs (16x2).
+AV1B_DEV void cdef_tap(uint32_t p2, uint32_t x2, uint32_t thr2, int adj, uint32_t amask, uint32_t w, uint32_t& T, uint32_t& P,
+    uint32_t& mx, uint32_t& mn)
+{
+    const uint32_t hi = __vmaxu2(p2, x2), lo = __vminu2(p2, x2);
+    const uint32_t a = hi - lo;                       // |p - x| per half
+    const uint32_t s = (a >> adj) & amask;            // |d| >> dampingAdj
+    const uint32_t t = __vmaxu2(thr2, s) - s;         // max(0, thr - s)
+    const uint32_t c = __vminu2(a, t);                // constrained magnitude
+    const uint32_t cp = __vminu2(c, hi - x2);         // ... of the positive differences only
+    T += w * c;
+    P += w * cp;
+    mx = __vmaxu2(mx, p2 & 0x00FF00FFu);              // CDEF_LARGE & 0xFF == 0: unavailable never wins
+    mn = __vminu2(mn, lo);
+}
+
+// Filter the sample pair at halfword index `ctr` of tile (a, b).  Returns the two output bytes.
+AV1B_DEV uint32_t cdef_filter_pair(const uint16_t* a, const uint16_t* b, int ctr, int pitch, int pri, int sec, int adjp, int adjs,
+    int dir)
+{
+    const uint32_t x2 = *(const uint32_t*)(a + ctr);
+    uint32_t T = 0, P = 0, mx = x2, mn = x2;
+    const uint32_t pri2 = (uint32_t)pri * 0x00010001u, sec2 = (uint32_t)sec * 0x00010001u;
+    const uint32_t maskp = (0xFFFFu >> adjp) * 0x00010001u, masks = (0xFFFFu >> adjs) * 0x00010001u;
+    AV1B_UNROLL
+    for (int k = 0; k < 2; k++) {
+        const uint32_t wp = (pri & 1) ? 3u : (k ? 2u : 4u);
+        const uint32_t ws = k ? 1u : 2u;
+        {
+            const int o = k_cdef_directions[dir][k][0] * pitch + k_cdef_directions[dir][k][1];
+            cdef_tap(cdef_pair(a, b, ctr + o), x2, pri2, adjp, maskp, wp, T, P, mx, mn);
+            cdef_tap(cdef_pair(a, b, ctr - o), x2, pri2, adjp, maskp, wp, T, P, mx, mn);
+        }
+        AV1B_UNROLL
+        for (int off = -2; off <= 2; off += 4) {
+            const int d2 = (dir + off) & 7;
+            const int o = k_cdef_directions[d2][k][0] * pitch + k_cdef_directions[d2][k][1];
+            cdef_tap(cdef_pair(a, b, ctr + o), x2, sec2, adjs, masks, ws, T, P, mx, mn);
+            cdef_tap(cdef_pair(a, b, ctr - o), x2, sec2, adjs, masks, ws, T, P, mx, mn);
         }
     }
-    int cost[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    for (int i = 0; i < 8; i++) {
-        cost[2] += partial[2][i] * partial[2][i];
-        cost[6] += partial[6][i] * partial[6][i];
+    uint32_t out = 0;
+    AV1B_UNROLL
+    for (int h = 0; h < 2; h++) {
+        const int sh = 16 * h;
+        const int sum = 2 * (int)((P >> sh) & 0xFFFF) - (int)((T >> sh) & 0xFFFF);
+        const int x = (x2 >> sh) & 0xFFFF;
+        const int y = clip3((int)((mn >> sh) & 0xFFFF), (int)((mx >> sh) & 0xFFFF), x + ((8 + sum - (sum < 0)) >> 4));
+        out |= (uint32_t)y << (8 * h);
     }
-    cost[2] *= 105;
-    cost[6] *= 105;
-    for (int i = 0; i < 7; i++) {
-        cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * k_cdef_div_table[i + 1];
-        cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * k_cdef_div_table[i + 1];
-    }
-    cost[0] += partial[0][7] * partial[0][7] * 105;
-    cost[4] += partial[4][7] * partial[4][7] * 105;
-    for (int i = 1; i < 8; i += 2) {
-        for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
-        cost[i] *= 105;
-        for (int j = 0; j < 3; j++)
-            cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * k_cdef_div_table[2 * j + 2];
-    }
-    int best = 0;
-    dir = 0;
-    for (int i = 0; i < 8; i++) {
-        if (cost[i] > best) {
-            best = cost[i];
-            dir = i;
+    return out;
+}
+
+// Stage rows [y0-2, y0-2+rows) x columns [x0-4, x0-4+4*words) of a plane into the 16-bit tiles.
+AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int pw, int ph, int rows, int words, int pitch, uint16_t* ta,
+    uint16_t* tb, int tid, int nt)
+{
+    for (int e = tid; e < rows * words; e += nt) {
+        const int r = e / words, wi = e - r * words;
+        const int y = y0 - 2 + r, xb = x0 - 4 + wi * 4;
+        const uint32_t v = __ldg((const uint32_t*)(src.p + (ptrdiff_t)y * src.stride + xb));
+        const bool yok = y >= 0 && y < ph;
+        AV1B_UNROLL
+        for (int k = 0; k < 4; k++) {
+            const int x = xb + k;
+            const int c = wi * 4 + k - 2; // tile column of this sample
+            const uint16_t px = (yok && x >= 0 && x < pw) ? (uint16_t)((v >> (8 * k)) & 0xFF) : (uint16_t)CDEF_LARGE;
+            if (c >= 0) ta[r * pitch + c] = px;
+            if (c >= 1) tb[r * pitch + c - 1] = px;
         }
     }
-    var = (best - cost[(dir + 4) & 7]) >> 10;
 }
 
 }  // namespace
 
-// One CTA per 64x64 luma area (8x8 CDEF blocks), all three planes.
 __global__ void __launch_bounds__(256) cdef_kernel(PostCtx c)
 {
-    __shared__ uint8_t s_idx[64];  // preset index or 0xFF
-    __shared__ uint8_t s_dir[64];
-    __shared__ int s_var[64];
+    __shared__ CdefShared S;
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const uint8_t* cdef8 = c.cmd + hdr->off_cdef8;
-    const Av1bCdefParams cp = hdr->cdef;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int c8 = hdr->mi_cols >> 1, r8 = hdr->mi_rows >> 1; // 8x8 blocks in the frame
     const int fbx = blockIdx.x * 8, fby = blockIdx.y * 8;      // first 8x8 block of this CTA
+    const int pw = hdr->mi_cols * 4, ph = hdr->mi_rows * 4;
+    // ---- 1. stage
+    cdef_stage(c.src.pl[0], fbx * 8, fby * 8, pw, ph, CY_ROWS, 18, CY_PITCH, S.ya, S.yb, tid, nt);
+    cdef_stage(c.src.pl[1], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 10, CC_PITCH, S.ca[0], S.cb[0], tid, nt);
+    cdef_stage(c.src.pl[2], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 10, CC_PITCH, S.ca[1], S.cb[1], tid, nt);
     for (int e = tid; e < 64; e += nt) {
         const int by = fby + (e >> 3), bx = fbx + (e & 7);
-        int idx = 0xFF, dir = 0, var = 0;
-        if (by < r8 && bx < c8) {
-            idx = cdef8[by * c8 + bx];
-            if (idx != 0xFF) cdef_direction(c.src.pl[0], bx * 8, by * 8, dir, var);
-        }
-        s_idx[e] = (uint8_t)idx;
-        s_dir[e] = (uint8_t)dir;
-        s_var[e] = var;
+        S.blk[e].idx = (by < r8 && bx < c8) ? cdef8[by * c8 + bx] : 0xFF;
     }
     __syncthreads();
-    for (int plane = 0; plane < 3; plane++) {
-        const int sub = plane ? 1 : 0;
-        const int bs = 8 >> sub;                   // block size in this plane
-        const int tile = 64 >> sub;                // CTA tile size in this plane
-        const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub; // MI-aligned plane size
-        const int x_base = (fbx * 8) >> sub, y_base = (fby * 8) >> sub;
-        const PlaneView src = c.src.pl[plane], dst = c.cdef.pl[plane];
-        for (int e = tid; e < tile * tile; e += nt) {
-            const int ly = e / tile, lx = e - ly * tile;
-            const int x = x_base + lx, y = y_base + ly;
-            if (x >= pw || y >= ph) continue;
-            const int b = (ly / bs) * 8 + (lx / bs);
-            const int px = __ldg(src.p + (size_t)y * src.stride + x);
-            const int idx = s_idx[b];
-            int out = px;
-            if (idx != 0xFF) {
-                int pri, sec, dir, damping;
-                const int ydir = s_dir[b];
-                if (!plane) {
-                    pri = cp.y_pri[idx];
-                    sec = cp.y_sec[idx];
-                    dir = pri == 0 ? 0 : ydir;
-                    const int var = s_var[b];
-                    const int var_str = (var >> 6) ? min(floor_log2((unsigned)(var >> 6)), 12) : 0;
-                    pri = var ? ((pri * (4 + var_str) + 8) >> 4) : 0;
-                    damping = cp.damping;
-                } else {
-                    pri = cp.uv_pri[idx];
-                    sec = cp.uv_sec[idx];
-                    dir = pri == 0 ? 0 : k_cdef_uv_dir[1][1][ydir];
-                    damping = cp.damping - 1;
-                }
-                int sum = 0, mx = px, mn = px;
-                AV1B_UNROLL
-                for (int k = 0; k < 2; k++) {
-                    AV1B_UNROLL
-                    for (int sgn = -1; sgn <= 1; sgn += 2) {
-                        {
-                            const int yy = y + sgn * k_cdef_directions[dir][k][0];
-                            const int xx = x + sgn * k_cdef_directions[dir][k][1];
-                            if (xx >= 0 && xx < pw && yy >= 0 && yy < ph) {
-                                const int p = __ldg(src.p + (size_t)yy * src.stride + xx);
-                                sum += k_cdef_pri_taps[pri & 1][k] * cdef_constrain(p - px, pri, damping);
-                                mx = max(mx, p);
-                                mn = min(mn, p);
-                            }
-                        }
-                        AV1B_UNROLL
-                        for (int off = -2; off <= 2; off += 4) {
-                            const int d2 = (dir + off) & 7;
-                            const int yy = y + sgn * k_cdef_directions[d2][k][0];
-                            const int xx = x + sgn * k_cdef_directions[d2][k][1];
-                            if (xx >= 0 && xx < pw && yy >= 0 && yy < ph) {
-                                const int p = __ldg(src.p + (size_t)yy * src.stride + xx);
-                                sum += k_cdef_sec_taps[pri & 1][k] * cdef_constrain(p - px, sec, damping);
-                                mx = max(mx, p);
-                                mn = min(mn, p);
-                            }
-                        }
-                    }
-                }
-                out = clip3(mn, mx, px + ((8 + sum - (sum < 0)) >> 4));
+    // ---- 2. direction search
+    for (int e = tid; e < 512; e += nt) {
+        const int b = e >> 3, d = e & 7;
+        if (S.blk[b].idx == 0xFF) continue;
+        S.cost[b][d] = cdef_cost_dyn(d, S.ya + ((b >> 3) * 8 + 2) * CY_PITCH + (b & 7) * 8 + 2);
+    }
+    __syncthreads();
+    const Av1bCdefParams& cp = hdr->cdef;
+    for (int e = tid; e < 64; e += nt) {
+        CdefBlk& B = S.blk[e];
+        if (B.idx == 0xFF) continue;
+        int best = 0, dir = 0;
+        for (int d = 0; d < 8; d++)
+            if (S.cost[e][d] > best) {
+                best = S.cost[e][d];
+                dir = d;
             }
-            dst.p[(size_t)y * dst.stride + x] = (uint8_t)out;
+        const int var = (best - S.cost[e][(dir + 4) & 7]) >> 10;
+        int pri = cp.y_pri[B.idx];
+        const int dir_y = pri == 0 ? 0 : dir;
+        const int var_str = (var >> 6) ? min(floor_log2((unsigned)(var >> 6)), 12) : 0;
+        pri = var ? ((pri * (4 + var_str) + 8) >> 4) : 0;
+        const int sec = cp.y_sec[B.idx];
+        const int pri_uv = cp.uv_pri[B.idx], sec_uv = cp.uv_sec[B.idx];
+        const int damp = cp.damping;
+        B.pri[0] = (uint8_t)pri;
+        B.sec[0] = (uint8_t)sec;
+        B.adjp[0] = (uint8_t)(pri ? max(0, damp - floor_log2((unsigned)pri)) : 0);
+        B.adjs[0] = (uint8_t)(sec ? max(0, damp - floor_log2((unsigned)sec)) : 0);
+        B.dir[0] = (uint8_t)dir_y;
+        B.pri[1] = (uint8_t)pri_uv;
+        B.sec[1] = (uint8_t)sec_uv;
+        B.adjp[1] = (uint8_t)(pri_uv ? max(0, damp - 1 - floor_log2((unsigned)pri_uv)) : 0);
+        B.adjs[1] = (uint8_t)(sec_uv ? max(0, damp - 1 - floor_log2((unsigned)sec_uv)) : 0);
+        B.dir[1] = (uint8_t)(pri_uv == 0 ? 0 : k_cdef_uv_dir[1][1][dir]);
+    }
+    __syncthreads();
+    // ---- 3. filter.  Work item = (plane group, block): 64 luma blocks (32 pairs each) then
+    //         2 x 64 chroma blocks (8 pairs each, four blocks per warp pass).
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = tid % nl, warp = tid / nl;
+    for (int b = warp; b < 64; b += nw) {
+        const CdefBlk B = S.blk[b];
+        const int bx = (fbx + (b & 7)) * 8, by = (fby + (b >> 3)) * 8;
+        if (bx >= pw || by >= ph) continue;
+        uint8_t* dst = c.cdef.pl[0].p + (size_t)by * c.cdef.pl[0].stride + bx;
+        const bool active = B.idx != 0xFF && (B.pri[0] | B.sec[0]);
+        for (int pr = lane; pr < 32; pr += nl) {
+            const int r = pr >> 2, cpair = pr & 3;
+            const int ctr = ((b >> 3) * 8 + r + 2) * CY_PITCH + (b & 7) * 8 + cpair * 2 + 2;
+            uint32_t out;
+            if (active) out = cdef_filter_pair(S.ya, S.yb, ctr, CY_PITCH, B.pri[0], B.sec[0], B.adjp[0], B.adjs[0], B.dir[0]);
+            else out = (uint32_t)S.ya[ctr] | ((uint32_t)S.ya[ctr + 1] << 8);
+            *(uint16_t*)(dst + (size_t)r * c.cdef.pl[0].stride + cpair * 2) = (uint16_t)out;
+        }
+    }
+    const int cpw = pw >> 1, cph = ph >> 1;
+    for (int item = warp; item < 32; item += nw) { // (plane, group of 4 blocks)
+        const int plane = 1 + (item >> 4), grp = item & 15;
+        const uint16_t* ta = S.ca[plane - 1];
+        const uint16_t* tb = S.cb[plane - 1];
+        const PlaneView dv = c.cdef.pl[plane];
+        for (int u = lane; u < 32; u += nl) {
+            const int b = grp * 4 + (u >> 3), pr = u & 7;
+            const CdefBlk B = S.blk[b];
+            const int bx = (fbx + (b & 7)) * 4, by = (fby + (b >> 3)) * 4;
+            if (bx >= cpw || by >= cph) continue;
+            const int r = pr >> 1, cpair = pr & 1;
+            const int ctr = ((b >> 3) * 4 + r + 2) * CC_PITCH + (b & 7) * 4 + cpair * 2 + 2;
+            uint32_t out;
+            if (B.idx != 0xFF && (B.pri[1] | B.sec[1])) out = cdef_filter_pair(ta, tb, ctr, CC_PITCH, B.pri[1], B.sec[1], B.adjp[1], B.adjs[1], B.dir[1]);
+            else out = (uint32_t)ta[ctr] | ((uint32_t)ta[ctr + 1] << 8);
+            *(uint16_t*)(dv.p + (size_t)(by + r) * dv.stride + bx + cpair * 2) = (uint16_t)out;
         }
     }
 }

@@ -234,6 +234,66 @@ def record_stream(pkg, eng_mod, name, data, want_md5, device):
     return rs
 
 
+def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
+    """Roofline leg: deblock + CDEF + LR on synthetic 3840x2160 frames resident in HBM, each kernel
+    timed by the engine with CUDA events on its stream; 256 MiB L2 flush between iterations."""
+    import torch
+    import av1dec_b200 as pkg
+    from av1dec_b200 import format as F
+    from av1dec_b200 import synth
+    from av1dec_b200.engine import Engine
+    hdr_size = C.sizeof(F.FrameHdr)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    W4, H4 = 3840, 2160
+    S = W4 * H4 * 3 // 2
+    eng = Engine(W4, H4, device=device, stream=None)
+    frames4k = []
+    for i in range(n_in):
+        sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist="B", lr_unit=64)
+        eng.set_ref(i, sf.planes, sf.mi_cols * 4, sf.mi_rows * 4)
+        frames4k.append((eng.upload(sf.cmd), sf.cmd[:hdr_size]))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def post_pass(n):
+        for k in range(n):
+            i = k % n_in
+            eng.input_from_slot(i)
+            eng.submit_resident(frames4k[i][0], frames4k[i][1], pkg.STAGE_POST, 0)
+    post_pass(n_in)
+    eng.sync()
+    eng.set_profiling(True)
+    for _ in range(reps):
+        flush.zero_()  # L2 flush between timed iterations (a 256 MiB write, larger than the 126 MB L2)
+        torch.cuda.synchronize()
+        post_pass(n_in)
+    ms, calls = eng.stage_times()
+    eng.close()
+    alg = {"deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S + S // 16}
+    post = {}
+    for k in ("deblock", "cdef", "lr"):
+        per = ms[k] / max(calls[k], 1) * 1e-3
+        post[k] = {"us_per_frame": per * 1e6, "algorithmic_bytes": alg[k], "gbs": alg[k] / per / 1e9 if per > 0 else None}
+    chain_s = sum(ms[k] / max(calls[k], 1) for k in alg) * 1e-3
+    post["chain"] = {"us_per_frame": chain_s * 1e6, "algorithmic_bytes": sum(alg.values()),
+                     "gbs": sum(alg.values()) / chain_s / 1e9, "frac_of_peak": sum(alg.values()) / chain_s / 1e9 / peak,
+                     "mpix_per_s": W4 * H4 / chain_s / 1e6}
+    dom = max(alg, key=lambda k: post[k]["us_per_frame"])
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(dom)
+    roofline = {"bound": "hbm", "kernel": {"deblock": "deblock_kernel (V+H passes)", "cdef": "cdef_kernel", "lr": "lr_kernel"}[dom],
+                "achieved": post[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": post[dom]["gbs"] / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "workload": "synthetic 3840x2160 4:2:0 8-bit, blocky-smooth pixels, random partition/levels/CDEF presets/LR units (configs[3])"}
+
+    return post, roofline
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import av1dec_b200 as pkg
@@ -360,56 +420,7 @@ def run_ours(args, rank, world, local_rank):
                 r.engine.free(ptr)
         r.engine.close()
 
-    # ---------------- roofline leg: post-filter chain on synthetic 4K frames (rank 0's GPU, every rank runs it)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    W4, H4 = 3840, 2160
-    S = W4 * H4 * 3 // 2
-    eng = Engine(W4, H4, device=device, stream=None)
-    frames4k = []
-    n_in = 8
-    for i in range(n_in):
-        sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist="B", lr_unit=64)
-        eng.set_ref(i, sf.planes, sf.mi_cols * 4, sf.mi_rows * 4)
-        frames4k.append((eng.upload(sf.cmd), sf.cmd[:hdr_size]))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def post_pass(n):
-        for k in range(n):
-            i = k % n_in
-            eng.input_from_slot(i)
-            eng.submit_resident(frames4k[i][0], frames4k[i][1], pkg.STAGE_POST, 0)
-    post_pass(n_in)
-    eng.sync()
-    eng.set_profiling(True)
-    reps = 3
-    for _ in range(reps):
-        flush.zero_()  # L2 flush between timed iterations (a 256 MiB write, larger than the 126 MB L2)
-        torch.cuda.synchronize()
-        post_pass(n_in)
-    ms, calls = eng.stage_times()
-    eng.close()
-    alg = {"deblock": 2 * S, "cdef": 2 * S, "lr": 2 * S + S // 16}
-    post = {}
-    for k in ("deblock", "cdef", "lr"):
-        per = ms[k] / max(calls[k], 1) * 1e-3
-        post[k] = {"us_per_frame": per * 1e6, "algorithmic_bytes": alg[k], "gbs": alg[k] / per / 1e9 if per > 0 else None}
-    chain_s = sum(ms[k] / max(calls[k], 1) for k in alg) * 1e-3
-    post["chain"] = {"us_per_frame": chain_s * 1e6, "algorithmic_bytes": sum(alg.values()),
-                     "gbs": sum(alg.values()) / chain_s / 1e9, "frac_of_peak": sum(alg.values()) / chain_s / 1e9 / peak,
-                     "mpix_per_s": W4 * H4 / chain_s / 1e6}
-    dom = max(alg, key=lambda k: post[k]["us_per_frame"])
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get(dom)
-    roofline = {"bound": "hbm", "kernel": {"deblock": "deblock_kernel (V+H passes)", "cdef": "cdef_kernel", "lr": "lr_kernel"}[dom],
-                "achieved": post[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": post[dom]["gbs"] / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "workload": "synthetic 3840x2160 4:2:0 8-bit, blocky-smooth pixels, random partition/levels/CDEF presets/LR units (configs[3])"}
+    post, roofline = postfilter_leg(device, dev)
 
     if rank != 0:
         return 0
@@ -447,12 +458,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=32)
+    ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
+    if args.only == "postfilter":
+        import torch
+        post, roofline = postfilter_leg(0, torch.device("cuda", 0), reps=max(args.steps, 1))
+        print(json.dumps({"postfilter_4k": post, "roofline": roofline}))
+        return 0
     if world > 1:
         import torch
         import torch.distributed as dist
