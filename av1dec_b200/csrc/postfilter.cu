@@ -46,29 +46,28 @@ AV1B_DEV LfLevel lf_strength(const Av1bLoopFilterParams& lf, const Av1bLfMi& mi,
 
 AV1B_DEV int f4clamp(int v) { return clip3(-128, 127, v); }
 
-// Filter one sample line across an edge. q0 at `p`, samples along the filter axis `step` apart.
-AV1B_DEV void lf_sample(uint8_t* p, int step, int plane, int limit, int blimit, int thresh, int filter_size)
+// Filter one sample line across an edge, in registers.  v[k] = sample at position k-8 relative
+// to the edge (v[8] = q0, v[7] = p0, ... v[1] = p6, v[14] = q6).  Returns the half-width of the
+// modified span n (samples v[8-n .. 8+n-1] changed) or 0.  (LoopFilter.cpp:127-289)
+AV1B_DEV int lf_line(int* v, int plane, int limit, int blimit, int thresh, int filter_size)
 {
-    const int q0 = p[0], q1 = p[step], q2 = p[2 * step], q3 = p[3 * step];
-    const int p0 = p[-step], p1 = p[-2 * step], p2 = p[-3 * step], p3 = p[-4 * step];
+    const int q0 = v[8], q1 = v[9], q2 = v[10], q3 = v[11];
+    const int p0 = v[7], p1 = v[6], p2 = v[5], p3 = v[4];
     const int hev = (iabs(p1 - p0) > thresh) | (iabs(q1 - q0) > thresh);
     const int filter_len = (filter_size == 4) ? 4 : (plane ? 6 : (filter_size == 8 ? 8 : 16));
-    int mask = (iabs(p1 - p0) > limit) | (iabs(q1 - q0) > limit) | ((iabs(p0 - q0) * 2 + iabs(p1 - q1) / 2) > blimit);
+    int mask = (iabs(p1 - p0) > limit) | (iabs(q1 - q0) > limit) | ((iabs(p0 - q0) * 2 + (iabs(p1 - q1) >> 1)) > blimit);
     if (filter_len >= 6) mask |= (iabs(p2 - p1) > limit) | (iabs(q2 - q1) > limit);
     if (filter_len >= 8) mask |= (iabs(p3 - p2) > limit) | (iabs(q3 - q2) > limit);
-    if (mask) return;
+    if (mask) return 0;
     int flat = 0, flat2 = 0;
     if (filter_size >= 8) {
         int m = (iabs(p1 - p0) > 1) | (iabs(q1 - q0) > 1) | (iabs(p2 - p0) > 1) | (iabs(q2 - q0) > 1);
         if (filter_len >= 8) m |= (iabs(p3 - p0) > 1) | (iabs(q3 - q0) > 1);
         flat = !m;
     }
-    int q4 = 0, q5 = 0, q6 = 0, p4 = 0, p5 = 0, p6 = 0;
-    if (filter_size >= 16) {
-        q4 = p[4 * step]; q5 = p[5 * step]; q6 = p[6 * step];
-        p4 = p[-5 * step]; p5 = p[-6 * step]; p6 = p[-7 * step];
-        int m = (iabs(p6 - p0) > 1) | (iabs(q6 - q0) > 1) | (iabs(p5 - p0) > 1) | (iabs(q5 - q0) > 1) | (iabs(p4 - p0) > 1)
-            | (iabs(q4 - q0) > 1);
+    if (filter_size >= 16 && flat) {
+        const int m = (iabs(v[1] - p0) > 1) | (iabs(v[14] - q0) > 1) | (iabs(v[2] - p0) > 1) | (iabs(v[13] - q0) > 1)
+            | (iabs(v[3] - p0) > 1) | (iabs(v[12] - q0) > 1);
         flat2 = !m;
     }
     if (filter_size == 4 || !flat) {
@@ -76,61 +75,66 @@ AV1B_DEV void lf_sample(uint8_t* p, int step, int plane, int limit, int blimit, 
         int f = hev ? f4clamp(ps1 - qs1) : 0;
         f = f4clamp(f + 3 * (qs0 - ps0));
         const int f1 = f4clamp(f + 4) >> 3, f2 = f4clamp(f + 3) >> 3;
-        p[0] = (uint8_t)(f4clamp(qs0 - f1) + 128);
-        p[-step] = (uint8_t)(f4clamp(ps0 + f2) + 128);
-        if (!hev) {
-            const int f3 = (f1 + 1) >> 1;
-            p[step] = (uint8_t)(f4clamp(qs1 - f3) + 128);
-            p[-2 * step] = (uint8_t)(f4clamp(ps1 + f3) + 128);
-        }
-    } else if (filter_size == 8 || !flat2) {
+        v[8] = f4clamp(qs0 - f1) + 128;
+        v[7] = f4clamp(ps0 + f2) + 128;
+        if (hev) return 1;
+        const int f3 = (f1 + 1) >> 1;
+        v[9] = f4clamp(qs1 - f3) + 128;
+        v[6] = f4clamp(ps1 + f3) + 128;
+        return 2;
+    }
+    if (filter_size == 8 || !flat2) {
         if (!plane) {
-            // 8-tap luma: n = 3, centre weight 2
-            const int v[8] = { p3, p2, p1, p0, q0, q1, q2, q3 }; // index = pos + 4
-            int F[6];
-            AV1B_UNROLL
-            for (int i = -3; i < 3; i++) {
-                int t = 0;
-                AV1B_UNROLL
-                for (int j = -3; j <= 3; j++) t += v[clip3(-4, 3, i + j) + 4] * (j == 0 ? 2 : 1);
-                F[i + 3] = (t + 4) >> 3;
-            }
-            AV1B_UNROLL
-            for (int i = -3; i < 3; i++) p[i * step] = (uint8_t)F[i + 3];
-        } else {
-            // 6-tap chroma: n = 2, weights 2 for |j| <= 1
-            const int v[6] = { p2, p1, p0, q0, q1, q2 }; // index = pos + 3
-            int F[4];
-            AV1B_UNROLL
-            for (int i = -2; i < 2; i++) {
-                int t = 0;
-                AV1B_UNROLL
-                for (int j = -2; j <= 2; j++) t += v[clip3(-3, 2, i + j) + 3] * ((j >= -1 && j <= 1) ? 2 : 1);
-                F[i + 2] = (t + 4) >> 3;
-            }
-            AV1B_UNROLL
-            for (int i = -2; i < 2; i++) p[i * step] = (uint8_t)F[i + 2];
+            // 8-tap luma (n = 3): sum of 7 neighbours (index clamped to p3..q3) + centre again
+            // F[i] = (sum_{j=-3..3} v[clamp(i+j)] + v[i]) >> 3, i = -3..2 ; slide the 7-window
+            int w = p3 * 3 + p2 + p1 + p0 + q0;              // window for i = -3: positions -6..0 -> clamp(-4)=p3 x3
+            const int o0 = (w + p2 + 4) >> 3;                 // i=-3 centre p2 (pos -3)
+            w += q1 - p3;                                     // i=-2: positions -5..1
+            const int o1 = (w + p1 + 4) >> 3;
+            w += q2 - p3;                                     // i=-1: positions -4..2
+            const int o2 = (w + p0 + 4) >> 3;
+            w += q3 - p3;                                     // i=0: positions -3..3
+            const int o3 = (w + q0 + 4) >> 3;
+            w += q3 - p2;                                     // i=1: positions -2..4 (clamp 4 -> q3)
+            const int o4 = (w + q1 + 4) >> 3;
+            w += q3 - p1;                                     // i=2: positions -1..5
+            const int o5 = (w + q2 + 4) >> 3;
+            v[5] = o0; v[6] = o1; v[7] = o2; v[8] = o3; v[9] = o4; v[10] = o5;
+            return 3;
         }
-    } else {
-        // 14-tap luma: n = 6, weights 2 for |j| <= 1
-        const int v[14] = { p6, p5, p4, p3, p2, p1, p0, q0, q1, q2, q3, q4, q5, q6 }; // index = pos + 7
-        int F[12];
+        // 6-tap chroma (n = 2): window of 5 (clamped to p2..q2), weights 2 for |j| <= 1
+        const int o0 = (p2 * 3 + p1 * 2 + p0 * 2 + q0 + 4) >> 3;           // i=-2: p2(x1 clamp + x2 w) ...
+        const int o1 = (p2 + p1 * 2 + p0 * 2 + q0 * 2 + q1 + 4) >> 3;      // i=-1
+        const int o2 = (p1 + p0 * 2 + q0 * 2 + q1 * 2 + q2 + 4) >> 3;      // i=0
+        const int o3 = (p0 + q0 * 2 + q1 * 2 + q2 * 3 + 4) >> 3;           // i=1
+        v[6] = o0; v[7] = o1; v[8] = o2; v[9] = o3;
+        return 2;
+    }
+    // 14-tap luma (n = 6): F[i] = (sum_{j=-6..6} v[clamp(i+j)] + v[i-1] + v[i] + v[i+1] + 8) >> 4, i = -6..5
+    {
+        int o[12];
+        const int p6 = v[1], q6 = v[14];
+        // window sum for i = -6: positions -12..0 clamped to >= -7 (p6): p6 x6 + p5 + p4 + p3 + p2 + p1 + p0 + q0
+        int w = p6 * 6 + v[2] + v[3] + p3 + p2 + p1 + p0 + q0;
+        (void)q6;
         AV1B_UNROLL
         for (int i = -6; i < 6; i++) {
-            int t = 0;
-            AV1B_UNROLL
-            for (int j = -6; j <= 6; j++) t += v[clip3(-7, 6, i + j) + 7] * ((j >= -1 && j <= 1) ? 2 : 1);
-            F[i + 6] = (t + 8) >> 4;
+            // centre extra weights: v[i-1] + v[i] + v[i+1] (positions relative to the edge, index = pos + 8)
+            const int c = v[clip3(1, 14, i - 1 + 8)] + v[i + 8] + v[clip3(1, 14, i + 1 + 8)];
+            o[i + 6] = (w + c + 8) >> 4;
+            // slide: drop position i-6, add position i+7 (both clamped to [-7, 6])
+            w += v[clip3(1, 14, i + 7 + 8)] - v[clip3(1, 14, i - 6 + 8)];
         }
         AV1B_UNROLL
-        for (int i = -6; i < 6; i++) p[i * step] = (uint8_t)F[i + 6];
+        for (int i = 0; i < 12; i++) v[2 + i] = o[i];
+        return 6;
     }
 }
 
 }  // namespace
 
-// One thread per (edge unit, sample line): 4 consecutive threads share one 4-sample edge unit.
-__global__ void __launch_bounds__(256) deblock_kernel(PostCtx c, int pass)
+// One thread per 4-sample edge unit.  PASS 0: vertical edges (filter along x), PASS 1: horizontal.
+template <int PASS> __global__ void __launch_bounds__(256) deblock_kernel(PostCtx c)
 {
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bLfMi* mis = (const Av1bLfMi*)(c.cmd + hdr->off_lfmi);
@@ -140,50 +144,90 @@ __global__ void __launch_bounds__(256) deblock_kernel(PostCtx c, int pass)
     const int sub = plane ? 1 : 0;
     const int mi_cols = hdr->mi_cols, mi_rows = hdr->mi_rows;
     const int ucols = mi_cols >> sub, urows = mi_rows >> sub; // edge units of this plane
-    const long long total = (long long)ucols * urows * 4;
+    const int total = ucols * urows;
     const PlaneView pv = c.src.pl[plane];
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        // pass 0 (vertical edges): consecutive threads walk down rows of one unit column slowly;
-        // pass 1 (horizontal edges): consecutive threads walk along x (coalesced).
-        int ur, uc, i;
-        if (pass == 0) {
-            // lines of the same edge column are 'stride' apart; order threads x-fastest over units
-            const long long line = t / ucols; // sample row index inside plane (units*4)
-            uc = (int)(t - line * ucols);
-            ur = (int)(line >> 2);
-            i = (int)(line & 3);
-        } else {
-            const long long urow = t / (ucols * 4);
-            const int rem = (int)(t - urow * (ucols * 4));
-            ur = (int)urow;
-            uc = rem >> 2;
-            i = rem & 3;
-        }
-        int row = (ur << sub), col = (uc << sub);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ur = t / ucols, uc = t - ur * ucols;
+        int row = ur << sub, col = uc << sub;
         const int x = col * 4, y = row * 4;
         if (x >= hdr->frame_w || y >= hdr->frame_h) continue;
-        if (pass == 0 ? (x == 0) : (y == 0)) continue;
+        if (PASS == 0 ? (x == 0) : (y == 0)) continue;
         row |= sub;
         col |= sub;
         const int xp = x >> sub, yp = y >> sub;
-        const int prev_row = row - ((pass == 1) ? (1 << sub) : 0);
-        const int prev_col = col - ((pass == 0) ? (1 << sub) : 0);
         const Av1bLfMi mi = mis[row * mi_cols + col];
-        const Av1bLfMi pm = mis[prev_row * mi_cols + prev_col];
-        const int tx = (mi.tx >> (5 * plane)) & 31, ptx = (pm.tx >> (5 * plane)) & 31;
+        const int tx = (mi.tx >> (5 * plane)) & 31;
+        // Tx_Width / Block_Width are powers of two: edge tests are masks
+        if (PASS == 0 ? (xp & (k_tx_w[tx] - 1)) : (yp & (k_tx_h[tx] - 1))) continue;
         const int bw = max(4, k_block_w[mi.mi_size] >> sub), bh = max(4, k_block_h[mi.mi_size] >> sub);
         const bool skip = mi.flags & 1;
         const bool is_intra = ((mi.flags >> 2) & 7) == 0;
-        const bool block_edge = pass == 0 ? (xp % bw == 0) : (yp % bh == 0);
-        const bool tx_edge = pass == 0 ? (xp % k_tx_w[tx] == 0) : (yp % k_tx_h[tx] == 0);
-        if (!(tx_edge && (block_edge || !skip || is_intra))) continue;
-        const int base = pass == 0 ? min(k_tx_w[ptx], k_tx_w[tx]) : min(k_tx_h[ptx], k_tx_h[tx]);
+        const bool block_edge = PASS == 0 ? !(xp & (bw - 1)) : !(yp & (bh - 1));
+        if (!(block_edge || !skip || is_intra)) continue;
+        const int prev_row = row - (PASS == 1 ? (1 << sub) : 0);
+        const int prev_col = col - (PASS == 0 ? (1 << sub) : 0);
+        const Av1bLfMi pm = mis[prev_row * mi_cols + prev_col];
+        const int ptx = (pm.tx >> (5 * plane)) & 31;
+        const int base = PASS == 0 ? min(k_tx_w[ptx], k_tx_w[tx]) : min(k_tx_h[ptx], k_tx_h[tx]);
         const int filter_size = plane ? min(8, base) : min(16, base);
-        LfLevel L = lf_strength(lf, mi, plane, pass);
-        if (!L.lvl) L = lf_strength(lf, pm, plane, pass);
+        LfLevel L = lf_strength(lf, mi, plane, PASS);
+        if (!L.lvl) L = lf_strength(lf, pm, plane, PASS);
         if (L.lvl <= 0) continue;
-        uint8_t* p = pv.p + (size_t)(yp + (pass == 0 ? i : 0)) * pv.stride + xp + (pass == 1 ? i : 0);
-        lf_sample(p, pass == 0 ? 1 : pv.stride, plane, L.limit, L.blimit, L.thresh, filter_size);
+        uint8_t* p = pv.p + (size_t)yp * pv.stride + xp;
+        if (PASS == 0) {
+            // rows yp..yp+3; per row the 16 samples x-8 .. x+7 come in as four aligned words
+            AV1B_UNROLL
+            for (int i = 0; i < 4; i++) {
+                uint8_t* r = p + (size_t)i * pv.stride;
+                int v[16];
+                const uint32_t w1 = *(const uint32_t*)(r - 4), w2 = *(const uint32_t*)r;
+                uint32_t w0 = 0, w3 = 0;
+                if (filter_size == 16) {
+                    w0 = *(const uint32_t*)(r - 8);
+                    w3 = *(const uint32_t*)(r + 4);
+                }
+                AV1B_UNROLL
+                for (int k = 0; k < 4; k++) {
+                    v[k] = (w0 >> (8 * k)) & 0xFF;
+                    v[4 + k] = (w1 >> (8 * k)) & 0xFF;
+                    v[8 + k] = (w2 >> (8 * k)) & 0xFF;
+                    v[12 + k] = (w3 >> (8 * k)) & 0xFF;
+                }
+                const int n = lf_line(v, plane, L.limit, L.blimit, L.thresh, filter_size);
+                // byte stores: the neighbouring edge units own the other bytes of these words
+                AV1B_UNROLL
+                for (int k = 1; k <= 6; k++) {
+                    if (k <= n) {
+                        r[-k] = (uint8_t)v[8 - k];
+                        r[k - 1] = (uint8_t)v[7 + k];
+                    }
+                }
+            }
+        } else {
+            // columns xp..xp+3 live in the byte lanes of one word per row; rows yp-8 .. yp+7
+            uint32_t w[16];
+            const int lo = filter_size == 16 ? 0 : 4, hi = filter_size == 16 ? 16 : 12;
+            AV1B_UNROLL
+            for (int k = 0; k < 16; k++) w[k] = (k >= lo && k < hi) ? *(const uint32_t*)(p + (ptrdiff_t)(k - 8) * pv.stride) : 0u;
+            int nmax = 0;
+            AV1B_UNROLL
+            for (int cidx = 0; cidx < 4; cidx++) {
+                int v[16];
+                AV1B_UNROLL
+                for (int k = 0; k < 16; k++) v[k] = (w[k] >> (8 * cidx)) & 0xFF;
+                const int n = lf_line(v, plane, L.limit, L.blimit, L.thresh, filter_size);
+                nmax = max(nmax, n);
+                AV1B_UNROLL
+                for (int k = 2; k < 14; k++) w[k] = (w[k] & ~(0xFFu << (8 * cidx))) | ((uint32_t)v[k] << (8 * cidx));
+            }
+            AV1B_UNROLL
+            for (int k = 1; k <= 6; k++) {
+                if (k <= nmax) {
+                    *(uint32_t*)(p - (ptrdiff_t)k * pv.stride) = w[8 - k];
+                    *(uint32_t*)(p + (ptrdiff_t)(k - 1) * pv.stride) = w[7 + k];
+                }
+            }
+        }
     }
 }
 
@@ -459,32 +503,39 @@ __global__ void __launch_bounds__(256) cdef_kernel(PostCtx c)
 // ==========================================================================================
 namespace {
 
-enum { LR_TW = 32, LR_MAXH = 64, LR_SW = LR_TW + 6, LR_SH = LR_MAXH + 6 };
+enum { LR_TW = 32, LR_MAXH = 64, LR_SW = 40, LR_SH = LR_MAXH + 6, LR_AW = LR_TW + 2, LR_AH = LR_MAXH + 2 };
 
 struct LrShared {
-    uint8_t src[LR_SH * LR_SW];          // source samples with 3-sample halo
-    int16_t wien[LR_SH * LR_TW];         // Wiener horizontal pass
-    int a[(LR_MAXH + 2) * (LR_TW + 2)];  // SGR A
-    int b[(LR_MAXH + 2) * (LR_TW + 2)];  // SGR B
-    int flt[2][LR_MAXH * LR_TW];         // SGR filtered planes
+    uint8_t src[LR_SH * LR_SW];        // source samples, 3-sample halo; src[r*LR_SW + c] = sample (x0-3+c-1, y0-3+r)
+    union {
+        int16_t wien[LR_SH * LR_TW];   // Wiener horizontal pass
+        struct {
+            uint16_t h1[LR_SH * LR_AW]; // horizontal box sums of x
+            uint32_t h2[LR_SH * LR_AW]; // horizontal box sums of x^2
+        } box;
+    };
+    uint16_t a[LR_AH * LR_AW];         // SGR A (a2)
+    uint32_t b[LR_AH * LR_AW];         // SGR B (b2)
+    uint16_t flt[2][LR_MAXH * LR_TW];  // SGR filtered planes
+    uint16_t xdiv[256];                // ((z << 8) + z/2) / (z + 1)
 };
 
-// get_source_sample + extendBorder(3) (LoopRestoration.cpp:234-246, VideoFrame.cpp:81-101)
-AV1B_DEV int lr_source(const PlaneView& cdef, const PlaneView& deb, int x, int y, int start, int end, int pw, int ph)
+// Row of the frame that get_source_sample() reads for tile row `y` (LoopRestoration.cpp:234-246
+// + extendBorder, VideoFrame.cpp:81-101); *from_deblocked tells which frame.
+AV1B_DEV int lr_source_row(int y, int start, int end, int ph, bool* from_deblocked)
 {
-    const PlaneView* s = &cdef;
+    *from_deblocked = false;
     if (y < start) {
         y = max(start - 2, y);
-        s = &deb;
+        *from_deblocked = true;
     } else if (y >= end) {
         y = min(end + 1, y);
-        s = &deb;
+        *from_deblocked = true;
     }
-    x = clip3(0, pw - 1, x);
-    y = clip3(0, ph - 1, y);
-    return __ldg(s->p + (size_t)y * s->stride + x);
+    return clip3(0, ph - 1, y);
 }
 
+// One self-guided pass.  Source samples sit at S.src[(i + 3) * LR_SW + (j + 4)] for tile sample (i, j).
 AV1B_DEV void sgr_pass(LrShared& S, int w, int h, int set, int pass, int r, int tid, int nt)
 {
     const int eps = k_sgr_params[set][pass * 2 + 1];
@@ -493,40 +544,65 @@ AV1B_DEV void sgr_pass(LrShared& S, int w, int h, int set, int pass, int r, int 
     const unsigned s = (unsigned)(((1 << 20) + n2e / 2) / n2e);
     const int one_over_n = ((1 << 12) + (n / 2)) / n;
     const int aw = w + 2;
-    for (int e = tid; e < (h + 2) * aw; e += nt) {
-        const int i = e / aw - 1, j = e - (i + 1) * aw - 1;
+    // horizontal box sums for rows -1-r .. h+r, columns -1 .. w
+    const int hr0 = -1 - r, hrows = h + 2 + 2 * r;
+    for (int e = tid; e < hrows * aw; e += nt) {
+        const int rr = e / aw, j = e - rr * aw - 1;
+        const uint8_t* p = S.src + (hr0 + rr + 3) * LR_SW + (j + 4);
+        int s1 = 0, s2 = 0;
+        for (int dx = -r; dx <= r; dx++) {
+            const int v = p[dx];
+            s1 += v;
+            s2 += v * v;
+        }
+        S.box.h1[rr * LR_AW + j + 1] = (uint16_t)s1;
+        S.box.h2[rr * LR_AW + j + 1] = (uint32_t)s2;
+    }
+    __syncthreads();
+    // vertical sums -> a2 / b2.  Pass 0 only ever reads A/B on rows whose index is odd.
+    const int rstep = pass == 0 ? 2 : 1;
+    const int nrows = pass == 0 ? (h + 2 + 1) / 2 : h + 2;
+    for (int e = tid; e < nrows * aw; e += nt) {
+        const int ri = e / aw, jj = e - ri * aw; // jj = j + 1
+        const int i = pass == 0 ? (2 * ri - 1) : (ri - 1);
+        if (i > h) continue;
         int a = 0, b = 0;
-        for (int dy = -r; dy <= r; dy++)
-            for (int dx = -r; dx <= r; dx++) {
-                const int cpx = S.src[(i + dy + 3) * LR_SW + (j + dx + 3)];
-                a += cpx * cpx;
-                b += cpx;
-            }
+        const int base = (i - r - hr0) * LR_AW + jj;
+        for (int dy = 0; dy <= 2 * r; dy++) {
+            b += S.box.h1[base + dy * LR_AW];
+            a += S.box.h2[base + dy * LR_AW];
+        }
         const unsigned p = (unsigned)max(0, a * n - b * b);
         const unsigned z = (p * s + (1u << 19)) >> 20;
-        int a2;
-        if (z >= 255) a2 = 256;
-        else if (z == 0) a2 = 1;
-        else a2 = (int)(((z << 8) + (z / 2)) / (z + 1));
+        const int a2 = z >= 255 ? 256 : (z == 0 ? 1 : S.xdiv[z]);
         const int b2 = (256 - a2) * b * one_over_n;
-        S.a[e] = a2;
-        S.b[e] = (b2 + (1 << 11)) >> 12;
+        S.a[(i + 1) * LR_AW + jj] = (uint16_t)a2;
+        S.b[(i + 1) * LR_AW + jj] = (uint32_t)((b2 + (1 << 11)) >> 12);
+        (void)rstep;
     }
     __syncthreads();
     for (int e = tid; e < w * h; e += nt) {
         const int i = e / w, j = e - i * w;
-        const int shift = (pass == 0 && (i & 1)) ? 4 : 5;
-        int a = 0, b = 0;
-        for (int dy = -1; dy <= 1; dy++)
-            for (int dx = -1; dx <= 1; dx++) {
-                int weight;
-                if (pass == 0) weight = ((i + dy) & 1) ? (dx == 0 ? 6 : 5) : 0;
-                else weight = (dx == 0 || dy == 0) ? 4 : 3;
-                a += weight * S.a[(i + dy + 1) * aw + (j + dx + 1)];
-                b += weight * S.b[(i + dy + 1) * aw + (j + dx + 1)];
+        const uint16_t* A = S.a + (i + 1) * LR_AW + (j + 1);
+        const uint32_t* B = S.b + (i + 1) * LR_AW + (j + 1);
+        int a, b, shift;
+        if (pass == 0) {
+            if (i & 1) {
+                a = 6 * A[0] + 5 * (A[-1] + A[1]);
+                b = 6 * (int)B[0] + 5 * (int)(B[-1] + B[1]);
+                shift = 4;
+            } else {
+                a = 6 * (A[-LR_AW] + A[LR_AW]) + 5 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
+                b = 6 * (int)(B[-LR_AW] + B[LR_AW]) + 5 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
+                shift = 5;
             }
-        const int v = a * S.src[(i + 3) * LR_SW + (j + 3)] + b;
-        S.flt[pass][i * LR_TW + j] = round2(v, 8 + shift - 4);
+        } else {
+            a = 4 * (A[0] + A[-1] + A[1] + A[-LR_AW] + A[LR_AW]) + 3 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
+            b = 4 * (int)(B[0] + B[-1] + B[1] + B[-LR_AW] + B[LR_AW]) + 3 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
+            shift = 5;
+        }
+        const int v = a * S.src[(i + 3) * LR_SW + (j + 4)] + b;
+        S.flt[pass][i * LR_TW + j] = (uint16_t)round2(v, 8 + shift - 4);
     }
     __syncthreads();
 }
@@ -558,15 +634,40 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
         type = unit.type;
     }
     if (type == 0) {
-        for (int e = tid; e < w * h; e += nt) {
-            const int i = e / w, j = e - i * w;
+        // RESTORE_NONE: the LR frame is a copy of the CDEF frame.  Word copies, byte tail.
+        const int ww = w >> 2;
+        for (int e = tid; e < h * ww; e += nt) {
+            const int i = e / ww, j = e - i * ww;
+            *(uint32_t*)(out.p + (size_t)(y0 + i) * out.stride + x0 + 4 * j) = __ldg((const uint32_t*)(cdef.p + (size_t)(y0 + i) * cdef.stride + x0 + 4 * j));
+        }
+        const int tail = w & 3;
+        for (int e = tid; e < h * tail; e += nt) {
+            const int i = e / tail, j = (w & ~3) + (e - i * tail);
             out.p[(size_t)(y0 + i) * out.stride + x0 + j] = __ldg(cdef.p + (size_t)(y0 + i) * cdef.stride + x0 + j);
         }
         return;
     }
-    for (int e = tid; e < (h + 6) * (w + 6); e += nt) {
-        const int i = e / (w + 6), j = e - i * (w + 6);
-        S.src[i * LR_SW + j] = (uint8_t)lr_source(cdef, deb, x0 + j - 3, y0 + i - 3, start, end, pw, ph);
+    // ---- stage source: rows y0-3 .. y0+h+2, columns x0-4 .. x0+35 (10 aligned words per row)
+    {
+        const bool interior = x0 >= 4 && x0 + 36 <= pw;
+        for (int e = tid; e < (h + 6) * 10; e += nt) {
+            const int r = e / 10, wi = e - r * 10;
+            bool fd;
+            const int sy = lr_source_row(y0 - 3 + r, start, end, ph, &fd);
+            const uint8_t* rowp = (fd ? deb.p : cdef.p) + (size_t)sy * (fd ? deb.stride : cdef.stride);
+            uint32_t v;
+            if (interior) {
+                v = __ldg((const uint32_t*)(rowp + x0 - 4 + wi * 4));
+            } else {
+                v = 0;
+                AV1B_UNROLL
+                for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rowp + clip3(0, pw - 1, x0 - 4 + wi * 4 + k)) << (8 * k);
+            }
+            *(uint32_t*)(S.src + r * LR_SW + wi * 4) = v;
+        }
+    }
+    if (type == 2) {
+        for (int z = tid; z < 256; z += nt) S.xdiv[z] = (uint16_t)(((z << 8) + (z >> 1)) / (z + 1));
     }
     __syncthreads();
     if (type == 1) {
@@ -581,17 +682,17 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
         }
         for (int e = tid; e < (h + 6) * w; e += nt) {
             const int r = e / w, cc = e - r * w;
-            int s = 0;
-            AV1B_UNROLL
-            for (int t = 0; t < 7; t++) s += hf[t] * S.src[r * LR_SW + cc + t];
+            const uint8_t* p = S.src + r * LR_SW + cc + 1; // sample (x0 + cc - 3) sits at column cc + 1
+            // symmetric taps: 3 adds + 4 multiplies
+            const int s = hf[0] * (p[0] + p[6]) + hf[1] * (p[1] + p[5]) + hf[2] * (p[2] + p[4]) + hf[3] * p[3];
             S.wien[r * LR_TW + cc] = (int16_t)clip3(-2048, 6143, (s + 4) >> 3);
         }
         __syncthreads();
         for (int e = tid; e < w * h; e += nt) {
             const int r = e / w, cc = e - r * w;
-            int s = 0;
-            AV1B_UNROLL
-            for (int t = 0; t < 7; t++) s += vf[t] * S.wien[(r + t) * LR_TW + cc];
+            const int16_t* q = S.wien + r * LR_TW + cc;
+            const int s = vf[0] * (q[0] + q[6 * LR_TW]) + vf[1] * (q[LR_TW] + q[5 * LR_TW]) + vf[2] * (q[2 * LR_TW] + q[4 * LR_TW])
+                + vf[3] * q[3 * LR_TW];
             out.p[(size_t)(y0 + r) * out.stride + x0 + cc] = (uint8_t)clip_u8((s + 1024) >> 11);
         }
     } else {
@@ -602,10 +703,10 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
         const int w0 = unit.sgr_xqd[0], w1 = unit.sgr_xqd[1], w2 = 128 - w0 - w1;
         for (int e = tid; e < w * h; e += nt) {
             const int i = e / w, j = e - i * w;
-            const int u = S.src[(i + 3) * LR_SW + (j + 3)] << 4;
+            const int u = S.src[(i + 3) * LR_SW + (j + 4)] << 4;
             int v = w1 * u;
-            v += w0 * (r0 ? S.flt[0][i * LR_TW + j] : u);
-            v += w2 * (r1 ? S.flt[1][i * LR_TW + j] : u);
+            v += w0 * (r0 ? (int)S.flt[0][i * LR_TW + j] : u);
+            v += w2 * (r1 ? (int)S.flt[1][i * LR_TW + j] : u);
             out.p[(size_t)(y0 + i) * out.stride + x0 + j] = (uint8_t)clip_u8(round2(v, 11));
         }
     }
@@ -617,10 +718,11 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
 void launch_deblock(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.lf.level[0] && !h.lf.level[1]) return;
-    const long long total = (long long)h.mi_cols * h.mi_rows * 4;
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 32) grid = 148 * 32;
-    for (int pass = 0; pass < 2; pass++) AV1B_LAUNCH(deblock_kernel, (grid, 1, 3), (256), st, c, pass);
+    const long long total = (long long)h.mi_cols * h.mi_rows;
+    int grid = (int)((total + 127) / 128);
+    if (grid > 148 * 64) grid = 148 * 64;
+    AV1B_LAUNCH(deblock_kernel<0>, (grid, 1, 3), (128), st, c);
+    AV1B_LAUNCH(deblock_kernel<1>, (grid, 1, 3), (128), st, c);
 }
 
 void launch_cdef(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
