@@ -150,10 +150,12 @@ def decode_ivf(data, device=0, stages=STAGE_ALL, want_yuv=True, lib=None):
     The yuv layout is the reference CLI's output file (tests/DecodeOutput.cpp:48-69)."""
     lib = lib or load_decoder()
     out_bytes, n_frames, pixels = C.c_size_t(0), C.c_int(0), C.c_uint64(0)
+    if len(data) < 32 or data[:4] != b"DKIF":
+        raise EngineError("not an IVF stream")
     # size the output from the IVF header (width, height, frame count) so one decode suffices
     w, h = int.from_bytes(data[12:14], "little"), int.from_bytes(data[14:16], "little")
     n = int.from_bytes(data[24:28], "little")
-    cap = max(w * h * 3 // 2 * max(n, 1) + (64 << 10), 1 << 16)
+    cap = min(max(w * h * 3 // 2 * max(n, 1) + (64 << 10), 1 << 16), 1 << 31)
     while True:
         buf = C.create_string_buffer(cap) if want_yuv else None
         rc = lib.av1b_decode_ivf(data, len(data), device, stages, buf, cap if want_yuv else 0,

@@ -169,6 +169,7 @@ struct av1b_ctx {
     int cur_slot = -1;
     int16_t* res = nullptr;
     size_t res_cap = 0;
+    int16_t* res_planes = nullptr; // frame-layout residual planes (luma aw x ah, chroma aw/2 x ah/2 each)
     int* sync = nullptr;
     size_t sync_cap = 0;
     uint8_t* wedge = nullptr;
@@ -284,6 +285,7 @@ static void ctx_free(av1b_ctx* c)
     for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
     for (auto e : c->event_pool) rt_event_destroy(e);
     rt_free(c->res);
+    rt_free(c->res_planes);
     rt_free(c->sync);
     if (c->own_stream) rt_stream_destroy(c->stream);
     delete c;
@@ -430,8 +432,16 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     if (h.magic != AV1B_MAGIC || h.version != AV1B_FORMAT_VERSION) return fail(c, AV1B_EINVAL, "bad command buffer magic/version");
     if (h.mi_cols * 4 > c->aw || h.mi_rows * 4 > c->ah || (h.sb_cols << h.sb_log2) > c->aw || (h.sb_rows << h.sb_log2) > c->ah)
         return fail(c, AV1B_EINVAL, "frame larger than the context");
-    // scratch
-    if ((stages & AV1B_STAGE_ITX) && h.n_res > c->res_cap) {
+    // scratch.  A lone ITX stage (stage-level test) writes the compact arena; any fuller submit
+    // writes residuals into frame-layout int16 planes that the inter and dependent passes read.
+    const bool arena_mode = (stages & AV1B_STAGE_RECON) == AV1B_STAGE_ITX;
+    const size_t plane_elems = (size_t)c->aw * c->ah * 3 / 2;
+    if (!arena_mode && h.n_itx && !c->res_planes) {
+        void* p = nullptr;
+        if (rt_malloc(&p, plane_elems * sizeof(int16_t))) return fail(c, AV1B_ENOMEM, "residual planes");
+        c->res_planes = (int16_t*)p;
+    }
+    if (arena_mode && h.n_res > c->res_cap) {
         rt_stream_sync(c->stream);
         rt_free(c->res);
         c->res = nullptr;
@@ -464,6 +474,21 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     for (int i = 0; i < 8; i++)
         if (c->ref_slot[i] >= 0) rc.ref[i] = c->frames[c->ref_slot[i]].v;
     rc.res = c->res;
+    if (!arena_mode && h.n_itx) {
+        rc.rp[0] = c->res_planes;
+        rc.rp[1] = c->res_planes + (size_t)c->aw * c->ah;
+        rc.rp[2] = rc.rp[1] + (size_t)(c->aw / 2) * (c->ah / 2);
+        rc.rpitch[0] = c->aw;
+        rc.rpitch[1] = rc.rpitch[2] = c->aw / 2;
+        if (stages & AV1B_STAGE_ITX) {
+            // zero only the area this frame can touch (SB-aligned rows of the luma plane + chroma)
+            const size_t rows = (size_t)h.sb_rows << h.sb_log2;
+            if (rt_memset(rc.rp[0], 0, rows * c->aw * sizeof(int16_t), c->stream)
+                || rt_memset(rc.rp[1], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), c->stream)
+                || rt_memset(rc.rp[2], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), c->stream))
+                return fail(c, AV1B_ECUDA, "memset");
+        }
+    }
     rc.wedge = c->wedge;
     rc.sync = c->sync;
     if (stages & AV1B_STAGE_ITX) {

@@ -41,7 +41,10 @@ struct Args {
     int fi_mode;
 };
 
-AV1B_DEV int px(const Args& a, int x, int y) { return __ldcg(a.plane + (size_t)y * a.stride + x); }
+// The plane pointer may address the superblock tile in shared memory (wave_kernel) or the frame
+// in global memory (legacy path for intrabc frames): a volatile generic load is correct for both
+// (it is never served from a stale L1 line).
+AV1B_DEV int px(const Args& a, int x, int y) { return *(const volatile uint8_t*)(a.plane + (ptrdiff_t)y * a.stride + x); }
 
 AV1B_DEV int edge_filter_strength(int w, int h, bool smooth, int delta)
 {
@@ -304,8 +307,8 @@ AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int
         int i = e >> a.log2w, j = e & (w - 1);
         int ly = min((a.y + i) << 1, max_luma_h - 2);
         int lx = min((a.x + j) << 1, max_luma_w - 2);
-        const uint8_t* q = luma + (size_t)ly * luma_stride + lx;
-        int t = __ldcg(q) + __ldcg(q + 1) + __ldcg(q + luma_stride) + __ldcg(q + luma_stride + 1);
+        const volatile uint8_t* q = luma + (ptrdiff_t)ly * luma_stride + lx;
+        int t = q[0] + q[1] + q[luma_stride] + q[luma_stride + 1];
         int v = t << 1;
         S.luma[e] = (int16_t)v;
         local += v;

@@ -8,7 +8,9 @@ struct ReconCtx {
     const uint8_t* cmd;   // device copy of the frame command buffer
     FrameView cur;        // frame being reconstructed
     FrameView ref[8];     // reference frames by frame-store slot
-    int16_t* res;         // residual arena (written by itx_kernel)
+    int16_t* res;         // compact residual arena (stage-level ITX test mode; used when rp[0] == null)
+    int16_t* rp[3];       // residual planes in frame layout (int16), zero where no coded TB
+    int rpitch[3];        // elements per row
     const uint8_t* wedge; // wedge mask table [9][2][16][32*32]
     int* sync;            // [0] = SB ticket counter, [1 + r] = finished SBs of SB row r
 };

@@ -35,20 +35,25 @@ AV1B_DEV void itx_rows(const int16_t* coef, int tw, int nz_rows, int16_t* tmp, i
 }
 
 template <int n>
-AV1B_DEV void itx_cols(const int16_t* tmp, int nz_rows, int16_t* out, int w, bool fud, bool flr, int kind, int col_shift,
-    int lane, int nl)
+AV1B_DEV void itx_cols(const int16_t* tmp, int nz_rows, int16_t* out, int out_stride, int w, bool fud, bool flr, int kind,
+    int col_shift, int lane, int nl)
 {
     for (int j = lane; j < w; j += nl) {
         int jo = flr ? (w - 1 - j) : j;
-        itx::col_pass<n>(tmp + j, ITX_TMP_STRIDE, nz_rows, out + jo, w, fud, kind, col_shift);
+        itx::col_pass<n>(tmp + j, ITX_TMP_STRIDE, nz_rows, out + jo, out_stride, fud, kind, col_shift);
     }
 }
 
 }  // namespace
 
+struct ResPlanes {
+    int16_t* p[3]; // frame-layout residual planes, or p[0] == null: compact arena mode
+    int pitch[3];
+};
+
 __global__ void __launch_bounds__(ITX_WARPS * 32)
     itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, int n_list,
-        const int16_t* __restrict__ coef, int16_t* __restrict__ res)
+        const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
 {
     __shared__ int16_t tmp_all[ITX_WARPS][ITX_TMP_ROWS * ITX_TMP_STRIDE];
     const int nl = min(32u, blockDim.x);
@@ -70,7 +75,15 @@ __global__ void __launch_bounds__(ITX_WARPS * 32)
         const int col_shift = lossless ? 0 : 4;
         const int nz_rows = min((int)op.nz_rows, min(h, 32));
         const int16_t* c = coef + op.coef_off;
-        int16_t* out = res + op.res_off;
+        int16_t* out;
+        int out_stride;
+        if (rp.p[0]) {
+            out = rp.p[op.plane] + (size_t)op.y * rp.pitch[op.plane] + op.x;
+            out_stride = rp.pitch[op.plane];
+        } else {
+            out = res + op.res_off;
+            out_stride = w;
+        }
         switch (lw) {
         case 2: itx_rows<2>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
         case 3: itx_rows<3>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
@@ -81,11 +94,11 @@ __global__ void __launch_bounds__(ITX_WARPS * 32)
         __syncwarp();
         const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
         switch (lh) {
-        case 2: itx_cols<2>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 3: itx_cols<3>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 4: itx_cols<4>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 5: itx_cols<5>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
-        default: itx_cols<6>(tmp, nz_rows, out, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 2: itx_cols<2>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 3: itx_cols<3>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 4: itx_cols<4>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
+        case 5: itx_cols<5>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
+        default: itx_cols<6>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
         }
         __syncwarp();
     }
@@ -139,6 +152,26 @@ __global__ void __launch_bounds__(256) inter_kernel(ReconCtx c)
             mc::run_ipu(P, u, M, tid, nt);
         }
         __syncthreads();
+        if ((blk.flags & AV1B_IBF_ADD_RESIDUAL) && c.rp[0]) {
+            // plain inter block: reconstruction = prediction + residual, no ordering constraint
+            const int np = (blk.flags & AV1B_IBF_HAS_CHROMA) ? 3 : 1;
+            for (int plane = 0; plane < np; plane++) {
+                const int bx = plane ? blk.cx : blk.x, by = plane ? blk.cy : blk.y;
+                const int bw = plane ? blk.cw : blk.bw, bh = plane ? blk.ch : blk.bh;
+                const PlaneView dst = c.cur.pl[plane];
+                const int16_t* rp = c.rp[plane];
+                const int rpitch = c.rpitch[plane];
+                for (int e = tid; e < bw * bh; e += nt) {
+                    const int i = e / bw, j = e - i * bw;
+                    const int r = rp[(size_t)(by + i) * rpitch + bx + j];
+                    if (r) {
+                        uint8_t* d = dst.p + (size_t)(by + i) * dst.stride + bx + j;
+                        *d = (uint8_t)clip_u8((int)*d + r);
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -147,28 +180,24 @@ __global__ void __launch_bounds__(256) inter_kernel(ReconCtx c)
 // ------------------------------------------------------------------------------------------
 namespace {
 
+// Where the op executor reads and writes samples / residuals of one plane.
+struct PlaneIo {
+    uint8_t* pix;        // address of sample (0,0) in frame coordinates (may point into the smem tile)
+    int pitch;
+    const int16_t* res;  // address of residual (0,0) in frame coordinates, or null
+    int rpitch;
+};
+
 struct WaveShared {
     intra::Scratch I;
     mc::Scratch M;
     int sb;
 };
 
-AV1B_DEV void store_with_residual(const PlaneView& dst, int x, int y, int w, int h, const uint8_t* pred,
-    const int16_t* res, int tid, int nt)
-{
-    for (int e = tid; e < w * h; e += nt) {
-        int i = e / w, j = e - i * w;
-        int v = pred[e];
-        if (res) v = clip_u8(v + res[e]);
-        dst.p[(size_t)(y + i) * dst.stride + x + j] = (uint8_t)v;
-    }
-}
-
-AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, WaveShared& S, int tid, int nt)
+AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, const PlaneIo* io, WaveShared& S, int tid, int nt)
 {
     const int plane = op.plane, sub = plane ? 1 : 0;
-    const PlaneView dst = c.cur.pl[plane];
-    const int16_t* res = (op.flags & AV1B_OPF_HAS_RESID) ? (c.res + op.res_off) : nullptr;
+    const PlaneIo& D = io[plane];
     int lw, lh;
     if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
         lw = op.tx_size & 15;
@@ -178,21 +207,24 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         lh = k_tx_hlog2[op.tx_size];
     }
     const int w = 1 << lw, h = 1 << lh;
+    const bool has_res = (op.flags & AV1B_OPF_HAS_RESID) && D.res;
+    uint8_t* dst = D.pix + (ptrdiff_t)op.y * D.pitch + op.x;
+    const int16_t* res = has_res ? (D.res + (ptrdiff_t)op.y * D.rpitch + op.x) : nullptr;
     switch (op.kind) {
     case AV1B_OP_INTER_RES: {
         if (!res) break;
         for (int e = tid; e < w * h; e += nt) {
-            int i = e >> lw, j = e & (w - 1);
-            uint8_t* d = dst.p + (size_t)(op.y + i) * dst.stride + op.x + j;
-            *d = (uint8_t)clip_u8((int)__ldcg(d) + res[e]);
+            const int i = e >> lw, j = e & (w - 1);
+            volatile uint8_t* d = dst + i * D.pitch + j;
+            *d = (uint8_t)clip_u8((int)*d + res[i * D.rpitch + j]);
         }
         break;
     }
     case AV1B_OP_INTRA:
     case AV1B_OP_INTERINTRA: {
         intra::Args a;
-        a.plane = dst.p;
-        a.stride = dst.stride;
+        a.plane = D.pix;
+        a.stride = D.pitch;
         a.x = op.x;
         a.y = op.y;
         a.log2w = lw;
@@ -213,17 +245,22 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         intra::predict(a, S.I, tid, nt);
         if (op.kind == AV1B_OP_INTRA) {
             if (op.flags & AV1B_OPF_CFL)
-                intra::apply_cfl(a, c.cur.pl[0].p, c.cur.pl[0].stride, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, tid, nt);
-            store_with_residual(dst, op.x, op.y, w, h, S.I.pred, res, tid, nt);
+                intra::apply_cfl(a, io[0].pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, tid, nt);
+            for (int e = tid; e < w * h; e += nt) {
+                const int i = e >> lw, j = e & (w - 1);
+                int v = S.I.pred[e];
+                if (res) v = clip_u8(v + res[i * D.rpitch + j]);
+                dst[i * D.pitch + j] = (uint8_t)v;
+            }
         } else {
-            // inter-intra blend over the inter prediction already in the frame
+            // inter-intra blend over the inter prediction already in place
             // (reference maskBlend, InterPredict.cpp:584-609; masks :555-582, :888-899)
             const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
             const uint8_t* W = aux->wedge_interintra ? mc::wedge_mask_ptr(c.wedge, aux->mi_size, aux->wedge_sign, aux->wedge_index) : nullptr;
             const int scale = 128 / max(w, h);
             const int iim = aux->interintra_mode;
             for (int e = tid; e < w * h; e += nt) {
-                int i = e >> lw, j = e & (w - 1);
+                const int i = e >> lw, j = e & (w - 1);
                 int m;
                 if (W) {
                     if (!plane) m = W[i * 32 + j];
@@ -235,8 +272,8 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
                 else if (iim == 2) m = k_ii_weights_1d[j * scale];
                 else if (iim == 3) m = k_ii_weights_1d[min(i, j) * scale];
                 else m = 32;
-                uint8_t* d = dst.p + (size_t)(op.y + i) * dst.stride + op.x + j;
-                int inter = __ldcg(d);
+                volatile uint8_t* d = dst + i * D.pitch + j;
+                const int inter = *d;
                 *d = (uint8_t)clip_u8(round2(m * S.I.pred[e] + (64 - m) * inter, 6));
             }
         }
@@ -250,14 +287,15 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         const int ox = op.x - aux->base_x[pi], oy = op.y - aux->base_y[pi];
         const uint8_t* colors = aux->pal_colors[plane];
         for (int e = tid; e < w * h; e += nt) {
-            int i = e >> lw, j = e & (w - 1);
+            const int i = e >> lw, j = e & (w - 1);
             int v = colors[map[(oy + i) * ms + ox + j]];
-            if (res) v = clip_u8(v + res[e]);
-            dst.p[(size_t)(op.y + i) * dst.stride + op.x + j] = (uint8_t)v;
+            if (res) v = clip_u8(v + res[i * D.rpitch + j]);
+            dst[i * D.pitch + j] = (uint8_t)v;
         }
         break;
     }
     case AV1B_OP_INTRABC: {
+        // only reached on the global-memory path (frames with allow_intrabc)
         const Av1bIpu u = ((const Av1bIpu*)(c.cmd + hdr->off_ipu))[op.aux];
         mc::Params P;
         setup_mc_params(c, hdr, u, nullptr, P);
@@ -268,9 +306,167 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
     __syncthreads();
 }
 
+// Wait until the superblocks this one depends on are finished, in ticket (raster) order.
+AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int tid)
+{
+    if (tid == 0) {
+        if (r > 0) {
+            const int need = min(col + 2, sb_cols);
+            while (av1b_ld_acquire(progress + r - 1) < need) av1b_nanosleep(64);
+        }
+        if (col > 0) {
+            while (av1b_ld_acquire(progress + r) < col) av1b_nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+AV1B_DEV void wave_signal(int* progress, int r, int col, int tid)
+{
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        av1b_st_release(progress + r, col + 1);
+    }
+    __syncthreads();
+}
+
+enum { WAVE_THREADS = 128 };
+
+// Shared-memory footprint of one superblock tile (bytes) for SB size `sb` (64 or 128):
+// luma (sb+1) x (2sb+8) samples with a one-sample halo row/column, two chroma planes,
+// and the three int16 residual tiles.
+#define WAVE_TILE_BYTES(sb) (((sb) + 1) * (2 * (sb) + 8) + 2 * ((sb) / 2 + 1) * ((sb) + 8) + 2 * ((sb) * (sb) + 2 * ((sb) / 2) * ((sb) / 2)))
+
 }  // namespace
 
-__global__ void __launch_bounds__(256) wave_kernel(ReconCtx c)
+int wave_tile_bytes(int sb) { return WAVE_TILE_BYTES(sb); }
+
+// Superblock-in-shared-memory wavefront: the SB's samples (all planes) live in a smem tile with a
+// one-sample halo row above (long enough for above-right reads) and halo column to the left, so
+// the serial chain of intra predictions never waits on L2.  Frames without intrabc only.
+__global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
+{
+    __shared__ WaveShared S;
+#ifdef AV1B_EMU
+    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64];
+#else
+    extern __shared__ __align__(16) uint8_t dyn[];
+#endif
+    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
+    const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
+    const int sbs_y = 1 << hdr->sb_log2;
+    const bool load_pred = !hdr->frame_is_intra; // inter prediction already sits in the frame
+    const bool have_res = c.rp[0] != nullptr && hdr->n_itx != 0;
+    int* ticket = c.sync;
+    int* progress = c.sync + 1;
+    // tile geometry per plane
+    int tsz[3], tpitch[3];
+    uint8_t* tpix[3];
+    int16_t* tres[3];
+    {
+        uint8_t* p = dyn;
+        for (int pl = 0; pl < 3; pl++) {
+            tsz[pl] = pl ? sbs_y >> 1 : sbs_y;
+            tpitch[pl] = 2 * tsz[pl] + 8;
+            tpix[pl] = p;
+            p += (tsz[pl] + 1) * tpitch[pl];
+        }
+        p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        for (int pl = 0; pl < 3; pl++) {
+            tres[pl] = (int16_t*)p;
+            p += 2 * tsz[pl] * tsz[pl];
+        }
+    }
+    for (;;) {
+        if (tid == 0) S.sb = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int sb = S.sb;
+        if (sb >= n_sb) break;
+        const int r = sb / sb_cols, col = sb - r * sb_cols;
+        const Av1bSb e = sbs[sb];
+        wave_wait(progress, r, col, sb_cols, tid);
+        if (e.n_ops == 0) {
+            wave_signal(progress, r, col, tid);
+            continue;
+        }
+        PlaneIo io[3];
+        // ---- load halo (+ current content for inter frames) and the residual tile
+        for (int pl = 0; pl < 3; pl++) {
+            const int sub = pl ? 1 : 0;
+            const int n = tsz[pl], pitch = tpitch[pl];
+            const int x0 = col * n, y0 = r * n;
+            const PlaneView g = c.cur.pl[pl];
+            uint8_t* t = tpix[pl];
+            // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 1)]
+            if (r > 0) { // above row: x0-1 .. x0+2n-1
+                const uint8_t* src = g.p + (size_t)(y0 - 1) * g.stride + x0 - 1;
+                for (int k = tid; k < 2 * n + 1; k += nt) t[k] = __ldcg(src + k);
+            }
+            if (col > 0) { // left column
+                const uint8_t* src = g.p + (size_t)y0 * g.stride + x0 - 1;
+                for (int k = tid; k < n; k += nt) t[(k + 1) * pitch] = __ldcg(src + (size_t)k * g.stride);
+            }
+            if (load_pred) {
+                const int words = n >> 2;
+                for (int k = tid; k < n * words; k += nt) {
+                    const int i = k / words, j = k - i * words;
+                    const uint32_t v = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
+                    uint8_t* d = t + (i + 1) * pitch + 1 + 4 * j;
+                    d[0] = (uint8_t)v;
+                    d[1] = (uint8_t)(v >> 8);
+                    d[2] = (uint8_t)(v >> 16);
+                    d[3] = (uint8_t)(v >> 24);
+                }
+            }
+            if (have_res) {
+                const int words = n >> 1; // two int16 per word
+                const int16_t* rs = c.rp[pl] + (size_t)y0 * c.rpitch[pl] + x0;
+                for (int k = tid; k < n * words; k += nt) {
+                    const int i = k / words, j = k - i * words;
+                    ((uint32_t*)(tres[pl] + i * n))[j] = __ldg((const uint32_t*)(rs + (size_t)i * c.rpitch[pl]) + j);
+                }
+            }
+            io[pl].pix = t + (ptrdiff_t)(1 - y0) * pitch + (1 - x0);
+            io[pl].pitch = pitch;
+            io[pl].res = have_res ? (tres[pl] - (ptrdiff_t)y0 * n - x0) : nullptr;
+            io[pl].rpitch = n;
+            (void)sub;
+        }
+        __syncthreads();
+        // ---- the ordered ops of this superblock, entirely in shared memory
+        for (unsigned k = 0; k < e.n_ops; k++) {
+            const Av1bOp op = ops[e.first_op + k];
+            exec_op(c, hdr, op, io, S, tid, nt);
+        }
+        __syncthreads();
+        // ---- flush the tile (MI-aligned area only)
+        for (int pl = 0; pl < 3; pl++) {
+            const int sub = pl ? 1 : 0;
+            const int n = tsz[pl], pitch = tpitch[pl];
+            const int x0 = col * n, y0 = r * n;
+            const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub;
+            const int cw = min(n, pw - x0), chh = min(n, ph - y0);
+            const PlaneView g = c.cur.pl[pl];
+            const uint8_t* t = tpix[pl];
+            const int words = cw >> 2; // MI-aligned widths are multiples of 4 in every plane
+            for (int k = tid; k < chh * words; k += nt) {
+                const int i = k / words, j = k - i * words;
+                const uint8_t* s = t + (i + 1) * pitch + 1 + 4 * j;
+                const uint32_t v = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+                *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = v;
+            }
+        }
+        wave_signal(progress, r, col, tid);
+    }
+}
+
+// Global-memory variant (frames with allow_intrabc: block copies read arbitrary earlier parts of
+// the frame being reconstructed).  Same ops, samples read through L2.
+__global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
 {
     __shared__ WaveShared S;
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
@@ -280,33 +476,26 @@ __global__ void __launch_bounds__(256) wave_kernel(ReconCtx c)
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     int* ticket = c.sync;
     int* progress = c.sync + 1;
+    PlaneIo io[3];
+    for (int pl = 0; pl < 3; pl++) {
+        io[pl].pix = c.cur.pl[pl].p;
+        io[pl].pitch = c.cur.pl[pl].stride;
+        io[pl].res = (c.rp[0] && hdr->n_itx) ? c.rp[pl] : nullptr;
+        io[pl].rpitch = c.rpitch[pl];
+    }
     for (;;) {
         if (tid == 0) S.sb = atomicAdd(ticket, 1);
         __syncthreads();
         const int sb = S.sb;
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
-        if (tid == 0) {
-            if (r > 0) {
-                const int need = min(col + 2, sb_cols);
-                while (av1b_ld_acquire(progress + r - 1) < need) av1b_nanosleep(100);
-            }
-            if (col > 0) {
-                while (av1b_ld_acquire(progress + r) < col) av1b_nanosleep(100);
-            }
-        }
-        __syncthreads();
+        wave_wait(progress, r, col, sb_cols, tid);
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
-            exec_op(c, hdr, op, S, tid, nt);
+            exec_op(c, hdr, op, io, S, tid, nt);
         }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            av1b_st_release(progress + r, col + 1);
-        }
-        __syncthreads();
+        wave_signal(progress, r, col, tid);
     }
 }
 
@@ -321,7 +510,12 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     const int16_t* coef = (const int16_t*)(c.cmd + h.off_coef);
     int grid = (int)((h.n_itx + ITX_WARPS - 1) / ITX_WARPS);
     if (grid > 148 * 16) grid = 148 * 16;
-    AV1B_LAUNCH(itx_kernel, (grid), (ITX_WARPS * 32), st, ops, list, (int)h.n_itx, coef, c.res);
+    ResPlanes rp;
+    for (int i = 0; i < 3; i++) {
+        rp.p[i] = c.rp[i];
+        rp.pitch[i] = c.rpitch[i];
+    }
+    AV1B_LAUNCH(itx_kernel, (grid), (ITX_WARPS * 32), st, ops, list, (int)h.n_itx, coef, c.res, rp);
 }
 
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
@@ -337,5 +531,20 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     if (!h.n_ops) return;
     int grid = (int)h.n_sb;
     if (grid > 148 * 2) grid = 148 * 2;
-    AV1B_LAUNCH(wave_kernel, (grid), (256), st, c);
+    if (h.allow_intrabc) {
+        AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);
+        return;
+    }
+    const int smem = wave_tile_bytes(1 << h.sb_log2) + 32;
+#ifndef AV1B_EMU
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 32);
+        configured = true;
+    }
+    wave_kernel<<<dim3(grid), dim3(WAVE_THREADS), smem, st>>>(c);
+#else
+    (void)smem;
+    AV1B_LAUNCH(wave_kernel, (grid), (WAVE_THREADS), st, c);
+#endif
 }

@@ -7,7 +7,7 @@ Sizes are cross-checked against the C structs by tests/test_host.py (av1b_struct
 import ctypes as C
 
 MAGIC = 0x42315641
-VERSION = 1
+VERSION = 2
 
 OP_INTER_RES, OP_INTRA, OP_PALETTE, OP_INTERINTRA, OP_INTRABC = range(5)
 OPF_HAVE_LEFT, OPF_HAVE_ABOVE, OPF_HAVE_ABOVE_RIGHT, OPF_HAVE_BELOW_LEFT = 1, 2, 4, 8
@@ -34,8 +34,9 @@ class Ipu(C.Structure):
 
 
 class InterBlk(C.Structure):
-    _fields_ = [("first_ipu", C.c_uint32), ("n_ipu", C.c_uint32), ("bw", C.c_uint16), ("bh", C.c_uint16),
-                ("pad", C.c_uint32)]
+    _fields_ = [("first_ipu", C.c_uint32), ("n_ipu", C.c_uint16), ("flags", C.c_uint16), ("x", C.c_uint16),
+                ("y", C.c_uint16), ("cx", C.c_uint16), ("cy", C.c_uint16), ("bw", C.c_uint8), ("bh", C.c_uint8),
+                ("cw", C.c_uint8), ("ch", C.c_uint8), ("pad", C.c_uint32)]
 
 
 class BlkAux(C.Structure):

@@ -11,6 +11,7 @@
 #include "Av1Decoder.h"
 #include "decoder_impl.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -92,6 +93,10 @@ struct Decoder::Impl {
     int frame_w[32], frame_h[32]; // visible size of each device frame id
     av1b200::DecoderOptions opt;
     std::string error;
+    // AV1B200_TIMING=1: cumulative host-side phase timers, printed when the decoder is destroyed
+    bool timing = getenv("AV1B200_TIMING") != nullptr;
+    double t_parse = 0, t_emit = 0, t_submit = 0, t_wait = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     bool fail(const char* what)
     {
@@ -132,6 +137,7 @@ struct Decoder::Impl {
     {
         FrameHeader& h = *frame;
         if (!ensureCtx()) return false;
+        const double t0 = now();
         emitter.begin(h, *parser->m_sequence);
         for (auto& t : ts) {
             emitter.emitTile(*t);
@@ -139,6 +145,8 @@ struct Decoder::Impl {
         }
         for (auto& t : ts) t->frame_end_update_cdf();
         emitter.finish();
+        const double t1 = now();
+        t_emit += t1 - t0;
         const size_t bytes = emitter.bytes();
         void* slot = nullptr;
         if (av1b_cmd_acquire(ctx, bytes, &slot) != AV1B_OK) return fail("av1b_cmd_acquire");
@@ -149,6 +157,7 @@ struct Decoder::Impl {
         frame_w[fid] = h.FrameWidth;
         frame_h[fid] = h.FrameHeight;
         if (h.show_frame && !queueOutput(fid)) return false;
+        t_submit += now() - t1;
         h.motionVectorStorage();
         parser->finishFrame();
         return true;
@@ -179,6 +188,8 @@ Decoder::Decoder()
 
 Decoder::~Decoder()
 {
+    if (m_impl->timing)
+        fprintf(stderr, "av1b200 timing: parse %.3fs emit %.3fs submit %.3fs wait %.3fs\n", m_impl->t_parse, m_impl->t_emit, m_impl->t_submit, m_impl->t_wait);
     if (m_impl->ctx) {
         av1b_sync(m_impl->ctx);
         m_impl->output.clear();
@@ -220,7 +231,9 @@ bool Decoder::decode(uint8_t* data, size_t size)
         }
         case OBU_FRAME: {
             TileGroup group;
+            const double tp = Impl::now();
             d.frame = parser.parseFrame(br, group);
+            d.t_parse += Impl::now() - tp;
             ok = d.frame ? d.decodeFrame(group) : false;
             d.tiles.clear();
             break;
@@ -241,7 +254,10 @@ std::shared_ptr<YuvFrame> Decoder::getOutput()
     if (d.output.empty()) return nullptr;
     Impl::Pending p = d.output.front();
     d.output.pop_front();
-    if (av1b_fence_wait(d.ctx, p.fence) != AV1B_OK) {
+    const double tw = Impl::now();
+    const int wrc = av1b_fence_wait(d.ctx, p.fence);
+    d.t_wait += Impl::now() - tw;
+    if (wrc != AV1B_OK) {
         d.fail("av1b_fence_wait");
         return nullptr;
     }

@@ -50,6 +50,7 @@ void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
     m_gmReady = false;
     m_sbs.assign((size_t)h.sb_cols * h.sb_rows, Av1bSb{ 0, 0 });
     m_ops.clear();
+    m_itxOnly.clear();
     m_itx.clear();
     m_iblk.clear();
     m_ipu.clear();
@@ -229,8 +230,21 @@ void FrameEmitter::emitInter(Block& b)
     Av1bInterBlk ib;
     memset(&ib, 0, sizeof(ib));
     ib.first_ipu = (uint32_t)m_ipu.size();
-    ib.bw = (uint16_t)b.bw;
-    ib.bh = (uint16_t)b.bh;
+    ib.x = (uint16_t)(b.MiCol * MI_SIZE);
+    ib.y = (uint16_t)(b.MiRow * MI_SIZE);
+    ib.bw = (uint8_t)b.bw;
+    ib.bh = (uint8_t)b.bh;
+    if (b.HasChroma) {
+        const int csz = seq.get_plane_residual_size(b.MiSize, 1);
+        ib.flags |= AV1B_IBF_HAS_CHROMA;
+        ib.cx = (uint16_t)((b.MiCol >> b.subsampling_x) * MI_SIZE);
+        ib.cy = (uint16_t)((b.MiRow >> b.subsampling_y) * MI_SIZE);
+        ib.cw = (uint8_t)(Num_4x4_Blocks_Wide[csz] * 4);
+        ib.ch = (uint8_t)(Num_4x4_Blocks_High[csz] * 4);
+    }
+    // plain inter blocks: the inter pass adds the residual itself (no ordering constraint);
+    // inter-intra blocks get it after the blend, inside the dependent pass
+    if (!interintra && !intrabc) ib.flags |= AV1B_IBF_ADD_RESIDUAL;
     const int subBlockMiRow = b.MiRow & b.sbMask, subBlockMiCol = b.MiCol & b.sbMask;
     // Block::compute_prediction (Block.cpp:100-174)
     for (int plane = 0; plane < 1 + b.HasChroma * 2; plane++) {
@@ -342,7 +356,7 @@ void FrameEmitter::emitInter(Block& b)
         }
         if (b.motion_mode == OBMC_CAUSAL) emitObmc(b, plane, predW, predH);
     }
-    ib.n_ipu = (uint32_t)m_ipu.size() - ib.first_ipu;
+    ib.n_ipu = (uint16_t)(m_ipu.size() - ib.first_ipu);
     if (!intrabc && ib.n_ipu) m_iblk.push_back(ib);
 }
 
@@ -488,8 +502,19 @@ void FrameEmitter::emitTb(Block& b, TransformBlock& t)
         m_nRes += (uint32_t)(Tx_Width[txSz] * Tx_Height[txSz]);
         m_itx.push_back((uint32_t)m_ops.size());
     }
-    if (op.kind != AV1B_OP_INTER_RES || (op.flags & AV1B_OPF_HAS_RESID)) m_ops.push_back(op);
-    else if (t.m_eob > 0) m_itx.pop_back();
+    // ops of the dependent pass: intra / palette TBs always; residual-only TBs just for
+    // inter-intra and intrabc blocks (plain inter blocks are finished by the inter pass).
+    // The inverse-transform list refers to ops by index, so coded TBs of plain inter blocks go
+    // to a separate op array that only the inverse transform reads.
+    const bool plainInter = b.is_inter && !b.use_intrabc && b.RefFrame[1] != INTRA_FRAME;
+    if (plainInter) {
+        if (op.flags & AV1B_OPF_HAS_RESID) {
+            m_itx.back() = 0x80000000u | (uint32_t)m_itxOnly.size();
+            m_itxOnly.push_back(op);
+        }
+    } else if (op.kind != AV1B_OP_INTER_RES || (op.flags & AV1B_OPF_HAS_RESID)) {
+        m_ops.push_back(op);
+    }
     // LoopfilterTxSizes + BlockDecoded bookkeeping (TransformBlock.cpp:2444-2454)
     const int miRows = f.MiRows, miCols = f.MiCols;
     uint8_t* lftx = &m_lftx[(size_t)plane * miRows * miCols];
@@ -614,8 +639,11 @@ void FrameEmitter::layout()
     };
     h.n_sb = (uint32_t)m_sbs.size();
     place(h.off_sb, m_sbs.size() * sizeof(Av1bSb));
+    // [ordered ops of the dependent pass][inverse-transform-only ops of plain inter blocks]
     h.n_ops = (uint32_t)m_ops.size();
-    place(h.off_ops, m_ops.size() * sizeof(Av1bOp));
+    place(h.off_ops, (m_ops.size() + m_itxOnly.size()) * sizeof(Av1bOp));
+    for (auto& i : m_itx)
+        if (i & 0x80000000u) i = (i & 0x7FFFFFFFu) + (uint32_t)m_ops.size();
     h.n_itx = (uint32_t)m_itx.size();
     place(h.off_itx, m_itx.size() * sizeof(uint32_t));
     h.n_iblk = (uint32_t)m_iblk.size();
@@ -646,6 +674,7 @@ void FrameEmitter::write(uint8_t* dst) const
     };
     put(h.off_sb, m_sbs.data(), m_sbs.size() * sizeof(Av1bSb));
     put(h.off_ops, m_ops.data(), m_ops.size() * sizeof(Av1bOp));
+    put(h.off_ops + (uint32_t)(m_ops.size() * sizeof(Av1bOp)), m_itxOnly.data(), m_itxOnly.size() * sizeof(Av1bOp));
     put(h.off_itx, m_itx.data(), m_itx.size() * sizeof(uint32_t));
     put(h.off_iblk, m_iblk.data(), m_iblk.size() * sizeof(Av1bInterBlk));
     put(h.off_ipu, m_ipu.data(), m_ipu.size() * sizeof(Av1bIpu));

@@ -46,6 +46,7 @@ private:
     Av1bFrameHdr m_hdr;
     std::vector<Av1bSb> m_sbs;
     std::vector<Av1bOp> m_ops;
+    std::vector<Av1bOp> m_itxOnly; // coded TBs of plain inter blocks (inverse transform only)
     std::vector<uint32_t> m_itx;
     std::vector<Av1bInterBlk> m_iblk;
     std::vector<Av1bIpu> m_ipu;

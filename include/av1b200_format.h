@@ -29,11 +29,12 @@ extern "C" {
 #endif
 
 #define AV1B_MAGIC 0x42315641u /* "AV1B" */
-#define AV1B_FORMAT_VERSION 1
+#define AV1B_FORMAT_VERSION 2
 
 /* ---- Av1bOp.kind ------------------------------------------------------------------- */
 enum {
-    AV1B_OP_INTER_RES = 0,  /* inter block TB: frame += residual (prediction already in frame) */
+    AV1B_OP_INTER_RES = 0,  /* TB of an inter-intra / intrabc block: frame += residual (other inter
+                               blocks get their residual added by the inter pass itself)        */
     AV1B_OP_INTRA = 1,      /* intra TB: predict from neighbours, + residual                      */
     AV1B_OP_PALETTE = 2,    /* palette TB: paint colour map, + residual                           */
     AV1B_OP_INTERINTRA = 3, /* whole plane-block: intra predict and blend over the inter pred    */
@@ -66,7 +67,8 @@ typedef struct Av1bOp {
     uint8_t nz_cols;    /* number of leading coefficient columns that may be non-zero      */
     uint8_t lossless;   /* 1: Walsh-Hadamard path (Block::Lossless)                         */
     uint32_t coef_off;  /* int16 index into the coefficient arena (tw*th values, row-major) */
-    uint32_t res_off;   /* int16 index into the device residual arena (w*h values)          */
+    uint32_t res_off;   /* int16 index into the compact residual arena (stage-level ITX test mode only;
+                           a full submit writes residuals into frame-layout int16 planes)   */
     uint32_t aux;       /* Av1bBlkAux index (palette, inter-intra) or Av1bIpu index (intrabc) */
     uint16_t max_luma_w, max_luma_h; /* CfL: Block::MaxLumaW/H at this TB                   */
 } Av1bOp;
@@ -108,11 +110,18 @@ typedef struct Av1bIpu {
     uint32_t aux;       /* Av1bBlkAux index (warp params, wedge, mask)                      */
 } Av1bIpu;
 
-/* One inter block = one CTA work item of the independent inter pass. 16 B */
+#define AV1B_IBF_HAS_CHROMA 0x01   /* the block carries chroma (Block::HasChroma)                   */
+#define AV1B_IBF_ADD_RESIDUAL 0x02 /* add the residual planes over the block after prediction        */
+
+/* One inter block = one CTA work item of the independent inter pass. 24 B */
 typedef struct Av1bInterBlk {
     uint32_t first_ipu;
-    uint32_t n_ipu;
-    uint16_t bw, bh; /* luma block size (mask scratch sizing) */
+    uint16_t n_ipu;
+    uint16_t flags;      /* AV1B_IBF_*                                   */
+    uint16_t x, y;       /* luma rectangle (samples)                     */
+    uint16_t cx, cy;     /* chroma rectangle origin (chroma samples)     */
+    uint8_t bw, bh;      /* luma size; 0 means 256 is never needed (<=128) */
+    uint8_t cw, ch;      /* chroma size                                  */
     uint32_t pad;
 } Av1bInterBlk;
 
