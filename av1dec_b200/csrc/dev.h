@@ -20,6 +20,9 @@ struct EmuDim3 {
     EmuDim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 typedef EmuDim3 dim3;
+struct uint4 {
+    unsigned x, y, z, w;
+};
 extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __global__
 #define __device__
@@ -90,6 +93,14 @@ static __device__ __forceinline__ void av1b_nanosleep(unsigned ns) { __nanosleep
 
 // ------------------------------------------------------------------ shared helpers
 #define AV1B_DEV static __device__ __forceinline__
+
+// Barrier for a CTA of nt threads: a single-warp CTA (the latency-critical intra wavefront runs
+// one warp per superblock) only needs warp-level ordering.
+AV1B_DEV void block_sync(int nt)
+{
+    if (nt > 32) __syncthreads();
+    else __syncwarp();
+}
 
 AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }

@@ -77,14 +77,14 @@ AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int
 {
     if (!strength) return;
     for (int k = tid; k < sz; k += nt) tmp[k] = edge[k - 1];
-    __syncthreads();
+    block_sync(nt);
     for (int i = 1 + tid; i < sz; i += nt) {
         int s = 0;
         AV1B_UNROLL
         for (int j = 0; j < 5; j++) s += k_intra_edge_kernel[strength - 1][j] * tmp[clip3(0, sz - 1, i - 2 + j)];
         edge[i - 1] = (uint8_t)((s + 8) >> 4);
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 // 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample)
@@ -92,14 +92,14 @@ AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt)
 {
     // tmp[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
     for (int k = tid; k < n + 3; k += nt) tmp[k] = edge[clip3(-1, n - 1, k - 2)];
-    __syncthreads();
+    block_sync(nt);
     if (tid == 0) edge[-2] = tmp[0];
     for (int i = tid; i < n; i += nt) {
         int s = -tmp[i] + 9 * tmp[i + 1] + 9 * tmp[i + 2] - tmp[i + 3];
         edge[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
         edge[2 * i] = tmp[i + 2];
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 // Predict one block into S.pred (pitch w).  All threads of the CTA must call it.
@@ -132,7 +132,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
             A[-1] = (uint8_t)c;
             L[-1] = (uint8_t)c;
         }
-        __syncthreads();
+        block_sync(nt);
     }
     uint8_t* P = S.pred;
     if (a.plane_idx == 0 && a.filter_intra) {
@@ -161,7 +161,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                 for (int i = 0; i < 7; i++) pr += k_intra_filter_taps[a.fi_mode][k][i] * p[i];
                 P[((i2 << 1) + i1) * w + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
             }
-            __syncthreads();
+            block_sync(nt);
         }
         return;
     }
@@ -177,7 +177,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                     L[-1] = (uint8_t)s;
                     A[-1] = (uint8_t)s;
                 }
-                __syncthreads();
+                block_sync(nt);
             }
             const int maxx_q = a.max_x + 1, maxy_q = a.max_y + 1; // quirk: no -1
             if (a.have_above) {
@@ -291,7 +291,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
             P[e] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
         }
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 // Chroma-from-luma on top of the DC prediction already in S.pred (IntraPredict.cpp:632-667).
@@ -301,7 +301,7 @@ AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int
 {
     const int w = 1 << a.log2w, h = 1 << a.log2h;
     if (tid == 0) S.acc = 0;
-    __syncthreads();
+    block_sync(nt);
     int local = 0;
     for (int e = tid; e < w * h; e += nt) {
         int i = e >> a.log2w, j = e & (w - 1);
@@ -314,13 +314,13 @@ AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int
         local += v;
     }
     atomicAdd(&S.acc, local);
-    __syncthreads();
+    block_sync(nt);
     const int avg = round2(S.acc, a.log2w + a.log2h);
     for (int e = tid; e < w * h; e += nt) {
         int scaled = round2s(alpha * (S.luma[e] - avg), 6);
         S.pred[e] = (uint8_t)clip_u8(S.pred[e] + scaled);
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 }  // namespace intra

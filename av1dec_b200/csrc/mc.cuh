@@ -105,7 +105,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
             for (int t = 0; t < 8; t++) sum += f[t] * ref_px(R, ix4 + i2 - 3 + t, iy4 + i1);
             s.inter[e] = (int16_t)((sum + 4) >> 3);
         }
-        __syncthreads();
+        block_sync(nt);
         for (int e = tid; e < nu * 64; e += nt) {
             int unit = e >> 6, k = e & 63;
             int i1 = (k >> 3) - 4, i2 = (k & 7) - 4;
@@ -124,7 +124,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
             for (int t = 0; t < 8; t++) sum += f[t] * in[(i1 + t + 4) * 8];
             pred[(uy * 8 + i1 + 4) * TILE + ux * 8 + i2 + 4] = (int16_t)round2(sum, round1);
         }
-        __syncthreads();
+        block_sync(nt);
         return;
     }
     // translational prediction
@@ -138,7 +138,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
             int r = e / tw, c = e - r * tw;
             pred[r * TILE + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
         }
-        __syncthreads();
+        block_sync(nt);
         return;
     }
     const int16_t* fh = k_subpel_filters[filter_row(u.w, u.filt[1])][fx];
@@ -152,7 +152,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
         for (int t = 0; t < 8; t++) sum += fh[t] * ref_px(R, x + t, y);
         s.inter[r * TILE + c] = (int16_t)((sum + 4) >> 3);
     }
-    __syncthreads();
+    block_sync(nt);
     for (int e = tid; e < tw * th; e += nt) {
         int r = e / tw, c = e - r * tw;
         int sum = 0;
@@ -160,7 +160,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
         for (int t = 0; t < 8; t++) sum += fv[t] * s.inter[(r + t) * TILE + c];
         pred[r * TILE + c] = (int16_t)round2(sum, round1);
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 // Execute one unit: predict every tile and write / blend it into the destination plane.
@@ -223,7 +223,7 @@ AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, in
                 }
                 *d = (uint8_t)out;
             }
-            __syncthreads();
+            block_sync(nt);
         }
     }
 }

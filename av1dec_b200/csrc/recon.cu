@@ -188,13 +188,14 @@ struct PlaneIo {
     int rpitch;
 };
 
-struct WaveShared {
+enum { WAVE_WARPS = 8, WAVE_THREADS = WAVE_WARPS * 32, WAVE_OP_CHUNK = 64 };
+
+struct OpScratch {
     intra::Scratch I;
-    mc::Scratch M;
-    int sb;
 };
 
-AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, const PlaneIo* io, WaveShared& S, int tid, int nt)
+AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, const PlaneIo* io, OpScratch& S, mc::Scratch* M,
+    int tid, int nt)
 {
     const int plane = op.plane, sub = plane ? 1 : 0;
     const PlaneIo& D = io[plane];
@@ -299,15 +300,15 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         const Av1bIpu u = ((const Av1bIpu*)(c.cmd + hdr->off_ipu))[op.aux];
         mc::Params P;
         setup_mc_params(c, hdr, u, nullptr, P);
-        mc::run_ipu(P, u, S.M, tid, nt);
+        mc::run_ipu(P, u, *M, tid, nt);
         break;
     }
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
 // Wait until the superblocks this one depends on are finished, in ticket (raster) order.
-AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int tid)
+AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int tid, int nt)
 {
     if (tid == 0) {
         if (r > 0) {
@@ -317,21 +318,19 @@ AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int tid)
         if (col > 0) {
             while (av1b_ld_acquire(progress + r) < col) av1b_nanosleep(64);
         }
-    }
-    __syncthreads();
-}
-
-AV1B_DEV void wave_signal(int* progress, int r, int col, int tid)
-{
-    __syncthreads();
-    if (tid == 0) {
         __threadfence();
-        av1b_st_release(progress + r, col + 1);
     }
-    __syncthreads();
+    block_sync(nt);
 }
 
-enum { WAVE_THREADS = 128 };
+AV1B_DEV void wave_signal(int* progress, int r, int col, int tid, int nt)
+{
+    __threadfence(); // every thread's tile stores are visible device-wide before the flag moves
+    block_sync(nt);
+    if (tid == 0) av1b_st_release(progress + r, col + 1);
+    block_sync(nt);
+}
+
 
 // Shared-memory footprint of one superblock tile (bytes) for SB size `sb` (64 or 128):
 // luma (sb+1) x (2sb+8) samples with a one-sample halo row/column, two chroma planes,
@@ -344,12 +343,16 @@ int wave_tile_bytes(int sb) { return WAVE_TILE_BYTES(sb); }
 
 // Superblock-in-shared-memory wavefront: the SB's samples (all planes) live in a smem tile with a
 // one-sample halo row above (long enough for above-right reads) and halo column to the left, so
-// the serial chain of intra predictions never waits on L2.  Frames without intrabc only.
+// the chain of intra predictions never waits on L2.  Inside the SB the ops come sorted by
+// dependency level (host/emitter.cpp scheduleSb): all ops of one level are independent, each is
+// executed by ONE warp, and the CTA only synchronises between levels -- a 128x128 SB of 4x4
+// blocks needs ~100 level steps instead of ~650 sequential ops.  Frames without intrabc only.
 __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
 {
-    __shared__ WaveShared S;
+    alignas(16) __shared__ Av1bOp s_ops[WAVE_OP_CHUNK];
+    __shared__ int s_sb;
 #ifdef AV1B_EMU
-    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64];
+    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64 + sizeof(OpScratch) * WAVE_WARPS];
 #else
     extern __shared__ __align__(16) uint8_t dyn[];
 #endif
@@ -357,6 +360,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
     const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = tid % nl, warp = tid / nl;
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     const int sbs_y = 1 << hdr->sb_log2;
     const bool load_pred = !hdr->frame_is_intra; // inter prediction already sits in the frame
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
     int tsz[3], tpitch[3];
     uint8_t* tpix[3];
     int16_t* tres[3];
+    OpScratch* scratch;
     {
         uint8_t* p = dyn;
         for (int pl = 0; pl < 3; pl++) {
@@ -380,23 +386,25 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
             tres[pl] = (int16_t*)p;
             p += 2 * tsz[pl] * tsz[pl];
         }
+        p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        scratch = (OpScratch*)p + warp;
     }
     for (;;) {
-        if (tid == 0) S.sb = atomicAdd(ticket, 1);
-        __syncthreads();
-        const int sb = S.sb;
+        block_sync(nt);
+        if (tid == 0) s_sb = atomicAdd(ticket, 1);
+        block_sync(nt);
+        const int sb = s_sb;
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
         const Av1bSb e = sbs[sb];
-        wave_wait(progress, r, col, sb_cols, tid);
+        wave_wait(progress, r, col, sb_cols, tid, nt);
         if (e.n_ops == 0) {
-            wave_signal(progress, r, col, tid);
+            wave_signal(progress, r, col, tid, nt);
             continue;
         }
         PlaneIo io[3];
         // ---- load halo (+ current content for inter frames) and the residual tile
         for (int pl = 0; pl < 3; pl++) {
-            const int sub = pl ? 1 : 0;
             const int n = tsz[pl], pitch = tpitch[pl];
             const int x0 = col * n, y0 = r * n;
             const PlaneView g = c.cur.pl[pl];
@@ -434,15 +442,39 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
             io[pl].pitch = pitch;
             io[pl].res = have_res ? (tres[pl] - (ptrdiff_t)y0 * n - x0) : nullptr;
             io[pl].rpitch = n;
-            (void)sub;
         }
-        __syncthreads();
-        // ---- the ordered ops of this superblock, entirely in shared memory
-        for (unsigned k = 0; k < e.n_ops; k++) {
-            const Av1bOp op = ops[e.first_op + k];
-            exec_op(c, hdr, op, io, S, tid, nt);
+        block_sync(nt);
+        // ---- the ops of this superblock, level by level, one warp per op
+        for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK) {
+            const unsigned nk = min((unsigned)WAVE_OP_CHUNK, e.n_ops - k0);
+            {
+                const uint4* src = (const uint4*)(ops + e.first_op + k0);
+                uint4* dstv = (uint4*)s_ops;
+                for (unsigned q = tid; q < nk * 2; q += nt) dstv[q] = __ldg(src + q);
+            }
+            block_sync(nt);
+            unsigned g0 = 0;
+            while (g0 < nk) {
+                const uint32_t level = s_ops[g0].res_off;
+                unsigned g1 = g0 + 1;
+                while (g1 < nk && s_ops[g1].res_off == level) g1++;
+#ifdef AV1B_EMU
+                // the emulation runs the ops of a level in REVERSE order: if the level analysis
+                // missed a dependency, the conformance MD5s under emulation break
+                for (unsigned k = g1; k-- > g0;) {
+                    const Av1bOp op = s_ops[k];
+                    exec_op(c, hdr, op, io, *scratch, nullptr, lane, nl);
+                }
+#else
+                for (unsigned k = g0 + warp; k < g1; k += nw) {
+                    const Av1bOp op = s_ops[k];
+                    exec_op(c, hdr, op, io, *scratch, nullptr, lane, nl);
+                }
+#endif
+                block_sync(nt);
+                g0 = g1;
+            }
         }
-        __syncthreads();
         // ---- flush the tile (MI-aligned area only)
         for (int pl = 0; pl < 3; pl++) {
             const int sub = pl ? 1 : 0;
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
                 *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = v;
             }
         }
-        wave_signal(progress, r, col, tid);
+        wave_signal(progress, r, col, tid, nt);
     }
 }
 
@@ -468,7 +500,9 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
 // the frame being reconstructed).  Same ops, samples read through L2.
 __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
 {
-    __shared__ WaveShared S;
+    __shared__ OpScratch S;
+    __shared__ mc::Scratch M;
+    __shared__ int s_sb;
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
@@ -484,18 +518,19 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         io[pl].rpitch = c.rpitch[pl];
     }
     for (;;) {
-        if (tid == 0) S.sb = atomicAdd(ticket, 1);
         __syncthreads();
-        const int sb = S.sb;
+        if (tid == 0) s_sb = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int sb = s_sb;
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
-        wave_wait(progress, r, col, sb_cols, tid);
+        wave_wait(progress, r, col, sb_cols, tid, nt);
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
-            exec_op(c, hdr, op, io, S, tid, nt);
+            exec_op(c, hdr, op, io, S, &M, tid, nt);
         }
-        wave_signal(progress, r, col, tid);
+        wave_signal(progress, r, col, tid, nt);
     }
 }
 
@@ -535,11 +570,11 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);
         return;
     }
-    const int smem = wave_tile_bytes(1 << h.sb_log2) + 32;
+    const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * WAVE_WARPS;
 #ifndef AV1B_EMU
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 32);
+        cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * WAVE_WARPS);
         configured = true;
     }
     wave_kernel<<<dim3(grid), dim3(WAVE_THREADS), smem, st>>>(c);

@@ -72,10 +72,91 @@ void FrameEmitter::emitTile(Tile& tile)
         tile.m_decoded.clear_block_decoded_flags(sb.m_r, sb.m_c, sb4);
         const size_t idx = (size_t)(sb.m_r / sb4) * m_hdr.sb_cols + (sb.m_c / sb4);
         const uint32_t first = (uint32_t)m_ops.size();
+        const size_t firstItx = m_itx.size();
         walk(sb);
         m_sbs[idx].first_op = first;
         m_sbs[idx].n_ops = (uint32_t)m_ops.size() - first;
+        scheduleSb(first, firstItx, sb.m_c * MI_SIZE, sb.m_r * MI_SIZE);
     }
+}
+
+// Dependency levels inside one superblock.  Ops are emitted in bitstream order; two ops may run
+// concurrently when neither reads nor overwrites samples the other writes.  Per plane, a 4x4-cell
+// map remembers the level of the last op that wrote each cell; an op's level is one more than the
+// largest level among the cells it reads (intra edges incl. above-right / below-left, CfL luma)
+// or rewrites.  The ops are then stably sorted by level (still a valid sequential order) and the
+// level is stored in Av1bOp::res_off, which frame submits do not otherwise use.
+void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
+{
+    const uint32_t n = (uint32_t)m_ops.size() - first;
+    if (!n) return;
+    const int sbPix = 1 << m_hdr.sb_log2;
+    enum { MAXC = 32 };
+    static thread_local uint16_t cell[3][MAXC][MAXC];
+    memset(cell, 0, sizeof(cell));
+    m_levels.resize(n);
+    uint32_t maxLevel = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        Av1bOp& op = m_ops[first + k];
+        const int pl = op.plane, sub = pl ? 1 : 0;
+        const int nc = (sbPix >> sub) >> 2; // cells per row/column of this plane's SB tile
+        int lw, lh;
+        if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
+            lw = op.tx_size & 15;
+            lh = op.tx_size >> 4;
+        } else {
+            lw = hk_tx_wlog2[op.tx_size];
+            lh = hk_tx_hlog2[op.tx_size];
+        }
+        if (op.kind == AV1B_OP_INTRABC) {
+            const Av1bIpu& u = m_ipu[op.aux];
+            lw = 0;
+            while ((1 << lw) < u.w) lw++;
+            lh = 0;
+            while ((1 << lh) < u.h) lh++;
+        }
+        const int w = 1 << lw, h = 1 << lh;
+        const int x = op.x - (sbx >> sub), y = op.y - (sby >> sub); // tile-relative
+        const int cx0 = std::max(0, x >> 2), cy0 = std::max(0, y >> 2);
+        const int cx1 = std::min(nc - 1, (x + w - 1) >> 2), cy1 = std::min(nc - 1, (y + h - 1) >> 2);
+        uint32_t lvl = 0;
+        auto rd = [&](int p, int cxa, int cxb, int cya, int cyb, int ncp) {
+            cxa = std::max(cxa, 0);
+            cya = std::max(cya, 0);
+            cxb = std::min(cxb, ncp - 1);
+            cyb = std::min(cyb, ncp - 1);
+            for (int cy = cya; cy <= cyb; cy++)
+                for (int cx = cxa; cx <= cxb; cx++) lvl = std::max<uint32_t>(lvl, cell[p][cy][cx]);
+        };
+        rd(pl, cx0, cx1, cy0, cy1, nc); // cells it (re)writes
+        if (op.kind == AV1B_OP_INTRA || op.kind == AV1B_OP_INTERINTRA) {
+            const int ar = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) ? 2 * w : w;
+            const int bl = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) ? 2 * h : h;
+            if (y > 0) rd(pl, (x - 1) >> 2, (x + ar - 1) >> 2, (y - 1) >> 2, (y - 1) >> 2, nc); // above row + corner
+            if (x > 0) rd(pl, (x - 1) >> 2, (x - 1) >> 2, (y - 1) >> 2, (y + bl - 1) >> 2, nc); // left column + corner
+            if (op.flags & AV1B_OPF_CFL) rd(0, (2 * x) >> 2, (2 * (x + w) - 1) >> 2, (2 * y) >> 2, (2 * (y + h) - 1) >> 2, nc * 2);
+        }
+        lvl += 1;
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int cx = cx0; cx <= cx1; cx++) cell[pl][cy][cx] = (uint16_t)lvl;
+        m_levels[k] = lvl;
+        maxLevel = std::max(maxLevel, lvl);
+    }
+    // stable counting sort by level
+    m_count.assign(maxLevel + 2, 0);
+    for (uint32_t k = 0; k < n; k++) m_count[m_levels[k] + 1]++;
+    for (uint32_t l = 1; l < m_count.size(); l++) m_count[l] += m_count[l - 1];
+    m_sorted.resize(n);
+    m_perm.resize(n);
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t pos = m_count[m_levels[k]]++;
+        m_sorted[pos] = m_ops[first + k];
+        m_sorted[pos].res_off = m_levels[k];
+        m_perm[k] = pos;
+    }
+    std::copy(m_sorted.begin(), m_sorted.end(), m_ops.begin() + first);
+    for (size_t i = firstItx; i < m_itx.size(); i++)
+        if (!(m_itx[i] & 0x80000000u)) m_itx[i] = first + m_perm[m_itx[i] - first];
 }
 
 void FrameEmitter::walk(Partition& p)

@@ -40,6 +40,7 @@ private:
     bool edgeSmooth(const YamiAv1::Block& b, int plane) const;
     void distanceWeights(int candRow, int candCol, int& fwd, int& bck) const;
     void layout();
+    void scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby);
 
     YamiAv1::FrameHeader* m_frame = nullptr;
     const YamiAv1::SequenceHeader* m_seq = nullptr;
@@ -57,6 +58,8 @@ private:
     std::vector<uint8_t> m_lftx; // [3][mi_rows*mi_cols] LoopfilterTxSizes
     std::vector<uint8_t> m_cdef8;
     std::vector<Av1bLrUnit> m_lru;
+    std::vector<uint32_t> m_levels, m_count, m_perm;
+    std::vector<Av1bOp> m_sorted;
     uint32_t m_nRes = 0;
     size_t m_total = 0;
     // per-block state
