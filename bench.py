@@ -457,7 +457,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cuda-streams", type=int, default=32)
+    ap.add_argument("--cuda-streams", type=int, default=64)
     ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -470,6 +470,12 @@ def main():
         post, roofline = postfilter_leg(0, torch.device("cuda", 0), reps=max(args.steps, 1))
         print(json.dumps({"postfilter_4k": post, "roofline": roofline}))
         return 0
+    # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on
+    # stdout, so everything but our final print goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -478,6 +484,7 @@ def main():
     try:
         return run_ours(args, rank, world, local_rank)
     finally:
+        sys.stdout.flush()
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
