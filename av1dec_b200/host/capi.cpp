@@ -4,6 +4,7 @@
 #include "decoder_impl.h"
 #include "VideoFrame.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -70,6 +71,7 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
     YamiAv1::Decoder dec;
     av1b200::decoderOptions(dec).device = device;
     av1b200::decoderOptions(dec).stages = stages;
+    av1b200::decoderSetAsync(dec, getenv("AV1B200_SYNC_EMIT") == nullptr);
     // keepInFlight frames may still be on the device while the next temporal unit is parsed
     auto drain = [&](size_t keepInFlight) {
         std::shared_ptr<Yami::YuvFrame> f;
@@ -96,9 +98,12 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
             break;
         }
         pos += sz;
-        drain(2);
+        drain(4);
     }
-    if (rc != -1) drain(0);
+    if (rc != -1) {
+        av1b200::decoderDrain(dec);
+        drain(0);
+    }
     if (out_bytes) *out_bytes = out;
     if (n_frames) *n_frames = frames;
     if (luma_pixels) *luma_pixels = pixels;

@@ -12,8 +12,11 @@
 #include "decoder_impl.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <thread>
 
 using namespace Yami;
 
@@ -89,7 +92,7 @@ struct Decoder::Impl {
         std::shared_ptr<YuvFrame> frame;
         uint64_t fence;
     };
-    std::deque<Pending> output;
+    std::deque<Pending> output;   // guarded by mu when the emit thread runs
     int frame_w[32], frame_h[32]; // visible size of each device frame id
     av1b200::DecoderOptions opt;
     std::string error;
@@ -109,10 +112,9 @@ struct Decoder::Impl {
         return false;
     }
 
-    bool ensureCtx()
+    bool ensureCtx(const SequenceHeader& s)
     {
         if (ctx) return true;
-        const SequenceHeader& s = *parser->m_sequence;
         const int mw = s.max_frame_width_minus_1 + 1, mh = s.max_frame_height_minus_1 + 1;
         if (s.BitDepth != 8 || !s.subsampling_x || !s.subsampling_y || s.mono_chrome) return fail("only 8-bit 4:2:0 streams are supported (same envelope as the reference)");
         if (av1b_ctx_create(&ctx, opt.device, mw, mh, nullptr) != AV1B_OK) return fail("av1b_ctx_create");
@@ -129,21 +131,24 @@ struct Decoder::Impl {
         if (av1b_frame_download(ctx, fid, dst, st, w, h) != AV1B_OK) return fail("av1b_frame_download");
         uint64_t fence = 0;
         if (av1b_fence_record(ctx, &fence) != AV1B_OK) return fail("av1b_fence_record");
-        output.push_back(Pending{ hf, fence });
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            output.push_back(Pending{ hf, fence });
+        }
         return true;
     }
 
-    bool decodeFrame(TileGroup& ts)
+    // ---- device side of one frame: serialise the parsed tree and hand it to the engine
+    bool submitFrame(const FramePtr& fr, TileGroup& ts, const std::shared_ptr<const SequenceHeader>& seq)
     {
-        FrameHeader& h = *frame;
-        if (!ensureCtx()) return false;
+        FrameHeader& h = *fr;
+        if (!ensureCtx(*seq)) return false;
         const double t0 = now();
-        emitter.begin(h, *parser->m_sequence);
+        emitter.begin(h, *seq);
         for (auto& t : ts) {
             emitter.emitTile(*t);
             t->m_sbs.clear(); // the block tree is no longer needed (Tile::decode pops as it goes)
         }
-        for (auto& t : ts) t->frame_end_update_cdf();
         emitter.finish();
         const double t1 = now();
         t_emit += t1 - t0;
@@ -158,23 +163,124 @@ struct Decoder::Impl {
         frame_h[fid] = h.FrameHeight;
         if (h.show_frame && !queueOutput(fid)) return false;
         t_submit += now() - t1;
+        return true;
+    }
+
+    bool submitShowExisting(int slotIdx, uint32_t refresh)
+    {
+        if (!ctx) return fail("show_existing_frame before any frame");
+        int fid = -1;
+        if (av1b_show_existing(ctx, slotIdx, refresh, &fid) != AV1B_OK) return fail("av1b_show_existing");
+        if (opt.sink) opt.sink(opt.sink_user, nullptr, (size_t)slotIdx, refresh, 1);
+        return queueOutput(fid);
+    }
+
+    // ---- optional emit thread: frame N is serialised + submitted while frame N+1 is parsed.
+    // Parsing N+1 needs only host state of N (CDFs, motion vectors, reference bookkeeping), which
+    // the parse thread finishes itself; the emit thread reads N's block tree and mode-info only.
+    struct Job {
+        FramePtr frame;
+        TileGroup tiles;
+        std::shared_ptr<const SequenceHeader> seq;
+        int showSlot = -1;
+        uint32_t refresh = 0;
+    };
+    bool async = false;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> jobs;
+    bool busy = false, stopping = false, failed = false;
+
+    void workerLoop()
+    {
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stopping || !jobs.empty(); });
+                if (jobs.empty()) return;
+                job = std::move(jobs.front());
+                jobs.pop_front();
+                busy = true;
+            }
+            const bool ok = job.showSlot >= 0 ? submitShowExisting(job.showSlot, job.refresh) : submitFrame(job.frame, job.tiles, job.seq);
+            job = Job();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                busy = false;
+                if (!ok) failed = true;
+            }
+            cv.notify_all();
+        }
+    }
+
+    bool post(Job&& job)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (!worker.joinable()) worker = std::thread([this] { workerLoop(); });
+        cv.wait(lk, [&] { return jobs.size() < 2; }); // bounded look-ahead
+        if (failed) return false;
+        jobs.push_back(std::move(job));
+        lk.unlock();
+        cv.notify_all();
+        return true;
+    }
+
+    void drainWorker()
+    {
+        if (!async) return;
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return jobs.empty() && !busy; });
+    }
+
+    void stopWorker()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stopping = true;
+        }
+        cv.notify_all();
+        if (worker.joinable()) worker.join();
+    }
+
+    bool decodeFrame(TileGroup& ts)
+    {
+        FrameHeader& h = *frame;
+        std::shared_ptr<const SequenceHeader> seq = parser->m_sequence;
+        bool ok;
+        if (async) {
+            Job job;
+            job.frame = frame;
+            job.tiles = ts;
+            job.seq = seq;
+            ok = post(std::move(job));
+        } else {
+            ok = submitFrame(frame, ts, seq);
+        }
+        // host-only state the next parse depends on (Av1Decoder.cpp:139,190; Parser.cpp:1784)
+        for (auto& t : ts) t->frame_end_update_cdf();
         h.motionVectorStorage();
         parser->finishFrame();
-        return true;
+        return ok;
     }
 
     bool showExisting()
     {
         FrameHeader& h = *frame;
-        if (!ctx) return fail("show_existing_frame before any frame");
-        int fid = -1;
-        if (av1b_show_existing(ctx, h.frame_to_show_map_idx, h.refresh_frame_flags, &fid) != AV1B_OK) return fail("av1b_show_existing");
-        if (opt.sink) opt.sink(opt.sink_user, nullptr, (size_t)h.frame_to_show_map_idx, h.refresh_frame_flags, 1);
-        if (!queueOutput(fid)) return false;
+        bool ok;
+        if (async) {
+            Job job;
+            job.showSlot = h.frame_to_show_map_idx;
+            job.refresh = h.refresh_frame_flags;
+            ok = post(std::move(job));
+        } else {
+            ok = submitShowExisting(h.frame_to_show_map_idx, h.refresh_frame_flags);
+        }
         h.referenceFrameLoading();
         h.motionVectorStorage();
         parser->finishFrame();
-        return true;
+        return ok;
     }
 };
 
@@ -188,6 +294,7 @@ Decoder::Decoder()
 
 Decoder::~Decoder()
 {
+    m_impl->stopWorker();
     if (m_impl->timing)
         fprintf(stderr, "av1b200 timing: parse %.3fs emit %.3fs submit %.3fs wait %.3fs\n", m_impl->t_parse, m_impl->t_emit, m_impl->t_submit, m_impl->t_wait);
     if (m_impl->ctx) {
@@ -251,9 +358,14 @@ bool Decoder::decode(uint8_t* data, size_t size)
 std::shared_ptr<YuvFrame> Decoder::getOutput()
 {
     Impl& d = *m_impl;
-    if (d.output.empty()) return nullptr;
-    Impl::Pending p = d.output.front();
-    d.output.pop_front();
+    d.drainWorker(); // reference semantics: every frame of the units decoded so far is available
+    Impl::Pending p;
+    {
+        std::lock_guard<std::mutex> lk(d.mu);
+        if (d.output.empty()) return nullptr;
+        p = d.output.front();
+        d.output.pop_front();
+    }
     const double tw = Impl::now();
     const int wrc = av1b_fence_wait(d.ctx, p.fence);
     d.t_wait += Impl::now() - tw;
@@ -283,15 +395,25 @@ bool decoderFormat(YamiAv1::Decoder& d, int& w, int& h)
 std::shared_ptr<Yami::YuvFrame> decoderPollOutput(YamiAv1::Decoder& d, size_t keepInFlight)
 {
     auto* i = implOf(d);
-    if (i->output.empty()) return nullptr;
-    auto& p = i->output.front();
-    if (i->output.size() <= keepInFlight && !av1b_fence_done(i->ctx, p.fence)) return nullptr;
-    return d.getOutput();
+    YamiAv1::Decoder::Impl::Pending p;
+    {
+        std::lock_guard<std::mutex> lk(i->mu);
+        if (i->output.empty()) return nullptr;
+        p = i->output.front();
+        if (i->output.size() <= keepInFlight && !av1b_fence_done(i->ctx, p.fence)) return nullptr;
+        i->output.pop_front();
+    }
+    if (av1b_fence_wait(i->ctx, p.fence) != AV1B_OK) return nullptr;
+    return p.frame;
 }
+void decoderSetAsync(YamiAv1::Decoder& d, bool on) { implOf(d)->async = on; }
+void decoderDrain(YamiAv1::Decoder& d) { implOf(d)->drainWorker(); }
 void decoderFlush(YamiAv1::Decoder& d)
 {
     auto* i = implOf(d);
+    i->drainWorker();
     if (i->ctx) av1b_sync(i->ctx);
+    std::lock_guard<std::mutex> lk(i->mu);
     i->output.clear();
 }
 }  // namespace av1b200

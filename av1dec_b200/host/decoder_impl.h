@@ -34,5 +34,9 @@ void decoderFlush(YamiAv1::Decoder& d);
 // Next output frame if it is already complete, or if more than keepInFlight frames are queued
 // (then it blocks); null otherwise.  Lets a whole-stream loop parse ahead of the device.
 std::shared_ptr<Yami::YuvFrame> decoderPollOutput(YamiAv1::Decoder& d, size_t keepInFlight);
+// Run command emission + device submission on a second thread, overlapped with the parse of the
+// next frame (used by the whole-stream entry point; getOutput() then waits for that thread).
+void decoderSetAsync(YamiAv1::Decoder& d, bool on);
+void decoderDrain(YamiAv1::Decoder& d);
 
 }  // namespace av1b200
