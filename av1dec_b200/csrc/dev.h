@@ -46,6 +46,15 @@ static inline void av1b_st_release(int* p, int v) { *p = v; }
 static inline void av1b_nanosleep(unsigned) {}
 using std::max;
 using std::min;
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+#define AV1B_NOINLINE
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
 {
     uint32_t lo = std::max(a & 0xFFFFu, b & 0xFFFFu), hi = std::max(a >> 16, b >> 16);
@@ -76,6 +85,7 @@ template <class F> static inline void emu_launch(dim3 grid, F f)
 #include <cuda_runtime.h>
 typedef cudaStream_t av1b_stream_t;
 #define AV1B_UNROLL _Pragma("unroll")
+#define AV1B_NOINLINE __noinline__
 #define AV1B_LAUNCH(kern, grid, block, stream, ...) kern<<<dim3 grid, dim3 block, 0, stream>>>(__VA_ARGS__)
 #define AV1T_CONST static __device__ const
 static __device__ __forceinline__ int av1b_ld_acquire(const int* p)

@@ -247,7 +247,7 @@ enum {
     CDEF_LARGE = 0x4000,
     CY_PITCH = 72,  // halfwords per luma tile row (36 words: conflict-free for 8 rows x 4 words)
     CY_ROWS = 68,
-    CC_PITCH = 48,  // halfwords per chroma tile row
+    CC_PITCH = 40,  // halfwords per chroma tile row
     CC_ROWS = 36,
 };
 
@@ -320,17 +320,9 @@ AV1B_DEV int cdef_cost_dyn(int d, const uint16_t* blk)
     }
 }
 
-// Aligned 32-bit load of the sample pair starting at halfword index `idx` (any parity): even
-// indices come from the tile, odd ones from the copy shifted by one sample.
-AV1B_DEV uint32_t cdef_pair(const uint16_t* a, const uint16_t* b, int idx)
-{
-    const uint16_t* base = (idx & 1) ? (b + idx - 1) : (a + idx);
-    return *(const uint32_t*)base;
-}
-
 // One constrained tap on two samples at once.  x2/p2: centre / tap sample pairs (16x2).
-AV1B_DEV void cdef_tap(uint32_t p2, uint32_t x2, uint32_t thr2, int adj, uint32_t amask, uint32_t w, uint32_t& T, uint32_t& P,
-    uint32_t& mx, uint32_t& mn)
+AV1B_DEV void cdef_tap(uint32_t p2, uint32_t x2, uint32_t thr2, int adj, uint32_t amask, uint32_t w, uint32_t emask, uint32_t& T,
+    uint32_t& P, uint32_t& mx, uint32_t& mn)
 {
     const uint32_t hi = __vmaxu2(p2, x2), lo = __vminu2(p2, x2);
     const uint32_t a = hi - lo;                       // |p - x| per half
@@ -340,64 +332,102 @@ AV1B_DEV void cdef_tap(uint32_t p2, uint32_t x2, uint32_t thr2, int adj, uint32_
     const uint32_t cp = __vminu2(c, hi - x2);         // ... of the positive differences only
     T += w * c;
     P += w * cp;
-    mx = __vmaxu2(mx, p2 & 0x00FF00FFu);              // CDEF_LARGE & 0xFF == 0: unavailable never wins
+    // CDEF_LARGE & 0xFF == 0: an unavailable sample never wins the max
+    mx = __vmaxu2(mx, p2 & emask);
     mn = __vminu2(mn, lo);
 }
 
-// Filter the sample pair at halfword index `ctr` of tile (a, b).  Returns the two output bytes.
-AV1B_DEV uint32_t cdef_filter_pair(const uint16_t* a, const uint16_t* b, int ctr, int pitch, int pri, int sec, int adjp, int adjs,
-    int dir)
+// Filter the sample pair at (even) halfword index `ctr`.  `offs` holds the twelve tap offsets
+// of the block (halfwords relative to the pair; already redirected into the shifted tile copy
+// for odd displacements, so every load is an aligned 32-bit LDS):
+//   [0..3] primary k=0 +/-, k=1 +/-   [4..7] secondary (dir+2) k=0 +/-, k=1 +/-   [8..11] (dir-2)
+// Returns the two output bytes.  (reference cdefFilter, Cdef.cpp:158-198)
+AV1B_DEV uint32_t cdef_filter_pair(const uint16_t* tile, int ctr, const int* offs, int pri, int sec, int adjp, int adjs)
 {
-    const uint32_t x2 = *(const uint32_t*)(a + ctr);
+    const uint16_t* q = tile + ctr;
+    const uint32_t x2 = *(const uint32_t*)q;
     uint32_t T = 0, P = 0, mx = x2, mn = x2;
     const uint32_t pri2 = (uint32_t)pri * 0x00010001u, sec2 = (uint32_t)sec * 0x00010001u;
     const uint32_t maskp = (0xFFFFu >> adjp) * 0x00010001u, masks = (0xFFFFu >> adjs) * 0x00010001u;
+    const uint32_t wp0 = (pri & 1) ? 3u : 4u, wp1 = (pri & 1) ? 3u : 2u;
+    const uint32_t emask = 0x00FF00FFu;
     AV1B_UNROLL
-    for (int k = 0; k < 2; k++) {
-        const uint32_t wp = (pri & 1) ? 3u : (k ? 2u : 4u);
-        const uint32_t ws = k ? 1u : 2u;
-        {
-            const int o = k_cdef_directions[dir][k][0] * pitch + k_cdef_directions[dir][k][1];
-            cdef_tap(cdef_pair(a, b, ctr + o), x2, pri2, adjp, maskp, wp, T, P, mx, mn);
-            cdef_tap(cdef_pair(a, b, ctr - o), x2, pri2, adjp, maskp, wp, T, P, mx, mn);
-        }
-        AV1B_UNROLL
-        for (int off = -2; off <= 2; off += 4) {
-            const int d2 = (dir + off) & 7;
-            const int o = k_cdef_directions[d2][k][0] * pitch + k_cdef_directions[d2][k][1];
-            cdef_tap(cdef_pair(a, b, ctr + o), x2, sec2, adjs, masks, ws, T, P, mx, mn);
-            cdef_tap(cdef_pair(a, b, ctr - o), x2, sec2, adjs, masks, ws, T, P, mx, mn);
-        }
-    }
-    uint32_t out = 0;
+    for (int k = 0; k < 4; k++)
+        cdef_tap(*(const uint32_t*)(q + offs[k]), x2, pri2, adjp, maskp, k < 2 ? wp0 : wp1, emask, T, P, mx, mn);
     AV1B_UNROLL
-    for (int h = 0; h < 2; h++) {
-        const int sh = 16 * h;
-        const int sum = 2 * (int)((P >> sh) & 0xFFFF) - (int)((T >> sh) & 0xFFFF);
-        const int x = (x2 >> sh) & 0xFFFF;
-        const int y = clip3((int)((mn >> sh) & 0xFFFF), (int)((mx >> sh) & 0xFFFF), x + ((8 + sum - (sum < 0)) >> 4));
-        out |= (uint32_t)y << (8 * h);
-    }
-    return out;
+    for (int k = 4; k < 12; k++)
+        cdef_tap(*(const uint32_t*)(q + offs[k]), x2, sec2, adjs, masks, (k & 2) ? 1u : 2u, emask, T, P, mx, mn);
+    // y = clip3(min, max, x + sign(sum) * ((|sum| + 8) >> 4)), sum = P - N, both halves at once
+    // ((8 + sum - (sum < 0)) >> 4 rounds half away from zero)
+    const uint32_t N = T - P;
+    const uint32_t big = __vmaxu2(P, N);
+    const uint32_t mpos = (((big - N) + 0x00080008u) >> 4) & 0x0FFF0FFFu;
+    const uint32_t mneg = (((big - P) + 0x00080008u) >> 4) & 0x0FFF0FFFu;
+    uint32_t y = __vminu2(x2 + mpos, mx);
+    y = __vmaxu2(y, mneg + mn) - mneg;
+    return (y & 0xFFu) | ((y >> 8) & 0xFF00u);
 }
 
-// Stage rows [y0-2, y0-2+rows) x columns [x0-4, x0-4+4*words) of a plane into the 16-bit tiles.
+// The twelve redirected tap offsets for direction `dir` (see cdef_filter_pair).  `copy` is the
+// halfword distance from the tile to its shifted copy.
+AV1B_DEV void cdef_offsets(int dir, int pitch, int copy, int* offs)
+{
+    AV1B_UNROLL
+    for (int g = 0; g < 3; g++) {
+        const int d = g == 0 ? dir : (g == 1 ? ((dir + 2) & 7) : ((dir + 6) & 7));
+        AV1B_UNROLL
+        for (int k = 0; k < 2; k++) {
+            const int o = k_cdef_directions[d][k][0] * pitch + k_cdef_directions[d][k][1];
+            const int redirect = (o & 1) ? copy - 1 : 0;
+            offs[g * 4 + k * 2] = o + redirect;
+            offs[g * 4 + k * 2 + 1] = -o + redirect;
+        }
+    }
+}
+
+// Stage rows [y0-2, y0-2+rows) x tile columns [0, 4*words-2) of a plane into the 16-bit tiles
+// (tile column c <-> frame column x0 - 2 + c).  Each work item converts four samples from two
+// aligned 32-bit loads into two words of the tile and two words of the shifted copy.
+// INTERIOR: the whole staged area lies inside the MI-aligned frame (no availability tests).
+template <bool INTERIOR>
 AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int pw, int ph, int rows, int words, int pitch, uint16_t* ta,
     uint16_t* tb, int tid, int nt)
 {
+    // item (r, wi): frame columns xb = x0 - 2 + 4*wi .. xb+3 (+ xb+4 for the shifted copy); x0 - 2 is
+    // 2 (mod 4), so the samples straddle two aligned words
+    const unsigned magic = (unsigned)((0x100000000ull + words - 1) / words);
     for (int e = tid; e < rows * words; e += nt) {
-        const int r = e / words, wi = e - r * words;
-        const int y = y0 - 2 + r, xb = x0 - 4 + wi * 4;
-        const uint32_t v = __ldg((const uint32_t*)(src.p + (ptrdiff_t)y * src.stride + xb));
-        const bool yok = y >= 0 && y < ph;
-        AV1B_UNROLL
-        for (int k = 0; k < 4; k++) {
-            const int x = xb + k;
-            const int c = wi * 4 + k - 2; // tile column of this sample
-            const uint16_t px = (yok && x >= 0 && x < pw) ? (uint16_t)((v >> (8 * k)) & 0xFF) : (uint16_t)CDEF_LARGE;
-            if (c >= 0) ta[r * pitch + c] = px;
-            if (c >= 1) tb[r * pitch + c - 1] = px;
+        const int r = (int)__umulhi((unsigned)e, magic), wi = e - r * words;
+        const int y = y0 - 2 + r, xa = x0 - 4 + wi * 4; // aligned word holding columns xa..xa+3
+        const uint8_t* rowp = src.p + (ptrdiff_t)y * src.stride + xa;
+        uint32_t lo = __ldg((const uint32_t*)rowp), hi = __ldg((const uint32_t*)rowp + 1);
+        // samples s0..s4 = frame columns xa+2 .. xa+6
+        uint32_t s01, s23, s12, s34;
+        if (INTERIOR) {
+            s01 = __byte_perm(lo, 0, 0x4342); // (lo.b2, 0, lo.b3, 0)
+            s23 = __byte_perm(hi, 0, 0x4140); // (hi.b0, 0, hi.b1, 0)
+            s12 = (lo >> 24) | ((hi & 0xFFu) << 16); // (lo.b3, 0, hi.b0, 0)
+            s34 = __byte_perm(hi, 0, 0x4241); // (hi.b1, 0, hi.b2, 0)
+        } else {
+            const bool yok = y >= 0 && y < ph;
+            uint32_t v[5];
+            AV1B_UNROLL
+            for (int k = 0; k < 5; k++) {
+                const int x = xa + 2 + k;
+                const uint32_t byte = k < 2 ? ((lo >> (16 + 8 * k)) & 0xFF) : ((hi >> (8 * (k - 2))) & 0xFF);
+                v[k] = (yok && x >= 0 && x < pw) ? byte : (uint32_t)CDEF_LARGE;
+            }
+            s01 = v[0] | (v[1] << 16);
+            s23 = v[2] | (v[3] << 16);
+            s12 = v[1] | (v[2] << 16);
+            s34 = v[3] | (v[4] << 16);
         }
+        uint32_t* da = (uint32_t*)(ta + r * pitch + wi * 4);
+        uint32_t* db = (uint32_t*)(tb + r * pitch + wi * 4);
+        da[0] = s01;
+        da[1] = s23;
+        db[0] = s12;
+        db[1] = s34;
     }
 }
 
@@ -412,10 +442,17 @@ __global__ void __launch_bounds__(256) cdef_kernel(PostCtx c)
     const int c8 = hdr->mi_cols >> 1, r8 = hdr->mi_rows >> 1; // 8x8 blocks in the frame
     const int fbx = blockIdx.x * 8, fby = blockIdx.y * 8;      // first 8x8 block of this CTA
     const int pw = hdr->mi_cols * 4, ph = hdr->mi_rows * 4;
-    // ---- 1. stage
-    cdef_stage(c.src.pl[0], fbx * 8, fby * 8, pw, ph, CY_ROWS, 18, CY_PITCH, S.ya, S.yb, tid, nt);
-    cdef_stage(c.src.pl[1], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 10, CC_PITCH, S.ca[0], S.cb[0], tid, nt);
-    cdef_stage(c.src.pl[2], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 10, CC_PITCH, S.ca[1], S.cb[1], tid, nt);
+    // ---- 1. stage (17 / 9 items per row: 68 / 36 tile columns)
+    const bool interior = fbx > 0 && fby > 0 && fbx * 8 + 68 <= pw && fby * 8 + 66 <= ph;
+    if (interior) {
+        cdef_stage<true>(c.src.pl[0], fbx * 8, fby * 8, pw, ph, CY_ROWS, 17, CY_PITCH, S.ya, S.yb, tid, nt);
+        cdef_stage<true>(c.src.pl[1], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 9, CC_PITCH, S.ca[0], S.cb[0], tid, nt);
+        cdef_stage<true>(c.src.pl[2], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 9, CC_PITCH, S.ca[1], S.cb[1], tid, nt);
+    } else {
+        cdef_stage<false>(c.src.pl[0], fbx * 8, fby * 8, pw, ph, CY_ROWS, 17, CY_PITCH, S.ya, S.yb, tid, nt);
+        cdef_stage<false>(c.src.pl[1], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 9, CC_PITCH, S.ca[0], S.cb[0], tid, nt);
+        cdef_stage<false>(c.src.pl[2], fbx * 4, fby * 4, pw >> 1, ph >> 1, CC_ROWS, 9, CC_PITCH, S.ca[1], S.cb[1], tid, nt);
+    }
     for (int e = tid; e < 64; e += nt) {
         const int by = fby + (e >> 3), bx = fbx + (e & 7);
         S.blk[e].idx = (by < r8 && bx < c8) ? cdef8[by * c8 + bx] : 0xFF;
@@ -423,7 +460,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(PostCtx c)
     __syncthreads();
     // ---- 2. direction search
     for (int e = tid; e < 512; e += nt) {
-        const int b = e >> 3, d = e & 7;
+        const int b = e & 63, d = e >> 6; // 64 consecutive threads share a direction: no divergence inside a warp
         if (S.blk[b].idx == 0xFF) continue;
         S.cost[b][d] = cdef_cost_dyn(d, S.ya + ((b >> 3) * 8 + 2) * CY_PITCH + (b & 7) * 8 + 2);
     }
@@ -458,42 +495,55 @@ __global__ void __launch_bounds__(256) cdef_kernel(PostCtx c)
         B.dir[1] = (uint8_t)(pri_uv == 0 ? 0 : k_cdef_uv_dir[1][1][dir]);
     }
     __syncthreads();
-    // ---- 3. filter.  Work item = (plane group, block): 64 luma blocks (32 pairs each) then
-    //         2 x 64 chroma blocks (8 pairs each, four blocks per warp pass).
+    // ---- 3. filter.  Luma: 16 lanes per 8x8 block (two sample pairs each); chroma: 8 lanes per
+    //         4x4 block.  Tap offsets are computed once per lane and block.
     const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
     const int lane = tid % nl, warp = tid / nl;
-    for (int b = warp; b < 64; b += nw) {
-        const CdefBlk B = S.blk[b];
-        const int bx = (fbx + (b & 7)) * 8, by = (fby + (b >> 3)) * 8;
-        if (bx >= pw || by >= ph) continue;
-        uint8_t* dst = c.cdef.pl[0].p + (size_t)by * c.cdef.pl[0].stride + bx;
-        const bool active = B.idx != 0xFF && (B.pri[0] | B.sec[0]);
-        for (int pr = lane; pr < 32; pr += nl) {
-            const int r = pr >> 2, cpair = pr & 3;
-            const int ctr = ((b >> 3) * 8 + r + 2) * CY_PITCH + (b & 7) * 8 + cpair * 2 + 2;
-            uint32_t out;
-            if (active) out = cdef_filter_pair(S.ya, S.yb, ctr, CY_PITCH, B.pri[0], B.sec[0], B.adjp[0], B.adjs[0], B.dir[0]);
-            else out = (uint32_t)S.ya[ctr] | ((uint32_t)S.ya[ctr + 1] << 8);
-            *(uint16_t*)(dst + (size_t)r * c.cdef.pl[0].stride + cpair * 2) = (uint16_t)out;
+    {
+        const int sub = min(16, nl), per = max(1, nl / sub); // lanes per block, blocks per warp pass
+        const int sl = lane % sub, sg = lane / sub;
+        const int copy = (int)(S.yb - S.ya);
+        for (int b = warp * per + sg; b < 64; b += nw * per) {
+            const CdefBlk B = S.blk[b];
+            const int bx = (fbx + (b & 7)) * 8, by = (fby + (b >> 3)) * 8;
+            if (bx >= pw || by >= ph) continue;
+            uint8_t* dst = c.cdef.pl[0].p + (size_t)by * c.cdef.pl[0].stride + bx;
+            const bool active = B.idx != 0xFF && (B.pri[0] | B.sec[0]);
+            int offs[12];
+            if (active) cdef_offsets(B.dir[0], CY_PITCH, copy, offs);
+            for (int pr = sl; pr < 32; pr += sub) {
+                const int r = pr >> 2, cpair = pr & 3;
+                const int ctr = ((b >> 3) * 8 + r + 2) * CY_PITCH + (b & 7) * 8 + cpair * 2 + 2;
+                uint32_t out;
+                if (active) out = cdef_filter_pair(S.ya, ctr, offs, B.pri[0], B.sec[0], B.adjp[0], B.adjs[0]);
+                else out = (uint32_t)S.ya[ctr] | ((uint32_t)S.ya[ctr + 1] << 8);
+                *(uint16_t*)(dst + (size_t)r * c.cdef.pl[0].stride + cpair * 2) = (uint16_t)out;
+            }
         }
     }
-    const int cpw = pw >> 1, cph = ph >> 1;
-    for (int item = warp; item < 32; item += nw) { // (plane, group of 4 blocks)
-        const int plane = 1 + (item >> 4), grp = item & 15;
-        const uint16_t* ta = S.ca[plane - 1];
-        const uint16_t* tb = S.cb[plane - 1];
-        const PlaneView dv = c.cdef.pl[plane];
-        for (int u = lane; u < 32; u += nl) {
-            const int b = grp * 4 + (u >> 3), pr = u & 7;
+    {
+        const int cpw = pw >> 1, cph = ph >> 1;
+        const int sub = min(8, nl), per = max(1, nl / sub);
+        const int sl = lane % sub, sg = lane / sub;
+        for (int it = warp * per + sg; it < 128; it += nw * per) {
+            const int plane = 1 + (it >> 6), b = it & 63;
             const CdefBlk B = S.blk[b];
             const int bx = (fbx + (b & 7)) * 4, by = (fby + (b >> 3)) * 4;
             if (bx >= cpw || by >= cph) continue;
-            const int r = pr >> 1, cpair = pr & 1;
-            const int ctr = ((b >> 3) * 4 + r + 2) * CC_PITCH + (b & 7) * 4 + cpair * 2 + 2;
-            uint32_t out;
-            if (B.idx != 0xFF && (B.pri[1] | B.sec[1])) out = cdef_filter_pair(ta, tb, ctr, CC_PITCH, B.pri[1], B.sec[1], B.adjp[1], B.adjs[1], B.dir[1]);
-            else out = (uint32_t)ta[ctr] | ((uint32_t)ta[ctr + 1] << 8);
-            *(uint16_t*)(dv.p + (size_t)(by + r) * dv.stride + bx + cpair * 2) = (uint16_t)out;
+            const uint16_t* ta = S.ca[plane - 1];
+            const int copy = (int)(S.cb[plane - 1] - ta);
+            const PlaneView dv = c.cdef.pl[plane];
+            const bool active = B.idx != 0xFF && (B.pri[1] | B.sec[1]);
+            int offs[12];
+            if (active) cdef_offsets(B.dir[1], CC_PITCH, copy, offs);
+            for (int pr = sl; pr < 8; pr += sub) {
+                const int r = pr >> 1, cpair = pr & 1;
+                const int ctr = ((b >> 3) * 4 + r + 2) * CC_PITCH + (b & 7) * 4 + cpair * 2 + 2;
+                uint32_t out;
+                if (active) out = cdef_filter_pair(ta, ctr, offs, B.pri[1], B.sec[1], B.adjp[1], B.adjs[1]);
+                else out = (uint32_t)ta[ctr] | ((uint32_t)ta[ctr + 1] << 8);
+                *(uint16_t*)(dv.p + (size_t)(by + r) * dv.stride + bx + cpair * 2) = (uint16_t)out;
+            }
         }
     }
 }
@@ -535,8 +585,22 @@ AV1B_DEV int lr_source_row(int y, int start, int end, int ph, bool* from_deblock
     return clip3(0, ph - 1, y);
 }
 
+// 2-D decomposition of the CTA's threads: tx walks columns (up to 32 wide), ty walks rows.
+struct Lane2D {
+    int tx, ty, ntx, nty;
+};
+AV1B_DEV Lane2D lane2d(int tid, int nt)
+{
+    Lane2D l;
+    l.ntx = min(nt, 32);
+    l.nty = max(1, nt / l.ntx);
+    l.tx = tid % l.ntx;
+    l.ty = tid / l.ntx;
+    return l;
+}
+
 // One self-guided pass.  Source samples sit at S.src[(i + 3) * LR_SW + (j + 4)] for tile sample (i, j).
-AV1B_DEV void sgr_pass(LrShared& S, int w, int h, int set, int pass, int r, int tid, int nt)
+AV1B_DEV void sgr_pass(LrShared& S, int w, int h, int set, int pass, int r, const Lane2D& L, int nt)
 {
     const int eps = k_sgr_params[set][pass * 2 + 1];
     const int n = (2 * r + 1) * (2 * r + 1);
@@ -546,63 +610,74 @@ AV1B_DEV void sgr_pass(LrShared& S, int w, int h, int set, int pass, int r, int 
     const int aw = w + 2;
     // horizontal box sums for rows -1-r .. h+r, columns -1 .. w
     const int hr0 = -1 - r, hrows = h + 2 + 2 * r;
-    for (int e = tid; e < hrows * aw; e += nt) {
-        const int rr = e / aw, j = e - rr * aw - 1;
-        const uint8_t* p = S.src + (hr0 + rr + 3) * LR_SW + (j + 4);
-        int s1 = 0, s2 = 0;
-        for (int dx = -r; dx <= r; dx++) {
-            const int v = p[dx];
-            s1 += v;
-            s2 += v * v;
+    const unsigned aw_magic = (unsigned)((0x100000000ull + aw - 1) / aw); // e / aw == umulhi(e, magic) for e < 2^16
+    for (int e = L.tx + L.ty * L.ntx; e < hrows * aw; e += L.ntx * L.nty) {
+        {
+            const int rr = (int)__umulhi((unsigned)e, aw_magic), jj = e - rr * aw; // jj = j + 1
+            const uint8_t* p = S.src + (hr0 + rr + 3) * LR_SW + (jj + 3);
+            int s1, s2;
+            if (r == 2) {
+                const int v0 = p[-2], v1 = p[-1], v2 = p[0], v3 = p[1], v4 = p[2];
+                s1 = v0 + v1 + v2 + v3 + v4;
+                s2 = v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3 + v4 * v4;
+            } else {
+                const int v1 = p[-1], v2 = p[0], v3 = p[1];
+                s1 = v1 + v2 + v3;
+                s2 = v1 * v1 + v2 * v2 + v3 * v3;
+            }
+            S.box.h1[rr * LR_AW + jj] = (uint16_t)s1;
+            S.box.h2[rr * LR_AW + jj] = (uint32_t)s2;
         }
-        S.box.h1[rr * LR_AW + j + 1] = (uint16_t)s1;
-        S.box.h2[rr * LR_AW + j + 1] = (uint32_t)s2;
     }
     __syncthreads();
     // vertical sums -> a2 / b2.  Pass 0 only ever reads A/B on rows whose index is odd.
-    const int rstep = pass == 0 ? 2 : 1;
-    const int nrows = pass == 0 ? (h + 2 + 1) / 2 : h + 2;
-    for (int e = tid; e < nrows * aw; e += nt) {
-        const int ri = e / aw, jj = e - ri * aw; // jj = j + 1
-        const int i = pass == 0 ? (2 * ri - 1) : (ri - 1);
-        if (i > h) continue;
-        int a = 0, b = 0;
-        const int base = (i - r - hr0) * LR_AW + jj;
-        for (int dy = 0; dy <= 2 * r; dy++) {
-            b += S.box.h1[base + dy * LR_AW];
-            a += S.box.h2[base + dy * LR_AW];
+    const int istep = pass == 0 ? 2 : 1;
+    const int nrows = pass == 0 ? (h + 3) / 2 : h + 2;
+    for (int e = L.tx + L.ty * L.ntx; e < nrows * aw; e += L.ntx * L.nty) {
+        {
+            const int ri = (int)__umulhi((unsigned)e, aw_magic), jj = e - ri * aw;
+            const int i = -1 + ri * istep;
+            const int base = (i - r - hr0) * LR_AW + jj;
+            int a, b;
+            if (r == 2) {
+                b = S.box.h1[base] + S.box.h1[base + LR_AW] + S.box.h1[base + 2 * LR_AW] + S.box.h1[base + 3 * LR_AW] + S.box.h1[base + 4 * LR_AW];
+                a = S.box.h2[base] + S.box.h2[base + LR_AW] + S.box.h2[base + 2 * LR_AW] + S.box.h2[base + 3 * LR_AW] + S.box.h2[base + 4 * LR_AW];
+            } else {
+                b = S.box.h1[base] + S.box.h1[base + LR_AW] + S.box.h1[base + 2 * LR_AW];
+                a = S.box.h2[base] + S.box.h2[base + LR_AW] + S.box.h2[base + 2 * LR_AW];
+            }
+            const unsigned p = (unsigned)max(0, a * n - b * b);
+            const unsigned z = (p * s + (1u << 19)) >> 20;
+            const int a2 = z >= 255 ? 256 : (z == 0 ? 1 : S.xdiv[z]);
+            const int b2 = (256 - a2) * b * one_over_n;
+            S.a[(i + 1) * LR_AW + jj] = (uint16_t)a2;
+            S.b[(i + 1) * LR_AW + jj] = (uint32_t)((b2 + (1 << 11)) >> 12);
         }
-        const unsigned p = (unsigned)max(0, a * n - b * b);
-        const unsigned z = (p * s + (1u << 19)) >> 20;
-        const int a2 = z >= 255 ? 256 : (z == 0 ? 1 : S.xdiv[z]);
-        const int b2 = (256 - a2) * b * one_over_n;
-        S.a[(i + 1) * LR_AW + jj] = (uint16_t)a2;
-        S.b[(i + 1) * LR_AW + jj] = (uint32_t)((b2 + (1 << 11)) >> 12);
-        (void)rstep;
     }
     __syncthreads();
-    for (int e = tid; e < w * h; e += nt) {
-        const int i = e / w, j = e - i * w;
-        const uint16_t* A = S.a + (i + 1) * LR_AW + (j + 1);
-        const uint32_t* B = S.b + (i + 1) * LR_AW + (j + 1);
-        int a, b, shift;
-        if (pass == 0) {
-            if (i & 1) {
-                a = 6 * A[0] + 5 * (A[-1] + A[1]);
-                b = 6 * (int)B[0] + 5 * (int)(B[-1] + B[1]);
-                shift = 4;
+    for (int i = L.ty; i < h; i += L.nty) {
+        for (int j = L.tx; j < w; j += L.ntx) {
+            const uint16_t* A = S.a + (i + 1) * LR_AW + (j + 1);
+            const uint32_t* B = S.b + (i + 1) * LR_AW + (j + 1);
+            int a, b, shift;
+            if (pass == 0) {
+                if (i & 1) {
+                    a = 6 * A[0] + 5 * (A[-1] + A[1]);
+                    b = 6 * (int)B[0] + 5 * (int)(B[-1] + B[1]);
+                    shift = 4;
+                } else {
+                    a = 6 * (A[-LR_AW] + A[LR_AW]) + 5 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
+                    b = 6 * (int)(B[-LR_AW] + B[LR_AW]) + 5 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
+                    shift = 5;
+                }
             } else {
-                a = 6 * (A[-LR_AW] + A[LR_AW]) + 5 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
-                b = 6 * (int)(B[-LR_AW] + B[LR_AW]) + 5 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
+                a = 4 * (A[0] + A[-1] + A[1] + A[-LR_AW] + A[LR_AW]) + 3 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
+                b = 4 * (int)(B[0] + B[-1] + B[1] + B[-LR_AW] + B[LR_AW]) + 3 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
                 shift = 5;
             }
-        } else {
-            a = 4 * (A[0] + A[-1] + A[1] + A[-LR_AW] + A[LR_AW]) + 3 * (A[-LR_AW - 1] + A[-LR_AW + 1] + A[LR_AW - 1] + A[LR_AW + 1]);
-            b = 4 * (int)(B[0] + B[-1] + B[1] + B[-LR_AW] + B[LR_AW]) + 3 * (int)(B[-LR_AW - 1] + B[-LR_AW + 1] + B[LR_AW - 1] + B[LR_AW + 1]);
-            shift = 5;
+            const int v = a * S.src[(i + 3) * LR_SW + (j + 4)] + b;
+            S.flt[pass][i * LR_TW + j] = (uint16_t)round2(v, 8 + shift - 4);
         }
-        const int v = a * S.src[(i + 3) * LR_SW + (j + 4)] + b;
-        S.flt[pass][i * LR_TW + j] = (uint16_t)round2(v, 8 + shift - 4);
     }
     __syncthreads();
 }
@@ -618,6 +693,7 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
     const int plane = blockIdx.z, sub = plane ? 1 : 0;
     const int pw = (hdr->frame_w + sub) >> sub, ph = (hdr->frame_h + sub) >> sub;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const Lane2D L = lane2d(tid, nt);
     const int x0 = blockIdx.x * LR_TW;
     const int start = (-8 + (int)blockIdx.y * 64) >> sub, end = start + (64 >> sub);
     const int y0 = max(start, 0), y1 = min(end, ph);
@@ -636,34 +712,32 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
     if (type == 0) {
         // RESTORE_NONE: the LR frame is a copy of the CDEF frame.  Word copies, byte tail.
         const int ww = w >> 2;
-        for (int e = tid; e < h * ww; e += nt) {
-            const int i = e / ww, j = e - i * ww;
-            *(uint32_t*)(out.p + (size_t)(y0 + i) * out.stride + x0 + 4 * j) = __ldg((const uint32_t*)(cdef.p + (size_t)(y0 + i) * cdef.stride + x0 + 4 * j));
-        }
-        const int tail = w & 3;
-        for (int e = tid; e < h * tail; e += nt) {
-            const int i = e / tail, j = (w & ~3) + (e - i * tail);
-            out.p[(size_t)(y0 + i) * out.stride + x0 + j] = __ldg(cdef.p + (size_t)(y0 + i) * cdef.stride + x0 + j);
+        for (int i = L.ty; i < h; i += L.nty) {
+            const uint8_t* srow = cdef.p + (size_t)(y0 + i) * cdef.stride + x0;
+            uint8_t* drow = out.p + (size_t)(y0 + i) * out.stride + x0;
+            for (int j = L.tx; j < ww; j += L.ntx) ((uint32_t*)drow)[j] = __ldg((const uint32_t*)srow + j);
+            for (int j = (w & ~3) + L.tx; j < w; j += L.ntx) drow[j] = __ldg(srow + j);
         }
         return;
     }
     // ---- stage source: rows y0-3 .. y0+h+2, columns x0-4 .. x0+35 (10 aligned words per row)
     {
         const bool interior = x0 >= 4 && x0 + 36 <= pw;
-        for (int e = tid; e < (h + 6) * 10; e += nt) {
-            const int r = e / 10, wi = e - r * 10;
+        for (int r = L.ty; r < h + 6; r += L.nty) {
             bool fd;
             const int sy = lr_source_row(y0 - 3 + r, start, end, ph, &fd);
             const uint8_t* rowp = (fd ? deb.p : cdef.p) + (size_t)sy * (fd ? deb.stride : cdef.stride);
-            uint32_t v;
-            if (interior) {
-                v = __ldg((const uint32_t*)(rowp + x0 - 4 + wi * 4));
-            } else {
-                v = 0;
-                AV1B_UNROLL
-                for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rowp + clip3(0, pw - 1, x0 - 4 + wi * 4 + k)) << (8 * k);
+            for (int wi = L.tx; wi < 10; wi += L.ntx) {
+                uint32_t v;
+                if (interior) {
+                    v = __ldg((const uint32_t*)(rowp + x0 - 4 + wi * 4));
+                } else {
+                    v = 0;
+                    AV1B_UNROLL
+                    for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rowp + clip3(0, pw - 1, x0 - 4 + wi * 4 + k)) << (8 * k);
+                }
+                *(uint32_t*)(S.src + r * LR_SW + wi * 4) = v;
             }
-            *(uint32_t*)(S.src + r * LR_SW + wi * 4) = v;
         }
     }
     if (type == 2) {
@@ -671,43 +745,45 @@ __global__ void __launch_bounds__(256) lr_kernel(PostCtx c)
     }
     __syncthreads();
     if (type == 1) {
-        int vf[7], hf[7];
+        int vf[4], hf[4];
         vf[3] = 128;
         hf[3] = 128;
         for (int k = 0; k < 3; k++) {
-            vf[k] = vf[6 - k] = unit.wiener[0][k];
-            hf[k] = hf[6 - k] = unit.wiener[1][k];
+            vf[k] = unit.wiener[0][k];
+            hf[k] = unit.wiener[1][k];
             vf[3] -= 2 * unit.wiener[0][k];
             hf[3] -= 2 * unit.wiener[1][k];
         }
-        for (int e = tid; e < (h + 6) * w; e += nt) {
-            const int r = e / w, cc = e - r * w;
-            const uint8_t* p = S.src + r * LR_SW + cc + 1; // sample (x0 + cc - 3) sits at column cc + 1
-            // symmetric taps: 3 adds + 4 multiplies
-            const int s = hf[0] * (p[0] + p[6]) + hf[1] * (p[1] + p[5]) + hf[2] * (p[2] + p[4]) + hf[3] * p[3];
-            S.wien[r * LR_TW + cc] = (int16_t)clip3(-2048, 6143, (s + 4) >> 3);
+        for (int r = L.ty; r < h + 6; r += L.nty) {
+            for (int cc = L.tx; cc < w; cc += L.ntx) {
+                const uint8_t* p = S.src + r * LR_SW + cc + 1; // sample (x0 + cc - 3) sits at column cc + 1
+                const int s = hf[0] * (p[0] + p[6]) + hf[1] * (p[1] + p[5]) + hf[2] * (p[2] + p[4]) + hf[3] * p[3];
+                S.wien[r * LR_TW + cc] = (int16_t)clip3(-2048, 6143, (s + 4) >> 3);
+            }
         }
         __syncthreads();
-        for (int e = tid; e < w * h; e += nt) {
-            const int r = e / w, cc = e - r * w;
-            const int16_t* q = S.wien + r * LR_TW + cc;
-            const int s = vf[0] * (q[0] + q[6 * LR_TW]) + vf[1] * (q[LR_TW] + q[5 * LR_TW]) + vf[2] * (q[2 * LR_TW] + q[4 * LR_TW])
-                + vf[3] * q[3 * LR_TW];
-            out.p[(size_t)(y0 + r) * out.stride + x0 + cc] = (uint8_t)clip_u8((s + 1024) >> 11);
+        for (int r = L.ty; r < h; r += L.nty) {
+            for (int cc = L.tx; cc < w; cc += L.ntx) {
+                const int16_t* q = S.wien + r * LR_TW + cc;
+                const int s = vf[0] * (q[0] + q[6 * LR_TW]) + vf[1] * (q[LR_TW] + q[5 * LR_TW]) + vf[2] * (q[2 * LR_TW] + q[4 * LR_TW])
+                    + vf[3] * q[3 * LR_TW];
+                out.p[(size_t)(y0 + r) * out.stride + x0 + cc] = (uint8_t)clip_u8((s + 1024) >> 11);
+            }
         }
     } else {
         const int set = unit.sgr_set;
         const int r0 = k_sgr_params[set][0], r1 = k_sgr_params[set][2];
-        if (r0) sgr_pass(S, w, h, set, 0, r0, tid, nt);
-        if (r1) sgr_pass(S, w, h, set, 1, r1, tid, nt);
+        if (r0) sgr_pass(S, w, h, set, 0, r0, L, nt);
+        if (r1) sgr_pass(S, w, h, set, 1, r1, L, nt);
         const int w0 = unit.sgr_xqd[0], w1 = unit.sgr_xqd[1], w2 = 128 - w0 - w1;
-        for (int e = tid; e < w * h; e += nt) {
-            const int i = e / w, j = e - i * w;
-            const int u = S.src[(i + 3) * LR_SW + (j + 4)] << 4;
-            int v = w1 * u;
-            v += w0 * (r0 ? (int)S.flt[0][i * LR_TW + j] : u);
-            v += w2 * (r1 ? (int)S.flt[1][i * LR_TW + j] : u);
-            out.p[(size_t)(y0 + i) * out.stride + x0 + j] = (uint8_t)clip_u8(round2(v, 11));
+        for (int i = L.ty; i < h; i += L.nty) {
+            for (int j = L.tx; j < w; j += L.ntx) {
+                const int u = S.src[(i + 3) * LR_SW + (j + 4)] << 4;
+                int v = w1 * u;
+                v += w0 * (r0 ? (int)S.flt[0][i * LR_TW + j] : u);
+                v += w2 * (r1 ? (int)S.flt[1][i * LR_TW + j] : u);
+                out.p[(size_t)(y0 + i) * out.stride + x0 + j] = (uint8_t)clip_u8(round2(v, 11));
+            }
         }
     }
 }
