@@ -51,8 +51,69 @@ struct ResPlanes {
     int pitch[3];
 };
 
+// Work split of one inverse-transform launch.  The list is sorted by size class c (max(w,h) =
+// 4, 8, 16, >=32); class c packs 32 / G_c transform blocks into a warp (G = 4, 8, 16, 32 lanes
+// per block: one lane per row, then one lane per column).
+struct ItxPlan {
+    uint32_t first[4], count[4]; // list range of each class
+    uint32_t block_begin[5];     // first CTA of each class (CTAs of ITX_WARPS warps)
+};
+
+namespace {
+
+// One transform block handled by the G lanes [lane_in_group = 0..G-1] of a warp.
+AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int16_t* __restrict__ res, const ResPlanes& rp,
+    int16_t* tmp, int tstride, int gl, int G)
+{
+    const int txs = op.tx_size;
+    const int lw = k_tx_wlog2[txs], lh = k_tx_hlog2[txs];
+    const int w = 1 << lw, h = 1 << lh;
+    const int tw = min(w, 32);
+    const bool lossless = op.lossless != 0;
+    const int rk = lossless ? itx::K_WHT : itx::row_kind(op.tx_type);
+    const int ck = lossless ? itx::K_WHT : itx::col_kind(op.tx_type);
+    const bool rect = (lw - lh == 1) || (lh - lw == 1);
+    const int row_shift = lossless ? 0 : k_tx_row_shift[txs];
+    const int col_shift = lossless ? 0 : 4;
+    const int nz_rows = min((int)op.nz_rows, min(h, 32));
+    const int16_t* c = coef + op.coef_off;
+    int16_t* out;
+    int out_stride;
+    if (rp.p[0]) {
+        out = rp.p[op.plane] + (size_t)op.y * rp.pitch[op.plane] + op.x;
+        out_stride = rp.pitch[op.plane];
+    } else {
+        out = res + op.res_off;
+        out_stride = w;
+    }
+    for (int i = gl; i < nz_rows; i += G) {
+        int16_t* trow = tmp + i * tstride;
+        switch (lw) {
+        case 2: itx::row_pass<2>(c + i * tw, tw, trow, rk, rect, row_shift); break;
+        case 3: itx::row_pass<3>(c + i * tw, tw, trow, rk, rect, row_shift); break;
+        case 4: itx::row_pass<4>(c + i * tw, tw, trow, rk, rect, row_shift); break;
+        case 5: itx::row_pass<5>(c + i * tw, tw, trow, rk, rect, row_shift); break;
+        default: itx::row_pass<6>(c + i * tw, tw, trow, rk, rect, row_shift); break;
+        }
+    }
+    __syncwarp();
+    const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
+    for (int j = gl; j < w; j += G) {
+        const int jo = flr ? (w - 1 - j) : j;
+        switch (lh) {
+        case 2: itx::col_pass<2>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
+        case 3: itx::col_pass<3>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
+        case 4: itx::col_pass<4>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
+        case 5: itx::col_pass<5>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
+        default: itx::col_pass<6>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
+        }
+    }
+}
+
+}  // namespace
+
 __global__ void __launch_bounds__(ITX_WARPS * 32)
-    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, int n_list,
+    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, ItxPlan plan,
         const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
 {
     __shared__ int16_t tmp_all[ITX_WARPS][ITX_TMP_ROWS * ITX_TMP_STRIDE];
@@ -60,45 +121,22 @@ __global__ void __launch_bounds__(ITX_WARPS * 32)
     const int nw = max(1u, blockDim.x / 32);
     const int lane = threadIdx.x % nl;
     const int warp = threadIdx.x / nl;
-    int16_t* tmp = tmp_all[warp];
-    for (int t = blockIdx.x * nw + warp; t < n_list; t += gridDim.x * nw) {
-        const Av1bOp op = ops[list[t]];
-        const int txs = op.tx_size;
-        const int lw = k_tx_wlog2[txs], lh = k_tx_hlog2[txs];
-        const int w = 1 << lw, h = 1 << lh;
-        const int tw = min(w, 32);
-        const bool lossless = op.lossless != 0;
-        const int rk = lossless ? itx::K_WHT : itx::row_kind(op.tx_type);
-        const int ck = lossless ? itx::K_WHT : itx::col_kind(op.tx_type);
-        const bool rect = (lw - lh == 1) || (lh - lw == 1);
-        const int row_shift = lossless ? 0 : k_tx_row_shift[txs];
-        const int col_shift = lossless ? 0 : 4;
-        const int nz_rows = min((int)op.nz_rows, min(h, 32));
-        const int16_t* c = coef + op.coef_off;
-        int16_t* out;
-        int out_stride;
-        if (rp.p[0]) {
-            out = rp.p[op.plane] + (size_t)op.y * rp.pitch[op.plane] + op.x;
-            out_stride = rp.pitch[op.plane];
-        } else {
-            out = res + op.res_off;
-            out_stride = w;
-        }
-        switch (lw) {
-        case 2: itx_rows<2>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
-        case 3: itx_rows<3>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
-        case 4: itx_rows<4>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
-        case 5: itx_rows<5>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
-        default: itx_rows<6>(c, tw, nz_rows, tmp, rk, rect, row_shift, lane, nl); break;
-        }
-        __syncwarp();
-        const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
-        switch (lh) {
-        case 2: itx_cols<2>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 3: itx_cols<3>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 4: itx_cols<4>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
-        case 5: itx_cols<5>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
-        default: itx_cols<6>(tmp, nz_rows, out, out_stride, w, fud, flr, ck, col_shift, lane, nl); break;
+    // which size class does this CTA serve?
+    int cls = 0;
+    while (cls < 3 && blockIdx.x >= plan.block_begin[cls + 1]) cls++;
+    const int G = min(4 << cls, nl);          // lanes per transform block
+    const int per = max(1, nl / G);           // transform blocks per warp pass
+    const int tstride = (cls == 3) ? ITX_TMP_STRIDE : ((4 << cls) + 2);
+    const int region = (cls == 3) ? ITX_TMP_ROWS * ITX_TMP_STRIDE : (4 << cls) * ((4 << cls) + 2);
+    const int gl = lane % G, grp = lane / G;
+    int16_t* tmp = tmp_all[warp] + grp * region;
+    const uint32_t n = plan.count[cls];
+    const uint32_t cta = blockIdx.x - plan.block_begin[cls], ncta = plan.block_begin[cls + 1] - plan.block_begin[cls];
+    for (uint32_t t0 = (cta * nw + warp) * per; t0 < n; t0 += ncta * nw * per) {
+        const uint32_t t = t0 + grp;
+        if (t < n) {
+            const Av1bOp op = ops[list[plan.first[cls] + t]];
+            itx_block(op, coef, res, rp, tmp, tstride, gl, G);
         }
         __syncwarp();
     }
@@ -543,14 +581,27 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + h.off_ops);
     const uint32_t* list = (const uint32_t*)(c.cmd + h.off_itx);
     const int16_t* coef = (const int16_t*)(c.cmd + h.off_coef);
-    int grid = (int)((h.n_itx + ITX_WARPS - 1) / ITX_WARPS);
-    if (grid > 148 * 16) grid = 148 * 16;
     ResPlanes rp;
     for (int i = 0; i < 3; i++) {
         rp.p[i] = c.rp[i];
         rp.pitch[i] = c.rpitch[i];
     }
-    AV1B_LAUNCH(itx_kernel, (grid), (ITX_WARPS * 32), st, ops, list, (int)h.n_itx, coef, c.res, rp);
+    ItxPlan plan;
+    uint32_t prev = 0, blocks = 0;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t end = h.itx_class_end[k] > h.n_itx ? h.n_itx : h.itx_class_end[k];
+        plan.first[k] = prev;
+        plan.count[k] = end > prev ? end - prev : 0;
+        prev = end > prev ? end : prev;
+        const uint32_t per_cta = ITX_WARPS * (32 / (4 << k));  // transform blocks per CTA pass
+        uint32_t nb = (plan.count[k] + per_cta - 1) / per_cta;
+        if (nb > 148 * 8) nb = 148 * 8;
+        plan.block_begin[k] = blocks;
+        blocks += nb;
+    }
+    plan.block_begin[4] = blocks;
+    if (!blocks) return;
+    AV1B_LAUNCH(itx_kernel, ((int)blocks), (ITX_WARPS * 32), st, ops, list, plan, coef, c.res, rp);
 }
 
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)

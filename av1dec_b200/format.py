@@ -7,7 +7,7 @@ Sizes are cross-checked against the C structs by tests/test_host.py (av1b_struct
 import ctypes as C
 
 MAGIC = 0x42315641
-VERSION = 2
+VERSION = 3
 
 OP_INTER_RES, OP_INTRA, OP_PALETTE, OP_INTERINTRA, OP_INTRABC = range(5)
 OPF_HAVE_LEFT, OPF_HAVE_ABOVE, OPF_HAVE_ABOVE_RIGHT, OPF_HAVE_BELOW_LEFT = 1, 2, 4, 8
@@ -82,7 +82,7 @@ class FrameHdr(C.Structure):
                 ("ref_slot", C.c_int8 * 8), ("ref_w", C.c_uint16 * 8), ("ref_h", C.c_uint16 * 8),
                 ("gm_params", (C.c_int32 * 6) * 8), ("gm_abgd", (C.c_int16 * 4) * 8), ("gm_warp_ok", C.c_uint8 * 8),
                 ("off_sb", C.c_uint32), ("n_sb", C.c_uint32), ("off_ops", C.c_uint32), ("n_ops", C.c_uint32),
-                ("off_itx", C.c_uint32), ("n_itx", C.c_uint32), ("off_iblk", C.c_uint32), ("n_iblk", C.c_uint32),
+                ("off_itx", C.c_uint32), ("n_itx", C.c_uint32), ("itx_class_end", C.c_uint32 * 4), ("off_iblk", C.c_uint32), ("n_iblk", C.c_uint32),
                 ("off_ipu", C.c_uint32), ("n_ipu", C.c_uint32), ("off_aux", C.c_uint32), ("n_aux", C.c_uint32),
                 ("off_coef", C.c_uint32), ("n_coef", C.c_uint32), ("n_res", C.c_uint32), ("off_pal", C.c_uint32),
                 ("n_pal", C.c_uint32), ("off_lfmi", C.c_uint32), ("off_cdef8", C.c_uint32), ("off_lru", C.c_uint32),
@@ -111,3 +111,20 @@ def build(hdr, sections):
     for o, blob in placed:
         buf[o:o + len(blob)] = blob
     return bytes(buf)
+
+
+TX_MAXDIM = [4, 8, 16, 32, 64, 8, 8, 16, 16, 32, 32, 64, 64, 16, 16, 32, 32, 64, 64]
+
+
+def sort_itx_list(hdr, itx, tx_sizes):
+    """Sort an inverse-transform work list (op indices) by size class and fill hdr.itx_class_end.
+    tx_sizes[i] is the TX_SIZE of op itx[i].  Returns the sorted list (numpy uint32)."""
+    import numpy as np
+    itx = np.asarray(itx, np.uint32)
+    md = np.array(TX_MAXDIM)[np.asarray(tx_sizes, np.int64)] if len(itx) else np.zeros(0, np.int64)
+    cls = np.where(md <= 4, 0, np.where(md <= 8, 1, np.where(md <= 16, 2, 3)))
+    order = np.argsort(cls, kind="stable")
+    ends = np.cumsum(np.bincount(cls, minlength=4)) if len(itx) else np.zeros(4, np.int64)
+    for k in range(4):
+        hdr.itx_class_end[k] = int(ends[k])
+    return itx[order]

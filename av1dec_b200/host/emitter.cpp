@@ -725,6 +725,23 @@ void FrameEmitter::layout()
     place(h.off_ops, (m_ops.size() + m_itxOnly.size()) * sizeof(Av1bOp));
     for (auto& i : m_itx)
         if (i & 0x80000000u) i = (i & 0x7FFFFFFFu) + (uint32_t)m_ops.size();
+    {
+        // stable counting sort of the inverse-transform list by size class (max(w,h) = 4 | 8 | 16 | >= 32):
+        // the device packs 32 / max(w,h) transform blocks into one warp
+        auto opAt = [&](uint32_t i) -> const Av1bOp& { return i < m_ops.size() ? m_ops[i] : m_itxOnly[i - m_ops.size()]; };
+        auto cls = [&](uint32_t i) {
+            const Av1bOp& o = opAt(i);
+            const int md = std::max(hk_tx_w[o.tx_size], hk_tx_h[o.tx_size]);
+            return md <= 4 ? 0 : (md <= 8 ? 1 : (md <= 16 ? 2 : 3));
+        };
+        uint32_t cnt[5] = { 0, 0, 0, 0, 0 };
+        for (uint32_t i : m_itx) cnt[cls(i) + 1]++;
+        for (int k = 1; k < 5; k++) cnt[k] += cnt[k - 1];
+        for (int k = 0; k < 4; k++) h.itx_class_end[k] = cnt[k + 1];
+        m_perm.resize(m_itx.size());
+        for (uint32_t i : m_itx) m_perm[cnt[cls(i)]++] = i;
+        m_itx.swap(m_perm);
+    }
     h.n_itx = (uint32_t)m_itx.size();
     place(h.off_itx, m_itx.size() * sizeof(uint32_t));
     h.n_iblk = (uint32_t)m_iblk.size();

@@ -254,6 +254,77 @@ def make_itx_cmd(batch):
     hdr.sb_cols = hdr.sb_rows = 1
     hdr.sb_log2 = 6
     hdr.n_ops, hdr.n_itx, hdr.n_coef, hdr.n_res = len(ops), len(itx), coef_off, res_off
-    cmd = F.build(hdr, {"off_ops": b"".join(ops), "off_itx": np.array(itx, np.uint32).tobytes(),
-                        "off_coef": b"".join(coefs)})
+    itx_sorted = F.sort_itx_list(hdr, itx, [b[0] for b in batch])
+    cmd = F.build(hdr, {"off_ops": b"".join(ops), "off_itx": itx_sorted.tobytes(), "off_coef": b"".join(coefs)})
     return cmd, res_off
+
+
+def make_itx_frame(w, h, seed=SEED, coded_frac=0.7):
+    """A whole frame of transform blocks (luma + both chroma planes) following a random
+    partition: every leaf block carries one luma TB of its own size (<= 64x64) and chroma TBs,
+    `coded_frac` of them coded with random coefficients.  Returns (cmd_bytes, n_tb, n_res, algo_bytes)
+    where algo_bytes = sum over coded TBs of 2*tw*th (coefficients read) + 2*w*h (residual written)."""
+    rng = SplitMix64(seed)
+    mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
+    level = np.zeros((mi_rows, mi_cols), np.int64)
+    for l in range(4):
+        cell = 16 >> l
+        r, c = (mi_rows + cell - 1) // cell, (mi_cols + cell - 1) // cell
+        split = _up(rng.uniform((r, c)) < (0.8, 0.65, 0.5, 0.4)[l], cell, mi_rows, mi_cols)
+        level = np.where((level == l) & split, l + 1, level)
+    tbs = []  # (plane, x, y, tx_size)
+    for l in range(5):
+        cell = 16 >> l  # MI units
+        size = 64 >> l
+        ys, xs = np.nonzero(level[::cell, ::cell][: (mi_rows + cell - 1) // cell, : (mi_cols + cell - 1) // cell] == l)
+        tx = [4, 3, 2, 1, 0][l]
+        for yy, xx in zip(ys.tolist(), xs.tolist()):
+            tbs.append((0, xx * size, yy * size, tx))
+            if l < 4:
+                ctx = [3, 2, 1, 0][l]
+                tbs.append((1, xx * size // 2, yy * size // 2, ctx))
+                tbs.append((2, xx * size // 2, yy * size // 2, ctx))
+            elif (xx & 1) and (yy & 1):
+                tbs.append((1, (xx - 1) * 2, (yy - 1) * 2, 0))
+                tbs.append((2, (xx - 1) * 2, (yy - 1) * 2, 0))
+    n = len(tbs)
+    coded = rng.uniform((n,)) < coded_frac
+    tys = rng.randint(0, 15, (n,))
+    ops = np.zeros(n, dtype=[("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("kind", "u1"), ("tx_size", "u1"), ("tx_type", "u1"),
+                             ("mode", "u1"), ("angle", "i1"), ("flags", "u1"), ("fi", "u1"), ("cfl", "i1"), ("nzr", "u1"),
+                             ("nzc", "u1"), ("lossless", "u1"), ("coef_off", "<u4"), ("res_off", "<u4"), ("aux", "<u4"),
+                             ("mlw", "<u2"), ("mlh", "<u2")])
+    assert ops.dtype.itemsize == 32
+    coefs, itx = [], []
+    coef_off = res_off = 0
+    algo = 0
+    for i, (pl, x, y, tx) in enumerate(tbs):
+        ops[i]["x"], ops[i]["y"], ops[i]["plane"], ops[i]["tx_size"] = x, y, pl, tx
+        if not coded[i]:
+            continue
+        legal = legal_tx_types(tx)
+        tw, th = min(TX_W[tx], 32), min(TX_H[tx], 32)
+        area = tw * th
+        k = max(1, area // 8)
+        pos = np.unique((rng.uniform((k,)) ** 2 * area).astype(np.int64))
+        coef = np.zeros(area, np.int16)
+        coef[pos] = np.clip((rng.normal((len(pos),)) * 120).astype(np.int64), -2000, 2000)
+        coef[0] = 64
+        nz = np.nonzero(coef)[0]
+        ops[i]["tx_type"] = legal[int(tys[i]) % len(legal)]
+        ops[i]["flags"] = F.OPF_HAS_RESID
+        ops[i]["nzr"], ops[i]["nzc"] = int((nz // tw).max()) + 1, int((nz % tw).max()) + 1
+        ops[i]["coef_off"], ops[i]["res_off"] = coef_off, res_off
+        coef_off += area
+        res_off += TX_W[tx] * TX_H[tx]
+        algo += 2 * area + 2 * TX_W[tx] * TX_H[tx]
+        coefs.append(coef.tobytes())
+        itx.append(i)
+    hdr = F.FrameHdr()
+    hdr.frame_w, hdr.frame_h, hdr.mi_cols, hdr.mi_rows = w, h, mi_cols, mi_rows
+    hdr.sb_log2 = 6
+    hdr.sb_cols, hdr.sb_rows = (mi_cols + 15) // 16, (mi_rows + 15) // 16
+    hdr.n_ops, hdr.n_itx, hdr.n_coef, hdr.n_res = n, len(itx), coef_off, res_off
+    itx_sorted = F.sort_itx_list(hdr, itx, [tbs[i][3] for i in itx])
+    cmd = F.build(hdr, {"off_ops": ops.tobytes(), "off_itx": itx_sorted.tobytes(), "off_coef": b"".join(coefs)})
+    return cmd, len(itx), res_off, algo

@@ -294,6 +294,29 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
     return post, roofline
 
 
+def itx_leg(device, reps=3):
+    """Inverse-transform throughput on a synthetic 3840x2160 frame of transform blocks."""
+    import av1dec_b200 as pkg
+    from av1dec_b200 import format as F
+    from av1dec_b200 import synth
+    from av1dec_b200.engine import Engine
+    hdr_size = C.sizeof(F.FrameHdr)
+    cmd, n_tb, n_res, algo = synth.make_itx_frame(3840, 2160)
+    eng = Engine(3840, 2160, device=device)
+    dev_cmd = eng.upload(cmd)
+    for _ in range(3):
+        eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_ITX, 0)
+    eng.sync()
+    eng.set_profiling(True)
+    for _ in range(reps * 4):
+        eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_ITX, 0)
+    ms, calls = eng.stage_times()
+    eng.close()
+    per = ms["itx"] / max(calls["itx"], 1) * 1e-3
+    return {"us_per_frame": per * 1e6, "transform_blocks": n_tb, "residual_samples": n_res, "algorithmic_bytes": algo,
+            "gbs": algo / per / 1e9, "mtb_per_s": n_tb / per / 1e6}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import av1dec_b200 as pkg
@@ -468,7 +491,7 @@ def main():
     if args.only == "postfilter":
         import torch
         post, roofline = postfilter_leg(0, torch.device("cuda", 0), reps=max(args.steps, 1))
-        print(json.dumps({"postfilter_4k": post, "roofline": roofline}))
+        print(json.dumps({"postfilter_4k": post, "itx_4k": itx_leg(0), "roofline": roofline}))
         return 0
     # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on
     # stdout, so everything but our final print goes to stderr.

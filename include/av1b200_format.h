@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define AV1B_MAGIC 0x42315641u /* "AV1B" */
-#define AV1B_FORMAT_VERSION 2
+#define AV1B_FORMAT_VERSION 3
 
 /* ---- Av1bOp.kind ------------------------------------------------------------------- */
 enum {
@@ -210,7 +210,9 @@ typedef struct Av1bFrameHdr {
     /* sections */
     uint32_t off_sb, n_sb;
     uint32_t off_ops, n_ops;
-    uint32_t off_itx, n_itx;   /* uint32 op indices that carry a residual (inverse-transform work list) */
+    uint32_t off_itx, n_itx;   /* uint32 op indices that carry a residual (inverse-transform work list),
+                                  sorted by size class: max(w,h) = 4 | 8 | 16 | >= 32                  */
+    uint32_t itx_class_end[4]; /* end index (exclusive) of each size class inside the list              */
     uint32_t off_iblk, n_iblk;
     uint32_t off_ipu, n_ipu;
     uint32_t off_aux, n_aux;
