@@ -48,6 +48,7 @@ using std::max;
 using std::min;
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #define AV1B_NOINLINE
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
     const uint64_t v = ((uint64_t)y << 32) | x;

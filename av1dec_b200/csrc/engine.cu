@@ -170,6 +170,7 @@ struct av1b_ctx {
     int16_t* res = nullptr;
     size_t res_cap = 0;
     int16_t* res_planes = nullptr; // frame-layout residual planes (luma aw x ah, chroma aw/2 x ah/2 each)
+    uint8_t* mask_plane = nullptr; // luma-resolution compound-mask scratch (aw x ah)
     int* sync = nullptr;
     size_t sync_cap = 0;
     uint8_t* wedge = nullptr;
@@ -286,6 +287,7 @@ static void ctx_free(av1b_ctx* c)
     for (auto e : c->event_pool) rt_event_destroy(e);
     rt_free(c->res);
     rt_free(c->res_planes);
+    rt_free(c->mask_plane);
     rt_free(c->sync);
     if (c->own_stream) rt_stream_destroy(c->stream);
     delete c;
@@ -488,6 +490,15 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
                 || rt_memset(rc.rp[2], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), c->stream))
                 return fail(c, AV1B_ECUDA, "memset");
         }
+    }
+    if (h.n_iblk && (stages & AV1B_STAGE_INTER)) {
+        if (!c->mask_plane) {
+            void* p = nullptr;
+            if (rt_malloc(&p, (size_t)c->aw * c->ah)) return fail(c, AV1B_ENOMEM, "mask plane");
+            c->mask_plane = (uint8_t*)p;
+        }
+        rc.mask = c->mask_plane;
+        rc.mask_pitch = c->aw;
     }
     rc.wedge = c->wedge;
     rc.sync = c->sync;

@@ -11,6 +11,8 @@ struct ReconCtx {
     int16_t* res;         // compact residual arena (stage-level ITX test mode; used when rp[0] == null)
     int16_t* rp[3];       // residual planes in frame layout (int16), zero where no coded TB
     int rpitch[3];        // elements per row
+    uint8_t* mask;        // luma-resolution scratch plane for diff-weighted compound masks
+    int mask_pitch;
     const uint8_t* wedge; // wedge mask table [9][2][16][32*32]
     int* sync;            // [0] = SB ticket counter, [1 + r] = finished SBs of SB row r
 };

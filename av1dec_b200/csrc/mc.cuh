@@ -15,11 +15,14 @@
 
 namespace mc {
 
-enum { TILE = 32, INTER_ELEMS = 16 * 15 * 8 /* >= (TILE+7)*TILE */ };
+// Tiles of TILE_W x TILE_H samples.  Scratch is per executing group (a warp in inter_kernel, the
+// CTA on the intrabc path): ~5 KB.
+enum { TILE_W = 32, TILE_H = 16, WIN_PITCH = TILE_W + 8, WIN_ROWS = TILE_H + 7, INTER_ELEMS = 8 * 15 * 8 };
 
 struct Scratch {
-    int16_t inter[INTER_ELEMS];   // horizontal-pass intermediates
-    int16_t pred[2][TILE * TILE]; // per-list predictions of the current tile
+    uint8_t win[WIN_ROWS * WIN_PITCH];   // reference window of the tile (+7 samples each way), clamped
+    int16_t inter[INTER_ELEMS];          // horizontal-pass intermediates (>= WIN_ROWS * TILE_W)
+    int16_t pred[2][TILE_W * TILE_H];    // per-list predictions of the current tile
 };
 
 struct RefPlane {
@@ -65,12 +68,16 @@ struct Params {
     const Av1bFrameHdr* hdr;
     const Av1bBlkAux* aux;   // may be null when the unit needs none
     const uint8_t* wedge;    // wedge table
-    uint8_t* mask;           // luma-resolution mask scratch (128 x 128), diff-weighted compound
+    uint8_t* mask;           // luma-resolution mask of the block (diff-weighted compound): address of
+    int mask_pitch;          //   the block's top-left sample, bytes per row
     PlaneView dst;           // destination plane of the current frame
     RefPlane ref[2];
 };
 
-// Prediction of list `l` for the tile at (tx,ty) size (tw,th) into s.pred[l].
+AV1B_DEV int ilog2_pow2(int v) { return 31 - __clz(v); }
+
+// Prediction of list `l` for the tile at (tx,ty) size (tw,th) into s.pred[l] (pitch TILE_W).
+// tw is a power of two (2..32), th <= TILE_H.
 AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int ty, int tw, int th,
     Scratch& s, int tid, int nt)
 {
@@ -78,6 +85,7 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
     const bool compound = (u.flags & AV1B_IPUF_COMPOUND) != 0;
     const int round1 = compound ? 7 : 11;
     const RefPlane& R = P.ref[l];
+    const int ltw = ilog2_pow2(tw);
     int use_warp = u.warp[l];
     if (u.w < 8 || u.h < 8) use_warp = 0;
     int16_t* pred = s.pred[l];
@@ -85,20 +93,20 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
         const int32_t* wp = (use_warp == 1) ? P.aux->warp_params : P.hdr->gm_params[u.ref_frame[l]];
         const int16_t* ab = (use_warp == 1) ? P.aux->warp_abgd : P.hdr->gm_abgd[u.ref_frame[l]];
         const int alpha = ab[0], beta = ab[1], gamma = ab[2], delta = ab[3];
-        const int nux = tw >> 3, nuy = th >> 3, nu = nux * nuy;
+        const int lnux = ltw - 3, nu = (tw >> 3) * (th >> 3);
         // horizontal pass: 15 x 8 per 8x8 unit
         for (int e = tid; e < nu * 120; e += nt) {
-            int unit = e / 120, k = e - unit * 120;
-            int i1 = k / 8 - 7, i2 = (k & 7) - 4;
-            int uy = unit / nux, ux = unit - uy * nux;
-            int srcx = (u.x + tx + ux * 8 + 4) << subx;
-            int srcy = (u.y + ty + uy * 8 + 4) << suby;
-            int dstx = wp[2] * srcx + wp[3] * srcy + wp[0];
-            int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
-            int x4 = dstx >> subx, y4 = dsty >> suby;
-            int ix4 = x4 >> 16, sx4 = x4 & 0xFFFF, iy4 = y4 >> 16;
-            int sx = sx4 + alpha * i2 + beta * i1;
-            int offs = ((sx + 512) >> 10) + 64;
+            const int unit = e / 120, k = e - unit * 120;
+            const int i1 = (k >> 3) - 7, i2 = (k & 7) - 4;
+            const int uy = unit >> lnux, ux = unit & ((1 << lnux) - 1);
+            const int srcx = (u.x + tx + ux * 8 + 4) << subx;
+            const int srcy = (u.y + ty + uy * 8 + 4) << suby;
+            const int dstx = wp[2] * srcx + wp[3] * srcy + wp[0];
+            const int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
+            const int x4 = dstx >> subx, y4 = dsty >> suby;
+            const int ix4 = x4 >> 16, sx4 = x4 & 0xFFFF, iy4 = y4 >> 16;
+            const int sx = sx4 + alpha * i2 + beta * i1;
+            const int offs = ((sx + 512) >> 10) + 64;
             const int16_t* f = k_warped_filters[offs];
             int sum = 0;
             AV1B_UNROLL
@@ -107,22 +115,22 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
         }
         block_sync(nt);
         for (int e = tid; e < nu * 64; e += nt) {
-            int unit = e >> 6, k = e & 63;
-            int i1 = (k >> 3) - 4, i2 = (k & 7) - 4;
-            int uy = unit / nux, ux = unit - uy * nux;
-            int srcx = (u.x + tx + ux * 8 + 4) << subx;
-            int srcy = (u.y + ty + uy * 8 + 4) << suby;
-            int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
-            int y4 = dsty >> suby;
-            int sy4 = y4 & 0xFFFF;
-            int sy = sy4 + gamma * i2 + delta * i1;
-            int offs = ((sy + 512) >> 10) + 64;
+            const int unit = e >> 6, k = e & 63;
+            const int i1 = (k >> 3) - 4, i2 = (k & 7) - 4;
+            const int uy = unit >> lnux, ux = unit & ((1 << lnux) - 1);
+            const int srcx = (u.x + tx + ux * 8 + 4) << subx;
+            const int srcy = (u.y + ty + uy * 8 + 4) << suby;
+            const int dsty = wp[4] * srcx + wp[5] * srcy + wp[1];
+            const int y4 = dsty >> suby;
+            const int sy4 = y4 & 0xFFFF;
+            const int sy = sy4 + gamma * i2 + delta * i1;
+            const int offs = ((sy + 512) >> 10) + 64;
             const int16_t* f = k_warped_filters[offs];
             const int16_t* in = s.inter + unit * 120 + (i2 + 4);
             int sum = 0;
             AV1B_UNROLL
             for (int t = 0; t < 8; t++) sum += f[t] * in[(i1 + t + 4) * 8];
-            pred[(uy * 8 + i1 + 4) * TILE + ux * 8 + i2 + 4] = (int16_t)round2(sum, round1);
+            pred[(uy * 8 + i1 + 4) * TILE_W + ux * 8 + i2 + 4] = (int16_t)round2(sum, round1);
         }
         block_sync(nt);
         return;
@@ -134,31 +142,53 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
     const int px0 = u.x + tx + (mvx >> 4), py0 = u.y + ty + (mvy >> 4);
     if (!fx && !fy) {
         const int sh = 14 - 3 - round1;
-        for (int e = tid; e < tw * th; e += nt) {
-            int r = e / tw, c = e - r * tw;
-            pred[r * TILE + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
+        for (int e = tid; e < (th << ltw); e += nt) {
+            const int r = e >> ltw, c = e & (tw - 1);
+            pred[r * TILE_W + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
         }
         block_sync(nt);
         return;
     }
-    const int16_t* fh = k_subpel_filters[filter_row(u.w, u.filt[1])][fx];
-    const int16_t* fv = k_subpel_filters[filter_row(u.h, u.filt[0])][fy];
-    const int ih = th + 7;
-    for (int e = tid; e < ih * tw; e += nt) {
-        int r = e / tw, c = e - r * tw;
-        int y = py0 + r - 3, x = px0 + c - 3;
-        int sum = 0;
-        AV1B_UNROLL
-        for (int t = 0; t < 8; t++) sum += fh[t] * ref_px(R, x + t, y);
-        s.inter[r * TILE + c] = (int16_t)((sum + 4) >> 3);
+    // stage the clamped reference window: rows py0-3 .. py0+th+3, columns px0-3 .. px0+tw+3
+    {
+        const int ww = tw + 7, wh = th + 7;
+        // ww in {9, 11, 15, 23, 39}: division by multiply-high
+        const unsigned magic = ww == 39 ? 110127367u : ww == 23 ? 186737709u : ww == 15 ? 286331154u : ww == 11 ? 390451573u : 477218589u;
+        const bool inside = px0 - 3 >= 0 && px0 + tw + 3 <= R.last_x && py0 - 3 >= 0 && py0 + th + 3 <= R.last_y;
+        const uint8_t* base = R.p + (ptrdiff_t)(py0 - 3) * R.stride + (px0 - 3);
+        for (int e = tid; e < ww * wh; e += nt) {
+            const int r = (int)__umulhi((unsigned)e, magic), c = e - r * ww;
+            int v;
+            if (inside) v = R.coherent ? (int)__ldcg(base + (ptrdiff_t)r * R.stride + c) : (int)__ldg(base + (ptrdiff_t)r * R.stride + c);
+            else v = ref_px(R, px0 - 3 + c, py0 - 3 + r);
+            s.win[r * WIN_PITCH + c] = (uint8_t)v;
+        }
     }
     block_sync(nt);
-    for (int e = tid; e < tw * th; e += nt) {
-        int r = e / tw, c = e - r * tw;
+    const int16_t* fh = k_subpel_filters[filter_row(u.w, u.filt[1])][fx];
+    const int16_t* fv = k_subpel_filters[filter_row(u.h, u.filt[0])][fy];
+    int f0[8], f1[8];
+    AV1B_UNROLL
+    for (int t = 0; t < 8; t++) {
+        f0[t] = fh[t];
+        f1[t] = fv[t];
+    }
+    for (int e = tid; e < ((th + 7) << ltw); e += nt) {
+        const int r = e >> ltw, c = e & (tw - 1);
+        const uint8_t* q = s.win + r * WIN_PITCH + c;
         int sum = 0;
         AV1B_UNROLL
-        for (int t = 0; t < 8; t++) sum += fv[t] * s.inter[(r + t) * TILE + c];
-        pred[r * TILE + c] = (int16_t)round2(sum, round1);
+        for (int t = 0; t < 8; t++) sum += f0[t] * q[t];
+        s.inter[r * TILE_W + c] = (int16_t)((sum + 4) >> 3);
+    }
+    block_sync(nt);
+    for (int e = tid; e < (th << ltw); e += nt) {
+        const int r = e >> ltw, c = e & (tw - 1);
+        const int16_t* q = s.inter + r * TILE_W + c;
+        int sum = 0;
+        AV1B_UNROLL
+        for (int t = 0; t < 8; t++) sum += f1[t] * q[t * TILE_W];
+        pred[r * TILE_W + c] = (int16_t)round2(sum, round1);
     }
     block_sync(nt);
 }
@@ -168,29 +198,30 @@ AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, in
 {
     const bool compound = (u.flags & AV1B_IPUF_COMPOUND) != 0;
     const int plane = u.plane;
-    for (int ty = 0; ty < u.h; ty += TILE) {
-        const int th = min((int)TILE, u.h - ty);
-        for (int tx = 0; tx < u.w; tx += TILE) {
-            const int tw = min((int)TILE, u.w - tx);
+    for (int ty = 0; ty < u.h; ty += TILE_H) {
+        const int th = min((int)TILE_H, u.h - ty);
+        for (int tx = 0; tx < u.w; tx += TILE_W) {
+            const int tw = min((int)TILE_W, u.w - tx);
+            const int ltw = ilog2_pow2(tw);
             predict_tile(P, u, 0, tx, ty, tw, th, s, tid, nt);
             if (compound) predict_tile(P, u, 1, tx, ty, tw, th, s, tid, nt);
-            for (int e = tid; e < tw * th; e += nt) {
-                int r = e / tw, c = e - r * tw;
-                int i = ty + r, j = tx + c; // position inside the unit
+            for (int e = tid; e < (th << ltw); e += nt) {
+                const int r = e >> ltw, c = e & (tw - 1);
+                const int i = ty + r, j = tx + c; // position inside the unit
                 uint8_t* d = P.dst.p + (size_t)(u.y + i) * P.dst.stride + (u.x + j);
-                int p0 = s.pred[0][r * TILE + c];
+                const int p0 = s.pred[0][r * TILE_W + c];
                 int out;
                 if (u.kind != AV1B_IPU_PRED) {
                     // OBMC strip (reference predict_overlap): mask runs along rows for the
                     // above pass, along columns for the left pass.
-                    int len = (u.kind == AV1B_IPU_OBMC_ABOVE) ? u.h : u.w;
-                    int m = k_obmc_mask[len - 2 + ((u.kind == AV1B_IPU_OBMC_ABOVE) ? i : j)];
-                    int cur = *d;
+                    const int len = (u.kind == AV1B_IPU_OBMC_ABOVE) ? u.h : u.w;
+                    const int m = k_obmc_mask[len - 2 + ((u.kind == AV1B_IPU_OBMC_ABOVE) ? i : j)];
+                    const int cur = *(volatile uint8_t*)d;
                     out = clip_u8(round2(m * cur + (64 - m) * clip_u8(p0), 6));
                 } else if (!compound) {
                     out = clip_u8(p0);
                 } else {
-                    int p1 = s.pred[1][r * TILE + c];
+                    const int p1 = s.pred[1][r * TILE_W + c];
                     if (u.comp_type == AV1B_COMP_AVERAGE) {
                         out = clip_u8(round2(p0 + p1, 5));
                     } else if (u.comp_type == AV1B_COMP_DISTANCE) {
@@ -210,11 +241,12 @@ AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, in
                                 diff = (diff + 8) >> 4;
                                 m = clip3(0, 64, 38 + diff / 16);
                                 if (P.aux->mask_type) m = 64 - m;
-                                P.mask[i * 128 + j] = (uint8_t)m;
+                                P.mask[i * P.mask_pitch + j] = (uint8_t)m;
                             } else {
-                                const uint8_t* M = P.mask;
-                                m = (M[(2 * i) * 128 + 2 * j] + M[(2 * i) * 128 + 2 * j + 1] + M[(2 * i + 1) * 128 + 2 * j]
-                                        + M[(2 * i + 1) * 128 + 2 * j + 1] + 2)
+                                const volatile uint8_t* M = P.mask;
+                                const int mp = P.mask_pitch;
+                                m = (M[(2 * i) * mp + 2 * j] + M[(2 * i) * mp + 2 * j + 1] + M[(2 * i + 1) * mp + 2 * j]
+                                        + M[(2 * i + 1) * mp + 2 * j + 1] + 2)
                                     >> 2;
                             }
                         }

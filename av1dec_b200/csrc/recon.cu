@@ -145,13 +145,16 @@ __global__ void __launch_bounds__(ITX_WARPS * 32)
 // ------------------------------------------------------------------------------------------
 // inter prediction (independent pass)
 // ------------------------------------------------------------------------------------------
-AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bIpu& u, uint8_t* mask, mc::Params& P)
+AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bIpu& u, mc::Params& P)
 {
     const int plane = u.plane, sub = plane ? 1 : 0;
     P.hdr = hdr;
     P.aux = (u.aux != 0xFFFFFFFFu) ? ((const Av1bBlkAux*)(c.cmd + hdr->off_aux) + u.aux) : nullptr;
     P.wedge = c.wedge;
-    P.mask = mask;
+    // mask of the block this unit belongs to (only compound diff-weighted blocks touch it: they
+    // are >= 8x8, so the luma origin is exactly the unit origin scaled back to luma)
+    P.mask = c.mask ? c.mask + (size_t)(u.y << sub) * c.mask_pitch + (u.x << sub) : nullptr;
+    P.mask_pitch = c.mask_pitch;
     P.dst = c.cur.pl[plane];
     const int nl = (u.flags & AV1B_IPUF_COMPOUND) ? 2 : 1;
     for (int l = 0; l < nl; l++) {
@@ -173,43 +176,49 @@ AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const 
     }
 }
 
-__global__ void __launch_bounds__(256) inter_kernel(ReconCtx c)
+// One WARP per inter block: its prediction units run back to back (prediction, then OBMC strips,
+// in emission order), then the residual is added.  No CTA-wide barrier: everything is ordered by
+// __syncwarp, each warp owns a private scratch area, and 8x8 blocks do not idle a whole CTA.
+enum { INTER_WARPS = 8 };
+
+__global__ void __launch_bounds__(INTER_WARPS * 32) inter_kernel(ReconCtx c)
 {
-    __shared__ mc::Scratch M;
-    __shared__ uint8_t mask[128 * 128];
+    __shared__ mc::Scratch M[INTER_WARPS];
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bInterBlk* blks = (const Av1bInterBlk*)(c.cmd + hdr->off_iblk);
     const Av1bIpu* ipus = (const Av1bIpu*)(c.cmd + hdr->off_ipu);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (unsigned b = blockIdx.x; b < hdr->n_iblk; b += gridDim.x) {
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
+    mc::Scratch& S = M[warp];
+    for (unsigned b = blockIdx.x * nw + warp; b < hdr->n_iblk; b += gridDim.x * nw) {
         const Av1bInterBlk blk = blks[b];
         for (unsigned k = 0; k < blk.n_ipu; k++) {
             const Av1bIpu u = ipus[blk.first_ipu + k];
             mc::Params P;
-            setup_mc_params(c, hdr, u, mask, P);
-            mc::run_ipu(P, u, M, tid, nt);
+            setup_mc_params(c, hdr, u, P);
+            mc::run_ipu(P, u, S, lane, nl);
         }
-        __syncthreads();
         if ((blk.flags & AV1B_IBF_ADD_RESIDUAL) && c.rp[0]) {
             // plain inter block: reconstruction = prediction + residual, no ordering constraint
             const int np = (blk.flags & AV1B_IBF_HAS_CHROMA) ? 3 : 1;
             for (int plane = 0; plane < np; plane++) {
                 const int bx = plane ? blk.cx : blk.x, by = plane ? blk.cy : blk.y;
                 const int bw = plane ? blk.cw : blk.bw, bh = plane ? blk.ch : blk.bh;
+                const int lbw = mc::ilog2_pow2(bw);
                 const PlaneView dst = c.cur.pl[plane];
                 const int16_t* rp = c.rp[plane];
                 const int rpitch = c.rpitch[plane];
-                for (int e = tid; e < bw * bh; e += nt) {
-                    const int i = e / bw, j = e - i * bw;
+                for (int e = lane; e < (bh << lbw); e += nl) {
+                    const int i = e >> lbw, j = e & (bw - 1);
                     const int r = rp[(size_t)(by + i) * rpitch + bx + j];
                     if (r) {
-                        uint8_t* d = dst.p + (size_t)(by + i) * dst.stride + bx + j;
+                        volatile uint8_t* d = dst.p + (size_t)(by + i) * dst.stride + bx + j;
                         *d = (uint8_t)clip_u8((int)*d + r);
                     }
                 }
             }
-            __syncthreads();
         }
+        block_sync(nl);
     }
 }
 
@@ -337,7 +346,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         // only reached on the global-memory path (frames with allow_intrabc)
         const Av1bIpu u = ((const Av1bIpu*)(c.cmd + hdr->off_ipu))[op.aux];
         mc::Params P;
-        setup_mc_params(c, hdr, u, nullptr, P);
+        setup_mc_params(c, hdr, u, P);
         mc::run_ipu(P, u, *M, tid, nt);
         break;
     }
@@ -607,9 +616,9 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.n_iblk) return;
-    int grid = (int)h.n_iblk;
-    if (grid > 148 * 8) grid = 148 * 8;
-    AV1B_LAUNCH(inter_kernel, (grid), (256), st, c);
+    int grid = (int)((h.n_iblk + INTER_WARPS - 1) / INTER_WARPS);
+    if (grid > 148 * 6) grid = 148 * 6;
+    AV1B_LAUNCH(inter_kernel, (grid), (INTER_WARPS * 32), st, c);
 }
 
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)

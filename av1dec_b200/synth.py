@@ -328,3 +328,69 @@ def make_itx_frame(w, h, seed=SEED, coded_frac=0.7):
     itx_sorted = F.sort_itx_list(hdr, itx, [tbs[i][3] for i in itx])
     cmd = F.build(hdr, {"off_ops": ops.tobytes(), "off_itx": itx_sorted.tobytes(), "off_coef": b"".join(coefs)})
     return cmd, len(itx), res_off, algo
+
+
+def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512):
+    """A whole frame of translational inter blocks (8x8 .. 64x64, random partition): random
+    1/8-pel motion vectors within +-max_mv/8 samples, random dual interpolation filters, references
+    in store slots 0 / 1 (RefFrame 1 / 2), `compound_frac` of the blocks compound-average.
+    Returns (cmd_bytes, n_blocks, algo_bytes); algo_bytes = (1 + refs) * samples (read + write)."""
+    rng = SplitMix64(seed)
+    mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
+    level = np.zeros((mi_rows, mi_cols), np.int64)
+    for l in range(3):
+        cell = 16 >> l
+        r, c = (mi_rows + cell - 1) // cell, (mi_cols + cell - 1) // cell
+        split = _up(rng.uniform((r, c)) < (0.8, 0.6, 0.45)[l], cell, mi_rows, mi_cols)
+        level = np.where((level == l) & split, l + 1, level)
+    xs_all, ys_all, sz_all = [], [], []
+    for l in range(4):
+        cell, size = 16 >> l, 64 >> l
+        ys, xs = np.nonzero(level[::cell, ::cell] == l)
+        xs_all.append(xs * size)
+        ys_all.append(ys * size)
+        sz_all.append(np.full(len(xs), size))
+    bx, by, bs = np.concatenate(xs_all), np.concatenate(ys_all), np.concatenate(sz_all)
+    nb = len(bx)
+    comp = rng.uniform((nb,)) < compound_frac
+    mv = rng.randint(-max_mv, max_mv, (nb, 2, 2))
+    filt = rng.randint(0, 2, (nb, 2))
+    ref0 = rng.randint(1, 2, (nb,))
+    ipu_t = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("kind", "u1"),
+                      ("mv", "<i2", (2, 2)), ("ref_slot", "i1", 2), ("ref_frame", "u1", 2), ("filt", "u1", 2),
+                      ("warp", "u1", 2), ("flags", "u1"), ("comp_type", "u1"), ("fwd_w", "u1"), ("bck_w", "u1"), ("aux", "<u4")])
+    assert ipu_t.itemsize == 32
+    ipu = np.zeros(nb * 3, ipu_t)
+    for pl in range(3):
+        sub = 1 if pl else 0
+        v = ipu[pl::3]
+        v["x"], v["y"], v["w"], v["h"], v["plane"] = bx >> sub, by >> sub, bs >> sub, bs >> sub, pl
+        v["mv"] = mv
+        v["ref_frame"][:, 0] = ref0
+        v["ref_frame"][:, 1] = 3 - ref0
+        v["ref_slot"][:, 0] = ref0 - 1
+        v["ref_slot"][:, 1] = np.where(comp, 2 - ref0, -1)
+        v["filt"] = filt
+        v["flags"] = comp.astype(np.uint8)  # AV1B_IPUF_COMPOUND
+        v["comp_type"] = 2                  # AV1B_COMP_AVERAGE
+        v["aux"] = 0xFFFFFFFF
+    blk_t = np.dtype([("first_ipu", "<u4"), ("n_ipu", "<u2"), ("flags", "<u2"), ("x", "<u2"), ("y", "<u2"), ("cx", "<u2"),
+                      ("cy", "<u2"), ("bw", "u1"), ("bh", "u1"), ("cw", "u1"), ("ch", "u1"), ("pad", "<u4")])
+    assert blk_t.itemsize == 24
+    blk = np.zeros(nb, blk_t)
+    blk["first_ipu"], blk["n_ipu"], blk["flags"] = np.arange(nb) * 3, 3, 1
+    blk["x"], blk["y"], blk["cx"], blk["cy"] = bx, by, bx >> 1, by >> 1
+    blk["bw"] = blk["bh"] = bs
+    blk["cw"] = blk["ch"] = bs >> 1
+    hdr = F.FrameHdr()
+    hdr.frame_w, hdr.frame_h, hdr.mi_cols, hdr.mi_rows = w, h, mi_cols, mi_rows
+    hdr.sb_log2 = 6
+    hdr.sb_cols, hdr.sb_rows = (mi_cols + 15) // 16, (mi_rows + 15) // 16
+    for rf in (1, 2):
+        hdr.ref_slot[rf] = rf - 1
+        hdr.ref_w[rf], hdr.ref_h[rf] = w, h
+    hdr.n_iblk, hdr.n_ipu = nb, nb * 3
+    cmd = F.build(hdr, {"off_iblk": blk.tobytes(), "off_ipu": ipu.tobytes()})
+    samples = (bs.astype(np.int64) ** 2 * 3 // 2)
+    algo = int((samples * (2 + comp.astype(np.int64))).sum())
+    return cmd, nb, algo

@@ -294,6 +294,33 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
     return post, roofline
 
 
+def inter_leg(device, reps=3):
+    """Motion-compensation throughput on a synthetic 3840x2160 frame of translational inter blocks."""
+    import av1dec_b200 as pkg
+    from av1dec_b200 import format as F
+    from av1dec_b200 import synth
+    from av1dec_b200.engine import Engine
+    hdr_size = C.sizeof(F.FrameHdr)
+    W4, H4 = 3840, 2160
+    cmd, n_blk, algo = synth.make_inter_frame(W4, H4)
+    eng = Engine(W4, H4, device=device)
+    rng = synth.SplitMix64(synth.SEED + 77)
+    for slot in range(2):
+        eng.set_ref(slot, synth.make_planes(rng, W4, H4, "B"), W4, H4)
+    dev_cmd = eng.upload(cmd)
+    for _ in range(3):
+        eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_INTER, 0)
+    eng.sync()
+    eng.set_profiling(True)
+    for _ in range(reps * 4):
+        eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_INTER, 0)
+    ms, calls = eng.stage_times()
+    eng.close()
+    per = ms["inter"] / max(calls["inter"], 1) * 1e-3
+    return {"us_per_frame": per * 1e6, "inter_blocks": n_blk, "algorithmic_bytes": algo, "gbs": algo / per / 1e9,
+            "mpix_per_s": W4 * H4 / per / 1e6}
+
+
 def itx_leg(device, reps=3):
     """Inverse-transform throughput on a synthetic 3840x2160 frame of transform blocks."""
     import av1dec_b200 as pkg
@@ -491,7 +518,7 @@ def main():
     if args.only == "postfilter":
         import torch
         post, roofline = postfilter_leg(0, torch.device("cuda", 0), reps=max(args.steps, 1))
-        print(json.dumps({"postfilter_4k": post, "itx_4k": itx_leg(0), "roofline": roofline}))
+        print(json.dumps({"postfilter_4k": post, "itx_4k": itx_leg(0), "inter_4k": inter_leg(0), "roofline": roofline}))
         return 0
     # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on
     # stdout, so everything but our final print goes to stderr.
