@@ -51,17 +51,12 @@ struct ResPlanes {
     int pitch[3];
 };
 
-// Work split of one inverse-transform launch.  The list is sorted by size class c (max(w,h) =
-// 4, 8, 16, >=32); class c packs 32 / G_c transform blocks into a warp (G = 4, 8, 16, 32 lanes
-// per block: one lane per row, then one lane per column).
-struct ItxPlan {
-    uint32_t first[4], count[4]; // list range of each class
-    uint32_t block_begin[5];     // first CTA of each class (CTAs of ITX_WARPS warps)
-};
-
 namespace {
 
-// One transform block handled by the G lanes [lane_in_group = 0..G-1] of a warp.
+// One transform block handled by the G lanes [lane_in_group = 0..G-1] of a warp.  MAXLOG bounds
+// log2 of both dimensions for this size class, so small classes compile to small, low-register
+// kernels (the 64-point butterflies alone need ~250 registers).
+template <int MAXLOG>
 AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int16_t* __restrict__ res, const ResPlanes& rp,
     int16_t* tmp, int tstride, int gl, int G)
 {
@@ -88,55 +83,49 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
     }
     for (int i = gl; i < nz_rows; i += G) {
         int16_t* trow = tmp + i * tstride;
-        switch (lw) {
-        case 2: itx::row_pass<2>(c + i * tw, tw, trow, rk, rect, row_shift); break;
-        case 3: itx::row_pass<3>(c + i * tw, tw, trow, rk, rect, row_shift); break;
-        case 4: itx::row_pass<4>(c + i * tw, tw, trow, rk, rect, row_shift); break;
-        case 5: itx::row_pass<5>(c + i * tw, tw, trow, rk, rect, row_shift); break;
-        default: itx::row_pass<6>(c + i * tw, tw, trow, rk, rect, row_shift); break;
-        }
+        if (MAXLOG >= 6 && lw == 6) itx::row_pass<6>(c + i * tw, tw, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 5 && lw == 5) itx::row_pass<5>(c + i * tw, tw, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 4 && lw == 4) itx::row_pass<4>(c + i * tw, tw, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 3 && lw == 3) itx::row_pass<3>(c + i * tw, tw, trow, rk, rect, row_shift);
+        else itx::row_pass<2>(c + i * tw, tw, trow, rk, rect, row_shift);
     }
     __syncwarp();
     const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
     for (int j = gl; j < w; j += G) {
         const int jo = flr ? (w - 1 - j) : j;
-        switch (lh) {
-        case 2: itx::col_pass<2>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
-        case 3: itx::col_pass<3>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
-        case 4: itx::col_pass<4>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
-        case 5: itx::col_pass<5>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
-        default: itx::col_pass<6>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift); break;
-        }
+        if (MAXLOG >= 6 && lh == 6) itx::col_pass<6>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+        else if (MAXLOG >= 5 && lh == 5) itx::col_pass<5>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+        else if (MAXLOG >= 4 && lh == 4) itx::col_pass<4>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+        else if (MAXLOG >= 3 && lh == 3) itx::col_pass<3>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+        else itx::col_pass<2>(tmp + j, tstride, nz_rows, out + jo, out_stride, fud, ck, col_shift);
     }
 }
 
 }  // namespace
 
+// One launch per size class CLS (0: 4x4, 1: max dim 8, 2: max dim 16, 3: 32 and 64).
+template <int CLS>
 __global__ void __launch_bounds__(ITX_WARPS * 32)
-    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, ItxPlan plan,
+    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n,
         const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
 {
-    __shared__ int16_t tmp_all[ITX_WARPS][ITX_TMP_ROWS * ITX_TMP_STRIDE];
+    constexpr int GMAX = 4 << CLS;
+    constexpr int TSTRIDE = (CLS == 3) ? (int)ITX_TMP_STRIDE : GMAX + 2;
+    constexpr int REGION = (CLS == 3) ? (int)ITX_TMP_ROWS * ITX_TMP_STRIDE : GMAX * (GMAX + 2);
+    __shared__ int16_t tmp_all[ITX_WARPS][(CLS == 3) ? REGION : (32 / GMAX) * REGION];
     const int nl = min(32u, blockDim.x);
     const int nw = max(1u, blockDim.x / 32);
     const int lane = threadIdx.x % nl;
     const int warp = threadIdx.x / nl;
-    // which size class does this CTA serve?
-    int cls = 0;
-    while (cls < 3 && blockIdx.x >= plan.block_begin[cls + 1]) cls++;
-    const int G = min(4 << cls, nl);          // lanes per transform block
-    const int per = max(1, nl / G);           // transform blocks per warp pass
-    const int tstride = (cls == 3) ? ITX_TMP_STRIDE : ((4 << cls) + 2);
-    const int region = (cls == 3) ? ITX_TMP_ROWS * ITX_TMP_STRIDE : (4 << cls) * ((4 << cls) + 2);
+    const int G = min(GMAX, nl);    // lanes per transform block
+    const int per = max(1, nl / G); // transform blocks per warp pass
     const int gl = lane % G, grp = lane / G;
-    int16_t* tmp = tmp_all[warp] + grp * region;
-    const uint32_t n = plan.count[cls];
-    const uint32_t cta = blockIdx.x - plan.block_begin[cls], ncta = plan.block_begin[cls + 1] - plan.block_begin[cls];
-    for (uint32_t t0 = (cta * nw + warp) * per; t0 < n; t0 += ncta * nw * per) {
+    int16_t* tmp = tmp_all[warp] + grp * REGION;
+    for (uint32_t t0 = (blockIdx.x * nw + warp) * per; t0 < n; t0 += gridDim.x * nw * per) {
         const uint32_t t = t0 + grp;
         if (t < n) {
-            const Av1bOp op = ops[list[plan.first[cls] + t]];
-            itx_block(op, coef, res, rp, tmp, tstride, gl, G);
+            const Av1bOp op = ops[list[t]];
+            itx_block<(CLS == 3) ? 6 : CLS + 2>(op, coef, res, rp, tmp, TSTRIDE, gl, G);
         }
         __syncwarp();
     }
@@ -595,22 +584,23 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         rp.p[i] = c.rp[i];
         rp.pitch[i] = c.rpitch[i];
     }
-    ItxPlan plan;
-    uint32_t prev = 0, blocks = 0;
+    uint32_t prev = 0;
     for (int k = 0; k < 4; k++) {
         const uint32_t end = h.itx_class_end[k] > h.n_itx ? h.n_itx : h.itx_class_end[k];
-        plan.first[k] = prev;
-        plan.count[k] = end > prev ? end - prev : 0;
+        const uint32_t cnt = end > prev ? end - prev : 0;
+        const uint32_t* lst = list + prev;
         prev = end > prev ? end : prev;
-        const uint32_t per_cta = ITX_WARPS * (32 / (4 << k));  // transform blocks per CTA pass
-        uint32_t nb = (plan.count[k] + per_cta - 1) / per_cta;
-        if (nb > 148 * 8) nb = 148 * 8;
-        plan.block_begin[k] = blocks;
-        blocks += nb;
+        if (!cnt) continue;
+        const uint32_t per_cta = ITX_WARPS * (32 / (4 << k)); // transform blocks per CTA pass
+        int nb = (int)((cnt + per_cta - 1) / per_cta);
+        if (nb > 148 * 16) nb = 148 * 16;
+        switch (k) {
+        case 0: AV1B_LAUNCH(itx_kernel<0>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
+        case 1: AV1B_LAUNCH(itx_kernel<1>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
+        case 2: AV1B_LAUNCH(itx_kernel<2>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
+        default: AV1B_LAUNCH(itx_kernel<3>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
+        }
     }
-    plan.block_begin[4] = blocks;
-    if (!blocks) return;
-    AV1B_LAUNCH(itx_kernel, ((int)blocks), (ITX_WARPS * 32), st, ops, list, plan, coef, c.res, rp);
 }
 
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
