@@ -23,6 +23,10 @@ typedef EmuDim3 dim3;
 struct uint4 {
     unsigned x, y, z, w;
 };
+struct uint2 {
+    unsigned x, y;
+};
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
 extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __global__
 #define __device__
@@ -32,6 +36,7 @@ extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __restrict__
 #define AV1B_UNROLL
+#define AV1B_UNROLL4
 static inline void __syncthreads() {}
 static inline void __syncwarp() {}
 static inline void __threadfence() {}
@@ -86,6 +91,7 @@ template <class F> static inline void emu_launch(dim3 grid, F f)
 #include <cuda_runtime.h>
 typedef cudaStream_t av1b_stream_t;
 #define AV1B_UNROLL _Pragma("unroll")
+#define AV1B_UNROLL4 _Pragma("unroll 4")
 #define AV1B_NOINLINE __noinline__
 #define AV1B_LAUNCH(kern, grid, block, stream, ...) kern<<<dim3 grid, dim3 block, 0, stream>>>(__VA_ARGS__)
 #define AV1T_CONST static __device__ const
@@ -112,6 +118,48 @@ AV1B_DEV void block_sync(int nt)
     if (nt > 32) __syncthreads();
     else __syncwarp();
 }
+
+// Integer dot products (IDP.4A / IDP.2A).  a = four unsigned bytes (dp4a) or two signed 16-bit
+// halves (dp2a); b = signed bytes; c = accumulator.
+#ifdef AV1B_EMU
+static inline int av1b_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
+    return c;
+}
+static inline int av1b_dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    return c + (int)(int16_t)(a & 0xFFFF) * (int)(int8_t)(b & 0xFF) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 8) & 0xFF);
+}
+static inline int av1b_dp2a_hi(uint32_t a, uint32_t b, int c)
+{
+    return c + (int)(int16_t)(a & 0xFFFF) * (int)(int8_t)((b >> 16) & 0xFF) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 24) & 0xFF);
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    sh &= 31;
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+}
+#else
+static __device__ __forceinline__ int av1b_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+static __device__ __forceinline__ int av1b_dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+static __device__ __forceinline__ int av1b_dp2a_hi(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#endif
 
 AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }

@@ -170,7 +170,7 @@ AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const 
 // __syncwarp, each warp owns a private scratch area, and 8x8 blocks do not idle a whole CTA.
 enum { INTER_WARPS = 8 };
 
-__global__ void __launch_bounds__(INTER_WARPS * 32) inter_kernel(ReconCtx c)
+__global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
 {
     __shared__ mc::Scratch M[INTER_WARPS];
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
