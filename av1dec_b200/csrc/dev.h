@@ -27,6 +27,7 @@ struct uint2 {
     unsigned x, y;
 };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{ x, y, z, w }; }
 extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __global__
 #define __device__
@@ -51,6 +52,11 @@ static inline void av1b_st_release(int* p, int v) { *p = v; }
 static inline void av1b_nanosleep(unsigned) {}
 using std::max;
 using std::min;
+// single-lane "warp": shuffles and votes see only lane 0
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #define AV1B_NOINLINE
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

@@ -77,11 +77,119 @@ struct Params {
 
 AV1B_DEV int ilog2_pow2(int v) { return 31 - __clz(v); }
 
-// Four halved filter taps as signed bytes.
-AV1B_DEV uint32_t pack_taps(const int16_t* f)
+// Translational prediction of one tile: the tw x th samples whose integer reference position
+// starts at (px0, py0), filtered with `taps` (packed halved taps: .x/.y horizontal, .z/.w
+// vertical) when `subpel`, into pred (pitch TILE_W).  tw is a power of two (2..32), th <= TILE_H.
+AV1B_DEV void convolve_tile(const RefPlane& R, int px0, int py0, bool subpel, uint4 taps, int tw, int th, int round1,
+    Scratch& s, int16_t* pred, int tid, int nt)
 {
-    return ((uint32_t)(f[0] >> 1) & 0xFF) | (((uint32_t)(f[1] >> 1) & 0xFF) << 8) | (((uint32_t)(f[2] >> 1) & 0xFF) << 16)
-        | (((uint32_t)(f[3] >> 1) & 0xFF) << 24);
+    const int ltw = ilog2_pow2(tw);
+    // word path: aligned plane, window fully inside the reference (the padding right of each
+    // row absorbs the <= 7 bytes a word read may run past the window)
+    const bool words = ((((uintptr_t)R.p) | (unsigned)R.stride) & 3) == 0;
+    if (!subpel) {
+        const int sh = 14 - 3 - round1;
+        const bool inside = px0 >= 0 && px0 + tw - 1 <= R.last_x && py0 >= 0 && py0 + th - 1 <= R.last_y;
+        if (words && inside && tw >= 4) {
+            const uint8_t* base = R.p + (ptrdiff_t)py0 * R.stride + px0;
+            const unsigned mis8 = ((unsigned)(uintptr_t)base & 3) * 8;
+            base -= mis8 >> 3;
+            const int lq = ltw - 2;
+            for (int e = tid; e < (th << lq); e += nt) {
+                const int r = e >> lq, q = e & ((1 << lq) - 1);
+                const uint32_t* g = (const uint32_t*)(base + (ptrdiff_t)r * R.stride) + q;
+                const uint32_t lo = R.coherent ? __ldcg(g) : __ldg(g);
+                const uint32_t hi = R.coherent ? __ldcg(g + 1) : __ldg(g + 1);
+                const uint32_t w = __funnelshift_r(lo, hi, mis8);
+                uint2 o;
+                o.x = (__byte_perm(w, 0, 0x4140)) << sh;
+                o.y = (__byte_perm(w, 0, 0x4342)) << sh;
+                *(uint2*)(pred + r * TILE_W + 4 * q) = o;
+            }
+        } else {
+            for (int e = tid; e < (th << ltw); e += nt) {
+                const int r = e >> ltw, c = e & (tw - 1);
+                pred[r * TILE_W + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
+            }
+        }
+        block_sync(nt);
+        return;
+    }
+    // stage the clamped reference window: rows py0-3 .. py0+th+3, columns px0-3 .. px0+tw+3
+    {
+        const int ww = tw + 7, wh = th + 7;
+        const bool inside = px0 - 3 >= 0 && px0 + tw + 3 <= R.last_x && py0 - 3 >= 0 && py0 + th + 3 <= R.last_y;
+        if (words && inside) {
+            const uint8_t* base = R.p + (ptrdiff_t)(py0 - 3) * R.stride + (px0 - 3);
+            const unsigned mis8 = ((unsigned)(uintptr_t)base & 3) * 8;
+            base -= mis8 >> 3;
+            const int nwr = (ww + 3) >> 2;              // window words per row: 3, 4, 6, 10
+            const unsigned inv = nwr == 3 ? 21846u : nwr == 4 ? 16385u : nwr == 6 ? 10923u : 6554u; // 65536 / nwr + 1
+            uint32_t* win32 = (uint32_t*)s.win;
+            AV1B_UNROLL4
+            for (int e = tid; e < nwr * wh; e += nt) {
+                const int r = (int)(((unsigned)e * inv) >> 16), k = e - r * nwr;
+                const uint32_t* g = (const uint32_t*)(base + (ptrdiff_t)r * R.stride) + k;
+                const uint32_t lo = R.coherent ? __ldcg(g) : __ldg(g);
+                const uint32_t hi = R.coherent ? __ldcg(g + 1) : __ldg(g + 1);
+                win32[r * (WIN_PITCH / 4) + k] = __funnelshift_r(lo, hi, mis8);
+            }
+        } else {
+            const unsigned magic = ww == 39 ? 110127367u : ww == 23 ? 186737709u : ww == 15 ? 286331154u : ww == 11 ? 390451573u : 477218589u;
+            for (int e = tid; e < ww * wh; e += nt) {
+                const int r = (int)__umulhi((unsigned)e, magic), c = e - r * ww;
+                s.win[r * WIN_PITCH + c] = (uint8_t)ref_px(R, px0 - 3 + c, py0 - 3 + r);
+            }
+        }
+    }
+    block_sync(nt);
+    // Every AV1 sub-pel tap is even (reference table InterPredict.cpp:99-); halved taps fit a
+    // signed byte, so the 8-tap sums run as packed dot products and the roundings drop one bit:
+    //   (2s + 4) >> 3 == (s + 2) >> 2,   round2(2s, n) == (s + (1 << (n - 2))) >> (n - 1).
+    const uint32_t fha = taps.x, fhb = taps.y, fva = taps.z, fvb = taps.w;
+    // horizontal pass, four outputs per lane; intermediates are stored TRANSPOSED
+    // (inter[c * INTER_PITCH + r]) so that the vertical pass reads row pairs as one word.
+    {
+        const int lq = ltw >= 2 ? ltw - 2 : 0;
+        const uint32_t* win32 = (const uint32_t*)s.win;
+        for (int e = tid; e < ((th + 7) << lq); e += nt) {
+            const int r = e >> lq, q = e & ((1 << lq) - 1);
+            const uint32_t* wp = win32 + r * (WIN_PITCH / 4) + q;
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            int16_t* o = s.inter + (4 * q) * INTER_PITCH + r;
+            int sum = av1b_dp4a_us(w1, fhb, av1b_dp4a_us(w0, fha, 2));
+            o[0] = (int16_t)(sum >> 2);
+            sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x4321), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x4321), fha, 2));
+            o[INTER_PITCH] = (int16_t)(sum >> 2);
+            if (tw > 2) {
+                sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x5432), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x5432), fha, 2));
+                o[2 * INTER_PITCH] = (int16_t)(sum >> 2);
+                sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x6543), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x6543), fha, 2));
+                o[3 * INTER_PITCH] = (int16_t)(sum >> 2);
+            }
+        }
+    }
+    block_sync(nt);
+    // vertical pass: one lane = one column, two output rows
+    {
+        const int rnd = 1 << (round1 - 2), shv = round1 - 1;
+        for (int e = tid; e < ((th >> 1) << ltw); e += nt) {
+            const int k = e >> ltw, c = e & (tw - 1);
+            const uint32_t* q = (const uint32_t*)(s.inter + c * INTER_PITCH) + k;
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+            int sum = av1b_dp2a_lo(w0, fva, rnd);
+            sum = av1b_dp2a_hi(w1, fva, sum);
+            sum = av1b_dp2a_lo(w2, fvb, sum);
+            sum = av1b_dp2a_hi(w3, fvb, sum);
+            pred[(2 * k) * TILE_W + c] = (int16_t)(sum >> shv);
+            sum = av1b_dp2a_lo(__funnelshift_r(w0, w1, 16), fva, rnd);
+            sum = av1b_dp2a_hi(__funnelshift_r(w1, w2, 16), fva, sum);
+            sum = av1b_dp2a_lo(__funnelshift_r(w2, w3, 16), fvb, sum);
+            sum = av1b_dp2a_hi(__funnelshift_r(w3, w4, 16), fvb, sum);
+            pred[(2 * k + 1) * TILE_W + c] = (int16_t)(sum >> shv);
+        }
+    }
+    block_sync(nt);
 }
 
 // Prediction of list `l` for the tile at (tx,ty) size (tw,th) into s.pred[l] (pitch TILE_W).
@@ -147,119 +255,12 @@ AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int
     const int mvx = (2 * u.mv[l][1]) >> subx; // 1/16 sample
     const int mvy = (2 * u.mv[l][0]) >> suby;
     const int fx = mvx & 15, fy = mvy & 15;
-    const int px0 = u.x + tx + (mvx >> 4), py0 = u.y + ty + (mvy >> 4);
-    // word path: aligned plane, window fully inside the reference (the padding right of each
-    // row absorbs the <= 7 bytes a word read may run past the window)
-    const bool words = ((((uintptr_t)R.p) | (unsigned)R.stride) & 3) == 0;
-    if (!fx && !fy) {
-        const int sh = 14 - 3 - round1;
-        const bool inside = px0 >= 0 && px0 + tw - 1 <= R.last_x && py0 >= 0 && py0 + th - 1 <= R.last_y;
-        if (words && inside && tw >= 4) {
-            const uint8_t* base = R.p + (ptrdiff_t)py0 * R.stride + px0;
-            const unsigned mis8 = ((unsigned)(uintptr_t)base & 3) * 8;
-            base -= mis8 >> 3;
-            const int lq = ltw - 2;
-            for (int e = tid; e < (th << lq); e += nt) {
-                const int r = e >> lq, q = e & ((1 << lq) - 1);
-                const uint32_t* g = (const uint32_t*)(base + (ptrdiff_t)r * R.stride) + q;
-                const uint32_t lo = R.coherent ? __ldcg(g) : __ldg(g);
-                const uint32_t hi = R.coherent ? __ldcg(g + 1) : __ldg(g + 1);
-                const uint32_t w = __funnelshift_r(lo, hi, mis8);
-                uint2 o;
-                o.x = (__byte_perm(w, 0, 0x4140)) << sh;
-                o.y = (__byte_perm(w, 0, 0x4342)) << sh;
-                *(uint2*)(pred + r * TILE_W + 4 * q) = o;
-            }
-        } else {
-            for (int e = tid; e < (th << ltw); e += nt) {
-                const int r = e >> ltw, c = e & (tw - 1);
-                pred[r * TILE_W + c] = (int16_t)(ref_px(R, px0 + c, py0 + r) << sh);
-            }
-        }
-        block_sync(nt);
-        return;
-    }
-    // stage the clamped reference window: rows py0-3 .. py0+th+3, columns px0-3 .. px0+tw+3
-    {
-        const int ww = tw + 7, wh = th + 7;
-        const bool inside = px0 - 3 >= 0 && px0 + tw + 3 <= R.last_x && py0 - 3 >= 0 && py0 + th + 3 <= R.last_y;
-        if (words && inside) {
-            const uint8_t* base = R.p + (ptrdiff_t)(py0 - 3) * R.stride + (px0 - 3);
-            const unsigned mis8 = ((unsigned)(uintptr_t)base & 3) * 8;
-            base -= mis8 >> 3;
-            const int nwr = (ww + 3) >> 2;              // window words per row: 3, 4, 6, 10
-            const unsigned inv = 65536u / nwr + 1;      // e / nwr for e < 256
-            uint32_t* win32 = (uint32_t*)s.win;
-            AV1B_UNROLL4
-            for (int e = tid; e < nwr * wh; e += nt) {
-                const int r = (int)(((unsigned)e * inv) >> 16), k = e - r * nwr;
-                const uint32_t* g = (const uint32_t*)(base + (ptrdiff_t)r * R.stride) + k;
-                const uint32_t lo = R.coherent ? __ldcg(g) : __ldg(g);
-                const uint32_t hi = R.coherent ? __ldcg(g + 1) : __ldg(g + 1);
-                win32[r * (WIN_PITCH / 4) + k] = __funnelshift_r(lo, hi, mis8);
-            }
-        } else {
-            const unsigned magic = ww == 39 ? 110127367u : ww == 23 ? 186737709u : ww == 15 ? 286331154u : ww == 11 ? 390451573u : 477218589u;
-            for (int e = tid; e < ww * wh; e += nt) {
-                const int r = (int)__umulhi((unsigned)e, magic), c = e - r * ww;
-                s.win[r * WIN_PITCH + c] = (uint8_t)ref_px(R, px0 - 3 + c, py0 - 3 + r);
-            }
-        }
-    }
-    block_sync(nt);
-    // Every AV1 sub-pel tap is even (reference table InterPredict.cpp:99-); halved taps fit a
-    // signed byte, so the 8-tap sums run as packed dot products and the roundings drop one bit:
-    //   (2s + 4) >> 3 == (s + 2) >> 2,   round2(2s, n) == (s + (1 << (n - 2))) >> (n - 1).
-    uint32_t fha, fhb, fva, fvb;
-    {
-        const int16_t* fh = k_subpel_filters[filter_row(u.w, u.filt[1])][fx];
-        const int16_t* fv = k_subpel_filters[filter_row(u.h, u.filt[0])][fy];
-        fha = pack_taps(fh), fhb = pack_taps(fh + 4);
-        fva = pack_taps(fv), fvb = pack_taps(fv + 4);
-    }
-    // horizontal pass, four outputs per lane; intermediates are stored TRANSPOSED
-    // (inter[c * INTER_PITCH + r]) so that the vertical pass reads row pairs as one word.
-    {
-        const int lq = ltw >= 2 ? ltw - 2 : 0;
-        const uint32_t* win32 = (const uint32_t*)s.win;
-        for (int e = tid; e < ((th + 7) << lq); e += nt) {
-            const int r = e >> lq, q = e & ((1 << lq) - 1);
-            const uint32_t* wp = win32 + r * (WIN_PITCH / 4) + q;
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            int16_t* o = s.inter + (4 * q) * INTER_PITCH + r;
-            int sum = av1b_dp4a_us(w1, fhb, av1b_dp4a_us(w0, fha, 2));
-            o[0] = (int16_t)(sum >> 2);
-            sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x4321), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x4321), fha, 2));
-            o[INTER_PITCH] = (int16_t)(sum >> 2);
-            if (tw > 2) {
-                sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x5432), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x5432), fha, 2));
-                o[2 * INTER_PITCH] = (int16_t)(sum >> 2);
-                sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x6543), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x6543), fha, 2));
-                o[3 * INTER_PITCH] = (int16_t)(sum >> 2);
-            }
-        }
-    }
-    block_sync(nt);
-    // vertical pass: one lane = one column, two output rows
-    {
-        const int rnd = 1 << (round1 - 2), shv = round1 - 1;
-        for (int e = tid; e < ((th >> 1) << ltw); e += nt) {
-            const int k = e >> ltw, c = e & (tw - 1);
-            const uint32_t* q = (const uint32_t*)(s.inter + c * INTER_PITCH) + k;
-            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
-            int sum = av1b_dp2a_lo(w0, fva, rnd);
-            sum = av1b_dp2a_hi(w1, fva, sum);
-            sum = av1b_dp2a_lo(w2, fvb, sum);
-            sum = av1b_dp2a_hi(w3, fvb, sum);
-            pred[(2 * k) * TILE_W + c] = (int16_t)(sum >> shv);
-            sum = av1b_dp2a_lo(__funnelshift_r(w0, w1, 16), fva, rnd);
-            sum = av1b_dp2a_hi(__funnelshift_r(w1, w2, 16), fva, sum);
-            sum = av1b_dp2a_lo(__funnelshift_r(w2, w3, 16), fvb, sum);
-            sum = av1b_dp2a_hi(__funnelshift_r(w3, w4, 16), fvb, sum);
-            pred[(2 * k + 1) * TILE_W + c] = (int16_t)(sum >> shv);
-        }
-    }
-    block_sync(nt);
+    uint4 taps;
+    taps.x = k_subpel_packed[filter_row(u.w, u.filt[1])][fx][0];
+    taps.y = k_subpel_packed[filter_row(u.w, u.filt[1])][fx][1];
+    taps.z = k_subpel_packed[filter_row(u.h, u.filt[0])][fy][0];
+    taps.w = k_subpel_packed[filter_row(u.h, u.filt[0])][fy][1];
+    convolve_tile(R, u.x + tx + (mvx >> 4), u.y + ty + (mvy >> 4), (fx | fy) != 0, taps, tw, th, round1, s, pred, tid, nt);
 }
 
 // Execute one unit: predict every tile and write / blend it into the destination plane.

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
     mc::Scratch& S = M[warp];
     for (unsigned b = blockIdx.x * nw + warp; b < hdr->n_iblk; b += gridDim.x * nw) {
         const Av1bInterBlk blk = blks[b];
+        if (blk.flags & AV1B_IBF_FAST) continue; // inter_fast_kernel's
         for (unsigned k = 0; k < blk.n_ipu; k++) {
             const Av1bIpu u = ipus[blk.first_ipu + k];
             mc::Params P;
@@ -208,6 +209,144 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
             }
         }
         block_sync(nl);
+    }
+}
+
+// Fast path for the units of AV1B_IBF_FAST blocks (plain translational prediction, the bulk of
+// any inter frame).  Units are independent, so the kernel walks the UNIT list, a warp taking 32
+// consecutive units at a time: each lane derives one unit's parameters (reference plane, clamp
+// limits, integer position, packed filter taps), then the warp runs the flagged units one after
+// the other with the parameters broadcast by shuffle -- the per-unit scalar set-up, which would
+// otherwise cost a full warp instruction per value per unit, is paid once per 32 units.  The
+// residual of plain inter blocks is added in the same store (AV1B_IPUF_ADD_RES).
+enum { FAST_WARPS = 4 };
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx c)
+{
+    __shared__ mc::Scratch M[FAST_WARPS];
+    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const uint4* ipus = (const uint4*)(c.cmd + hdr->off_ipu);
+    const unsigned n_ipu = hdr->n_ipu;
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
+    const unsigned FULL = 0xFFFFFFFFu;
+    mc::Scratch& S = M[warp];
+    for (unsigned chunk = blockIdx.x * nl; chunk < n_ipu; chunk += gridDim.x * nl) {
+        // ---- lane-parallel set-up: lane i <-> unit chunk + i
+        const unsigned idx = chunk + lane;
+        uint32_t u_xy = 0, u_dim = 0, u_fl = 0;   // x|y<<16, w|h<<8|plane<<16|kind<<24, flags|comp|fwd|bck
+        uint32_t r_lo[2] = { 0, 0 }, r_hi[2] = { 0, 0 }, r_stride[2] = { 0, 0 }, r_last[2] = { 0, 0 };
+        int r_px[2] = { 0, 0 }, r_py[2] = { 0, 0 };
+        uint4 r_taps[2] = {};
+        uint32_t subpel = 0;
+        bool fast = false;
+        if (idx < n_ipu) {
+            const uint4 a = __ldg(ipus + 2 * idx), b = __ldg(ipus + 2 * idx + 1);
+            u_xy = a.x, u_dim = a.y, u_fl = b.z;
+            fast = (u_fl & AV1B_IPUF_FAST) != 0;
+            if (fast) {
+                const int x = u_xy & 0xFFFF, y = u_xy >> 16, w = u_dim & 0xFF, h = (u_dim >> 8) & 0xFF;
+                const int plane = (u_dim >> 16) & 0xFF, sub = plane ? 1 : 0;
+                const int lists = (u_fl & AV1B_IPUF_COMPOUND) ? 2 : 1;
+                const int filt_v = b.y & 0xFF, filt_h = (b.y >> 8) & 0xFF;
+                for (int l = 0; l < lists; l++) {
+                    const int slot = (int8_t)((b.x >> (8 * l)) & 0xFF), rf = (b.x >> (16 + 8 * l)) & 0xFF;
+                    const PlaneView& pv = c.ref[slot & 7].pl[plane];
+                    r_lo[l] = (uint32_t)(uintptr_t)pv.p;
+                    r_hi[l] = (uint32_t)((uintptr_t)pv.p >> 32);
+                    r_stride[l] = (uint32_t)pv.stride;
+                    r_last[l] = (uint32_t)(((hdr->ref_w[rf] + sub) >> sub) - 1) | ((uint32_t)(((hdr->ref_h[rf] + sub) >> sub) - 1) << 16);
+                    const uint32_t mvw = l ? a.w : a.z;
+                    const int mvx = (2 * (int)(int16_t)(mvw >> 16)) >> sub, mvy = (2 * (int)(int16_t)(mvw & 0xFFFF)) >> sub;
+                    const int fx = mvx & 15, fy = mvy & 15;
+                    r_px[l] = x + (mvx >> 4);
+                    r_py[l] = y + (mvy >> 4);
+                    if (fx | fy) subpel |= 1u << l;
+                    const uint32_t* th = k_subpel_packed[mc::filter_row(w, filt_h)][fx];
+                    const uint32_t* tv = k_subpel_packed[mc::filter_row(h, filt_v)][fy];
+                    r_taps[l] = make_uint4(th[0], th[1], tv[0], tv[1]);
+                }
+            }
+        }
+        // ---- jobs = (unit, tile) pairs in unit order, dealt round-robin to the CTA's warps (every
+        // warp of the CTA did the same set-up); parameters are broadcast from the unit's lane
+        const int my_w = u_dim & 0xFF, my_h = (u_dim >> 8) & 0xFF;
+        const int my_tiles = fast ? ((my_w + mc::TILE_W - 1) / mc::TILE_W) * ((my_h + mc::TILE_H - 1) / mc::TILE_H) : 0;
+        int incl = my_tiles;
+        for (int d = 1; d < nl; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int excl = incl - my_tiles;
+        const int total = __shfl_sync(FULL, incl, nl - 1);
+        for (int job = warp; job < total; job += nw) {
+            const int j = 31 - __clz(__ballot_sync(FULL, excl <= job));
+            const int tile = job - __shfl_sync(FULL, excl, j);
+            const uint32_t xy = __shfl_sync(FULL, u_xy, j), dim = __shfl_sync(FULL, u_dim, j), fl = __shfl_sync(FULL, u_fl, j);
+            const uint32_t sp = __shfl_sync(FULL, subpel, j);
+            const int x = xy & 0xFFFF, y = xy >> 16, w = dim & 0xFF, h = (dim >> 8) & 0xFF, plane = (dim >> 16) & 0xFF;
+            const bool compound = (fl & AV1B_IPUF_COMPOUND) != 0;
+            const int comp = (fl >> 8) & 0xFF;
+            const int round1 = compound ? 7 : 11;
+            mc::RefPlane R[2];
+            int px[2], py[2];
+            uint4 taps[2];
+            AV1B_UNROLL
+            for (int l = 0; l < 2; l++) {
+                if (l && !compound) break;
+                R[l].p = (const uint8_t*)(uintptr_t)((uint64_t)__shfl_sync(FULL, r_lo[l], j) | ((uint64_t)__shfl_sync(FULL, r_hi[l], j) << 32));
+                R[l].stride = (int)__shfl_sync(FULL, r_stride[l], j);
+                const uint32_t last = __shfl_sync(FULL, r_last[l], j);
+                R[l].last_x = last & 0xFFFF;
+                R[l].last_y = last >> 16;
+                R[l].coherent = false;
+                px[l] = __shfl_sync(FULL, r_px[l], j);
+                py[l] = __shfl_sync(FULL, r_py[l], j);
+                taps[l].x = __shfl_sync(FULL, r_taps[l].x, j);
+                taps[l].y = __shfl_sync(FULL, r_taps[l].y, j);
+                taps[l].z = __shfl_sync(FULL, r_taps[l].z, j);
+                taps[l].w = __shfl_sync(FULL, r_taps[l].w, j);
+            }
+            const PlaneView dst = c.cur.pl[plane];
+            const int16_t* res = ((fl & AV1B_IPUF_ADD_RES) && c.rp[0]) ? c.rp[plane] : nullptr;
+            const int rpitch = c.rpitch[plane];
+            // blend weights: single (1,0,>>0), average (8,8,>>8 == (p0+p1+16)>>5), distance (fwd,bck,>>8)
+            const int w0 = !compound ? 1 : (comp == AV1B_COMP_AVERAGE ? 8 : (int)((fl >> 16) & 0xFF));
+            const int w1 = !compound ? 0 : (comp == AV1B_COMP_AVERAGE ? 8 : (int)(fl >> 24));
+            const int sh = compound ? 8 : 0;
+            {
+                // w is a power of two: tiles per row is 1, 2 or 4
+                const int ltr = w > 64 ? 2 : (w > 32 ? 1 : 0);
+                const int ty = (tile >> ltr) * mc::TILE_H, tx = (tile & ((1 << ltr) - 1)) * mc::TILE_W;
+                const int th = min((int)mc::TILE_H, h - ty);
+                {
+                    const int tw = min((int)mc::TILE_W, w - tx);
+                    const int lq = mc::ilog2_pow2(tw) - 2;
+                    mc::convolve_tile(R[0], px[0] + tx, py[0] + ty, (sp & 1) != 0, taps[0], tw, th, round1, S, S.pred[0], lane, nl);
+                    if (compound) mc::convolve_tile(R[1], px[1] + tx, py[1] + ty, (sp & 2) != 0, taps[1], tw, th, round1, S, S.pred[1], lane, nl);
+                    for (int e = lane; e < (th << lq); e += nl) {
+                        const int r = e >> lq, q = e & ((1 << lq) - 1);
+                        const uint2 p0 = *(const uint2*)(S.pred[0] + r * mc::TILE_W + 4 * q);
+                        uint2 p1 = make_uint2(0, 0);
+                        if (compound) p1 = *(const uint2*)(S.pred[1] + r * mc::TILE_W + 4 * q);
+                        int o0 = clip_u8(round2(w0 * (int)(int16_t)(p0.x & 0xFFFF) + w1 * (int)(int16_t)(p1.x & 0xFFFF), sh));
+                        int o1 = clip_u8(round2(w0 * ((int)p0.x >> 16) + w1 * ((int)p1.x >> 16), sh));
+                        int o2 = clip_u8(round2(w0 * (int)(int16_t)(p0.y & 0xFFFF) + w1 * (int)(int16_t)(p1.y & 0xFFFF), sh));
+                        int o3 = clip_u8(round2(w0 * ((int)p0.y >> 16) + w1 * ((int)p1.y >> 16), sh));
+                        const int yy = y + ty + r, xx = x + tx + 4 * q;
+                        if (res) {
+                            const uint2 rr = *(const uint2*)(res + (size_t)yy * rpitch + xx);
+                            o0 = clip_u8(o0 + (int)(int16_t)(rr.x & 0xFFFF));
+                            o1 = clip_u8(o1 + ((int)rr.x >> 16));
+                            o2 = clip_u8(o2 + (int)(int16_t)(rr.y & 0xFFFF));
+                            o3 = clip_u8(o3 + ((int)rr.y >> 16));
+                        }
+                        *(uint32_t*)(dst.p + (size_t)yy * dst.stride + xx) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+                    }
+                    block_sync(nl);
+                }
+            }
+        }
     }
 }
 
@@ -609,6 +748,9 @@ void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     int grid = (int)((h.n_iblk + INTER_WARPS - 1) / INTER_WARPS);
     if (grid > 148 * 6) grid = 148 * 6;
     AV1B_LAUNCH(inter_kernel, (grid), (INTER_WARPS * 32), st, c);
+    int fgrid = (int)((h.n_ipu + 31) / 32); // one 32-unit chunk per CTA pass
+    if (fgrid > 148 * 48) fgrid = 148 * 48;
+    if (fgrid) AV1B_LAUNCH(inter_fast_kernel, (fgrid), (FAST_WARPS * 32), st, c);
 }
 
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)

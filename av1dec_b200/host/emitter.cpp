@@ -438,7 +438,22 @@ void FrameEmitter::emitInter(Block& b)
         if (b.motion_mode == OBMC_CAUSAL) emitObmc(b, plane, predW, predH);
     }
     ib.n_ipu = (uint16_t)(m_ipu.size() - ib.first_ipu);
-    if (!intrabc && ib.n_ipu) m_iblk.push_back(ib);
+    if (!intrabc && ib.n_ipu) {
+        // plain translational blocks: independent units, fast kernel
+        bool fast = true;
+        for (size_t k = ib.first_ipu; k < m_ipu.size() && fast; k++) {
+            const Av1bIpu& u = m_ipu[k];
+            const bool big = u.w >= 8 && u.h >= 8;
+            fast = u.kind == AV1B_IPU_PRED && u.w >= 4 && !(big && (u.warp[0] || u.warp[1]))
+                && (!(u.flags & AV1B_IPUF_COMPOUND) || u.comp_type == AV1B_COMP_AVERAGE || u.comp_type == AV1B_COMP_DISTANCE);
+        }
+        if (fast) {
+            ib.flags |= AV1B_IBF_FAST;
+            const uint8_t add = (ib.flags & AV1B_IBF_ADD_RESIDUAL) ? AV1B_IPUF_ADD_RES : 0;
+            for (size_t k = ib.first_ipu; k < m_ipu.size(); k++) m_ipu[k].flags |= AV1B_IPUF_FAST | add;
+        }
+        m_iblk.push_back(ib);
+    }
 }
 
 // overlappedMotionCompensation (InterPredict.cpp:658-709): which neighbours contribute strips

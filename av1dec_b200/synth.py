@@ -371,14 +371,14 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512):
         v["ref_slot"][:, 0] = ref0 - 1
         v["ref_slot"][:, 1] = np.where(comp, 2 - ref0, -1)
         v["filt"] = filt
-        v["flags"] = comp.astype(np.uint8)  # AV1B_IPUF_COMPOUND
+        v["flags"] = comp.astype(np.uint8) | 0x08  # AV1B_IPUF_COMPOUND, AV1B_IPUF_FAST
         v["comp_type"] = 2                  # AV1B_COMP_AVERAGE
         v["aux"] = 0xFFFFFFFF
     blk_t = np.dtype([("first_ipu", "<u4"), ("n_ipu", "<u2"), ("flags", "<u2"), ("x", "<u2"), ("y", "<u2"), ("cx", "<u2"),
                       ("cy", "<u2"), ("bw", "u1"), ("bh", "u1"), ("cw", "u1"), ("ch", "u1"), ("pad", "<u4")])
     assert blk_t.itemsize == 24
     blk = np.zeros(nb, blk_t)
-    blk["first_ipu"], blk["n_ipu"], blk["flags"] = np.arange(nb) * 3, 3, 1
+    blk["first_ipu"], blk["n_ipu"], blk["flags"] = np.arange(nb) * 3, 3, 1 | 4  # HAS_CHROMA | FAST
     blk["x"], blk["y"], blk["cx"], blk["cy"] = bx, by, bx >> 1, by >> 1
     blk["bw"] = blk["bh"] = bs
     blk["cw"] = blk["ch"] = bs >> 1

@@ -114,6 +114,10 @@ def main():
     sub = extract("decoder/InterPredict.cpp", "Subpel_Filters")
     assert dims(sub) == [6, 16, 8]
     T.append(emit("int16_t", "k_subpel_filters", sub))
+    # the same taps halved (every tap is even) and packed as signed bytes, four per word
+    packed = [[[sum(((t >> 1) & 0xFF) << (8 * i) for i, t in enumerate(f[k:k + 4])) for k in (0, 4)] for f in row] for row in sub]
+    assert all(t % 2 == 0 and -128 <= (t >> 1) <= 127 for row in sub for f in row for t in f)
+    T.append(emit("uint32_t", "k_subpel_packed", packed, per_line=8))
     warp = extract("decoder/InterPredict.cpp", "Warped_Filters")
     assert dims(warp) == [193, 8]
     T.append(emit("int16_t", "k_warped_filters", warp))
