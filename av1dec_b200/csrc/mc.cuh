@@ -192,6 +192,86 @@ AV1B_DEV void convolve_tile(const RefPlane& R, int px0, int py0, bool subpel, ui
     block_sync(nt);
 }
 
+// ---- fast translational path (inter_fast_kernel): no staged window, no prediction buffer ----
+// Horizontal pass straight from global memory into the transposed intermediate, then one pass
+// that filters vertically, blends the lists, adds the residual and stores, 4x2 samples a lane.
+struct FastScratch {
+    alignas(8) int16_t inter[2][TILE_W * INTER_PITCH];
+};
+
+// True when every sample an 8-tap window around the tile touches lies inside the reference and
+// the plane can be read by aligned words.
+AV1B_DEV bool fast_tile_ok(const RefPlane& R, int px0, int py0, int tw, int th)
+{
+    return px0 - 3 >= 0 && px0 + tw + 3 <= R.last_x && py0 - 3 >= 0 && py0 + th + 3 <= R.last_y
+        && ((((uintptr_t)R.p) | (unsigned)R.stride) & 3) == 0;
+}
+
+// Horizontal pass of one list: rows py0-3 .. py0+th+3 (sub-pel) or py0 .. py0+th-1 (integer
+// position; the value stored is then already the prediction, sample << sh).
+AV1B_DEV void fast_h(const RefPlane& R, int px0, int py0, bool subpel, uint32_t fha, uint32_t fhb, int ltw, int th, int sh,
+    int16_t* inter, int tid, int nt)
+{
+    const int lq = ltw - 2;
+    if (subpel) {
+        const uint8_t* g0 = R.p + (ptrdiff_t)(py0 - 3) * R.stride + (px0 - 3);
+        const unsigned mis8 = ((unsigned)(uintptr_t)g0 & 3) * 8;
+        g0 -= mis8 >> 3;
+        for (int e = tid; e < ((th + 7) << lq); e += nt) {
+            const int r = e >> lq, q = e & ((1 << lq) - 1);
+            const uint32_t* g = (const uint32_t*)(g0 + (ptrdiff_t)r * R.stride) + q;
+            const uint32_t a0 = __ldg(g), a1 = __ldg(g + 1), a2 = __ldg(g + 2), a3 = __ldg(g + 3);
+            const uint32_t w0 = __funnelshift_r(a0, a1, mis8), w1 = __funnelshift_r(a1, a2, mis8), w2 = __funnelshift_r(a2, a3, mis8);
+            int16_t* o = inter + (4 * q) * INTER_PITCH + r;
+            int sum = av1b_dp4a_us(w1, fhb, av1b_dp4a_us(w0, fha, 2));
+            o[0] = (int16_t)(sum >> 2);
+            sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x4321), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x4321), fha, 2));
+            o[INTER_PITCH] = (int16_t)(sum >> 2);
+            sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x5432), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x5432), fha, 2));
+            o[2 * INTER_PITCH] = (int16_t)(sum >> 2);
+            sum = av1b_dp4a_us(__byte_perm(w1, w2, 0x6543), fhb, av1b_dp4a_us(__byte_perm(w0, w1, 0x6543), fha, 2));
+            o[3 * INTER_PITCH] = (int16_t)(sum >> 2);
+        }
+    } else {
+        const uint8_t* g0 = R.p + (ptrdiff_t)py0 * R.stride + px0;
+        const unsigned mis8 = ((unsigned)(uintptr_t)g0 & 3) * 8;
+        g0 -= mis8 >> 3;
+        for (int e = tid; e < (th << lq); e += nt) {
+            const int r = e >> lq, q = e & ((1 << lq) - 1);
+            const uint32_t* g = (const uint32_t*)(g0 + (ptrdiff_t)r * R.stride) + q;
+            const uint32_t w = __funnelshift_r(__ldg(g), __ldg(g + 1), mis8);
+            int16_t* o = inter + (4 * q) * INTER_PITCH + r;
+            o[0] = (int16_t)((w & 0xFF) << sh);
+            o[INTER_PITCH] = (int16_t)(((w >> 8) & 0xFF) << sh);
+            o[2 * INTER_PITCH] = (int16_t)(((w >> 16) & 0xFF) << sh);
+            o[3 * INTER_PITCH] = (int16_t)((w >> 24) << sh);
+        }
+    }
+}
+
+// Vertical pass for column c, output rows 2k and 2k+1 (v0, v1: predictions before blending).
+AV1B_DEV void fast_v(const int16_t* inter, int c, int k, bool subpel, uint32_t fva, uint32_t fvb, int rnd, int shv, int& v0, int& v1)
+{
+    const uint32_t* q = (const uint32_t*)(inter + c * INTER_PITCH) + k;
+    if (!subpel) {
+        const uint32_t w = q[0];
+        v0 = (int)(int16_t)(w & 0xFFFF);
+        v1 = (int)w >> 16;
+        return;
+    }
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+    int sum = av1b_dp2a_lo(w0, fva, rnd);
+    sum = av1b_dp2a_hi(w1, fva, sum);
+    sum = av1b_dp2a_lo(w2, fvb, sum);
+    sum = av1b_dp2a_hi(w3, fvb, sum);
+    v0 = sum >> shv;
+    sum = av1b_dp2a_lo(__funnelshift_r(w0, w1, 16), fva, rnd);
+    sum = av1b_dp2a_hi(__funnelshift_r(w1, w2, 16), fva, sum);
+    sum = av1b_dp2a_lo(__funnelshift_r(w2, w3, 16), fvb, sum);
+    sum = av1b_dp2a_hi(__funnelshift_r(w3, w4, 16), fvb, sum);
+    v1 = sum >> shv;
+}
+
 // Prediction of list `l` for the tile at (tx,ty) size (tw,th) into s.pred[l] (pitch TILE_W).
 // tw is a power of two (2..32), th <= TILE_H.
 AV1B_DEV void predict_tile(const Params& P, const Av1bIpu& u, int l, int tx, int ty, int tw, int th,

@@ -212,6 +212,16 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
     }
 }
 
+// Four packed samples plus four int16 residuals, each clipped to 8 bits.
+AV1B_DEV uint32_t add_res4(uint32_t px, uint2 r)
+{
+    const int o0 = clip_u8((int)(px & 0xFF) + (int)(int16_t)(r.x & 0xFFFF));
+    const int o1 = clip_u8((int)((px >> 8) & 0xFF) + ((int)r.x >> 16));
+    const int o2 = clip_u8((int)((px >> 16) & 0xFF) + (int)(int16_t)(r.y & 0xFFFF));
+    const int o3 = clip_u8((int)(px >> 24) + ((int)r.y >> 16));
+    return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+}
+
 // Fast path for the units of AV1B_IBF_FAST blocks (plain translational prediction, the bulk of
 // any inter frame).  Units are independent, so the kernel walks the UNIT list, a warp taking 32
 // consecutive units at a time: each lane derives one unit's parameters (reference plane, clamp
@@ -319,9 +329,46 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
                 const int ltr = w > 64 ? 2 : (w > 32 ? 1 : 0);
                 const int ty = (tile >> ltr) * mc::TILE_H, tx = (tile & ((1 << ltr) - 1)) * mc::TILE_W;
                 const int th = min((int)mc::TILE_H, h - ty);
+                const int tw = min((int)mc::TILE_W, w - tx);
+                const int ltw = mc::ilog2_pow2(tw), lq = ltw - 2;
+                if (mc::fast_tile_ok(R[0], px[0] + tx, py[0] + ty, tw, th) && (!compound || mc::fast_tile_ok(R[1], px[1] + tx, py[1] + ty, tw, th))) {
+                    mc::FastScratch& F = *(mc::FastScratch*)&S;
+                    const int shi = 14 - 3 - round1; // integer-position prediction = sample << shi
+                    mc::fast_h(R[0], px[0] + tx, py[0] + ty, (sp & 1) != 0, taps[0].x, taps[0].y, ltw, th, shi, F.inter[0], lane, nl);
+                    if (compound) mc::fast_h(R[1], px[1] + tx, py[1] + ty, (sp & 2) != 0, taps[1].x, taps[1].y, ltw, th, shi, F.inter[1], lane, nl);
+                    block_sync(nl);
+                    const int rnd = 1 << (round1 - 2), shv = round1 - 1;
+                    for (int e = lane; e < ((th >> 1) << lq); e += nl) {
+                        const int k = e >> lq, q = e & ((1 << lq) - 1);
+                        uint32_t row0 = 0, row1 = 0;
+                        AV1B_UNROLL
+                        for (int i = 0; i < 4; i++) {
+                            int a0, a1;
+                            mc::fast_v(F.inter[0], 4 * q + i, k, (sp & 1) != 0, taps[0].z, taps[0].w, rnd, shv, a0, a1);
+                            if (compound) {
+                                int b0, b1;
+                                mc::fast_v(F.inter[1], 4 * q + i, k, (sp & 2) != 0, taps[1].z, taps[1].w, rnd, shv, b0, b1);
+                                a0 = round2(w0 * a0 + w1 * b0, 8);
+                                a1 = round2(w0 * a1 + w1 * b1, 8);
+                            }
+                            row0 |= (uint32_t)clip_u8(a0) << (8 * i);
+                            row1 |= (uint32_t)clip_u8(a1) << (8 * i);
+                        }
+                        const int yy = y + ty + 2 * k, xx = x + tx + 4 * q;
+                        if (res) {
+                            const uint2 r0 = *(const uint2*)(res + (size_t)yy * rpitch + xx), r1 = *(const uint2*)(res + (size_t)(yy + 1) * rpitch + xx);
+                            row0 = add_res4(row0, r0);
+                            row1 = add_res4(row1, r1);
+                        }
+                        uint8_t* d = dst.p + (size_t)yy * dst.stride + xx;
+                        *(uint32_t*)d = row0;
+                        *(uint32_t*)(d + dst.stride) = row1;
+                    }
+                    block_sync(nl);
+                    continue;
+                }
+                // tile touching the reference border: staged, clamped window
                 {
-                    const int tw = min((int)mc::TILE_W, w - tx);
-                    const int lq = mc::ilog2_pow2(tw) - 2;
                     mc::convolve_tile(R[0], px[0] + tx, py[0] + ty, (sp & 1) != 0, taps[0], tw, th, round1, S, S.pred[0], lane, nl);
                     if (compound) mc::convolve_tile(R[1], px[1] + tx, py[1] + ty, (sp & 2) != 0, taps[1], tw, th, round1, S, S.pred[1], lane, nl);
                     for (int e = lane; e < (th << lq); e += nl) {
