@@ -55,6 +55,7 @@ using std::min;
 // single-lane "warp": shuffles and votes see only lane 0
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }

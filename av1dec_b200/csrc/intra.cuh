@@ -248,24 +248,24 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
             P[e] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
         }
     } else if (mode == 0) {
-        // ---- DC
-        int avg;
-        if (a.have_left && a.have_above) {
-            int sum = 0;
-            for (int k = 0; k < h; k++) sum += L[k];
-            for (int k = 0; k < w; k++) sum += A[k];
-            avg = (sum + ((w + h) >> 1)) / (w + h);
-        } else if (a.have_left) {
-            int sum = 0;
-            for (int k = 0; k < h; k++) sum += L[k];
-            avg = clip_u8((sum + (h >> 1)) >> a.log2h);
-        } else if (a.have_above) {
-            int sum = 0;
-            for (int k = 0; k < w; k++) sum += A[k];
-            avg = clip_u8((sum + (w >> 1)) >> a.log2w);
+        // ---- DC (sums split over the lanes of a warp-sized group, folded by shuffle)
+        int sl = 0, sa = 0;
+        if (nt <= 32) {
+            for (int k = tid; k < h; k += nt) sl += L[k];
+            for (int k = tid; k < w; k += nt) sa += A[k];
+            for (int d = 1; d < nt; d <<= 1) {
+                sl += __shfl_xor_sync(0xFFFFFFFFu, sl, d);
+                sa += __shfl_xor_sync(0xFFFFFFFFu, sa, d);
+            }
         } else {
-            avg = 128;
+            for (int k = 0; k < h; k++) sl += L[k];
+            for (int k = 0; k < w; k++) sa += A[k];
         }
+        int avg;
+        if (a.have_left && a.have_above) avg = (sl + sa + ((w + h) >> 1)) / (w + h);
+        else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
+        else if (a.have_above) avg = clip_u8((sa + (w >> 1)) >> a.log2w);
+        else avg = 128;
         for (int e = tid; e < w * h; e += nt) P[e] = (uint8_t)avg;
     } else if (mode == 9) {
         const uint8_t* wx = k_sm_weights + (w - 4);

@@ -410,14 +410,31 @@ struct PlaneIo {
     int rpitch;
 };
 
-enum { WAVE_WARPS = 8, WAVE_THREADS = WAVE_WARPS * 32, WAVE_OP_CHUNK = 64 };
+enum { WAVE_WARPS = 16, WAVE_THREADS = WAVE_WARPS * 32, WAVE_OP_CHUNK = 64 };
 
 struct OpScratch {
     intra::Scratch I;
 };
 
-AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& op, const PlaneIo* io, OpScratch& S, mc::Scratch* M,
-    int tid, int nt)
+// Frame constants the op executor needs, read from the header once per kernel.
+struct FrameConst {
+    int max_x[2], max_y[2]; // ((MiCols*4)>>sub)-1, ((MiRows*4)>>sub)-1 for luma / chroma
+    bool edge_filter;
+};
+
+AV1B_DEV FrameConst frame_const(const Av1bFrameHdr* hdr)
+{
+    FrameConst f;
+    for (int sub = 0; sub < 2; sub++) {
+        f.max_x[sub] = ((hdr->mi_cols * 4) >> sub) - 1;
+        f.max_y[sub] = ((hdr->mi_rows * 4) >> sub) - 1;
+    }
+    f.edge_filter = hdr->enable_intra_edge_filter != 0;
+    return f;
+}
+
+AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameConst& fc, const Av1bOp& op, const PlaneIo* io, OpScratch& S,
+    mc::Scratch* M, int tid, int nt)
 {
     const int plane = op.plane, sub = plane ? 1 : 0;
     const PlaneIo& D = io[plane];
@@ -452,8 +469,8 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         a.y = op.y;
         a.log2w = lw;
         a.log2h = lh;
-        a.max_x = ((hdr->mi_cols * 4) >> sub) - 1;
-        a.max_y = ((hdr->mi_rows * 4) >> sub) - 1;
+        a.max_x = sub ? fc.max_x[1] : fc.max_x[0];
+        a.max_y = sub ? fc.max_y[1] : fc.max_y[0];
         a.plane_idx = plane;
         a.mode = op.mode;
         a.angle_delta = op.angle_delta;
@@ -461,7 +478,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const Av1bOp& 
         a.have_above = (op.flags & AV1B_OPF_HAVE_ABOVE) != 0;
         a.have_above_right = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) != 0;
         a.have_below_left = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) != 0;
-        a.edge_filter_enabled = hdr->enable_intra_edge_filter != 0;
+        a.edge_filter_enabled = fc.edge_filter;
         a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
         a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
         a.fi_mode = op.fi_mode;
@@ -581,6 +598,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
+    const FrameConst fc = frame_const(hdr);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
     const int lane = tid % nl, warp = tid / nl;
@@ -677,20 +695,20 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
             block_sync(nt);
             unsigned g0 = 0;
             while (g0 < nk) {
-                const uint32_t level = s_ops[g0].res_off;
-                unsigned g1 = g0 + 1;
-                while (g1 < nk && s_ops[g1].res_off == level) g1++;
+                // res_off >> 16 = ops left in this level (emitter scheduleSb); 0 from a producer
+                // that does not fill it: one op per step, still a valid order
+                const unsigned g1 = min(nk, g0 + max(1u, s_ops[g0].res_off >> 16));
 #ifdef AV1B_EMU
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
                 for (unsigned k = g1; k-- > g0;) {
                     const Av1bOp op = s_ops[k];
-                    exec_op(c, hdr, op, io, *scratch, nullptr, lane, nl);
+                    exec_op(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #else
                 for (unsigned k = g0 + warp; k < g1; k += nw) {
                     const Av1bOp op = s_ops[k];
-                    exec_op(c, hdr, op, io, *scratch, nullptr, lane, nl);
+                    exec_op(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #endif
                 block_sync(nt);
@@ -728,6 +746,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bSb* sbs = (const Av1bSb*)(c.cmd + hdr->off_sb);
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + hdr->off_ops);
+    const FrameConst fc = frame_const(hdr);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     int* ticket = c.sync;
@@ -750,7 +769,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
-            exec_op(c, hdr, op, io, S, &M, tid, nt);
+            exec_op(c, hdr, fc, op, io, S, &M, tid, nt);
         }
         wave_signal(progress, r, col, tid, nt);
     }

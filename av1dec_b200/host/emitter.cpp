@@ -85,7 +85,8 @@ void FrameEmitter::emitTile(Tile& tile)
 // map remembers the level of the last op that wrote each cell; an op's level is one more than the
 // largest level among the cells it reads (intra edges incl. above-right / below-left, CfL luma)
 // or rewrites.  The ops are then stably sorted by level (still a valid sequential order) and the
-// level is stored in Av1bOp::res_off, which frame submits do not otherwise use.
+// level (low half) and the run length to the end of the level (high half) are stored in
+// Av1bOp::res_off, which frame submits do not otherwise use.
 void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
 {
     const uint32_t n = (uint32_t)m_ops.size() - first;
@@ -151,8 +152,14 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t pos = m_count[m_levels[k]]++;
         m_sorted[pos] = m_ops[first + k];
-        m_sorted[pos].res_off = m_levels[k];
+        m_sorted[pos].res_off = m_levels[k] & 0xFFFF;
         m_perm[k] = pos;
+    }
+    // res_off = level | (ops left in this level, this one included) << 16: the device finds the end
+    // of a level without scanning
+    for (uint32_t k = n, rem = 0; k-- > 0;) {
+        rem = (k + 1 < n && (m_sorted[k + 1].res_off & 0xFFFF) == m_sorted[k].res_off) ? std::min<uint32_t>(rem + 1, 0xFFFF) : 1;
+        m_sorted[k].res_off |= rem << 16;
     }
     std::copy(m_sorted.begin(), m_sorted.end(), m_ops.begin() + first);
     for (size_t i = firstItx; i < m_itx.size(); i++)

@@ -67,8 +67,10 @@ typedef struct Av1bOp {
     uint8_t nz_cols;    /* number of leading coefficient columns that may be non-zero      */
     uint8_t lossless;   /* 1: Walsh-Hadamard path (Block::Lossless)                         */
     uint32_t coef_off;  /* int16 index into the coefficient arena (tw*th values, row-major) */
-    uint32_t res_off;   /* int16 index into the compact residual arena (stage-level ITX test mode only;
-                           a full submit writes residuals into frame-layout int16 planes)   */
+    uint32_t res_off;   /* stage-level ITX test mode: int16 index into the compact residual arena.
+                           Full submits (residuals go to frame-layout int16 planes): dependency
+                           level of the op inside its superblock in the low 16 bits, number of ops
+                           left in that level (this one included) in the high 16 bits            */
     uint32_t aux;       /* Av1bBlkAux index (palette, inter-intra) or Av1bIpu index (intrabc) */
     uint16_t max_luma_w, max_luma_h; /* CfL: Block::MaxLumaW/H at this TB                   */
 } Av1bOp;
