@@ -9,6 +9,7 @@
 #include "av1_tables_host.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -41,6 +42,7 @@ static int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
 static void rt_event_destroy(rt_event_t) {}
 static int rt_event_record(rt_event_t, av1b_stream_t) { return 0; }
 static int rt_event_sync(rt_event_t) { return 0; }
+static int rt_stream_wait(av1b_stream_t, rt_event_t) { return 0; }
 static int rt_event_done(rt_event_t) { return 1; }
 static const char* rt_error() { return "emu"; }
 static int rt_check() { return 0; }
@@ -69,6 +71,7 @@ static int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, c
 static void rt_event_destroy(rt_event_t e) { cudaEventDestroy(e); }
 static int rt_event_record(rt_event_t e, av1b_stream_t s) { return cudaEventRecord(e, s) != cudaSuccess; }
 static int rt_event_sync(rt_event_t e) { return cudaEventSynchronize(e) != cudaSuccess; }
+static int rt_stream_wait(av1b_stream_t s, rt_event_t e) { return cudaStreamWaitEvent(s, e, 0) != cudaSuccess; }
 static int rt_event_done(rt_event_t e) { return cudaEventQuery(e) == cudaSuccess; }
 static const char* rt_error() { return cudaGetErrorString(cudaGetLastError()); }
 static int rt_check() { return cudaGetLastError() != cudaSuccess; }
@@ -139,12 +142,33 @@ void build_wedge_table(uint8_t* out)
 // context
 // ------------------------------------------------------------------------------------------
 namespace {
-enum { N_SLOTS = 3, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = 16 };
+enum { N_SLOTS = 8, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = AV1B_MAX_FRAME_IDS, MAX_LANES = 8, MAIN_LANE = MAX_LANES };
 
+// Frames are reconstructed on LANES: internal streams a context deals its frames to round-robin,
+// so that frames with no dependency between them (intra-only frames, frames of different
+// temporal layers) overlap on the GPU instead of queueing behind each other -- the superblock
+// wavefront of a small frame fills a handful of SMs only.  Ordering comes from events: a frame
+// waits for the `ready` event of every reference it reads, and a buffer taken from the pool waits
+// for the lanes that last wrote or read it.  MAIN_LANE stands for the context's own stream
+// (downloads, debug uploads).
 struct DevFrame {
     uint8_t* base = nullptr;
     FrameView v;
     int refcnt = 0;
+    rt_event_t ready;         // recorded after the last kernel of the submit that wrote (or used) the frame
+    rt_event_t copied;        // recorded on the context stream after the last download / copy out of it
+    int writer = MAIN_LANE;   // lane of that submit
+    uint32_t readers = 0;     // lanes that read it since (bit MAIN_LANE = the context stream)
+};
+
+// Per-lane scratch: nothing here is shared between frames in flight on different lanes.
+struct Lane {
+    av1b_stream_t stream = nullptr;
+    rt_event_t mark;               // scratch event for cross-lane ordering
+    int16_t* res_planes = nullptr; // frame-layout residual planes (luma aw x ah, chroma aw/2 x ah/2 each)
+    uint8_t* mask_plane = nullptr; // luma-resolution compound-mask scratch (aw x ah)
+    int* sync = nullptr;
+    size_t sync_cap = 0;
 };
 
 struct CmdSlot {
@@ -167,12 +191,13 @@ struct av1b_ctx {
     int ref_slot[8];
     CmdSlot slots[N_SLOTS];
     int cur_slot = -1;
-    int16_t* res = nullptr;
+    int16_t* res = nullptr; // compact residual arena (stage-level ITX test mode, lane 0 only)
     size_t res_cap = 0;
-    int16_t* res_planes = nullptr; // frame-layout residual planes (luma aw x ah, chroma aw/2 x ah/2 each)
-    uint8_t* mask_plane = nullptr; // luma-resolution compound-mask scratch (aw x ah)
-    int* sync = nullptr;
-    size_t sync_cap = 0;
+    Lane lanes[MAX_LANES];
+    int n_lanes = 1;
+    uint64_t frame_seq = 0;
+    bool joined = true;     // no lane work outstanding relative to the context stream
+    rt_event_t main_mark;
     uint8_t* wedge = nullptr;
     int pending_input = -1;
     rt_event_t fences[N_FENCES];
@@ -208,18 +233,19 @@ struct StageTimer {
         rt_tevent_create(&e);
         return e;
     }
-    StageTimer(av1b_ctx* ctx, int st, bool active)
-        : c(ctx), stage(st), on(active && ctx->profiling)
+    av1b_stream_t stream;
+    StageTimer(av1b_ctx* ctx, int st, bool active, av1b_stream_t str)
+        : c(ctx), stage(st), on(active && ctx->profiling), stream(str)
     {
         if (!on) return;
         a = get(c);
         b = get(c);
-        rt_event_record(a, c->stream);
+        rt_event_record(a, stream);
     }
     ~StageTimer()
     {
         if (!on) return;
-        rt_event_record(b, c->stream);
+        rt_event_record(b, stream);
         c->spans.push_back(av1b_ctx::Span{ stage, a, b });
     }
 };
@@ -237,11 +263,24 @@ static int fail(av1b_ctx* c, int code, const char* what)
     return code;
 }
 
-static int frame_alloc(av1b_ctx* c)
+static av1b_stream_t lane_stream(av1b_ctx* c, int lane) { return lane == MAIN_LANE ? c->stream : c->lanes[lane].stream; }
+
+// A free frame buffer for a writer on `lane`.  Preference: a buffer only this lane touched (no
+// wait at all); a buffer whose last writer has finished and that no other lane read (the waits
+// frame_claim adds are on completed events); a new buffer while the pool may grow; any free one.
+static int frame_alloc(av1b_ctx* c, int lane = MAIN_LANE)
 {
-    for (size_t i = 0; i < c->frames.size(); i++)
-        if (c->frames[i].refcnt == 0) return (int)i;
-    if (c->frames.size() >= POOL_MAX) return -1;
+    const uint32_t mine = (1u << lane) | (1u << MAIN_LANE);
+    int idle = -1, any = -1;
+    for (size_t i = 0; i < c->frames.size(); i++) {
+        const DevFrame& f = c->frames[i];
+        if (f.refcnt) continue;
+        if (f.writer == lane && !(f.readers & ~(1u << lane))) return (int)i;
+        if (idle < 0 && !(f.readers & ~mine) && rt_event_done(f.ready)) idle = (int)i;
+        if (any < 0) any = (int)i;
+    }
+    if (idle >= 0) return idle;
+    if (c->frames.size() >= POOL_MAX || (any >= 0 && c->n_lanes == 1)) return any;
     DevFrame f;
     void* p = nullptr;
     if (rt_malloc(&p, c->frame_bytes)) return -1;
@@ -256,8 +295,52 @@ static int frame_alloc(av1b_ctx* c)
     f.v.pl[1].stride = c->stride_c;
     f.v.pl[2].p = v + (size_t)PAD_Y * c->stride_c + PAD_X;
     f.v.pl[2].stride = c->stride_c;
+    if (rt_event_create(&f.ready) || rt_event_create(&f.copied)) {
+        rt_free(f.base);
+        return -1;
+    }
+    f.writer = lane;
     c->frames.push_back(f);
     return (int)c->frames.size() - 1;
+}
+
+// `lane` is about to WRITE frame f: order it after the lanes that wrote or read the buffer.
+static int frame_claim(av1b_ctx* c, int f, int lane)
+{
+    DevFrame& fr = c->frames[f];
+    av1b_stream_t st = lane_stream(c, lane);
+    // exact: the submit that last wrote it, the last copy out of it on the context stream
+    if (fr.writer != lane && rt_stream_wait(st, fr.ready)) return 1;
+    if ((fr.readers & (1u << MAIN_LANE)) && lane != MAIN_LANE && rt_stream_wait(st, fr.copied)) return 1;
+    // conservative: everything queued so far on the other lanes that read it as a reference
+    const uint32_t others = fr.readers & ~((1u << lane) | (1u << MAIN_LANE));
+    for (int m = 0; m < MAX_LANES; m++) {
+        if (!(others & (1u << m))) continue;
+        if (rt_event_record(c->lanes[m].mark, c->lanes[m].stream) || rt_stream_wait(st, c->lanes[m].mark)) return 1;
+    }
+    fr.readers = 0;
+    fr.writer = lane;
+    return 0;
+}
+
+// `lane` is about to READ frame f.
+static int frame_read(av1b_ctx* c, int f, int lane)
+{
+    DevFrame& fr = c->frames[f];
+    if (fr.writer != lane && rt_stream_wait(lane_stream(c, lane), fr.ready)) return 1;
+    fr.readers |= 1u << lane;
+    return 0;
+}
+
+// Make the context stream wait for everything queued on the lanes.  `rejoin`: also order the
+// lanes' NEXT frame behind whatever the caller enqueues on the context stream from here on.
+static int join_lanes(av1b_ctx* c, bool rejoin)
+{
+    if (c->joined) return 0;
+    for (int m = 0; m < c->n_lanes; m++)
+        if (rt_event_record(c->lanes[m].mark, c->lanes[m].stream) || rt_stream_wait(c->stream, c->lanes[m].mark)) return 1;
+    c->joined = rejoin;
+    return 0;
 }
 
 extern "C" {
@@ -277,7 +360,21 @@ static void ctx_free(av1b_ctx* c)
 {
     rt_set_device(c->device);
     rt_stream_sync(c->stream);
-    for (auto& f : c->frames) rt_free(f.base);
+    for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
+    for (auto& f : c->frames) {
+        rt_free(f.base);
+        rt_event_destroy(f.ready);
+        rt_event_destroy(f.copied);
+    }
+    for (int m = 0; m < c->n_lanes; m++) {
+        Lane& L = c->lanes[m];
+        rt_free(L.res_planes);
+        rt_free(L.mask_plane);
+        rt_free(L.sync);
+        rt_event_destroy(L.mark);
+        rt_stream_destroy(L.stream);
+    }
+    rt_event_destroy(c->main_mark);
     for (int i = 0; i < N_SLOTS; i++) {
         rt_host_free(c->slots[i].host);
         rt_free(c->slots[i].dev);
@@ -286,9 +383,6 @@ static void ctx_free(av1b_ctx* c)
     for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
     for (auto e : c->event_pool) rt_event_destroy(e);
     rt_free(c->res);
-    rt_free(c->res_planes);
-    rt_free(c->mask_plane);
-    rt_free(c->sync);
     if (c->own_stream) rt_stream_destroy(c->stream);
     delete c;
 }
@@ -325,6 +419,15 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
     c->stride_y = c->aw + 2 * PAD_X;
     c->stride_c = c->aw / 2 + 2 * PAD_X;
     c->frame_bytes = (size_t)(c->ah + 2 * PAD_Y) * c->stride_y + 2 * (size_t)(c->ah / 2 + 2 * PAD_Y) * c->stride_c;
+    {
+        // AV1B200_LANES: frames in flight per context (default 4, 1 = strictly serial)
+        const char* e = getenv("AV1B200_LANES");
+        int n = e ? atoi(e) : 4;
+        c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
+    }
+    for (int m = 0; m < c->n_lanes; m++)
+        if (rt_stream_create(&c->lanes[m].stream) || rt_event_create(&c->lanes[m].mark)) return fail(c, AV1B_ECUDA, "lane stream");
+    if (rt_event_create(&c->main_mark)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     for (int i = 0; i < N_SLOTS; i++)
         if (rt_event_create(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     for (int i = 0; i < N_FENCES; i++)
@@ -350,10 +453,15 @@ void av1b_ctx_destroy(av1b_ctx* c)
 {
     if (!c) return;
     rt_set_device(c->device);
+    for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
     rt_stream_sync(c->stream);
     if (c->own_stream && c->wedge) {
-        // recycle: reset the decode state, keep every allocation
-        for (auto& f : c->frames) f.refcnt = 0;
+        // recycle: reset the decode state, keep every allocation (everything is idle: no hazards)
+        for (auto& f : c->frames) {
+            f.refcnt = 0;
+            f.readers = 0;
+        }
+        c->joined = true;
         for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
         for (int i = 0; i < N_SLOTS; i++) c->slots[i].pending = false;
         c->pending_input = -1;
@@ -427,23 +535,26 @@ int av1b_cmd_acquire(av1b_ctx* c, size_t bytes, void** host_ptr)
     return AV1B_OK;
 }
 
-static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* hdr, uint32_t stages, uint32_t refresh_mask,
+static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1bFrameHdr* hdr, uint32_t stages, uint32_t refresh_mask,
     int* frame_id)
 {
     const Av1bFrameHdr& h = *hdr;
     if (h.magic != AV1B_MAGIC || h.version != AV1B_FORMAT_VERSION) return fail(c, AV1B_EINVAL, "bad command buffer magic/version");
     if (h.mi_cols * 4 > c->aw || h.mi_rows * 4 > c->ah || (h.sb_cols << h.sb_log2) > c->aw || (h.sb_rows << h.sb_log2) > c->ah)
         return fail(c, AV1B_EINVAL, "frame larger than the context");
+    Lane& L = c->lanes[lane];
+    av1b_stream_t st = L.stream;
     // scratch.  A lone ITX stage (stage-level test) writes the compact arena; any fuller submit
     // writes residuals into frame-layout int16 planes that the inter and dependent passes read.
     const bool arena_mode = (stages & AV1B_STAGE_RECON) == AV1B_STAGE_ITX;
     const size_t plane_elems = (size_t)c->aw * c->ah * 3 / 2;
-    if (!arena_mode && h.n_itx && !c->res_planes) {
+    if (!arena_mode && h.n_itx && !L.res_planes) {
         void* p = nullptr;
         if (rt_malloc(&p, plane_elems * sizeof(int16_t))) return fail(c, AV1B_ENOMEM, "residual planes");
-        c->res_planes = (int16_t*)p;
+        L.res_planes = (int16_t*)p;
     }
     if (arena_mode && h.n_res > c->res_cap) {
+        for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
         rt_stream_sync(c->stream);
         rt_free(c->res);
         c->res = nullptr;
@@ -454,68 +565,85 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
         c->res = (int16_t*)p;
         c->res_cap = cap;
     }
+    if (arena_mode) {
+        // the arena is shared: order this lane behind everything queued on the others
+        for (int m = 0; m < c->n_lanes; m++)
+            if (m != lane && (rt_event_record(c->lanes[m].mark, c->lanes[m].stream) || rt_stream_wait(st, c->lanes[m].mark)))
+                return fail(c, AV1B_ECUDA, "stream wait");
+    }
     const size_t sync_need = 1 + (size_t)h.sb_rows;
-    if (sync_need > c->sync_cap) {
-        rt_stream_sync(c->stream);
-        rt_free(c->sync);
+    if (sync_need > L.sync_cap) {
+        rt_stream_sync(st);
+        rt_free(L.sync);
+        L.sync = nullptr;
+        L.sync_cap = 0;
         void* p = nullptr;
         if (rt_malloc(&p, (sync_need + 64) * sizeof(int))) return fail(c, AV1B_ENOMEM, "sync buffer");
-        c->sync = (int*)p;
-        c->sync_cap = sync_need + 64;
+        L.sync = (int*)p;
+        L.sync_cap = sync_need + 64;
     }
-    // frames
+    // frames: the one being written, then the references it reads
     int cur = c->pending_input;
+    const bool preloaded = cur >= 0; // debug input: already holds samples written on the context stream
     c->pending_input = -1;
-    if (cur < 0) cur = frame_alloc(c);
+    if (cur < 0) cur = frame_alloc(c, lane);
     if (cur < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
     c->frames[cur].refcnt++;
+    if (preloaded) {
+        if (frame_read(c, cur, lane)) return fail(c, AV1B_ECUDA, "stream wait");
+        c->frames[cur].readers = 0;
+        c->frames[cur].writer = lane;
+    } else if (frame_claim(c, cur, lane)) return fail(c, AV1B_ECUDA, "stream wait");
     ReconCtx rc;
     memset(&rc, 0, sizeof(rc));
     rc.cmd = dev_cmd;
     rc.cur = c->frames[cur].v;
     for (int i = 0; i < 8; i++)
-        if (c->ref_slot[i] >= 0) rc.ref[i] = c->frames[c->ref_slot[i]].v;
+        if (c->ref_slot[i] >= 0) {
+            rc.ref[i] = c->frames[c->ref_slot[i]].v;
+            if (h.n_iblk && frame_read(c, c->ref_slot[i], lane)) return fail(c, AV1B_ECUDA, "stream wait");
+        }
     rc.res = c->res;
     if (!arena_mode && h.n_itx) {
-        rc.rp[0] = c->res_planes;
-        rc.rp[1] = c->res_planes + (size_t)c->aw * c->ah;
+        rc.rp[0] = L.res_planes;
+        rc.rp[1] = L.res_planes + (size_t)c->aw * c->ah;
         rc.rp[2] = rc.rp[1] + (size_t)(c->aw / 2) * (c->ah / 2);
         rc.rpitch[0] = c->aw;
         rc.rpitch[1] = rc.rpitch[2] = c->aw / 2;
         if (stages & AV1B_STAGE_ITX) {
             // zero only the area this frame can touch (SB-aligned rows of the luma plane + chroma)
             const size_t rows = (size_t)h.sb_rows << h.sb_log2;
-            if (rt_memset(rc.rp[0], 0, rows * c->aw * sizeof(int16_t), c->stream)
-                || rt_memset(rc.rp[1], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), c->stream)
-                || rt_memset(rc.rp[2], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), c->stream))
+            if (rt_memset(rc.rp[0], 0, rows * c->aw * sizeof(int16_t), st)
+                || rt_memset(rc.rp[1], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), st)
+                || rt_memset(rc.rp[2], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), st))
                 return fail(c, AV1B_ECUDA, "memset");
         }
     }
     if (h.n_iblk && (stages & AV1B_STAGE_INTER)) {
-        if (!c->mask_plane) {
+        if (!L.mask_plane) {
             void* p = nullptr;
             if (rt_malloc(&p, (size_t)c->aw * c->ah)) return fail(c, AV1B_ENOMEM, "mask plane");
-            c->mask_plane = (uint8_t*)p;
+            L.mask_plane = (uint8_t*)p;
         }
-        rc.mask = c->mask_plane;
+        rc.mask = L.mask_plane;
         rc.mask_pitch = c->aw;
     }
     rc.wedge = c->wedge;
-    rc.sync = c->sync;
+    rc.sync = L.sync;
     if (stages & AV1B_STAGE_ITX) {
-        StageTimer t(c, 0, h.n_itx != 0);
-        launch_itx(rc, h, c->stream);
+        StageTimer t(c, 0, h.n_itx != 0, st);
+        launch_itx(rc, h, st);
         c->launches += h.n_itx ? 1 : 0;
     }
     if (stages & AV1B_STAGE_INTER) {
-        StageTimer t(c, 1, h.n_iblk != 0);
-        launch_inter(rc, h, c->stream);
+        StageTimer t(c, 1, h.n_iblk != 0, st);
+        launch_inter(rc, h, st);
         c->launches += h.n_iblk ? 1 : 0;
     }
     if (stages & AV1B_STAGE_WAVE) {
-        if (rt_memset(c->sync, 0, sync_need * sizeof(int), c->stream)) return fail(c, AV1B_ECUDA, "memset");
-        StageTimer t(c, 2, h.n_ops != 0);
-        launch_wave(rc, h, c->stream);
+        if (rt_memset(L.sync, 0, sync_need * sizeof(int), st)) return fail(c, AV1B_ECUDA, "memset");
+        StageTimer t(c, 2, h.n_ops != 0, st);
+        launch_wave(rc, h, st);
         c->launches += h.n_ops ? 1 : 0;
     }
     PostCtx pc;
@@ -524,32 +652,39 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     pc.src = c->frames[cur].v;
     int final_frame = cur, cdef = -1, lr = -1;
     if ((stages & AV1B_STAGE_DEBLOCK) && (h.lf.level[0] || h.lf.level[1])) {
-        StageTimer t(c, 3, true);
-        launch_deblock(pc, h, c->stream);
+        StageTimer t(c, 3, true, st);
+        launch_deblock(pc, h, st);
         c->launches += 2;
     }
     pc.cdef = pc.src;
     if ((stages & AV1B_STAGE_CDEF) && h.cdef.enabled) {
-        cdef = frame_alloc(c);
+        cdef = frame_alloc(c, lane);
         if (cdef < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
         c->frames[cdef].refcnt++;
+        if (frame_claim(c, cdef, lane)) return fail(c, AV1B_ECUDA, "stream wait");
         pc.cdef = c->frames[cdef].v;
-        StageTimer t(c, 4, true);
-        launch_cdef(pc, h, c->stream);
+        StageTimer t(c, 4, true, st);
+        launch_cdef(pc, h, st);
         c->launches += 1;
         final_frame = cdef;
     }
     if ((stages & AV1B_STAGE_LR) && h.lr.uses_lr) {
-        lr = frame_alloc(c);
+        lr = frame_alloc(c, lane);
         if (lr < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
         c->frames[lr].refcnt++;
+        if (frame_claim(c, lr, lane)) return fail(c, AV1B_ECUDA, "stream wait");
         pc.lr = c->frames[lr].v;
-        StageTimer t(c, 5, true);
-        launch_lr(pc, h, c->stream);
+        StageTimer t(c, 5, true, st);
+        launch_lr(pc, h, st);
         c->launches += 1;
         final_frame = lr;
     }
     if (rt_check()) return fail(c, AV1B_ECUDA, "kernel launch");
+    // one completion point for every buffer this submit wrote or used as an intermediate
+    if (rt_event_record(c->frames[final_frame].ready, st) || (cur != final_frame && rt_event_record(c->frames[cur].ready, st))
+        || (cdef >= 0 && cdef != final_frame && rt_event_record(c->frames[cdef].ready, st)))
+        return fail(c, AV1B_ECUDA, "event record");
+    c->joined = false;
     // reference refresh (Decoder::updateFrameStore)
     for (int i = 0; i < 8; i++) {
         if (refresh_mask & (1u << i)) {
@@ -565,16 +700,30 @@ static int submit_impl(av1b_ctx* c, const uint8_t* dev_cmd, const Av1bFrameHdr* 
     return AV1B_OK;
 }
 
+// Lane of the next frame.  The first frame after a join also orders every lane behind the work
+// already queued on the context stream (the caller's own stream, when one was supplied).
+static int next_lane(av1b_ctx* c)
+{
+    if (c->joined) {
+        if (rt_event_record(c->main_mark, c->stream)) return -1;
+        for (int m = 0; m < c->n_lanes; m++)
+            if (rt_stream_wait(c->lanes[m].stream, c->main_mark)) return -1;
+    }
+    return (int)(c->frame_seq++ % (uint64_t)c->n_lanes);
+}
+
 int av1b_frame_submit(av1b_ctx* c, size_t bytes, uint32_t stages, uint32_t refresh_mask, int* frame_id)
 {
     if (!c || c->cur_slot < 0) return AV1B_ESTATE;
     rt_set_device(c->device);
     CmdSlot& sl = c->slots[c->cur_slot];
     if (bytes > sl.cap || bytes < sizeof(Av1bFrameHdr)) return fail(c, AV1B_EINVAL, "command size");
-    if (rt_h2d(sl.dev, sl.host, bytes, c->stream)) return fail(c, AV1B_ECUDA, "command upload");
-    int r = submit_impl(c, sl.dev, (const Av1bFrameHdr*)sl.host, stages, refresh_mask, frame_id);
+    const int lane = next_lane(c);
+    if (lane < 0) return fail(c, AV1B_ECUDA, "lane");
+    if (rt_h2d(sl.dev, sl.host, bytes, c->lanes[lane].stream)) return fail(c, AV1B_ECUDA, "command upload");
+    int r = submit_impl(c, lane, sl.dev, (const Av1bFrameHdr*)sl.host, stages, refresh_mask, frame_id);
     if (r) return r;
-    if (rt_event_record(sl.done, c->stream)) return fail(c, AV1B_ECUDA, "event record");
+    if (rt_event_record(sl.done, c->lanes[lane].stream)) return fail(c, AV1B_ECUDA, "event record");
     sl.pending = true;
     return AV1B_OK;
 }
@@ -584,7 +733,9 @@ int av1b_frame_submit_resident(av1b_ctx* c, const void* dev_cmd, const Av1bFrame
 {
     if (!c || !dev_cmd || !hdr) return AV1B_EINVAL;
     rt_set_device(c->device);
-    return submit_impl(c, (const uint8_t*)dev_cmd, hdr, stages, refresh_mask, frame_id);
+    const int lane = next_lane(c);
+    if (lane < 0) return fail(c, AV1B_ECUDA, "lane");
+    return submit_impl(c, lane, (const uint8_t*)dev_cmd, hdr, stages, refresh_mask, frame_id);
 }
 
 int av1b_show_existing(av1b_ctx* c, int slot, uint32_t refresh_mask, int* frame_id)
@@ -607,12 +758,14 @@ int av1b_frame_download(av1b_ctx* c, int frame_id, uint8_t* const dst[3], const 
 {
     if (!c || frame_id < 0 || frame_id >= (int)c->frames.size()) return AV1B_EINVAL;
     rt_set_device(c->device);
+    if (frame_read(c, frame_id, MAIN_LANE)) return fail(c, AV1B_ECUDA, "stream wait");
     const FrameView& v = c->frames[frame_id].v;
     for (int p = 0; p < 3; p++) {
         const int pw = p ? (w >> 1) : w, ph = p ? (h >> 1) : h;
         if (!dst[p] || pw <= 0 || ph <= 0) continue;
         if (rt_copy2d(dst[p], dst_stride[p], v.pl[p].p, v.pl[p].stride, pw, ph, c->stream, 1)) return fail(c, AV1B_ECUDA, "download");
     }
+    if (rt_event_record(c->frames[frame_id].copied, c->stream)) return fail(c, AV1B_ECUDA, "event record");
     return AV1B_OK;
 }
 
@@ -620,7 +773,18 @@ int av1b_sync(av1b_ctx* c)
 {
     if (!c) return AV1B_EINVAL;
     rt_set_device(c->device);
+    for (int m = 0; m < c->n_lanes; m++)
+        if (rt_stream_sync(c->lanes[m].stream)) return fail(c, AV1B_ECUDA, "sync");
     if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
+    c->joined = true;
+    return AV1B_OK;
+}
+
+int av1b_join(av1b_ctx* c)
+{
+    if (!c) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (join_lanes(c, true)) return fail(c, AV1B_ECUDA, "join");
     return AV1B_OK;
 }
 
@@ -629,6 +793,7 @@ int av1b_fence_record(av1b_ctx* c, uint64_t* fence)
     if (!c || !fence) return AV1B_EINVAL;
     rt_set_device(c->device);
     const uint64_t id = c->fence_next++;
+    if (join_lanes(c, false)) return fail(c, AV1B_ECUDA, "join");
     if (rt_event_record(c->fences[id % N_FENCES], c->stream)) return fail(c, AV1B_ECUDA, "fence record");
     *fence = id;
     return AV1B_OK;
@@ -694,12 +859,13 @@ int av1b_dev_upload(av1b_ctx* c, void* dev_dst, const void* host_src, size_t byt
 
 static int upload_planes(av1b_ctx* c, int f, const uint8_t* const src[3], const int src_stride[3], int w, int h)
 {
+    if (frame_claim(c, f, MAIN_LANE)) return fail(c, AV1B_ECUDA, "stream wait");
     const FrameView& v = c->frames[f].v;
     for (int p = 0; p < 3; p++) {
         const int pw = p ? (w >> 1) : w, ph = p ? (h >> 1) : h;
         if (rt_copy2d(v.pl[p].p, v.pl[p].stride, src[p], src_stride[p], pw, ph, c->stream, 0)) return fail(c, AV1B_ECUDA, "upload planes");
     }
-    if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "upload planes");
+    if (rt_event_record(c->frames[f].ready, c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "upload planes");
     return AV1B_OK;
 }
 
@@ -729,6 +895,7 @@ int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
 {
     if (!c || n > c->res_cap) return AV1B_EINVAL;
     rt_set_device(c->device);
+    if (join_lanes(c, false)) return fail(c, AV1B_ECUDA, "join");
     if (rt_d2h(dst, c->res, n * sizeof(int16_t), c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "residual download");
     return AV1B_OK;
 }
@@ -746,6 +913,8 @@ int av1b_get_stage_times(av1b_ctx* c, double ms[AV1B_N_STAGES], uint64_t calls[A
 {
     if (!c) return AV1B_EINVAL;
     rt_set_device(c->device);
+    for (int m = 0; m < c->n_lanes; m++)
+        if (rt_stream_sync(c->lanes[m].stream)) return fail(c, AV1B_ECUDA, "sync");
     if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
     for (auto& sp : c->spans) {
         c->stage_ms[sp.stage] += rt_event_ms(sp.a, sp.b);
@@ -772,7 +941,10 @@ int av1b_debug_input_from_slot(av1b_ctx* c, int slot)
     int f = c->pending_input >= 0 ? c->pending_input : frame_alloc(c);
     if (f < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
     c->pending_input = f;
-    if (rt_d2d(c->frames[f].base, c->frames[c->ref_slot[slot]].base, c->frame_bytes, c->stream)) return fail(c, AV1B_ECUDA, "d2d copy");
+    if (frame_read(c, c->ref_slot[slot], MAIN_LANE) || frame_claim(c, f, MAIN_LANE)) return fail(c, AV1B_ECUDA, "stream wait");
+    if (rt_d2d(c->frames[f].base, c->frames[c->ref_slot[slot]].base, c->frame_bytes, c->stream)
+        || rt_event_record(c->frames[f].ready, c->stream) || rt_event_record(c->frames[c->ref_slot[slot]].copied, c->stream))
+        return fail(c, AV1B_ECUDA, "d2d copy");
     return AV1B_OK;
 }
 

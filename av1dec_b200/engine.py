@@ -84,6 +84,10 @@ class Engine:
     def sync(self):
         self._check(self.lib.av1b_sync(self.ctx), "av1b_sync")
 
+    def join(self):
+        """Make the context stream wait (device-side) for every frame submitted so far."""
+        self._check(self.lib.av1b_join(self.ctx), "av1b_join")
+
     def set_profiling(self, on=True):
         self._check(self.lib.av1b_set_profiling(self.ctx, 1 if on else 0), "av1b_set_profiling")
 

@@ -93,7 +93,7 @@ struct Decoder::Impl {
         uint64_t fence;
     };
     std::deque<Pending> output;   // guarded by mu when the emit thread runs
-    int frame_w[32], frame_h[32]; // visible size of each device frame id
+    int frame_w[AV1B_MAX_FRAME_IDS], frame_h[AV1B_MAX_FRAME_IDS]; // visible size of each device frame id
     av1b200::DecoderOptions opt;
     std::string error;
     // AV1B200_TIMING=1: cumulative host-side phase timers, printed when the decoder is destroyed

@@ -407,6 +407,8 @@ def run_ours(args, rank, world, local_rank):
             s.wait_event(start)
         for _ in range(steps):
             replay_once()
+        for r in recs:
+            r.engine.join()  # side stream waits for the frames in flight on the context's lanes
         for s in side_streams:
             ev = torch.cuda.Event()
             ev.record(s)

@@ -78,11 +78,21 @@ int av1b_frame_submit_resident(av1b_ctx* ctx, const void* dev_cmd, const Av1bFra
  * store slot `slot` and applies refresh_mask. */
 int av1b_show_existing(av1b_ctx* ctx, int slot, uint32_t refresh_mask, int* frame_id);
 
+/* Frame ids returned by submit / show_existing are pool indices below this bound. */
+#define AV1B_MAX_FRAME_IDS 48
+
 /* Asynchronous copy of the visible w x h (and chroma) area of a device frame to host planes
  * (pinned memory from av1b_host_alloc gives a true async copy).  Decoder::getOutput(). */
 int av1b_frame_download(av1b_ctx* ctx, int frame_id, uint8_t* const dst[3], const int dst_stride[3], int w, int h);
 /* Block until everything enqueued so far (kernels and copies) has finished. */
 int av1b_sync(av1b_ctx* ctx);
+/* Frames are reconstructed on internal streams ("lanes", AV1B200_LANES, default 4) so that frames
+ * that do not depend on each other overlap; downloads and fences run on the context stream and
+ * wait for the frames they need.  av1b_join makes the context stream wait (on the device, without
+ * blocking the host) for every frame submitted so far, and orders the next submitted frame behind
+ * whatever the caller enqueues on that stream afterwards: call it before recording your own event
+ * on a stream passed to av1b_ctx_create. */
+int av1b_join(av1b_ctx* ctx);
 /* Mark a fence after the work enqueued so far / wait for it: lets a caller overlap parsing of
  * the next frame with this frame's device work. */
 int av1b_fence_record(av1b_ctx* ctx, uint64_t* fence);

@@ -55,6 +55,7 @@ def main():
         s.record(side)
         for _ in range(a.reps):
             replay()
+        eng.join()
         e.record(side)
         e.synchronize()
         total = s.elapsed_time(e) / a.reps
