@@ -34,7 +34,7 @@ ENGINE_SYMBOLS = [
 STAGE_NAMES = ["itx", "inter", "wave", "deblock", "cdef", "lr"]
 DECODER_SYMBOLS = [
     "av1b_decoder_create", "av1b_decoder_destroy", "av1b_decoder_set_stages", "av1b_decoder_set_cmd_sink",
-    "av1b_decoder_decode", "av1b_decoder_get_output", "av1b_decoder_error", "av1b_decode_ivf",
+    "av1b_decoder_decode", "av1b_decoder_get_output", "av1b_decoder_error", "av1b_decode_ivf", "av1b_ivf_segments",
     "createVideoDecoder", "releaseVideoDecoder",
 ]
 
@@ -98,6 +98,7 @@ def _bind_decoder(lib):
     lib.av1b_decoder_error.restype = C.c_char_p
     lib.av1b_decode_ivf.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.av1b_ivf_segments.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_int]
     return lib
 
 
@@ -169,6 +170,18 @@ def decode_ivf(data, device=0, stages=STAGE_ALL, want_yuv=True, lib=None):
         break
     yuv = buf.raw[:out_bytes.value] if want_yuv else None
     return yuv, n_frames.value, pixels.value
+
+
+def ivf_segments(data, lib=None):
+    """Temporal-unit index of the first unit of every closed segment (random access point) of an
+    IVF byte string; av1b_decode_ivf decodes these segments in parallel."""
+    lib = lib or load_decoder()
+    n = lib.av1b_ivf_segments(data, len(data), None, 0)
+    if n < 0:
+        raise EngineError("not an IVF stream")
+    arr = (C.c_uint32 * max(n, 1))()
+    lib.av1b_ivf_segments(data, len(data), arr, n)
+    return list(arr[:n])
 
 
 class Decoder:

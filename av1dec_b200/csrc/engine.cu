@@ -280,7 +280,10 @@ static int frame_alloc(av1b_ctx* c, int lane = MAIN_LANE)
         if (any < 0) any = (int)i;
     }
     if (idle >= 0) return idle;
-    if (c->frames.size() >= POOL_MAX || (any >= 0 && c->n_lanes == 1)) return any;
+    // growing the pool costs a cudaMalloc (device-wide synchronisation): past the working set of
+    // the lanes (3 buffers per frame in flight + 8 references + 1 pending output) reuse instead
+    const size_t soft_cap = (size_t)3 * c->n_lanes + 9;
+    if (c->frames.size() >= POOL_MAX || (any >= 0 && (c->n_lanes == 1 || c->frames.size() >= soft_cap))) return any;
     DevFrame f;
     void* p = nullptr;
     if (rt_malloc(&p, c->frame_bytes)) return -1;

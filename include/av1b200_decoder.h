@@ -46,6 +46,15 @@ const char* av1b_decoder_error(av1b_decoder* d);
 int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages, uint8_t* out_yuv, size_t out_cap,
     size_t* out_bytes, int* n_frames, uint64_t* luma_pixels);
 
+/* Closed segments of an IVF stream: a segment starts at every temporal unit that carries a
+ * sequence header followed by a shown key frame (a random access point: all reference slots and
+ * CDFs reset there).  Writes the temporal-unit index of each segment start into seg_first (up to
+ * cap entries) and returns the number of segments, 0 for a stream with no temporal unit, -1 for a
+ * buffer that is not IVF.  av1b_decode_ivf decodes the segments in parallel (one front end +
+ * device context per worker, AV1B200_GOP_THREADS workers, default min(8, host threads)) and
+ * stitches the output back in stream order. */
+int av1b_ivf_segments(const uint8_t* ivf, size_t len, uint32_t* seg_first, int cap);
+
 #ifdef __cplusplus
 }
 #endif

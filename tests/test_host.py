@@ -98,6 +98,19 @@ def test_decoder_class_mirrors_reference_api(md5_table):
 
 
 @need_emu
+def test_ivf_segments_split_at_random_access_points():
+    lib = checks.emu_decoder()
+    rd = lambda n: open(os.path.join(BITS, n), "rb").read()
+    # every temporal unit of the all-intra stream is sequence header + shown key frame
+    assert pkg.ivf_segments(rd("av1-1-b8-02-allintra.ivf"), lib=lib) == list(range(39))
+    # ordinary streams: one key frame up front, one segment
+    assert pkg.ivf_segments(rd("av1-1-b8-00-quantizer-00.ivf"), lib=lib) == [0]
+    assert pkg.ivf_segments(rd("av1-1-b8-06-mfmv.ivf"), lib=lib) == [0]
+    with pytest.raises(pkg.EngineError):
+        pkg.ivf_segments(b"garbage" * 10, lib=lib)
+
+
+@need_emu
 def test_decode_rejects_garbage():
     dec = pkg.Decoder(lib=checks.emu_decoder())
     assert dec.decode(b"\xff" * 40) is False
