@@ -8,6 +8,7 @@
 #include "../../include/av1b200.h"
 #include "av1_tables_host.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -153,6 +154,7 @@ enum { N_SLOTS = 8, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = AV1B_MAX_
 // (downloads, debug uploads).
 struct DevFrame {
     uint8_t* base = nullptr;
+    bool owned = true;        // own cudaMalloc (false: carved out of the context's slab)
     FrameView v;
     int refcnt = 0;
     rt_event_t ready;         // recorded after the last kernel of the submit that wrote (or used) the frame
@@ -195,6 +197,7 @@ struct av1b_ctx {
     size_t res_cap = 0;
     Lane lanes[MAX_LANES];
     int n_lanes = 1;
+    uint8_t* slab = nullptr; // one allocation holding the lanes' working set of frame buffers
     uint64_t frame_seq = 0;
     bool joined = true;     // no lane work outstanding relative to the context stream
     rt_event_t main_mark;
@@ -263,6 +266,35 @@ static int fail(av1b_ctx* c, int code, const char* what)
     return code;
 }
 
+// Working set of the lanes: 3 buffers per frame in flight + 8 references + 1 pending output.
+static size_t pool_soft_cap(const av1b_ctx* c) { return std::min<size_t>(POOL_MAX, (size_t)3 * c->n_lanes + 9); }
+
+// Register one frame buffer (planes laid out inside `base`) with the pool.
+static int frame_add(av1b_ctx* c, uint8_t* base, bool owned, int lane)
+{
+    DevFrame f;
+    f.base = base;
+    f.owned = owned;
+    const size_t luma_rows = (size_t)c->ah + 2 * PAD_Y, chroma_rows = (size_t)c->ah / 2 + 2 * PAD_Y;
+    uint8_t* y = f.base;
+    uint8_t* u = y + luma_rows * c->stride_y;
+    uint8_t* v = u + chroma_rows * c->stride_c;
+    f.v.pl[0].p = y + (size_t)PAD_Y * c->stride_y + PAD_X;
+    f.v.pl[0].stride = c->stride_y;
+    f.v.pl[1].p = u + (size_t)PAD_Y * c->stride_c + PAD_X;
+    f.v.pl[1].stride = c->stride_c;
+    f.v.pl[2].p = v + (size_t)PAD_Y * c->stride_c + PAD_X;
+    f.v.pl[2].stride = c->stride_c;
+    if (rt_event_create(&f.ready)) return 1;
+    if (rt_event_create(&f.copied)) {
+        rt_event_destroy(f.ready);
+        return 1;
+    }
+    f.writer = lane;
+    c->frames.push_back(f);
+    return 0;
+}
+
 static av1b_stream_t lane_stream(av1b_ctx* c, int lane) { return lane == MAIN_LANE ? c->stream : c->lanes[lane].stream; }
 
 // A free frame buffer for a writer on `lane`.  Preference: a buffer only this lane touched (no
@@ -282,28 +314,14 @@ static int frame_alloc(av1b_ctx* c, int lane = MAIN_LANE)
     if (idle >= 0) return idle;
     // growing the pool costs a cudaMalloc (device-wide synchronisation): past the working set of
     // the lanes (3 buffers per frame in flight + 8 references + 1 pending output) reuse instead
-    const size_t soft_cap = (size_t)3 * c->n_lanes + 9;
+    const size_t soft_cap = pool_soft_cap(c);
     if (c->frames.size() >= POOL_MAX || (any >= 0 && (c->n_lanes == 1 || c->frames.size() >= soft_cap))) return any;
-    DevFrame f;
     void* p = nullptr;
     if (rt_malloc(&p, c->frame_bytes)) return -1;
-    f.base = (uint8_t*)p;
-    const size_t luma_rows = (size_t)c->ah + 2 * PAD_Y, chroma_rows = (size_t)c->ah / 2 + 2 * PAD_Y;
-    uint8_t* y = f.base;
-    uint8_t* u = y + luma_rows * c->stride_y;
-    uint8_t* v = u + chroma_rows * c->stride_c;
-    f.v.pl[0].p = y + (size_t)PAD_Y * c->stride_y + PAD_X;
-    f.v.pl[0].stride = c->stride_y;
-    f.v.pl[1].p = u + (size_t)PAD_Y * c->stride_c + PAD_X;
-    f.v.pl[1].stride = c->stride_c;
-    f.v.pl[2].p = v + (size_t)PAD_Y * c->stride_c + PAD_X;
-    f.v.pl[2].stride = c->stride_c;
-    if (rt_event_create(&f.ready) || rt_event_create(&f.copied)) {
-        rt_free(f.base);
+    if (frame_add(c, (uint8_t*)p, true, lane)) {
+        rt_free(p);
         return -1;
     }
-    f.writer = lane;
-    c->frames.push_back(f);
     return (int)c->frames.size() - 1;
 }
 
@@ -365,10 +383,11 @@ static void ctx_free(av1b_ctx* c)
     rt_stream_sync(c->stream);
     for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
     for (auto& f : c->frames) {
-        rt_free(f.base);
+        if (f.owned) rt_free(f.base);
         rt_event_destroy(f.ready);
         rt_event_destroy(f.copied);
     }
+    rt_free(c->slab);
     for (int m = 0; m < c->n_lanes; m++) {
         Lane& L = c->lanes[m];
         rt_free(L.res_planes);
@@ -431,6 +450,16 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
     for (int m = 0; m < c->n_lanes; m++)
         if (rt_stream_create(&c->lanes[m].stream) || rt_event_create(&c->lanes[m].mark)) return fail(c, AV1B_ECUDA, "lane stream");
     if (rt_event_create(&c->main_mark)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+    {
+        // the working set comes from ONE allocation made here: no cudaMalloc (a device-wide
+        // synchronisation) in the middle of a decode; only a deeper pipeline grows the pool later
+        const size_t n = pool_soft_cap(c);
+        void* p = nullptr;
+        if (rt_malloc(&p, c->frame_bytes * n)) return fail(c, AV1B_ENOMEM, "frame slab");
+        c->slab = (uint8_t*)p;
+        for (size_t i = 0; i < n; i++)
+            if (frame_add(c, c->slab + i * c->frame_bytes, false, MAIN_LANE)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+    }
     for (int i = 0; i < N_SLOTS; i++)
         if (rt_event_create(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     for (int i = 0; i < N_FENCES; i++)
@@ -552,9 +581,13 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     const bool arena_mode = (stages & AV1B_STAGE_RECON) == AV1B_STAGE_ITX;
     const size_t plane_elems = (size_t)c->aw * c->ah * 3 / 2;
     if (!arena_mode && h.n_itx && !L.res_planes) {
-        void* p = nullptr;
-        if (rt_malloc(&p, plane_elems * sizeof(int16_t))) return fail(c, AV1B_ENOMEM, "residual planes");
-        L.res_planes = (int16_t*)p;
+        // first coded residual of the stream: every lane gets its planes now (no cudaMalloc later)
+        for (int m = 0; m < c->n_lanes; m++) {
+            void* p = nullptr;
+            if (c->lanes[m].res_planes) continue;
+            if (rt_malloc(&p, plane_elems * sizeof(int16_t))) return fail(c, AV1B_ENOMEM, "residual planes");
+            c->lanes[m].res_planes = (int16_t*)p;
+        }
     }
     if (arena_mode && h.n_res > c->res_cap) {
         for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
@@ -624,9 +657,12 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     }
     if (h.n_iblk && (stages & AV1B_STAGE_INTER)) {
         if (!L.mask_plane) {
-            void* p = nullptr;
-            if (rt_malloc(&p, (size_t)c->aw * c->ah)) return fail(c, AV1B_ENOMEM, "mask plane");
-            L.mask_plane = (uint8_t*)p;
+            for (int m = 0; m < c->n_lanes; m++) {
+                void* p = nullptr;
+                if (c->lanes[m].mask_plane) continue;
+                if (rt_malloc(&p, (size_t)c->aw * c->ah)) return fail(c, AV1B_ENOMEM, "mask plane");
+                c->lanes[m].mask_plane = (uint8_t*)p;
+            }
         }
         rc.mask = L.mask_plane;
         rc.mask_pitch = c->aw;

@@ -387,16 +387,27 @@ def run_ours(args, rank, world, local_rank):
     d2h_step = sum(r.yuv_bytes for r in recs)
     max_frames = max(len(r.frames) for r in recs)
 
-    def replay_once():
-        # interleave streams frame by frame so the GPU always has independent work queued
-        for f in range(max_frames):
-            for r in recs:
+    # Submission is host work too (a dozen driver calls per frame): the streams are dealt to
+    # `host_threads` submitter threads, each interleaving its own streams frame by frame so the GPU
+    # always has independent work queued.  An engine is only ever touched by its own thread.
+    n_sub = max(1, min(args.submit_threads or host_threads, len(recs)))
+    groups = [recs[i::n_sub] for i in range(n_sub)]
+    submit_pool = cf.ThreadPoolExecutor(n_sub)
+
+    def replay_group(group):
+        for f in range(max(len(r.frames) for r in group)):
+            for r in group:
                 if f < len(r.frames):
                     ptr, hdr, refresh, slot = r.frames[f]
                     if ptr is None:
                         r.engine.show_existing(slot, refresh)
                     else:
                         r.engine.submit_resident(ptr, hdr, pkg.STAGE_ALL, refresh)
+        for r in group:
+            r.engine.join()  # the side stream waits for the frames in flight on the context's lanes
+
+    def replay_once():
+        list(submit_pool.map(replay_group, groups))
 
     main = torch.cuda.current_stream(dev)
 
@@ -407,8 +418,6 @@ def run_ours(args, rank, world, local_rank):
             s.wait_event(start)
         for _ in range(steps):
             replay_once()
-        for r in recs:
-            r.engine.join()  # side stream waits for the frames in flight on the context's lanes
         for s in side_streams:
             ev = torch.cuda.Event()
             ev.record(s)
@@ -431,6 +440,8 @@ def run_ours(args, rank, world, local_rank):
     secs = timed_replay(args.steps)
     barrier()
     launches = sum(r.engine.launches() for r in recs) - launches0
+    if os.environ.get("BENCH_TRACE"):  # development aid: spread of single-step times inside one process
+        print("trace ms/step:", [round(1e3 * timed_replay(1), 1) for _ in range(12)], file=sys.stderr)
     total_px, tmax = reduce_result(float(pixels_step * args.steps), secs, dev)
     value = total_px / tmax / 1e6
 
@@ -458,10 +469,14 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_t = 0.0
     e2e_px = 0
+    trace = []
     for _ in range(args.steps):
         t, px = e2e_pass()
+        trace.append(round(1e3 * t))
         e2e_t += t
         e2e_px += px
+    if os.environ.get("BENCH_TRACE"):
+        print("trace e2e ms/step:", trace, [round(1e3 * e2e_pass()[0]) for _ in range(6)], file=sys.stderr)
     barrier()
     clocks = sampler.stop()
     e2e_total, e2e_tmax = reduce_result(float(e2e_px), e2e_t, dev)
@@ -510,6 +525,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
+    ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = all of this rank's)")
     ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
