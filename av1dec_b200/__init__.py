@@ -10,6 +10,12 @@ and mirrors the reference's decoder interface (decoder/Av1Decoder.h:47-51: ``dec
 ``getOutput``) as :class:`Decoder`.  There is no CPU fallback: if the CUDA libraries are missing
 or no GPU is present, loading / decoding raises.
 """
+import os as _os
+
+# Work from many decoder streams is ordered by events; with CUDA's default 8 hardware queues a
+# wait at the head of a queue stalls unrelated streams.  Must be set before CUDA initialises.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import ctypes as C
 import os
 

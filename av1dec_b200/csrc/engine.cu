@@ -412,6 +412,13 @@ static void ctx_free(av1b_ctx* c)
 int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream)
 {
     if (!out || max_w <= 0 || max_h <= 0 || max_w > 16384 || max_h > 16384) return AV1B_EINVAL;
+#ifndef AV1B_EMU
+    // Many short streams with event waits between them: with the default 8 hardware work queues
+    // a wait at the head of a queue stalls unrelated streams behind it.  Only effective when the
+    // CUDA context does not exist yet; hosts that initialise CUDA first set it themselves.
+    static const int once = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    (void)once;
+#endif
     const int aw = (max_w + 127) & ~127, ah = (max_h + 127) & ~127;
     if (!stream) {
         std::lock_guard<std::mutex> lk(g_mu);

@@ -21,8 +21,7 @@ struct Scratch {
     uint8_t above[EDGE_LEN]; // AboveRow[i] at above[EDGE_OFF + i]
     uint8_t left[EDGE_LEN];
     uint8_t tmp[EDGE_LEN];   // filter / upsample staging
-    uint8_t pred[64 * 64];
-    int16_t luma[32 * 32];   // CfL sub-sampled luma
+    uint8_t pred[32 * 32];   // inter-intra only: the intra half of the blend (<= 32x32)
     int acc;                 // CfL sum
 };
 
@@ -102,8 +101,10 @@ AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt)
     block_sync(nt);
 }
 
-// Predict one block into S.pred (pitch w).  All threads of the CTA must call it.
-AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
+// Predict one block into P (row pitch pp).  P may be the block's own position in the plane: the
+// edges are copied out first and nothing else of the plane is read afterwards.  All threads of
+// the group must call it.
+AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, int nt)
 {
     const int w = 1 << a.log2w, h = 1 << a.log2h;
     uint8_t* A = S.above + EDGE_OFF;
@@ -134,7 +135,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
         }
         block_sync(nt);
     }
-    uint8_t* P = S.pred;
+    const int lw = a.log2w;
     if (a.plane_idx == 0 && a.filter_intra) {
         // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront
         const int w4 = w >> 2, h2 = h >> 1;
@@ -149,17 +150,17 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                 for (int i = 0; i < 5; i++) {
                     if (!i2) p[i] = A[(j4 << 2) + i - 1];
                     else if (!j4 && !i) p[i] = L[(i2 << 1) - 1];
-                    else p[i] = P[((i2 << 1) - 1) * w + (j4 << 2) + i - 1];
+                    else p[i] = P[((i2 << 1) - 1) * pp + (j4 << 2) + i - 1];
                 }
                 AV1B_UNROLL
                 for (int i = 5; i < 7; i++) {
                     if (!j4) p[i] = L[(i2 << 1) + i - 5];
-                    else p[i] = P[((i2 << 1) + i - 5) * w + (j4 << 2) - 1];
+                    else p[i] = P[((i2 << 1) + i - 5) * pp + (j4 << 2) - 1];
                 }
                 int pr = 0;
                 AV1B_UNROLL
                 for (int i = 0; i < 7; i++) pr += k_intra_filter_taps[a.fi_mode][k][i] * p[i];
-                P[((i2 << 1) + i1) * w + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
+                P[((i2 << 1) + i1) * pp + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
             }
             block_sync(nt);
         }
@@ -203,7 +204,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                 int idx = (i + 1) * dx;
                 int base = (idx >> (6 - up_above)) + (j << up_above);
                 int shift = ((idx << up_above) >> 1) & 31;
-                P[e] = (uint8_t)(base < max_base ? ((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base]);
+                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)(base < max_base ? ((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base]);
             }
         } else if (p_angle > 90 && p_angle < 180) {
             const int dx = k_dr_intra_derivative[180 - p_angle];
@@ -222,7 +223,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                     int shift = ((idx << up_left) >> 1) & 31;
                     v = (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
                 }
-                P[e] = (uint8_t)v;
+                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)v;
             }
         } else if (p_angle > 180) {
             const int dy = k_dr_intra_derivative[270 - p_angle];
@@ -231,12 +232,12 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
                 int idx = (j + 1) * dy;
                 int base = (idx >> (6 - up_left)) + (i << up_left);
                 int shift = ((idx << up_left) >> 1) & 31;
-                P[e] = (uint8_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
             }
         } else if (p_angle == 90) {
-            for (int e = tid; e < w * h; e += nt) P[e] = A[e & (w - 1)];
+            for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = A[e & (w - 1)];
         } else {
-            for (int e = tid; e < w * h; e += nt) P[e] = L[e >> a.log2w];
+            for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = L[e >> a.log2w];
         }
     } else if (mode == 12) {
         // ---- Paeth
@@ -245,7 +246,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
             int i = e >> a.log2w, j = e & (w - 1);
             int base = A[j] + L[i] - tl;
             int pl = iabs(base - L[i]), pt = iabs(base - A[j]), ptl = iabs(base - tl);
-            P[e] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
+            P[(e >> lw) * pp + (e & (w - 1))] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
         }
     } else if (mode == 0) {
         // ---- DC (sums split over the lanes of a warp-sized group, folded by shuffle)
@@ -266,7 +267,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
         else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
         else if (a.have_above) avg = clip_u8((sa + (w >> 1)) >> a.log2w);
         else avg = 128;
-        for (int e = tid; e < w * h; e += nt) P[e] = (uint8_t)avg;
+        for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)avg;
     } else if (mode == 9) {
         const uint8_t* wx = k_sm_weights + (w - 4);
         const uint8_t* wy = k_sm_weights + (h - 4);
@@ -274,51 +275,53 @@ AV1B_DEV void predict(const Args& a, Scratch& S, int tid, int nt)
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
             int v = wy[i] * A[j] + (256 - wy[i]) * bl + wx[j] * L[i] + (256 - wx[j]) * tr;
-            P[e] = (uint8_t)((v + 256) >> 9);
+            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((v + 256) >> 9);
         }
     } else if (mode == 10) {
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = L[h - 1];
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
-            P[e] = (uint8_t)((wy[i] * A[j] + (256 - wy[i]) * bl + 128) >> 8);
+            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wy[i] * A[j] + (256 - wy[i]) * bl + 128) >> 8);
         }
     } else { // mode == 11, SMOOTH_H
         const uint8_t* wx = k_sm_weights + (w - 4);
         const int tr = A[w - 1];
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
-            P[e] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
+            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
         }
     }
     block_sync(nt);
 }
 
-// Chroma-from-luma on top of the DC prediction already in S.pred (IntraPredict.cpp:632-667).
-// `luma` is plane 0 of the current frame (already reconstructed for this block).
+// Chroma-from-luma on top of the DC prediction already in P (IntraPredict.cpp:632-667).
+// `luma` is plane 0 of the current frame (already reconstructed for this block).  Two passes over
+// the sub-sampled luma (sum, then apply) instead of a staging buffer.
+AV1B_DEV int cfl_luma(const Args& a, const uint8_t* luma, int luma_stride, int max_luma_w, int max_luma_h, int i, int j)
+{
+    const int ly = min((a.y + i) << 1, max_luma_h - 2);
+    const int lx = min((a.x + j) << 1, max_luma_w - 2);
+    const volatile uint8_t* q = luma + (ptrdiff_t)ly * luma_stride + lx;
+    return (q[0] + q[1] + q[luma_stride] + q[luma_stride + 1]) << 1;
+}
+
 AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int alpha, int max_luma_w, int max_luma_h,
-    Scratch& S, int tid, int nt)
+    Scratch& S, uint8_t* P, int pp, int tid, int nt)
 {
     const int w = 1 << a.log2w, h = 1 << a.log2h;
     if (tid == 0) S.acc = 0;
     block_sync(nt);
     int local = 0;
-    for (int e = tid; e < w * h; e += nt) {
-        int i = e >> a.log2w, j = e & (w - 1);
-        int ly = min((a.y + i) << 1, max_luma_h - 2);
-        int lx = min((a.x + j) << 1, max_luma_w - 2);
-        const volatile uint8_t* q = luma + (ptrdiff_t)ly * luma_stride + lx;
-        int t = q[0] + q[1] + q[luma_stride] + q[luma_stride + 1];
-        int v = t << 1;
-        S.luma[e] = (int16_t)v;
-        local += v;
-    }
+    for (int e = tid; e < w * h; e += nt) local += cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, e >> a.log2w, e & (w - 1));
     atomicAdd(&S.acc, local);
     block_sync(nt);
     const int avg = round2(S.acc, a.log2w + a.log2h);
     for (int e = tid; e < w * h; e += nt) {
-        int scaled = round2s(alpha * (S.luma[e] - avg), 6);
-        S.pred[e] = (uint8_t)clip_u8(S.pred[e] + scaled);
+        const int i = e >> a.log2w, j = e & (w - 1);
+        const int scaled = round2s(alpha * (cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, i, j) - avg), 6);
+        uint8_t* d = P + i * pp + j;
+        *d = (uint8_t)clip_u8(*d + scaled);
     }
     block_sync(nt);
 }

@@ -18,6 +18,8 @@
 #include "intra.cuh"
 #include "mc.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------
 // inverse transform
@@ -410,7 +412,7 @@ struct PlaneIo {
     int rpitch;
 };
 
-enum { WAVE_WARPS = 16, WAVE_THREADS = WAVE_WARPS * 32, WAVE_OP_CHUNK = 64 };
+enum { WAVE_OP_CHUNK = 64 };
 
 struct OpScratch {
     intra::Scratch I;
@@ -482,17 +484,30 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
         a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
         a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
         a.fi_mode = op.fi_mode;
-        intra::predict(a, S.I, tid, nt);
         if (op.kind == AV1B_OP_INTRA) {
+            // predict straight into the block's place, then add the residual over it.  The first
+            // residual words are requested before the prediction so their latency hides behind it.
+            const int lw2 = lw - 1, n2 = (w * h) >> 1; // pairs of samples
+            uint32_t r0 = 0, r1 = 0;
+            if (res) {
+                if (tid < n2) r0 = *(const uint32_t*)(res + (tid >> lw2) * D.rpitch + 2 * (tid & ((1 << lw2) - 1)));
+                if (tid + nt < n2) r1 = *(const uint32_t*)(res + ((tid + nt) >> lw2) * D.rpitch + 2 * ((tid + nt) & ((1 << lw2) - 1)));
+            }
+            intra::predict(a, S.I, dst, D.pitch, tid, nt);
             if (op.flags & AV1B_OPF_CFL)
-                intra::apply_cfl(a, io[0].pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, tid, nt);
-            for (int e = tid; e < w * h; e += nt) {
-                const int i = e >> lw, j = e & (w - 1);
-                int v = S.I.pred[e];
-                if (res) v = clip_u8(v + res[i * D.rpitch + j]);
-                dst[i * D.pitch + j] = (uint8_t)v;
+                intra::apply_cfl(a, io[0].pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
+            if (res) {
+                int k = 0;
+                for (int e = tid; e < n2; e += nt, k++) {
+                    const int i = e >> lw2, j = 2 * (e & ((1 << lw2) - 1));
+                    const uint32_t rr = k == 0 ? r0 : (k == 1 ? r1 : *(const uint32_t*)(res + i * D.rpitch + j));
+                    uint8_t* d = dst + i * D.pitch + j;
+                    d[0] = (uint8_t)clip_u8((int)d[0] + (int)(int16_t)(rr & 0xFFFF));
+                    d[1] = (uint8_t)clip_u8((int)d[1] + ((int)rr >> 16));
+                }
             }
         } else {
+            intra::predict(a, S.I, S.I.pred, w, tid, nt);
             // inter-intra blend over the inter prediction already in place
             // (reference maskBlend, InterPredict.cpp:584-609; masks :555-582, :888-899)
             const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
@@ -572,9 +587,8 @@ AV1B_DEV void wave_signal(int* progress, int r, int col, int tid, int nt)
 
 
 // Shared-memory footprint of one superblock tile (bytes) for SB size `sb` (64 or 128):
-// luma (sb+1) x (2sb+8) samples with a one-sample halo row/column, two chroma planes,
-// and the three int16 residual tiles.
-#define WAVE_TILE_BYTES(sb) (((sb) + 1) * (2 * (sb) + 8) + 2 * ((sb) / 2 + 1) * ((sb) + 8) + 2 * ((sb) * (sb) + 2 * ((sb) / 2) * ((sb) / 2)))
+// luma (sb+1) x (2sb+8) samples with a one-sample halo row/column, and two chroma planes.
+#define WAVE_TILE_BYTES(sb) (((sb) + 1) * (2 * (sb) + 8) + 2 * ((sb) / 2 + 1) * ((sb) + 8))
 
 }  // namespace
 
@@ -586,12 +600,13 @@ int wave_tile_bytes(int sb) { return WAVE_TILE_BYTES(sb); }
 // dependency level (host/emitter.cpp scheduleSb): all ops of one level are independent, each is
 // executed by ONE warp, and the CTA only synchronises between levels -- a 128x128 SB of 4x4
 // blocks needs ~100 level steps instead of ~650 sequential ops.  Frames without intrabc only.
-__global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
+template <int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 {
     alignas(16) __shared__ Av1bOp s_ops[WAVE_OP_CHUNK];
     __shared__ int s_sb;
 #ifdef AV1B_EMU
-    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64 + sizeof(OpScratch) * WAVE_WARPS];
+    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64 + sizeof(OpScratch) * WARPS];
 #else
     extern __shared__ __align__(16) uint8_t dyn[];
 #endif
@@ -611,7 +626,6 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
     // tile geometry per plane
     int tsz[3], tpitch[3];
     uint8_t* tpix[3];
-    int16_t* tres[3];
     OpScratch* scratch;
     {
         uint8_t* p = dyn;
@@ -620,11 +634,6 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
             tpitch[pl] = 2 * tsz[pl] + 8;
             tpix[pl] = p;
             p += (tsz[pl] + 1) * tpitch[pl];
-        }
-        p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        for (int pl = 0; pl < 3; pl++) {
-            tres[pl] = (int16_t*)p;
-            p += 2 * tsz[pl] * tsz[pl];
         }
         p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
         scratch = (OpScratch*)p + warp;
@@ -670,18 +679,11 @@ __global__ void __launch_bounds__(WAVE_THREADS) wave_kernel(ReconCtx c)
                     d[3] = (uint8_t)(v >> 24);
                 }
             }
-            if (have_res) {
-                const int words = n >> 1; // two int16 per word
-                const int16_t* rs = c.rp[pl] + (size_t)y0 * c.rpitch[pl] + x0;
-                for (int k = tid; k < n * words; k += nt) {
-                    const int i = k / words, j = k - i * words;
-                    ((uint32_t*)(tres[pl] + i * n))[j] = __ldg((const uint32_t*)(rs + (size_t)i * c.rpitch[pl]) + j);
-                }
-            }
             io[pl].pix = t + (ptrdiff_t)(1 - y0) * pitch + (1 - x0);
             io[pl].pitch = pitch;
-            io[pl].res = have_res ? (tres[pl] - (ptrdiff_t)y0 * n - x0) : nullptr;
-            io[pl].rpitch = n;
+            // residuals stay in the frame-layout planes (L2): exec_op requests them ahead of use
+            io[pl].res = have_res ? c.rp[pl] : nullptr;
+            io[pl].rpitch = c.rpitch[pl];
         }
         block_sync(nt);
         // ---- the ops of this superblock, level by level, one warp per op
@@ -822,22 +824,35 @@ void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.n_ops) return;
-    int grid = (int)h.n_sb;
+    // CTAs take superblocks by ticket in raster order and wait for the left and above-right
+    // neighbours: with that 2-superblock lag at most min(rows, ceil(cols / 2)) superblocks can be
+    // in progress at once.  More CTAs than that would only spin on SM slots other streams need.
+    int grid = std::min<int>((int)h.sb_rows, ((int)h.sb_cols + 1) / 2);
+    grid = std::max(1, std::min(grid, (int)h.n_sb));
     if (grid > 148 * 2) grid = 148 * 2;
     if (h.allow_intrabc) {
         AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);
         return;
     }
-    const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * WAVE_WARPS;
+    // Two builds: 16 warps, one CTA per SM (lowest latency for a lone stream), and 8 warps at
+    // <= 80 registers, three CTAs per SM (a busy multi-stream device is bound by CTA slots: the
+    // wavefront of one superblock keeps a warp scheduler mostly idle).  AV1B200_WAVE_WARPS picks.
+    static const int warps = [] {
+        const char* e = getenv("AV1B200_WAVE_WARPS");
+        return (e && atoi(e) == 8) ? 8 : 16;
+    }();
+    const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * warps;
 #ifndef AV1B_EMU
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * WAVE_WARPS);
+        cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 16);
+        cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 8);
         configured = true;
     }
-    wave_kernel<<<dim3(grid), dim3(WAVE_THREADS), smem, st>>>(c);
+    if (warps == 16) wave_kernel<16, 1><<<dim3(grid), dim3(512), smem, st>>>(c);
+    else wave_kernel<8, 3><<<dim3(grid), dim3(256), smem, st>>>(c);
 #else
     (void)smem;
-    AV1B_LAUNCH(wave_kernel, (grid), (WAVE_THREADS), st, c);
+    AV1B_LAUNCH((wave_kernel<8, 3>), (grid), (256), st, c);
 #endif
 }

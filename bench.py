@@ -33,6 +33,10 @@ import sys
 import threading
 import time
 
+# hundreds of short decoder streams ordered by events: use every hardware work queue (must be in
+# the environment before CUDA initialises; av1dec_b200/__init__.py sets the same default)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 BITS = os.path.join(ROOT, "tests", "golden", "bits")
@@ -390,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
     # Submission is host work too (a dozen driver calls per frame): the streams are dealt to
     # `host_threads` submitter threads, each interleaving its own streams frame by frame so the GPU
     # always has independent work queued.  An engine is only ever touched by its own thread.
-    n_sub = max(1, min(args.submit_threads or host_threads, len(recs)))
+    n_sub = max(1, min(args.submit_threads or min(4, host_threads), len(recs)))
     groups = [recs[i::n_sub] for i in range(n_sub)]
     submit_pool = cf.ThreadPoolExecutor(n_sub)
 
@@ -525,7 +529,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
-    ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = all of this rank's)")
+    ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
