@@ -197,6 +197,7 @@ struct av1b_ctx {
     size_t res_cap = 0;
     Lane lanes[MAX_LANES];
     int n_lanes = 1;
+    int lanes_made = 0; // lanes whose stream and event exist
     uint8_t* slab = nullptr; // one allocation holding the lanes' working set of frame buffers
     uint64_t frame_seq = 0;
     bool joined = true;     // no lane work outstanding relative to the context stream
@@ -381,14 +382,14 @@ static void ctx_free(av1b_ctx* c)
 {
     rt_set_device(c->device);
     rt_stream_sync(c->stream);
-    for (int m = 0; m < c->n_lanes; m++) rt_stream_sync(c->lanes[m].stream);
+    for (int m = 0; m < c->lanes_made; m++) rt_stream_sync(c->lanes[m].stream);
     for (auto& f : c->frames) {
         if (f.owned) rt_free(f.base);
         rt_event_destroy(f.ready);
         rt_event_destroy(f.copied);
     }
     rt_free(c->slab);
-    for (int m = 0; m < c->n_lanes; m++) {
+    for (int m = 0; m < c->lanes_made; m++) {
         Lane& L = c->lanes[m];
         rt_free(L.res_planes);
         rt_free(L.mask_plane);
@@ -454,8 +455,10 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
         int n = e ? atoi(e) : 4;
         c->n_lanes = n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n);
     }
-    for (int m = 0; m < c->n_lanes; m++)
+    for (int m = 0; m < c->n_lanes; m++) {
         if (rt_stream_create(&c->lanes[m].stream) || rt_event_create(&c->lanes[m].mark)) return fail(c, AV1B_ECUDA, "lane stream");
+        c->lanes_made = m + 1;
+    }
     if (rt_event_create(&c->main_mark)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     {
         // the working set comes from ONE allocation made here: no cudaMalloc (a device-wide
@@ -823,6 +826,19 @@ int av1b_sync(av1b_ctx* c)
         if (rt_stream_sync(c->lanes[m].stream)) return fail(c, AV1B_ECUDA, "sync");
     if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
     c->joined = true;
+    return AV1B_OK;
+}
+
+int av1b_set_lanes(av1b_ctx* c, int n)
+{
+    if (!c || n < 1 || n > MAX_LANES) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (av1b_sync(c)) return AV1B_ECUDA;
+    for (int m = c->lanes_made; m < n; m++) {
+        if (rt_stream_create(&c->lanes[m].stream) || rt_event_create(&c->lanes[m].mark)) return fail(c, AV1B_ECUDA, "lane stream");
+        c->lanes_made = m + 1;
+    }
+    c->n_lanes = n;
     return AV1B_OK;
 }
 

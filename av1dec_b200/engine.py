@@ -84,6 +84,10 @@ class Engine:
     def sync(self):
         self._check(self.lib.av1b_sync(self.ctx), "av1b_sync")
 
+    def set_lanes(self, n):
+        """Frames in flight on the device at once (1 = strictly one after the other)."""
+        self._check(self.lib.av1b_set_lanes(self.ctx, n), "av1b_set_lanes")
+
     def join(self):
         """Make the context stream wait (device-side) for every frame submitted so far."""
         self._check(self.lib.av1b_join(self.ctx), "av1b_join")

@@ -255,6 +255,7 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
     W4, H4 = 3840, 2160
     S = W4 * H4 * 3 // 2
     eng = Engine(W4, H4, device=device, stream=None)
+    eng.set_lanes(1)  # per-kernel timing: one frame on the device at a time
     frames4k = []
     for i in range(n_in):
         sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist="B", lr_unit=64)
@@ -308,6 +309,7 @@ def inter_leg(device, reps=3):
     W4, H4 = 3840, 2160
     cmd, n_blk, algo = synth.make_inter_frame(W4, H4)
     eng = Engine(W4, H4, device=device)
+    eng.set_lanes(1)
     rng = synth.SplitMix64(synth.SEED + 77)
     for slot in range(2):
         eng.set_ref(slot, synth.make_planes(rng, W4, H4, "B"), W4, H4)
@@ -334,6 +336,7 @@ def itx_leg(device, reps=3):
     hdr_size = C.sizeof(F.FrameHdr)
     cmd, n_tb, n_res, algo = synth.make_itx_frame(3840, 2160)
     eng = Engine(3840, 2160, device=device)
+    eng.set_lanes(1)
     dev_cmd = eng.upload(cmd)
     for _ in range(3):
         eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_ITX, 0)
@@ -492,6 +495,7 @@ def run_ours(args, rank, world, local_rank):
         r.engine.close()
 
     post, roofline = postfilter_leg(device, dev)
+    kernels_4k = {"itx": itx_leg(device), "inter": inter_leg(device)} if rank == 0 else None
 
     if rank != 0:
         return 0
@@ -516,6 +520,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": roofline,
         "postfilter_4k": post,
+        "recon_4k": kernels_4k,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

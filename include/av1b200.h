@@ -93,6 +93,9 @@ int av1b_sync(av1b_ctx* ctx);
  * whatever the caller enqueues on that stream afterwards: call it before recording your own event
  * on a stream passed to av1b_ctx_create. */
 int av1b_join(av1b_ctx* ctx);
+/* Number of lanes of this context from now on (1..8; waits for the context to go idle first).
+ * 1 makes every frame run alone on the device -- what a per-kernel timing wants. */
+int av1b_set_lanes(av1b_ctx* ctx, int n);
 /* Mark a fence after the work enqueued so far / wait for it: lets a caller overlap parsing of
  * the next frame with this frame's device work. */
 int av1b_fence_record(av1b_ctx* ctx, uint64_t* fence);

@@ -59,6 +59,7 @@ def main():
         e.record(side)
         e.synchronize()
         total = s.elapsed_time(e) / a.reps
+        eng.set_lanes(1)  # the per-stage split is taken with one frame on the device at a time
         eng.set_profiling(True)
         eng.stage_times(reset=True)
         for _ in range(a.reps):
