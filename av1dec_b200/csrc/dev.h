@@ -60,6 +60,7 @@ static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #define AV1B_NOINLINE
+#define AV1B_ASSUME_SHARED(p) ((void)0)
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
@@ -100,6 +101,8 @@ typedef cudaStream_t av1b_stream_t;
 #define AV1B_UNROLL _Pragma("unroll")
 #define AV1B_UNROLL4 _Pragma("unroll 4")
 #define AV1B_NOINLINE __noinline__
+// address-space hint: lets the compiler turn generic accesses through p into LDS / STS
+#define AV1B_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #define AV1B_LAUNCH(kern, grid, block, stream, ...) kern<<<dim3 grid, dim3 block, 0, stream>>>(__VA_ARGS__)
 #define AV1T_CONST static __device__ const
 static __device__ __forceinline__ int av1b_ld_acquire(const int* p)

@@ -435,11 +435,20 @@ AV1B_DEV FrameConst frame_const(const Av1bFrameHdr* hdr)
     return f;
 }
 
+// SMEM: the planes in `io` are the superblock tile in shared memory (wave_kernel) -- said to the
+// compiler so that sample accesses become shared-memory instructions instead of generic ones.
+template <bool SMEM>
 AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameConst& fc, const Av1bOp& op, const PlaneIo* io, OpScratch& S,
     mc::Scratch* M, int tid, int nt)
 {
     const int plane = op.plane, sub = plane ? 1 : 0;
     const PlaneIo& D = io[plane];
+    uint8_t* const pix = D.pix;
+    uint8_t* const luma_pix = io[0].pix;
+    if (SMEM) {
+        AV1B_ASSUME_SHARED(pix);
+        AV1B_ASSUME_SHARED(luma_pix);
+    }
     int lw, lh;
     if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
         lw = op.tx_size & 15;
@@ -450,7 +459,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     }
     const int w = 1 << lw, h = 1 << lh;
     const bool has_res = (op.flags & AV1B_OPF_HAS_RESID) && D.res;
-    uint8_t* dst = D.pix + (ptrdiff_t)op.y * D.pitch + op.x;
+    uint8_t* dst = pix + (ptrdiff_t)op.y * D.pitch + op.x;
     const int16_t* res = has_res ? (D.res + (ptrdiff_t)op.y * D.rpitch + op.x) : nullptr;
     switch (op.kind) {
     case AV1B_OP_INTER_RES: {
@@ -465,7 +474,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     case AV1B_OP_INTRA:
     case AV1B_OP_INTERINTRA: {
         intra::Args a;
-        a.plane = D.pix;
+        a.plane = pix;
         a.stride = D.pitch;
         a.x = op.x;
         a.y = op.y;
@@ -495,7 +504,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
             }
             intra::predict(a, S.I, dst, D.pitch, tid, nt);
             if (op.flags & AV1B_OPF_CFL)
-                intra::apply_cfl(a, io[0].pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
+                intra::apply_cfl(a, luma_pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
             if (res) {
                 int k = 0;
                 for (int e = tid; e < n2; e += nt, k++) {
@@ -705,12 +714,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 // missed a dependency, the conformance MD5s under emulation break
                 for (unsigned k = g1; k-- > g0;) {
                     const Av1bOp op = s_ops[k];
-                    exec_op(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
+                    exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #else
                 for (unsigned k = g0 + warp; k < g1; k += nw) {
                     const Av1bOp op = s_ops[k];
-                    exec_op(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
+                    exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #endif
                 block_sync(nt);
@@ -771,7 +780,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
-            exec_op(c, hdr, fc, op, io, S, &M, tid, nt);
+            exec_op<false>(c, hdr, fc, op, io, S, &M, tid, nt);
         }
         wave_signal(progress, r, col, tid, nt);
     }
