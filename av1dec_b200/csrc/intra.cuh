@@ -71,6 +71,17 @@ AV1B_DEV int edge_upsample(int w, int h, bool smooth, int delta)
     return smooth ? (wh <= 8) : (wh <= 16);
 }
 
+// Sum of `v` over the nt (<= 32) lanes of the group, in every lane.
+AV1B_DEV unsigned warp_sum(unsigned v, int nt)
+{
+#ifdef AV1B_EMU
+    (void)nt;
+    return v;
+#else
+    return nt == 32 ? __reduce_add_sync(0xFFFFFFFFu, v) : v; // nt < 32 only in single-lane test configurations
+#endif
+}
+
 // In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter)
 AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int tid, int nt)
 {
@@ -249,22 +260,27 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
             P[(e >> lw) * pp + (e & (w - 1))] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
         }
     } else if (mode == 0) {
-        // ---- DC (sums split over the lanes of a warp-sized group, folded by shuffle)
+        // ---- DC.  Both edge sums travel in one word (each <= 64 * 255) through one warp
+        // reduction; the divisor w + h is 2^k, 3 * 2^k or 5 * 2^k, so the division is a shift and
+        // an exact multiply-high.
         int sl = 0, sa = 0;
         if (nt <= 32) {
-            for (int k = tid; k < h; k += nt) sl += L[k];
-            for (int k = tid; k < w; k += nt) sa += A[k];
-            for (int d = 1; d < nt; d <<= 1) {
-                sl += __shfl_xor_sync(0xFFFFFFFFu, sl, d);
-                sa += __shfl_xor_sync(0xFFFFFFFFu, sa, d);
-            }
+            unsigned part = 0;
+            for (int k = tid; k < h; k += nt) part += (unsigned)L[k] << 16;
+            for (int k = tid; k < w; k += nt) part += A[k];
+            part = warp_sum(part, nt);
+            sl = (int)(part >> 16);
+            sa = (int)(part & 0xFFFF);
         } else {
             for (int k = 0; k < h; k++) sl += L[k];
             for (int k = 0; k < w; k++) sa += A[k];
         }
         int avg;
-        if (a.have_left && a.have_above) avg = (sl + sa + ((w + h) >> 1)) / (w + h);
-        else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
+        if (a.have_left && a.have_above) {
+            const int lmin = min(a.log2w, a.log2h), ratio = iabs(a.log2w - a.log2h); // w + h = (1 + 2^ratio) << lmin
+            const unsigned q = (unsigned)(sl + sa + ((w + h) >> 1)) >> lmin;
+            avg = ratio == 0 ? (int)(q >> 1) : (ratio == 1 ? (int)(__umulhi(q, 0xAAAAAAABu) >> 1) : (int)(__umulhi(q, 0xCCCCCCCDu) >> 2));
+        } else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
         else if (a.have_above) avg = clip_u8((sa + (w >> 1)) >> a.log2w);
         else avg = 128;
         for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)avg;

@@ -63,7 +63,7 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
     int16_t* tmp, int tstride, int gl, int G)
 {
     const int txs = op.tx_size;
-    const int lw = k_tx_wlog2[txs], lh = k_tx_hlog2[txs];
+    const int lw = (int)((AV1T_TX_WLOG2_PACKED >> (3 * txs)) & 7), lh = (int)((AV1T_TX_HLOG2_PACKED >> (3 * txs)) & 7);
     const int w = 1 << lw, h = 1 << lh;
     const int tw = min(w, 32);
     const bool lossless = op.lossless != 0;
@@ -454,8 +454,8 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
         lw = op.tx_size & 15;
         lh = op.tx_size >> 4;
     } else {
-        lw = k_tx_wlog2[op.tx_size];
-        lh = k_tx_hlog2[op.tx_size];
+        lw = (int)((AV1T_TX_WLOG2_PACKED >> (3 * op.tx_size)) & 7);
+        lh = (int)((AV1T_TX_HLOG2_PACKED >> (3 * op.tx_size)) & 7);
     }
     const int w = 1 << lw, h = 1 << lh;
     const bool has_res = (op.flags & AV1B_OPF_HAS_RESID) && D.res;
@@ -612,7 +612,7 @@ int wave_tile_bytes(int sb) { return WAVE_TILE_BYTES(sb); }
 template <int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 {
-    alignas(16) __shared__ Av1bOp s_ops[WAVE_OP_CHUNK];
+    alignas(16) __shared__ Av1bOp s_ops[2][WAVE_OP_CHUNK];
     __shared__ int s_sb;
 #ifdef AV1B_EMU
     static uint8_t dyn[WAVE_TILE_BYTES(128) + 64 + sizeof(OpScratch) * WARPS];
@@ -695,35 +695,53 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             io[pl].rpitch = c.rpitch[pl];
         }
         block_sync(nt);
-        // ---- the ops of this superblock, level by level, one warp per op
-        for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK) {
+        // ---- the ops of this superblock, level by level, one warp per op.  The op list streams
+        // through a double buffer: the next chunk is requested before the current one runs, so
+        // its L2 latency hides behind the levels in between.
+        {
+            const uint4* src = (const uint4*)(ops + e.first_op);
+            const unsigned n0 = min((unsigned)WAVE_OP_CHUNK, e.n_ops);
+            uint4* dstv = (uint4*)s_ops[0];
+            for (unsigned q = tid; q < n0 * 2; q += nt) dstv[q] = __ldg(src + q);
+        }
+        block_sync(nt);
+        int buf = 0;
+        for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK, buf ^= 1) {
             const unsigned nk = min((unsigned)WAVE_OP_CHUNK, e.n_ops - k0);
-            {
-                const uint4* src = (const uint4*)(ops + e.first_op + k0);
-                uint4* dstv = (uint4*)s_ops;
-                for (unsigned q = tid; q < nk * 2; q += nt) dstv[q] = __ldg(src + q);
-            }
-            block_sync(nt);
+            const Av1bOp* cur_ops = s_ops[buf];
+            const unsigned k1 = k0 + WAVE_OP_CHUNK;
+            const unsigned nn = k1 < e.n_ops ? min((unsigned)WAVE_OP_CHUNK, e.n_ops - k1) : 0;
+            uint4 pre = make_uint4(0, 0, 0, 0);
+            static_assert(WAVE_OP_CHUNK * 2 <= 256, "one uint4 of the next chunk per thread");
+            if ((unsigned)tid < nn * 2) pre = __ldg((const uint4*)(ops + e.first_op + k1) + tid);
             unsigned g0 = 0;
             while (g0 < nk) {
                 // res_off >> 16 = ops left in this level (emitter scheduleSb); 0 from a producer
                 // that does not fill it: one op per step, still a valid order
-                const unsigned g1 = min(nk, g0 + max(1u, s_ops[g0].res_off >> 16));
+                const unsigned g1 = min(nk, g0 + max(1u, cur_ops[g0].res_off >> 16));
 #ifdef AV1B_EMU
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
                 for (unsigned k = g1; k-- > g0;) {
-                    const Av1bOp op = s_ops[k];
+                    const Av1bOp op = cur_ops[k];
                     exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #else
                 for (unsigned k = g0 + warp; k < g1; k += nw) {
-                    const Av1bOp op = s_ops[k];
+                    const Av1bOp op = cur_ops[k];
                     exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #endif
                 block_sync(nt);
                 g0 = g1;
+            }
+            if (nn) {
+#ifdef AV1B_EMU
+                for (unsigned q = 0; q < nn * 2; q++) ((uint4*)s_ops[buf ^ 1])[q] = ((const uint4*)(ops + e.first_op + k1))[q];
+#else
+                if ((unsigned)tid < nn * 2) ((uint4*)s_ops[buf ^ 1])[tid] = pre;
+#endif
+                block_sync(nt);
             }
         }
         // ---- flush the tile (MI-aligned area only)

@@ -160,6 +160,12 @@ def main():
                     ("Tx_Width_Log2", "k_tx_wlog2"), ("Tx_Height_Log2", "k_tx_hlog2"),
                     ("Block_Width", "k_block_w"), ("Block_Height", "k_block_h")):
         T.append(emit("uint8_t", out, extract("decoder/Av1Common.h", nm)))
+    # Tx_*_Log2 again as 19 three-bit fields of one word: (PACKED >> 3*tx_size) & 7 costs no memory
+    # access on the wavefront's critical path
+    for nm, out in (("Tx_Width_Log2", "AV1T_TX_WLOG2_PACKED"), ("Tx_Height_Log2", "AV1T_TX_HLOG2_PACKED")):
+        v = extract("decoder/Av1Common.h", nm)
+        assert len(v) == 19 and max(v) < 8
+        T.append(f"#define {out} 0x{sum(x << (3 * i) for i, x in enumerate(v)):x}ULL")
 
     print("// GENERATED by tools/gen_tables.py -- AV1 specification constant tables. Do not edit.")
     print("// Data only; see the generator's docstring for provenance of each array.")
@@ -167,7 +173,7 @@ def main():
     print("#include <stdint.h>")
     if HOST:
         keep = ("hk_wedge_master", "hk_wedge_codebook", "hk_block_w", "hk_block_h", "hk_quant_dist", "hk_tx_")
-        T = [t.replace("AV1T_CONST", "static const") for t in T if t.split()[2].startswith(keep)]
+        T = [t.replace("AV1T_CONST", "static const") for t in T if not t.startswith("#define") and t.split()[2].startswith(keep)]
     else:
         print("#ifndef AV1T_CONST")
         print("#define AV1T_CONST static const")
