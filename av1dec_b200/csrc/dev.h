@@ -38,6 +38,7 @@ extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __restrict__
 #define AV1B_UNROLL
 #define AV1B_UNROLL4
+#define AV1B_NOUNROLL
 static inline void __syncthreads() {}
 static inline void __syncwarp() {}
 static inline void __threadfence() {}
@@ -100,6 +101,7 @@ template <class F> static inline void emu_launch(dim3 grid, F f)
 typedef cudaStream_t av1b_stream_t;
 #define AV1B_UNROLL _Pragma("unroll")
 #define AV1B_UNROLL4 _Pragma("unroll 4")
+#define AV1B_NOUNROLL _Pragma("unroll 1")
 #define AV1B_NOINLINE __noinline__
 // address-space hint: lets the compiler turn generic accesses through p into LDS / STS
 #define AV1B_ASSUME_SHARED(p) __builtin_assume(__isShared(p))

@@ -83,11 +83,15 @@ AV1B_DEV unsigned warp_sum(unsigned v, int nt)
 }
 
 // In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter)
-AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int tid, int nt)
+template <int NTC>
+AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int tid, int nt_rt)
 {
+    const int nt = NTC ? NTC : nt_rt;
     if (!strength) return;
+    AV1B_NOUNROLL
     for (int k = tid; k < sz; k += nt) tmp[k] = edge[k - 1];
     block_sync(nt);
+    AV1B_NOUNROLL
     for (int i = 1 + tid; i < sz; i += nt) {
         int s = 0;
         AV1B_UNROLL
@@ -98,12 +102,16 @@ AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int
 }
 
 // 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample)
-AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt)
+template <int NTC>
+AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt_rt)
 {
+    const int nt = NTC ? NTC : nt_rt;
     // tmp[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
+    AV1B_NOUNROLL
     for (int k = tid; k < n + 3; k += nt) tmp[k] = edge[clip3(-1, n - 1, k - 2)];
     block_sync(nt);
     if (tid == 0) edge[-2] = tmp[0];
+    AV1B_NOUNROLL
     for (int i = tid; i < n; i += nt) {
         int s = -tmp[i] + 9 * tmp[i + 1] + 9 * tmp[i + 2] - tmp[i + 3];
         edge[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
@@ -115,8 +123,11 @@ AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt)
 // Predict one block into P (row pitch pp).  P may be the block's own position in the plane: the
 // edges are copied out first and nothing else of the plane is read afterwards.  All threads of
 // the group must call it.
-AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, int nt)
+// NTC: the group size when it is a compile-time constant (32 = one warp per op), 0 = use nt_rt.
+template <int NTC>
+AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, int nt_rt)
 {
+    const int nt = NTC ? NTC : nt_rt;
     const int w = 1 << a.log2w, h = 1 << a.log2h;
     uint8_t* A = S.above + EDGE_OFF;
     uint8_t* L = S.left + EDGE_OFF;
@@ -131,6 +142,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
         else if (!ha && !hl) left_const = 129;
         const int above_limit = min(a.max_x, x + (a.have_above_right ? 2 * w : w) - 1);
         const int left_limit = min(a.max_y, y + (a.have_below_left ? 2 * h : h) - 1);
+        AV1B_NOUNROLL
         for (int i = tid; i < w + h; i += nt) {
             A[i] = (uint8_t)(above_const >= 0 ? above_const : px(a, min(above_limit, x + i), y - 1));
             L[i] = (uint8_t)(left_const >= 0 ? left_const : px(a, x - 1, min(left_limit, y + i)));
@@ -153,6 +165,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
         for (int d = 0; d < w4 + h2 - 1; d++) {
             int j_lo = max(0, d - (h2 - 1)), j_hi = min(w4 - 1, d);
             int nsb = j_hi - j_lo + 1;
+            AV1B_NOUNROLL
             for (int e = tid; e < nsb * 8; e += nt) {
                 int j4 = j_lo + (e >> 3), i2 = d - j4, k = e & 7;
                 int i1 = k >> 2, j1 = k & 3;
@@ -195,21 +208,22 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
             if (a.have_above) {
                 int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
                 int num = min(w, maxx_q - x + 1) + (p_angle < 90 ? h : 0) + 1;
-                filter_edge(A, S.tmp, num, strength, tid, nt);
+                filter_edge<NTC>(A, S.tmp, num, strength, tid, nt);
             }
             if (a.have_left) {
                 int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
                 int num = min(h, maxy_q - y + 1) + (p_angle > 180 ? w : 0) + 1;
-                filter_edge(L, S.tmp, num, strength, tid, nt);
+                filter_edge<NTC>(L, S.tmp, num, strength, tid, nt);
             }
             up_above = edge_upsample(w, h, a.edge_smooth, p_angle - 90);
-            if (up_above) upsample_edge(A, S.tmp, w + (p_angle < 90 ? h : 0), tid, nt);
+            if (up_above) upsample_edge<NTC>(A, S.tmp, w + (p_angle < 90 ? h : 0), tid, nt);
             up_left = edge_upsample(w, h, a.edge_smooth, p_angle - 180);
-            if (up_left) upsample_edge(L, S.tmp, h + (p_angle > 180 ? w : 0), tid, nt);
+            if (up_left) upsample_edge<NTC>(L, S.tmp, h + (p_angle > 180 ? w : 0), tid, nt);
         }
         if (p_angle < 90) {
             const int dx = k_dr_intra_derivative[p_angle];
             const int max_base = (w + h - 1) << up_above;
+            AV1B_NOUNROLL
             for (int e = tid; e < w * h; e += nt) {
                 int i = e >> a.log2w, j = e & (w - 1);
                 int idx = (i + 1) * dx;
@@ -220,6 +234,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
         } else if (p_angle > 90 && p_angle < 180) {
             const int dx = k_dr_intra_derivative[180 - p_angle];
             const int dy = k_dr_intra_derivative[p_angle - 90];
+            AV1B_NOUNROLL
             for (int e = tid; e < w * h; e += nt) {
                 int i = e >> a.log2w, j = e & (w - 1);
                 int idx = (j << 6) - (i + 1) * dx;
@@ -238,6 +253,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
             }
         } else if (p_angle > 180) {
             const int dy = k_dr_intra_derivative[270 - p_angle];
+            AV1B_NOUNROLL
             for (int e = tid; e < w * h; e += nt) {
                 int i = e >> a.log2w, j = e & (w - 1);
                 int idx = (j + 1) * dy;
@@ -246,13 +262,16 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
                 P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
             }
         } else if (p_angle == 90) {
+            AV1B_NOUNROLL
             for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = A[e & (w - 1)];
         } else {
+            AV1B_NOUNROLL
             for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = L[e >> a.log2w];
         }
     } else if (mode == 12) {
         // ---- Paeth
         const int tl = A[-1];
+        AV1B_NOUNROLL
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
             int base = A[j] + L[i] - tl;
@@ -266,7 +285,9 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
         int sl = 0, sa = 0;
         if (nt <= 32) {
             unsigned part = 0;
+            AV1B_NOUNROLL
             for (int k = tid; k < h; k += nt) part += (unsigned)L[k] << 16;
+            AV1B_NOUNROLL
             for (int k = tid; k < w; k += nt) part += A[k];
             part = warp_sum(part, nt);
             sl = (int)(part >> 16);
@@ -283,11 +304,13 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
         } else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
         else if (a.have_above) avg = clip_u8((sa + (w >> 1)) >> a.log2w);
         else avg = 128;
+        AV1B_NOUNROLL
         for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)avg;
     } else if (mode == 9) {
         const uint8_t* wx = k_sm_weights + (w - 4);
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = L[h - 1], tr = A[w - 1];
+        AV1B_NOUNROLL
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
             int v = wy[i] * A[j] + (256 - wy[i]) * bl + wx[j] * L[i] + (256 - wx[j]) * tr;
@@ -296,6 +319,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
     } else if (mode == 10) {
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = L[h - 1];
+        AV1B_NOUNROLL
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
             P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wy[i] * A[j] + (256 - wy[i]) * bl + 128) >> 8);
@@ -303,6 +327,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
     } else { // mode == 11, SMOOTH_H
         const uint8_t* wx = k_sm_weights + (w - 4);
         const int tr = A[w - 1];
+        AV1B_NOUNROLL
         for (int e = tid; e < w * h; e += nt) {
             int i = e >> a.log2w, j = e & (w - 1);
             P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
@@ -322,17 +347,21 @@ AV1B_DEV int cfl_luma(const Args& a, const uint8_t* luma, int luma_stride, int m
     return (q[0] + q[1] + q[luma_stride] + q[luma_stride + 1]) << 1;
 }
 
+template <int NTC>
 AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int alpha, int max_luma_w, int max_luma_h,
-    Scratch& S, uint8_t* P, int pp, int tid, int nt)
+    Scratch& S, uint8_t* P, int pp, int tid, int nt_rt)
 {
+    const int nt = NTC ? NTC : nt_rt;
     const int w = 1 << a.log2w, h = 1 << a.log2h;
     if (tid == 0) S.acc = 0;
     block_sync(nt);
     int local = 0;
+    AV1B_NOUNROLL
     for (int e = tid; e < w * h; e += nt) local += cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, e >> a.log2w, e & (w - 1));
     atomicAdd(&S.acc, local);
     block_sync(nt);
     const int avg = round2(S.acc, a.log2w + a.log2h);
+    AV1B_NOUNROLL
     for (int e = tid; e < w * h; e += nt) {
         const int i = e >> a.log2w, j = e & (w - 1);
         const int scaled = round2s(alpha * (cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, i, j) - avg), 6);

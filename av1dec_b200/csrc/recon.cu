@@ -412,7 +412,22 @@ struct PlaneIo {
     int rpitch;
 };
 
+// The three planes of a frame (or of a superblock tile) as scalars picked by select: no array, so
+// the pointers stay in registers and the compiler can see that a tile lives in shared memory
+// (LDS / STS instead of generic accesses).
+struct PlaneSet {
+    uint8_t *pix0, *pix1, *pix2;
+    int pitch0, pitch12;
+    const int16_t *res0, *res1, *res2;
+    int rpitch0, rpitch12;
+};
+
 enum { WAVE_OP_CHUNK = 64 };
+#ifdef AV1B_EMU
+enum { WAVE_NT = 0 }; // the emulation runs every group with one thread
+#else
+enum { WAVE_NT = 32 };
+#endif
 
 struct OpScratch {
     intra::Scratch I;
@@ -437,18 +452,20 @@ AV1B_DEV FrameConst frame_const(const Av1bFrameHdr* hdr)
 
 // SMEM: the planes in `io` are the superblock tile in shared memory (wave_kernel) -- said to the
 // compiler so that sample accesses become shared-memory instructions instead of generic ones.
-template <bool SMEM>
-AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameConst& fc, const Av1bOp& op, const PlaneIo* io, OpScratch& S,
-    mc::Scratch* M, int tid, int nt)
+// NTC: compile-time group size (32: one warp per op) or 0 = runtime nt_rt.
+template <bool SMEM, int NTC>
+AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameConst& fc, const Av1bOp& op, const PlaneSet& io, OpScratch& S,
+    mc::Scratch* M, int tid, int nt_rt)
 {
+    const int nt = NTC ? NTC : nt_rt;
     const int plane = op.plane, sub = plane ? 1 : 0;
-    const PlaneIo& D = io[plane];
+    PlaneIo D;
+    D.pix = plane == 0 ? io.pix0 : (plane == 1 ? io.pix1 : io.pix2);
+    D.pitch = plane == 0 ? io.pitch0 : io.pitch12;
+    D.res = plane == 0 ? io.res0 : (plane == 1 ? io.res1 : io.res2);
+    D.rpitch = plane == 0 ? io.rpitch0 : io.rpitch12;
     uint8_t* const pix = D.pix;
-    uint8_t* const luma_pix = io[0].pix;
-    if (SMEM) {
-        AV1B_ASSUME_SHARED(pix);
-        AV1B_ASSUME_SHARED(luma_pix);
-    }
+    uint8_t* const luma_pix = io.pix0;
     int lw, lh;
     if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
         lw = op.tx_size & 15;
@@ -493,20 +510,23 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
         a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
         a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
         a.fi_mode = op.fi_mode;
-        if (op.kind == AV1B_OP_INTRA) {
-            // predict straight into the block's place, then add the residual over it.  The first
-            // residual words are requested before the prediction so their latency hides behind it.
-            const int lw2 = lw - 1, n2 = (w * h) >> 1; // pairs of samples
-            uint32_t r0 = 0, r1 = 0;
-            if (res) {
-                if (tid < n2) r0 = *(const uint32_t*)(res + (tid >> lw2) * D.rpitch + 2 * (tid & ((1 << lw2) - 1)));
-                if (tid + nt < n2) r1 = *(const uint32_t*)(res + ((tid + nt) >> lw2) * D.rpitch + 2 * ((tid + nt) & ((1 << lw2) - 1)));
-            }
-            intra::predict(a, S.I, dst, D.pitch, tid, nt);
+        // Intra blocks are predicted straight into their place and the residual is added over it;
+        // the first residual words are requested before the prediction so their latency hides
+        // behind it.  Inter-intra blocks predict into scratch (the place holds the inter half).
+        const bool in_place = op.kind == AV1B_OP_INTRA;
+        const int lw2 = lw - 1, n2 = (w * h) >> 1; // pairs of samples
+        uint32_t r0 = 0, r1 = 0;
+        if (in_place && res) {
+            if (tid < n2) r0 = *(const uint32_t*)(res + (tid >> lw2) * D.rpitch + 2 * (tid & ((1 << lw2) - 1)));
+            if (tid + nt < n2) r1 = *(const uint32_t*)(res + ((tid + nt) >> lw2) * D.rpitch + 2 * ((tid + nt) & ((1 << lw2) - 1)));
+        }
+        intra::predict<NTC>(a, S.I, in_place ? dst : S.I.pred, in_place ? D.pitch : w, tid, nt);
+        if (in_place) {
             if (op.flags & AV1B_OPF_CFL)
-                intra::apply_cfl(a, luma_pix, io[0].pitch, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
+                intra::apply_cfl<NTC>(a, luma_pix, io.pitch0, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
             if (res) {
                 int k = 0;
+                AV1B_NOUNROLL
                 for (int e = tid; e < n2; e += nt, k++) {
                     const int i = e >> lw2, j = 2 * (e & ((1 << lw2) - 1));
                     const uint32_t rr = k == 0 ? r0 : (k == 1 ? r1 : *(const uint32_t*)(res + i * D.rpitch + j));
@@ -516,7 +536,6 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
                 }
             }
         } else {
-            intra::predict(a, S.I, S.I.pred, w, tid, nt);
             // inter-intra blend over the inter prediction already in place
             // (reference maskBlend, InterPredict.cpp:584-609; masks :555-582, :888-899)
             const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
@@ -560,6 +579,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     }
     case AV1B_OP_INTRABC: {
         // only reached on the global-memory path (frames with allow_intrabc)
+        if (SMEM) break;
         const Av1bIpu u = ((const Av1bIpu*)(c.cmd + hdr->off_ipu))[op.aux];
         mc::Params P;
         setup_mc_params(c, hdr, u, P);
@@ -632,21 +652,14 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     const bool have_res = c.rp[0] != nullptr && hdr->n_itx != 0;
     int* ticket = c.sync;
     int* progress = c.sync + 1;
-    // tile geometry per plane
-    int tsz[3], tpitch[3];
-    uint8_t* tpix[3];
-    OpScratch* scratch;
-    {
-        uint8_t* p = dyn;
-        for (int pl = 0; pl < 3; pl++) {
-            tsz[pl] = pl ? sbs_y >> 1 : sbs_y;
-            tpitch[pl] = 2 * tsz[pl] + 8;
-            tpix[pl] = p;
-            p += (tsz[pl] + 1) * tpitch[pl];
-        }
-        p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        scratch = (OpScratch*)p + warp;
-    }
+    // tile geometry: luma n0 x n0 with pitch 2*n0 + 8 (one halo row long enough for above-right
+    // reads, one halo column), chroma likewise
+    const int n0 = sbs_y, n1 = sbs_y >> 1;
+    const int pitch0 = 2 * n0 + 8, pitch1 = 2 * n1 + 8;
+    uint8_t* const t0 = dyn;
+    uint8_t* const t1 = t0 + (n0 + 1) * pitch0;
+    uint8_t* const t2 = t1 + (n1 + 1) * pitch1;
+    OpScratch* const scratch = (OpScratch*)(dyn + (((n0 + 1) * pitch0 + 2 * (n1 + 1) * pitch1 + 15) & ~15)) + warp;
     for (;;) {
         block_sync(nt);
         if (tid == 0) s_sb = atomicAdd(ticket, 1);
@@ -660,26 +673,26 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             wave_signal(progress, r, col, tid, nt);
             continue;
         }
-        PlaneIo io[3];
-        // ---- load halo (+ current content for inter frames) and the residual tile
-        for (int pl = 0; pl < 3; pl++) {
-            const int n = tsz[pl], pitch = tpitch[pl];
+        // ---- load halo (+ current content for inter frames)
+        auto load_plane = [&](int pl, uint8_t* t, int n, int pitch) {
             const int x0 = col * n, y0 = r * n;
             const PlaneView g = c.cur.pl[pl];
-            uint8_t* t = tpix[pl];
             // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 1)]
             if (r > 0) { // above row: x0-1 .. x0+2n-1
                 const uint8_t* src = g.p + (size_t)(y0 - 1) * g.stride + x0 - 1;
+                AV1B_NOUNROLL
                 for (int k = tid; k < 2 * n + 1; k += nt) t[k] = __ldcg(src + k);
             }
             if (col > 0) { // left column
                 const uint8_t* src = g.p + (size_t)y0 * g.stride + x0 - 1;
+                AV1B_NOUNROLL
                 for (int k = tid; k < n; k += nt) t[(k + 1) * pitch] = __ldcg(src + (size_t)k * g.stride);
             }
             if (load_pred) {
-                const int words = n >> 2;
-                for (int k = tid; k < n * words; k += nt) {
-                    const int i = k / words, j = k - i * words;
+                const int lwords = mc::ilog2_pow2(n) - 2; // n is 32, 64 or 128
+                AV1B_NOUNROLL
+                for (int k = tid; k < (n << lwords); k += nt) {
+                    const int i = k >> lwords, j = k & ((1 << lwords) - 1);
                     const uint32_t v = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
                     uint8_t* d = t + (i + 1) * pitch + 1 + 4 * j;
                     d[0] = (uint8_t)v;
@@ -688,12 +701,22 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                     d[3] = (uint8_t)(v >> 24);
                 }
             }
-            io[pl].pix = t + (ptrdiff_t)(1 - y0) * pitch + (1 - x0);
-            io[pl].pitch = pitch;
-            // residuals stay in the frame-layout planes (L2): exec_op requests them ahead of use
-            io[pl].res = have_res ? c.rp[pl] : nullptr;
-            io[pl].rpitch = c.rpitch[pl];
-        }
+        };
+        load_plane(0, t0, n0, pitch0);
+        load_plane(1, t1, n1, pitch1);
+        load_plane(2, t2, n1, pitch1);
+        PlaneSet io;
+        io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (1 - col * n0);
+        io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (1 - col * n1);
+        io.pix2 = t2 + (ptrdiff_t)(1 - r * n1) * pitch1 + (1 - col * n1);
+        io.pitch0 = pitch0;
+        io.pitch12 = pitch1;
+        // residuals stay in the frame-layout planes (L2): exec_op requests them ahead of use
+        io.res0 = have_res ? c.rp[0] : nullptr;
+        io.res1 = have_res ? c.rp[1] : nullptr;
+        io.res2 = have_res ? c.rp[2] : nullptr;
+        io.rpitch0 = c.rpitch[0];
+        io.rpitch12 = c.rpitch[1];
         block_sync(nt);
         // ---- the ops of this superblock, level by level, one warp per op.  The op list streams
         // through a double buffer: the next chunk is requested before the current one runs, so
@@ -724,12 +747,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 // missed a dependency, the conformance MD5s under emulation break
                 for (unsigned k = g1; k-- > g0;) {
                     const Av1bOp op = cur_ops[k];
-                    exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
+                    exec_op<true, WAVE_NT>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #else
                 for (unsigned k = g0 + warp; k < g1; k += nw) {
                     const Av1bOp op = cur_ops[k];
-                    exec_op<true>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
+                    exec_op<true, WAVE_NT>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
                 }
 #endif
                 block_sync(nt);
@@ -745,22 +768,24 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             }
         }
         // ---- flush the tile (MI-aligned area only)
-        for (int pl = 0; pl < 3; pl++) {
+        auto flush_plane = [&](int pl, const uint8_t* t, int n, int pitch) {
             const int sub = pl ? 1 : 0;
-            const int n = tsz[pl], pitch = tpitch[pl];
             const int x0 = col * n, y0 = r * n;
             const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub;
             const int cw = min(n, pw - x0), chh = min(n, ph - y0);
             const PlaneView g = c.cur.pl[pl];
-            const uint8_t* t = tpix[pl];
             const int words = cw >> 2; // MI-aligned widths are multiples of 4 in every plane
+            AV1B_NOUNROLL
             for (int k = tid; k < chh * words; k += nt) {
                 const int i = k / words, j = k - i * words;
                 const uint8_t* s = t + (i + 1) * pitch + 1 + 4 * j;
                 const uint32_t v = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
                 *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = v;
             }
-        }
+        };
+        flush_plane(0, t0, n0, pitch0);
+        flush_plane(1, t1, n1, pitch1);
+        flush_plane(2, t2, n1, pitch1);
         wave_signal(progress, r, col, tid, nt);
     }
 }
@@ -780,13 +805,12 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     int* ticket = c.sync;
     int* progress = c.sync + 1;
-    PlaneIo io[3];
-    for (int pl = 0; pl < 3; pl++) {
-        io[pl].pix = c.cur.pl[pl].p;
-        io[pl].pitch = c.cur.pl[pl].stride;
-        io[pl].res = (c.rp[0] && hdr->n_itx) ? c.rp[pl] : nullptr;
-        io[pl].rpitch = c.rpitch[pl];
-    }
+    const bool have_res = c.rp[0] && hdr->n_itx;
+    PlaneSet io;
+    io.pix0 = c.cur.pl[0].p, io.pix1 = c.cur.pl[1].p, io.pix2 = c.cur.pl[2].p;
+    io.pitch0 = c.cur.pl[0].stride, io.pitch12 = c.cur.pl[1].stride;
+    io.res0 = have_res ? c.rp[0] : nullptr, io.res1 = have_res ? c.rp[1] : nullptr, io.res2 = have_res ? c.rp[2] : nullptr;
+    io.rpitch0 = c.rpitch[0], io.rpitch12 = c.rpitch[1];
     for (;;) {
         __syncthreads();
         if (tid == 0) s_sb = atomicAdd(ticket, 1);
@@ -798,7 +822,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
-            exec_op<false>(c, hdr, fc, op, io, S, &M, tid, nt);
+            exec_op<false, 0>(c, hdr, fc, op, io, S, &M, tid, nt);
         }
         wave_signal(progress, r, col, tid, nt);
     }
