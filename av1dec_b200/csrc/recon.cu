@@ -231,7 +231,11 @@ AV1B_DEV uint32_t add_res4(uint32_t px, uint2 r)
 // the other with the parameters broadcast by shuffle -- the per-unit scalar set-up, which would
 // otherwise cost a full warp instruction per value per unit, is paid once per 32 units.  The
 // residual of plain inter blocks is added in the same store (AV1B_IPUF_ADD_RES).
-enum { FAST_WARPS = 4 };
+#ifdef AV1B_EMU
+enum { FAST_WARPS = 4, FAST_SLICES = 4, FAST_JOBS_PER_SLICE = 2 }; // one unit per chunk under emulation: still exercise the slicing
+#else
+enum { FAST_WARPS = 4, FAST_SLICES = 4, FAST_JOBS_PER_SLICE = 48 };
+#endif
 
 __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx c)
 {
@@ -252,10 +256,28 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
         uint4 r_taps[2] = {};
         uint32_t subpel = 0;
         bool fast = false;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
         if (idx < n_ipu) {
-            const uint4 a = __ldg(ipus + 2 * idx), b = __ldg(ipus + 2 * idx + 1);
+            a = __ldg(ipus + 2 * idx), b = __ldg(ipus + 2 * idx + 1);
             u_xy = a.x, u_dim = a.y, u_fl = b.z;
             fast = (u_fl & AV1B_IPUF_FAST) != 0;
+        }
+        // ---- jobs = (unit, tile) pairs in unit order.  A chunk of large units holds up to 8x the
+        // jobs of a chunk of small ones: it is shared by up to FAST_SLICES CTAs (blockIdx.y), each
+        // repeating the set-up and taking every n_slices-th group of jobs; the CTAs a light chunk
+        // does not need leave here.
+        const int my_w = u_dim & 0xFF, my_h = (u_dim >> 8) & 0xFF;
+        const int my_tiles = fast ? ((my_w + mc::TILE_W - 1) / mc::TILE_W) * ((my_h + mc::TILE_H - 1) / mc::TILE_H) : 0;
+        int incl = my_tiles;
+        for (int d = 1; d < nl; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int excl = incl - my_tiles;
+        const int total = __shfl_sync(FULL, incl, nl - 1);
+        const int n_slices = min((int)gridDim.y, (total + FAST_JOBS_PER_SLICE - 1) / FAST_JOBS_PER_SLICE);
+        if ((int)blockIdx.y >= n_slices) continue;
+        {
             if (fast) {
                 const int x = u_xy & 0xFFFF, y = u_xy >> 16, w = u_dim & 0xFF, h = (u_dim >> 8) & 0xFF;
                 const int plane = (u_dim >> 16) & 0xFF, sub = plane ? 1 : 0;
@@ -280,18 +302,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
                 }
             }
         }
-        // ---- jobs = (unit, tile) pairs in unit order, dealt round-robin to the CTA's warps (every
-        // warp of the CTA did the same set-up); parameters are broadcast from the unit's lane
-        const int my_w = u_dim & 0xFF, my_h = (u_dim >> 8) & 0xFF;
-        const int my_tiles = fast ? ((my_w + mc::TILE_W - 1) / mc::TILE_W) * ((my_h + mc::TILE_H - 1) / mc::TILE_H) : 0;
-        int incl = my_tiles;
-        for (int d = 1; d < nl; d <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int excl = incl - my_tiles;
-        const int total = __shfl_sync(FULL, incl, nl - 1);
-        for (int job = warp; job < total; job += nw) {
+        // the slice's jobs, dealt round-robin to its warps; parameters are broadcast from the unit's lane
+        for (int job = (int)blockIdx.y * nw + warp; job < total; job += n_slices * nw) {
             const int j = 31 - __clz(__ballot_sync(FULL, excl <= job));
             const int tile = job - __shfl_sync(FULL, excl, j);
             const uint32_t xy = __shfl_sync(FULL, u_xy, j), dim = __shfl_sync(FULL, u_dim, j), fl = __shfl_sync(FULL, u_fl, j);
@@ -869,7 +881,7 @@ void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     AV1B_LAUNCH(inter_kernel, (grid), (INTER_WARPS * 32), st, c);
     int fgrid = (int)((h.n_ipu + 31) / 32); // one 32-unit chunk per CTA pass
     if (fgrid > 148 * 48) fgrid = 148 * 48;
-    if (fgrid) AV1B_LAUNCH(inter_fast_kernel, (fgrid), (FAST_WARPS * 32), st, c);
+    if (fgrid) AV1B_LAUNCH(inter_fast_kernel, (fgrid, FAST_SLICES), (FAST_WARPS * 32), st, c);
 }
 
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
@@ -888,10 +900,8 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     // Two builds: 16 warps, one CTA per SM (lowest latency for a lone stream), and 8 warps at
     // <= 80 registers, three CTAs per SM (a busy multi-stream device is bound by CTA slots: the
     // wavefront of one superblock keeps a warp scheduler mostly idle).  AV1B200_WAVE_WARPS picks.
-    static const int warps = [] {
-        const char* e = getenv("AV1B200_WAVE_WARPS");
-        return (e && atoi(e) == 8) ? 8 : 16;
-    }();
+    const char* wenv = getenv("AV1B200_WAVE_WARPS");
+    const int warps = (wenv && atoi(wenv) == 8) ? 8 : 16;
     const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * warps;
 #ifndef AV1B_EMU
     static bool configured = false;

@@ -381,6 +381,7 @@ def run_ours(args, rank, world, local_rank):
         rs = record_stream(pkg, None, name, data, want, device)
         rs.engine = Engine(max(rs.max_w, 16), max(rs.max_h, 16), device=device, stream=side_streams[i % len(side_streams)].cuda_stream)
         rs.side = side_streams[i % len(side_streams)]
+        rs.engine.set_lanes(args.lanes)
         for buf, n, refresh, show in rs.host_frames:
             if buf is None:
                 rs.frames.append((None, None, refresh, n))
@@ -510,7 +511,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "bits/ conformance streams (committed fixtures); synthetic 4K frames for the roofline leg",
-        "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams),
+        "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams), "lanes_per_context": args.lanes,
                    "host_threads_per_gpu": host_threads, "host_cores": cores,
                    "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
                    "stage_share_ms": share},
@@ -534,6 +535,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
     args = ap.parse_args()

@@ -132,3 +132,27 @@ def test_postfilter_4k_is_deterministic_and_launches_kernels(eng):
     for p in range(3):
         h, w = (360, 640) if p == 0 else (180, 320)
         assert np.array_equal(only_deblock[p][:h, :w], with_lr[p][:h, :w])
+
+
+@pytest.mark.parametrize("env", [{"AV1B200_LANES": "1", "AV1B200_GOP_THREADS": "1"},
+                                 {"AV1B200_LANES": "16", "AV1B200_GOP_THREADS": "8"},
+                                 {"AV1B200_LANES": "3", "AV1B200_WAVE_WARPS": "8"}])
+def test_concurrency_knobs_do_not_change_pixels(dec, md5_table, env, monkeypatch):
+    """Frame lanes, closed-segment workers and the wavefront build only reorder work: an
+    all-intra stream (39 independent frames), an inter stream with compound / OBMC references and
+    an intrabc frame must come out bit-identical under every setting."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pkg.load_engine().av1b_pool_purge()  # pooled contexts keep the lane count they were created with
+    try:
+        for name in ("av1-1-b8-02-allintra.ivf", "av1-1-b8-06-mfmv.ivf", "av1-1-b8-04-cdfupdate.ivf",
+                     "Halo_426x240_1frames_intrabc.ivf"):
+            got, _, _ = checks.stream_md5(dec, os.path.join(BITS, name))
+            assert got == md5_table[name], (name, env)
+    finally:
+        pkg.load_engine().av1b_pool_purge()  # contexts created under these settings must not be recycled
+
+
+def test_segments_of_all_intra_stream(dec):
+    data = open(os.path.join(BITS, "av1-1-b8-02-allintra.ivf"), "rb").read()
+    assert pkg.ivf_segments(data) == list(range(39))
