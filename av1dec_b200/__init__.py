@@ -34,7 +34,7 @@ ENGINE_SYMBOLS = [
     "av1b_frame_submit", "av1b_frame_submit_resident", "av1b_show_existing", "av1b_frame_download",
     "av1b_sync", "av1b_fence_record", "av1b_fence_wait", "av1b_fence_done", "av1b_pool_purge", "av1b_host_alloc", "av1b_host_free",
     "av1b_dev_alloc", "av1b_dev_free", "av1b_dev_upload", "av1b_debug_set_input", "av1b_debug_set_ref",
-    "av1b_debug_get_residual", "av1b_join", "av1b_set_lanes", "av1b_launch_count", "av1b_set_profiling", "av1b_get_stage_times",
+    "av1b_debug_get_residual", "av1b_debug_counters", "av1b_join", "av1b_set_lanes", "av1b_launch_count", "av1b_set_profiling", "av1b_get_stage_times",
     "av1b_debug_input_from_slot", "av1b_struct_size",
 ]
 STAGE_NAMES = ["itx", "inter", "wave", "deblock", "cdef", "lr"]
@@ -80,6 +80,8 @@ def _bind_engine(lib):
     lib.av1b_launch_count.argtypes = [C.c_void_p]
     lib.av1b_launch_count.restype = C.c_uint64
     lib.av1b_join.argtypes = [C.c_void_p]
+    lib.av1b_debug_counters.argtypes = [C.POINTER(C.c_uint64)]
+    lib.av1b_debug_counters.restype = None
     lib.av1b_set_lanes.argtypes = [C.c_void_p, C.c_int]
     lib.av1b_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.av1b_get_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
@@ -177,6 +179,14 @@ def decode_ivf(data, device=0, stages=STAGE_ALL, want_yuv=True, lib=None):
         break
     yuv = buf.raw[:out_bytes.value] if want_yuv else None
     return yuv, n_frames.value, pixels.value
+
+
+def alloc_counters(lib=None):
+    """(contexts created, contexts recycled, device allocations, pinned allocations) so far."""
+    lib = lib or load_engine()
+    out = (C.c_uint64 * 4)()
+    lib.av1b_debug_counters(out)
+    return tuple(int(v) for v in out)
 
 
 def ivf_segments(data, lib=None):

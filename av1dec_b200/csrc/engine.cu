@@ -9,6 +9,7 @@
 #include "av1_tables_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,9 @@
 #include <string>
 #include <vector>
 
+// allocation counters (av1b_debug_counters): a steady-state decode service should stop moving them
+static std::atomic<uint64_t> g_n_ctx_new{ 0 }, g_n_ctx_reused{ 0 }, g_n_dev_alloc{ 0 }, g_n_pinned_alloc{ 0 };
+
 // ------------------------------------------------------------------------------------------
 // thin runtime layer (CUDA, or libc for the test-only emulation build)
 // ------------------------------------------------------------------------------------------
@@ -24,9 +28,9 @@
 EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 typedef int rt_event_t;
 static int rt_set_device(int) { return 0; }
-static int rt_malloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
+static int rt_malloc(void** p, size_t n) { g_n_dev_alloc++; *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
 static void rt_free(void* p) { free(p); }
-static int rt_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static int rt_host_alloc(void** p, size_t n) { g_n_pinned_alloc++; *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 static void rt_host_free(void* p) { free(p); }
 static int rt_h2d(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
 static int rt_d2h(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
@@ -54,9 +58,9 @@ const char* av1b_backend(void) { return "emu"; }
 #else
 typedef cudaEvent_t rt_event_t;
 static int rt_set_device(int d) { return cudaSetDevice(d) != cudaSuccess; }
-static int rt_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
+static int rt_malloc(void** p, size_t n) { g_n_dev_alloc++; return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
 static void rt_free(void* p) { if (p) cudaFree(p); }
-static int rt_host_alloc(void** p, size_t n) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess; }
+static int rt_host_alloc(void** p, size_t n) { g_n_pinned_alloc++; return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess; }
 static void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
 static int rt_h2d(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) != cudaSuccess; }
 static int rt_d2h(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st) != cudaSuccess; }
@@ -374,9 +378,45 @@ extern "C" {
 // table and pinned output buffers are recycled instead of being freed.
 static std::mutex g_mu;
 static std::vector<av1b_ctx*> g_ctx_pool;
+
 static std::map<int, uint8_t*> g_wedge;           // per device
 static std::map<void*, size_t> g_pinned_size;     // every live pinned block -> its bucket size
 static std::map<size_t, std::vector<void*>> g_pinned_free;
+static std::map<std::pair<int, size_t>, std::vector<void*>> g_dev_free; // (device, bucket) -> free device blocks
+
+static size_t bucket_of(size_t bytes)
+{
+    size_t bucket = 64 << 10;
+    while (bucket < bytes) bucket <<= 1;
+    return bucket;
+}
+
+// Device blocks for the command ring, recycled process-wide in power-of-two buckets like the
+// pinned ones: contexts are handed from stream to stream, and a ring slot that had to grow for a
+// bigger frame would otherwise cost a cudaMalloc + cudaHostAlloc in the middle of a decode.
+static void* dev_bucket_alloc(int device, size_t bucket)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto& fl = g_dev_free[std::make_pair(device, bucket)];
+        if (!fl.empty()) {
+            void* p = fl.back();
+            fl.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    return rt_malloc(&p, bucket) ? nullptr : p;
+}
+static void dev_bucket_free(int device, size_t bucket, void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_dev_free[std::make_pair(device, bucket)].push_back(p);
+}
+
+void* av1b_host_alloc(size_t bytes);
+void av1b_host_free(void* p);
 
 static void ctx_free(av1b_ctx* c)
 {
@@ -399,8 +439,8 @@ static void ctx_free(av1b_ctx* c)
     }
     rt_event_destroy(c->main_mark);
     for (int i = 0; i < N_SLOTS; i++) {
-        rt_host_free(c->slots[i].host);
-        rt_free(c->slots[i].dev);
+        av1b_host_free(c->slots[i].host);
+        dev_bucket_free(c->device, c->slots[i].cap, c->slots[i].dev);
         rt_event_destroy(c->slots[i].done);
     }
     for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
@@ -427,12 +467,14 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
             av1b_ctx* c = g_ctx_pool[i];
             if (c->device == device && c->aw >= aw && c->ah >= ah && (size_t)c->aw * c->ah <= 2 * (size_t)aw * ah) {
                 g_ctx_pool.erase(g_ctx_pool.begin() + i);
+                g_n_ctx_reused++;
                 *out = c;
                 return AV1B_OK;
             }
         }
     }
     av1b_ctx* c = new av1b_ctx;
+    g_n_ctx_new++;
     *out = c;
     c->device = device;
     for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
@@ -542,6 +584,11 @@ void av1b_pool_purge(void)
             rt_host_free(p);
         }
     g_pinned_free.clear();
+    for (auto& kv : g_dev_free) {
+        rt_set_device(kv.first.first);
+        for (void* p : kv.second) rt_free(p);
+    }
+    g_dev_free.clear();
 }
 
 const char* av1b_last_error(av1b_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -557,15 +604,17 @@ int av1b_cmd_acquire(av1b_ctx* c, size_t bytes, void** host_ptr)
         sl.pending = false;
     }
     if (sl.cap < bytes) {
-        size_t cap = bytes + bytes / 2 + 4096;
-        rt_host_free(sl.host);
-        rt_free(sl.dev);
+        // the slot is idle (its event was waited for above): trade both halves for a bigger bucket
+        av1b_host_free(sl.host);
+        dev_bucket_free(c->device, sl.cap, sl.dev);
         sl.host = sl.dev = nullptr;
         sl.cap = 0;
-        void *h = nullptr, *d = nullptr;
-        if (rt_host_alloc(&h, cap)) return fail(c, AV1B_ENOMEM, "pinned command slot");
-        if (rt_malloc(&d, cap)) {
-            rt_host_free(h);
+        const size_t cap = bucket_of(bytes);
+        void* h = av1b_host_alloc(cap);
+        if (!h) return fail(c, AV1B_ENOMEM, "pinned command slot");
+        void* d = dev_bucket_alloc(c->device, cap);
+        if (!d) {
+            av1b_host_free(h);
             return fail(c, AV1B_ENOMEM, "device command slot");
         }
         sl.host = (uint8_t*)h;
@@ -880,8 +929,7 @@ int av1b_fence_wait(av1b_ctx* c, uint64_t fence)
 
 void* av1b_host_alloc(size_t bytes)
 {
-    size_t bucket = 64 << 10;
-    while (bucket < bytes) bucket <<= 1;
+    const size_t bucket = bucket_of(bytes);
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto& fl = g_pinned_free[bucket];
@@ -963,6 +1011,11 @@ int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
 }
 
 uint64_t av1b_launch_count(av1b_ctx* c) { return c ? c->launches : 0; }
+
+void av1b_debug_counters(uint64_t out[4])
+{
+    out[0] = g_n_ctx_new, out[1] = g_n_ctx_reused, out[2] = g_n_dev_alloc, out[3] = g_n_pinned_alloc;
+}
 
 int av1b_set_profiling(av1b_ctx* c, int on)
 {

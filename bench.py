@@ -470,10 +470,13 @@ def run_ours(args, rank, world, local_rank):
             yuv, frames, px = pkg.decode_ivf(s[1], device=device)
             return px, len(yuv)
         t0 = time.perf_counter()
-        with cf.ThreadPoolExecutor(host_threads) as ex:
+        # every decoder runs two host threads (parser, command emitter) and a stream of closed
+        # segments adds workers of its own: cores / 2 callers keep the cores busy without thrashing
+        with cf.ThreadPoolExecutor(args.e2e_threads or max(1, host_threads // 2)) as ex:
             res = list(ex.map(one, sorted(mine, key=lambda s: -len(s[1]))))
         return time.perf_counter() - t0, sum(p for p, _ in res)
-    e2e_pass()
+    for _ in range(2):  # untimed: fills the context / pinned / command-slot pools
+        e2e_pass()
     barrier()
     e2e_t = 0.0
     e2e_px = 0
@@ -484,7 +487,12 @@ def run_ours(args, rank, world, local_rank):
         e2e_t += t
         e2e_px += px
     if os.environ.get("BENCH_TRACE"):
-        print("trace e2e ms/step:", trace, [round(1e3 * e2e_pass()[0]) for _ in range(6)], file=sys.stderr)
+        extra = []
+        for _ in range(6):
+            c0 = pkg.alloc_counters()
+            t = e2e_pass()[0]
+            extra.append((round(1e3 * t), tuple(b - a for a, b in zip(c0, pkg.alloc_counters()))))
+        print("trace e2e ms/step:", trace, "then (ms, new ctx / reused ctx / device allocs / pinned allocs):", extra, file=sys.stderr)
     barrier()
     clocks = sampler.stop()
     e2e_total, e2e_tmax = reduce_result(float(e2e_px), e2e_t, dev)
@@ -512,7 +520,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "bits/ conformance streams (committed fixtures); synthetic 4K frames for the roofline leg",
         "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams), "lanes_per_context": args.lanes,
-                   "host_threads_per_gpu": host_threads, "host_cores": cores,
+                   "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads // 2), "host_cores": cores,
                    "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
                    "stage_share_ms": share},
         "clocks": clocks,
@@ -535,6 +543,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = this rank's share of the cores)")
     ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")

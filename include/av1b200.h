@@ -120,6 +120,9 @@ int av1b_debug_set_ref(av1b_ctx* ctx, int slot, const uint8_t* const src[3], con
 int av1b_debug_get_residual(av1b_ctx* ctx, int16_t* dst, size_t n);
 /* Number of kernel launches issued by this context so far. */
 uint64_t av1b_launch_count(av1b_ctx* ctx);
+/* Process-wide allocation counters: contexts created, contexts recycled from the pool, device
+ * allocations, pinned host allocations.  A steady-state service should stop moving [0], [2], [3]. */
+void av1b_debug_counters(uint64_t out[4]);
 /* Per-stage device timing.  With profiling on, the engine brackets every launch group with CUDA
  * events on its stream; av1b_get_stage_times() synchronises and returns accumulated milliseconds
  * and call counts per stage (index: 0 itx, 1 inter, 2 wavefront, 3 deblock, 4 cdef, 5 lr). */
