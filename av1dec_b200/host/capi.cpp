@@ -207,10 +207,21 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
     std::vector<Tu> tus;
     std::vector<size_t> seg;
     if (!scan_ivf(ivf, len, tus, seg)) return -1;
-    const bool async = getenv("AV1B200_SYNC_EMIT") == nullptr;
+    // The command emitter can run on a worker thread one frame behind the parser: lower latency
+    // for a lone stream, but ~35 % more CPU in total (the parsed tree crosses cores).  Once the
+    // process already keeps the cores busy with other decodes, emit inline instead.
+    static std::atomic<int> active{ 0 };
+    struct Busy {
+        std::atomic<int>& n;
+        explicit Busy(std::atomic<int>& a) : n(a) { n++; }
+        ~Busy() { n--; }
+    };
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     auto setup = [&](YamiAv1::Decoder& dec) {
         av1b200::decoderOptions(dec).device = device;
         av1b200::decoderOptions(dec).stages = stages;
+        const char* e = getenv("AV1B200_SYNC_EMIT");
+        const bool async = e ? atoi(e) == 0 : 2 * active.load() <= hw;
         av1b200::decoderSetAsync(dec, async);
     };
     unsigned workers = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
@@ -222,6 +233,7 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
     int frames = 0;
     uint64_t pixels = 0;
     if (workers <= 1) {
+        Busy busy(active);
         YamiAv1::Decoder dec;
         setup(dec);
         Sink sink{ out_yuv, out_cap, nullptr };
@@ -236,6 +248,7 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
         std::atomic<size_t> next{ 0 };
         std::atomic<bool> failed{ false };
         auto work = [&]() {
+            Busy busy(active);
             YamiAv1::Decoder dec;
             setup(dec);
             for (size_t s; !failed && (s = next++) < nseg;) {
