@@ -548,6 +548,8 @@ void av1b_ctx_destroy(av1b_ctx* c)
         c->joined = true;
         for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
         for (int i = 0; i < N_SLOTS; i++) c->slots[i].pending = false;
+        c->cur_slot = -1; // the next stream starts on the slots that already own a buffer
+        c->frame_seq = 0;
         c->pending_input = -1;
         c->profiling = false;
         for (auto& sp : c->spans) {
