@@ -578,21 +578,21 @@ void FrameEmitter::emitTb(Block& b, TransformBlock& t)
         const int dcq = t.get_dc_quant(), acq = t.get_ac_quant();
         const int denom = t.dqDenom;
         const size_t off = m_coef.size();
-        m_coef.resize(off + (size_t)tw * th);
+        m_coef.resize(off + (size_t)tw * th); // zero-filled: only non-zero levels are written below
         int16_t* out = &m_coef[off];
         int nzr = 0, nzc = 0;
+        const int dshift = denom == 1 ? 0 : (denom == 2 ? 1 : 2); // dqDenom is 1, 2 or 4: magnitude division by shift
+        const auto* quant = &t.Quant[0];
         for (int i = 0; i < th; i++) {
+            const auto* qrow = quant + i * tw;
             for (int j = 0; j < tw; j++) {
-                const int q = t.Quant[i * tw + j];
-                int v = 0;
-                if (q) {
-                    const int dq = (int)((unsigned)q * (unsigned)((i | j) ? acq : dcq));
-                    const int mag = (int)(((dq < 0) ? (0u - (unsigned)dq) : (unsigned)dq) & 0xffffffu) / denom;
-                    v = clip3(-32768, 32767, dq < 0 ? -mag : mag);
-                    if (i + 1 > nzr) nzr = i + 1;
-                    if (j + 1 > nzc) nzc = j + 1;
-                }
-                out[i * tw + j] = (int16_t)v;
+                const int q = qrow[j];
+                if (!q) continue;
+                const int dq = (int)((unsigned)q * (unsigned)((i | j) ? acq : dcq));
+                const int mag = (int)((((dq < 0) ? (0u - (unsigned)dq) : (unsigned)dq) & 0xffffffu) >> dshift);
+                out[i * tw + j] = (int16_t)clip3(-32768, 32767, dq < 0 ? -mag : mag);
+                if (i + 1 > nzr) nzr = i + 1;
+                if (j + 1 > nzc) nzc = j + 1;
             }
         }
         op.flags |= AV1B_OPF_HAS_RESID;
