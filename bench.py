@@ -453,6 +453,10 @@ def run_ours(args, rank, world, local_rank):
     total_px, tmax = reduce_result(float(pixels_step * args.steps), secs, dev)
     value = total_px / tmax / 1e6
 
+    if args.only == "replay":  # development aid: the resident replay alone
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": 1e3 * tmax / args.steps, "launches": launches}))
+        return 0
     # per-stage share of device time for the stream workload (one extra profiled pass)
     for r in recs:
         r.engine.set_profiling(True)
@@ -555,7 +559,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = this rank's share of the cores)")
     ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
-    ap.add_argument("--only", default="", choices=["", "postfilter"], help="run a single leg (development aid)")
+    ap.add_argument("--only", default="", choices=["", "postfilter", "replay"], help="run a single leg (development aid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
