@@ -330,10 +330,13 @@ def make_itx_frame(w, h, seed=SEED, coded_frac=0.7):
     return cmd, len(itx), res_off, algo
 
 
-def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512):
+def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512, fixed_mv=None, fast=True, same_ref=False):
     """A whole frame of translational inter blocks (8x8 .. 64x64, random partition): random
     1/8-pel motion vectors within +-max_mv/8 samples, random dual interpolation filters, references
     in store slots 0 / 1 (RefFrame 1 / 2), `compound_frac` of the blocks compound-average.
+    `fixed_mv` = (row, col) in 1/8 luma pel gives every block that vector for both lists;
+    `fast=False` leaves the AV1B_IBF_FAST / AV1B_IPUF_FAST flags off (general kernel);
+    `same_ref` makes both lists of a compound block read store slot 0.
     Returns (cmd_bytes, n_blocks, algo_bytes); algo_bytes = (1 + refs) * samples (read + write)."""
     rng = SplitMix64(seed)
     mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
@@ -354,8 +357,12 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512):
     nb = len(bx)
     comp = rng.uniform((nb,)) < compound_frac
     mv = rng.randint(-max_mv, max_mv, (nb, 2, 2))
+    if fixed_mv is not None:
+        mv[:, :, 0], mv[:, :, 1] = fixed_mv[0], fixed_mv[1]
     filt = rng.randint(0, 2, (nb, 2))
     ref0 = rng.randint(1, 2, (nb,))
+    if same_ref:
+        ref0[:] = 1
     ipu_t = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("kind", "u1"),
                       ("mv", "<i2", (2, 2)), ("ref_slot", "i1", 2), ("ref_frame", "u1", 2), ("filt", "u1", 2),
                       ("warp", "u1", 2), ("flags", "u1"), ("comp_type", "u1"), ("fwd_w", "u1"), ("bck_w", "u1"), ("aux", "<u4")])
@@ -369,16 +376,16 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512):
         v["ref_frame"][:, 0] = ref0
         v["ref_frame"][:, 1] = 3 - ref0
         v["ref_slot"][:, 0] = ref0 - 1
-        v["ref_slot"][:, 1] = np.where(comp, 2 - ref0, -1)
+        v["ref_slot"][:, 1] = np.where(comp, 0 if same_ref else 2 - ref0, -1)
         v["filt"] = filt
-        v["flags"] = comp.astype(np.uint8) | 0x08  # AV1B_IPUF_COMPOUND, AV1B_IPUF_FAST
+        v["flags"] = comp.astype(np.uint8) | (0x08 if fast else 0)  # AV1B_IPUF_COMPOUND, AV1B_IPUF_FAST
         v["comp_type"] = 2                  # AV1B_COMP_AVERAGE
         v["aux"] = 0xFFFFFFFF
     blk_t = np.dtype([("first_ipu", "<u4"), ("n_ipu", "<u2"), ("flags", "<u2"), ("x", "<u2"), ("y", "<u2"), ("cx", "<u2"),
                       ("cy", "<u2"), ("bw", "u1"), ("bh", "u1"), ("cw", "u1"), ("ch", "u1"), ("pad", "<u4")])
     assert blk_t.itemsize == 24
     blk = np.zeros(nb, blk_t)
-    blk["first_ipu"], blk["n_ipu"], blk["flags"] = np.arange(nb) * 3, 3, 1 | 4  # HAS_CHROMA | FAST
+    blk["first_ipu"], blk["n_ipu"], blk["flags"] = np.arange(nb) * 3, 3, 1 | (4 if fast else 0)  # HAS_CHROMA | FAST
     blk["x"], blk["y"], blk["cx"], blk["cy"] = bx, by, bx >> 1, by >> 1
     blk["bw"] = blk["bh"] = bs
     blk["cw"] = blk["ch"] = bs >> 1

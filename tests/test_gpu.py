@@ -156,3 +156,10 @@ def test_concurrency_knobs_do_not_change_pixels(dec, md5_table, env, monkeypatch
 def test_segments_of_all_intra_stream(dec):
     data = open(os.path.join(BITS, "av1-1-b8-02-allintra.ivf"), "rb").read()
     assert pkg.ivf_segments(data) == list(range(39))
+
+
+@pytest.mark.parametrize("w,h", [(640, 384), (3840, 2160)])
+def test_inter_prediction_properties(eng, w, h):
+    """Motion compensation on whole synthetic frames (4K = BASELINE's per-kernel size): identity,
+    shifted copy, and the fast kernel against the general one."""
+    checks.check_inter_properties(eng, w, h)

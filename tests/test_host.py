@@ -98,6 +98,11 @@ def test_decoder_class_mirrors_reference_api(md5_table):
 
 
 @need_emu
+def test_inter_prediction_properties_under_emulation():
+    checks.check_inter_properties(checks.emu_engine(), 192, 128)
+
+
+@need_emu
 def test_ivf_segments_split_at_random_access_points():
     lib = checks.emu_decoder()
     rd = lambda n: open(os.path.join(BITS, n), "rb").read()
