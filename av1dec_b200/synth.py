@@ -401,3 +401,130 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512, fixed_mv=N
     samples = (bs.astype(np.int64) ** 2 * 3 // 2)
     algo = int((samples * (2 + comp.astype(np.int64))).sum())
     return cmd, nb, algo
+
+
+def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
+    """A frame for the superblock wavefront (prediction only): a random `intra_frac` of the blocks
+    of a non-intra frame are intra-predicted over whatever the frame already holds (the caller
+    supplies it as the input picture, standing for the inter prediction), so every edge carries
+    real data.  Per superblock one block size (8 / 16 / 32 luma, half of it chroma), blocks in
+    raster order inside the superblock, every mode (DC, directional with angle deltas and the edge
+    filter, smooth, Paeth, filter-intra, chroma-from-luma).  The availability flags follow the
+    decoding order exactly -- above-right only where the neighbour precedes the block, below-left
+    only at the left column next to a finished superblock -- so no op reads samples a later op
+    overwrites, and the dependency levels (level | run length << 16 in res_off, ops stably sorted
+    by level inside each superblock) are computed the way the host emitter does (4x4-cell map).
+    `levelled=False` keeps the ops in decoding order, one per step (res_off = 0): the reference
+    the level analysis is checked against.  Returns the command buffer."""
+    rng = SplitMix64(seed)
+    sb = 1 << sb_log2
+    mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
+    fw, fh = mi_cols * 4, mi_rows * 4  # MI-aligned plane size (luma)
+    sb_cols, sb_rows = (fw + sb - 1) // sb, (fh + sb - 1) // sb
+    op_t = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("kind", "u1"), ("tx_size", "u1"), ("tx_type", "u1"),
+                     ("mode", "u1"), ("angle", "i1"), ("flags", "u1"), ("fi", "u1"), ("cfl", "i1"), ("nzr", "u1"),
+                     ("nzc", "u1"), ("lossless", "u1"), ("coef_off", "<u4"), ("res_off", "<u4"), ("aux", "<u4"),
+                     ("mlw", "<u2"), ("mlh", "<u2")])
+    assert op_t.itemsize == 32
+    all_ops, sbs = [], []
+    sq_tx = {4: 0, 8: 1, 16: 2, 32: 3}
+    size_pick = rng.randint(0, 2, (sb_rows, sb_cols))
+    for r in range(sb_rows):
+        for c in range(sb_cols):
+            bs = (8, 16, 32)[int(size_pick[r, c])]
+            x0, y0 = c * sb, r * sb
+            nbx, nby = min(sb, fw - x0) // bs, min(sb, fh - y0) // bs
+            n_blk = nbx * nby
+            pick = rng.uniform((max(n_blk, 1),)) < intra_frac
+            modes = rng.randint(0, 12, (max(n_blk, 1), 2))
+            deltas = rng.randint(-3, 3, (max(n_blk, 1), 2))
+            misc = rng.randint(0, 255, (max(n_blk, 1), 4))
+            ops = []
+            for by in range(nby):
+                for bx in range(nbx):
+                    k = by * nbx + bx
+                    if not pick[k]:
+                        continue
+                    for pl in range(3):
+                        sub = 1 if pl else 0
+                        n = sb >> sub
+                        s = bs >> sub
+                        x, y = (x0 >> sub) + bx * s, (y0 >> sub) + by * s
+                        pw, ph = fw >> sub, fh >> sub
+                        fl = 0
+                        if x > 0:
+                            fl |= F.OPF_HAVE_LEFT
+                        if y > 0:
+                            fl |= F.OPF_HAVE_ABOVE
+                        top_row = by == 0
+                        if y > 0 and x + s < pw and (top_row or x + s < (x0 >> sub) + n):
+                            fl |= F.OPF_HAVE_ABOVE_RIGHT
+                        if bx == 0 and c > 0 and by + 1 < nby and y + 2 * s <= ph:
+                            fl |= F.OPF_HAVE_BELOW_LEFT
+                        mode = int(modes[k, 1 if pl else 0])
+                        o = np.zeros((), op_t)
+                        o["x"], o["y"], o["plane"], o["kind"], o["tx_size"] = x, y, pl, F.OP_INTRA, sq_tx[s]
+                        o["mode"] = mode
+                        if 1 <= mode <= 8:
+                            o["angle"] = int(deltas[k, 1 if pl else 0])
+                            if misc[k, 0] & 1:
+                                fl |= F.OPF_EDGE_SMOOTH
+                        if pl == 0 and s <= 32 and misc[k, 1] < 48:
+                            o["mode"], o["angle"], o["fi"] = 0, 0, int(misc[k, 2]) % 5
+                            fl |= F.OPF_FILTER_INTRA
+                        if pl > 0 and misc[k, 3] < 64:
+                            o["mode"], o["angle"] = 0, 0
+                            o["cfl"] = int(misc[k, 2 if pl == 1 else 1]) % 31 - 15
+                            o["mlw"], o["mlh"] = x0 + bx * bs + bs, y0 + by * bs + bs
+                            fl = (fl | F.OPF_CFL) & ~F.OPF_EDGE_SMOOTH
+                        o["flags"] = fl
+                        ops.append(o)
+            # dependency levels: 4x4-cell map per plane, like host/emitter.cpp scheduleSb
+            cell = [np.zeros((sb >> 2, sb >> 2), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64)]
+            levels = []
+            for o in ops:
+                pl = int(o["plane"])
+                sub = 1 if pl else 0
+                nc = (sb >> sub) >> 2
+                s = 4 << int(o["tx_size"])
+                x, y = int(o["x"]) - (x0 >> sub), int(o["y"]) - (y0 >> sub)
+
+                def rd(p, cxa, cxb, cya, cyb, ncp):
+                    cxa, cya, cxb, cyb = max(cxa, 0), max(cya, 0), min(cxb, ncp - 1), min(cyb, ncp - 1)
+                    if cxa > cxb or cya > cyb:
+                        return 0
+                    return int(cell[p][cya:cyb + 1, cxa:cxb + 1].max())
+                cx0, cy0, cx1, cy1 = x >> 2, y >> 2, (x + s - 1) >> 2, (y + s - 1) >> 2
+                lvl = rd(pl, cx0, cx1, cy0, cy1, nc)
+                ar = 2 * s if int(o["flags"]) & F.OPF_HAVE_ABOVE_RIGHT else s
+                bl = 2 * s if int(o["flags"]) & F.OPF_HAVE_BELOW_LEFT else s
+                if y > 0:
+                    lvl = max(lvl, rd(pl, (x - 1) >> 2, (x + ar - 1) >> 2, (y - 1) >> 2, (y - 1) >> 2, nc))
+                if x > 0:
+                    lvl = max(lvl, rd(pl, (x - 1) >> 2, (x - 1) >> 2, (y - 1) >> 2, (y + bl - 1) >> 2, nc))
+                if int(o["flags"]) & F.OPF_CFL:
+                    lvl = max(lvl, rd(0, (2 * x) >> 2, (2 * (x + s) - 1) >> 2, (2 * y) >> 2, (2 * (y + s) - 1) >> 2, nc * 2))
+                lvl += 1
+                cell[pl][cy0:cy1 + 1, cx0:cx1 + 1] = lvl
+                levels.append(lvl)
+            if not levelled:
+                sbs.append((len(all_ops), len(ops)))
+                all_ops.extend(ops)
+                continue
+            order = np.argsort(np.asarray(levels, np.int64), kind="stable") if ops else []
+            sorted_ops = [ops[i] for i in order]
+            lv = [levels[i] for i in order]
+            rem = 0
+            for k in range(len(sorted_ops) - 1, -1, -1):
+                rem = rem + 1 if (k + 1 < len(sorted_ops) and lv[k + 1] == lv[k]) else 1
+                sorted_ops[k]["res_off"] = (lv[k] & 0xFFFF) | (min(rem, 0xFFFF) << 16)
+            sbs.append((len(all_ops), len(sorted_ops)))
+            all_ops.extend(sorted_ops)
+    hdr = F.FrameHdr()
+    hdr.frame_w, hdr.frame_h, hdr.mi_cols, hdr.mi_rows = w, h, mi_cols, mi_rows
+    hdr.sb_log2, hdr.sb_cols, hdr.sb_rows = sb_log2, sb_cols, sb_rows
+    hdr.enable_intra_edge_filter, hdr.frame_is_intra = 1, 0
+    hdr.n_sb, hdr.n_ops = len(sbs), len(all_ops)
+    ops_blob = np.array(all_ops, op_t).tobytes() if all_ops else b""
+    sb_blob = np.array(sbs, np.dtype([("first", "<u4"), ("n", "<u4")])).tobytes()
+    return F.build(hdr, {"off_sb": sb_blob, "off_ops": ops_blob})

@@ -115,6 +115,35 @@ def check_inter_properties(lib, w, h):
         assert np.array_equal(a[p], b[p]), f"fast vs general kernel, plane {p}"
 
 
+def run_wave(lib, w, h, planes, cmd):
+    """Superblock wavefront alone over the input picture `planes`.  Returns the planes."""
+    from av1dec_b200 import STAGE_WAVE
+    eng = Engine(w, h, lib=lib)
+    eng.set_input(planes, w, h)
+    fid = eng.submit(cmd, stages=STAGE_WAVE)
+    out = eng.download(fid, w, h)
+    eng.close()
+    return out
+
+
+def check_wave(lib, w, h, sb_log2, ref_lib=None):
+    """Superblock wavefront on a synthetic frame (synth.make_intra_frame): the level-scheduled
+    command buffer through `lib` must equal the same ops in plain decoding order through
+    `ref_lib` (default: `lib` itself).  Under emulation the ops of a level run in reverse order, so
+    this checks the level analysis; on the GPU it checks the cross-superblock synchronisation,
+    the shared-memory tile and the warp-per-op execution at full frame size."""
+    rng = synth.SplitMix64(synth.SEED + 11)
+    planes = synth.make_planes(rng, w, h, "B")
+    seq = run_wave(ref_lib or lib, w, h, planes, synth.make_intra_frame(w, h, sb_log2=sb_log2, levelled=False))
+    lev = run_wave(lib, w, h, planes, synth.make_intra_frame(w, h, sb_log2=sb_log2, levelled=True))
+    changed = 0
+    for p in range(3):
+        assert np.array_equal(seq[p], lev[p]), f"wavefront sb_log2={sb_log2} plane {p}"
+        changed += int((lev[p] != planes[p]).sum())
+    assert changed > w * h // 4  # the ops really did something
+    return lev
+
+
 def check_postfilter(lib, w, h, stages, **kw):
     s = synth.make_postfilter_frame(w, h, **kw)
     got = run_postfilter(lib, s, stages)

@@ -163,3 +163,11 @@ def test_inter_prediction_properties(eng, w, h):
     """Motion compensation on whole synthetic frames (4K = BASELINE's per-kernel size): identity,
     shifted copy, and the fast kernel against the general one."""
     checks.check_inter_properties(eng, w, h)
+
+
+@pytest.mark.skipif(not checks.emu_available(), reason="tests/emu not built")
+@pytest.mark.parametrize("w,h,sb_log2", [(1920, 1080, 6), (1920, 1080, 7), (3840, 2160, 6)])
+def test_wavefront_full_frames_vs_sequential_emulation(eng, w, h, sb_log2):
+    """The wavefront kernel at sizes no conformance stream reaches (up to 60x34 superblocks in
+    flight): GPU level-scheduled execution against the emulation's sequential one."""
+    checks.check_wave(eng, w, h, sb_log2, ref_lib=checks.emu_engine())

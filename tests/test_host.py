@@ -98,6 +98,12 @@ def test_decoder_class_mirrors_reference_api(md5_table):
 
 
 @need_emu
+@pytest.mark.parametrize("w,h,sb_log2", [(328, 200, 6), (456, 264, 7)])
+def test_wavefront_level_schedule_under_emulation(w, h, sb_log2):
+    checks.check_wave(checks.emu_engine(), w, h, sb_log2)
+
+
+@need_emu
 def test_inter_prediction_properties_under_emulation():
     checks.check_inter_properties(checks.emu_engine(), 192, 128)
 
