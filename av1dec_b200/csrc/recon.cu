@@ -602,12 +602,37 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     block_sync(nt);
 }
 
-// Wait until the superblocks this one depends on are finished, in ticket (raster) order.
-AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int tid, int nt)
+// Superblock scheduling.  A superblock (r, c) may start once its left neighbour and the
+// superblocks of the row above up to column c + lag - 1 are finished (lag = 2: the above-right
+// neighbour, all an intra edge can reach; frames with intrabc use the reach of the spec's block
+// vector constraint, see wave_kernel_global).  CTAs draw tickets from an atomic counter; ticket t
+// is the t-th superblock in WAVEFRONT order -- sorted by d = c + lag * r, then by row -- so the
+// in-flight tickets are the superblocks that can actually run together.  (Raster order would keep
+// a window of consecutive tickets inside one or two rows: a 4K frame then runs ~1.5 superblocks at
+// a time instead of ~30.)  Both dependencies have a smaller d, hence a smaller ticket, hence are
+// already owned by a running CTA: no deadlock whatever the number of CTAs.
+AV1B_DEV void sb_from_ticket(int t, int rows, int cols, int lag, int& r, int& c)
+{
+    for (int d = 0;; d++) {
+        // superblocks on diagonal d: rows r with 0 <= d - lag * r <= cols - 1
+        const int r_hi = min(rows - 1, d / lag);
+        const int r_lo = d > cols - 1 ? (d - (cols - 1) + lag - 1) / lag : 0;
+        const int cnt = r_hi - r_lo + 1;
+        if (cnt <= 0) continue;
+        if (t < cnt) {
+            r = r_lo + t;
+            c = d - lag * r;
+            return;
+        }
+        t -= cnt;
+    }
+}
+
+AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int lag, int tid, int nt)
 {
     if (tid == 0) {
         if (r > 0) {
-            const int need = min(col + 2, sb_cols);
+            const int need = min(col + lag, sb_cols);
             while (av1b_ld_acquire(progress + r - 1) < need) av1b_nanosleep(64);
         }
         if (col > 0) {
@@ -674,22 +699,57 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     OpScratch* const scratch = (OpScratch*)(dyn + (((n0 + 1) * pitch0 + 2 * (n1 + 1) * pitch1 + 15) & ~15)) + warp;
     for (;;) {
         block_sync(nt);
-        if (tid == 0) s_sb = atomicAdd(ticket, 1);
+        if (tid == 0) {
+            const int t = atomicAdd(ticket, 1);
+            int rr = 0, cc = 0;
+            if (t < n_sb) sb_from_ticket(t, hdr->sb_rows, sb_cols, 2, rr, cc);
+            s_sb = t < n_sb ? rr * sb_cols + cc : n_sb;
+        }
         block_sync(nt);
         const int sb = s_sb;
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
         const Av1bSb e = sbs[sb];
-        wave_wait(progress, r, col, sb_cols, tid, nt);
         if (e.n_ops == 0) {
+            wave_wait(progress, r, col, sb_cols, 2, tid, nt);
             wave_signal(progress, r, col, tid, nt);
             continue;
         }
-        // ---- load halo (+ current content for inter frames)
-        auto load_plane = [&](int pl, uint8_t* t, int n, int pitch) {
+        // ---- everything that does not depend on the neighbours is requested BEFORE the wait (a
+        // CTA standing by on the next diagonal has it done when its dependencies finish): the first
+        // chunk of the op list and, for inter frames, the superblock's own samples.
+        {
+            const uint4* src = (const uint4*)(ops + e.first_op);
+            const unsigned n0c = min((unsigned)WAVE_OP_CHUNK, e.n_ops);
+            uint4* dstv = (uint4*)s_ops[0];
+            for (unsigned q = tid; q < n0c * 2; q += nt) dstv[q] = __ldg(src + q);
+        }
+        auto load_own = [&](int pl, uint8_t* t, int n, int pitch) {
+            // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 1)]
             const int x0 = col * n, y0 = r * n;
             const PlaneView g = c.cur.pl[pl];
-            // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 1)]
+            const int lwords = mc::ilog2_pow2(n) - 2; // n is 32, 64 or 128
+            AV1B_NOUNROLL
+            for (int k = tid; k < (n << lwords); k += nt) {
+                const int i = k >> lwords, j = k & ((1 << lwords) - 1);
+                const uint32_t v = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
+                uint8_t* d = t + (i + 1) * pitch + 1 + 4 * j;
+                d[0] = (uint8_t)v;
+                d[1] = (uint8_t)(v >> 8);
+                d[2] = (uint8_t)(v >> 16);
+                d[3] = (uint8_t)(v >> 24);
+            }
+        };
+        if (load_pred) {
+            load_own(0, t0, n0, pitch0);
+            load_own(1, t1, n1, pitch1);
+            load_own(2, t2, n1, pitch1);
+        }
+        wave_wait(progress, r, col, sb_cols, 2, tid, nt);
+        // ---- halo: the row above (long enough for above-right reads) and the column to the left
+        auto load_halo = [&](int pl, uint8_t* t, int n, int pitch) {
+            const int x0 = col * n, y0 = r * n;
+            const PlaneView g = c.cur.pl[pl];
             if (r > 0) { // above row: x0-1 .. x0+2n-1
                 const uint8_t* src = g.p + (size_t)(y0 - 1) * g.stride + x0 - 1;
                 AV1B_NOUNROLL
@@ -700,23 +760,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 AV1B_NOUNROLL
                 for (int k = tid; k < n; k += nt) t[(k + 1) * pitch] = __ldcg(src + (size_t)k * g.stride);
             }
-            if (load_pred) {
-                const int lwords = mc::ilog2_pow2(n) - 2; // n is 32, 64 or 128
-                AV1B_NOUNROLL
-                for (int k = tid; k < (n << lwords); k += nt) {
-                    const int i = k >> lwords, j = k & ((1 << lwords) - 1);
-                    const uint32_t v = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
-                    uint8_t* d = t + (i + 1) * pitch + 1 + 4 * j;
-                    d[0] = (uint8_t)v;
-                    d[1] = (uint8_t)(v >> 8);
-                    d[2] = (uint8_t)(v >> 16);
-                    d[3] = (uint8_t)(v >> 24);
-                }
-            }
         };
-        load_plane(0, t0, n0, pitch0);
-        load_plane(1, t1, n1, pitch1);
-        load_plane(2, t2, n1, pitch1);
+        load_halo(0, t0, n0, pitch0);
+        load_halo(1, t1, n1, pitch1);
+        load_halo(2, t2, n1, pitch1);
         PlaneSet io;
         io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (1 - col * n0);
         io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (1 - col * n1);
@@ -729,16 +776,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         io.res2 = have_res ? c.rp[2] : nullptr;
         io.rpitch0 = c.rpitch[0];
         io.rpitch12 = c.rpitch[1];
-        block_sync(nt);
         // ---- the ops of this superblock, level by level, one warp per op.  The op list streams
         // through a double buffer: the next chunk is requested before the current one runs, so
         // its L2 latency hides behind the levels in between.
-        {
-            const uint4* src = (const uint4*)(ops + e.first_op);
-            const unsigned n0 = min((unsigned)WAVE_OP_CHUNK, e.n_ops);
-            uint4* dstv = (uint4*)s_ops[0];
-            for (unsigned q = tid; q < n0 * 2; q += nt) dstv[q] = __ldg(src + q);
-        }
         block_sync(nt);
         int buf = 0;
         for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK, buf ^= 1) {
@@ -817,6 +857,11 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     int* ticket = c.sync;
     int* progress = c.sync + 1;
+    // An intrabc block vector may point into the row k superblock rows above up to 5k - 4 columns
+    // (64-sample units) to the right of the current one (spec 7.11.3.2 / libaom av1_is_dv_valid:
+    // gradient 1 + INTRABC_DELAY_SB64 [+ 1 for 128x128]); waiting for the row above through column
+    // c + lag - 1 with lag 6 (SB64) / 4 (SB128) covers every row by induction.
+    const int lag = hdr->sb_log2 == 6 ? 6 : 4;
     const bool have_res = c.rp[0] && hdr->n_itx;
     PlaneSet io;
     io.pix0 = c.cur.pl[0].p, io.pix1 = c.cur.pl[1].p, io.pix2 = c.cur.pl[2].p;
@@ -825,12 +870,17 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
     io.rpitch0 = c.rpitch[0], io.rpitch12 = c.rpitch[1];
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_sb = atomicAdd(ticket, 1);
+        if (tid == 0) {
+            const int t = atomicAdd(ticket, 1);
+            int rr = 0, cc = 0;
+            if (t < n_sb) sb_from_ticket(t, hdr->sb_rows, sb_cols, lag, rr, cc);
+            s_sb = t < n_sb ? rr * sb_cols + cc : n_sb;
+        }
         __syncthreads();
         const int sb = s_sb;
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
-        wave_wait(progress, r, col, sb_cols, tid, nt);
+        wave_wait(progress, r, col, sb_cols, lag, tid, nt);
         const Av1bSb e = sbs[sb];
         for (unsigned k = 0; k < e.n_ops; k++) {
             const Av1bOp op = ops[e.first_op + k];
@@ -887,11 +937,12 @@ void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.n_ops) return;
-    // CTAs take superblocks by ticket in raster order and wait for the left and above-right
-    // neighbours: with that 2-superblock lag at most min(rows, ceil(cols / 2)) superblocks can be
-    // in progress at once.  More CTAs than that would only spin on SM slots other streams need.
-    int grid = std::min<int>((int)h.sb_rows, ((int)h.sb_cols + 1) / 2);
-    grid = std::max(1, std::min(grid, (int)h.n_sb));
+    // At most min(rows, ceil(cols / lag)) superblocks can be in progress at once (see
+    // sb_from_ticket); half as many CTAs again stand by on the next diagonal so that a finished
+    // dependency is picked up at once.  More would only spin on SM slots other streams need.
+    const int lag = h.allow_intrabc ? (h.sb_log2 == 6 ? 6 : 4) : 2;
+    const int width = std::max(1, std::min<int>((int)h.sb_rows, ((int)h.sb_cols + lag - 1) / lag));
+    int grid = std::min<int>((int)h.n_sb, width + width / 2 + 1);
     if (grid > 148 * 2) grid = 148 * 2;
     if (h.allow_intrabc) {
         AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);

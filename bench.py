@@ -327,6 +327,39 @@ def inter_leg(device, reps=3):
             "mpix_per_s": W4 * H4 / per / 1e6}
 
 
+def wave_leg(device, reps=3):
+    """Superblock-wavefront throughput on a synthetic 3840x2160 frame: 60 % of the blocks (8 / 16 /
+    32 luma per superblock) intra-predicted over the existing picture, every mode."""
+    import av1dec_b200 as pkg
+    from av1dec_b200 import format as F
+    from av1dec_b200 import synth
+    from av1dec_b200.engine import Engine
+    hdr_size = C.sizeof(F.FrameHdr)
+    W4, H4 = 3840, 2160
+    cmd = synth.make_intra_frame(W4, H4, sb_log2=6)
+    hdr = F.FrameHdr.from_buffer_copy(cmd[:hdr_size])
+    eng = Engine(W4, H4, device=device)
+    eng.set_lanes(1)
+    rng = synth.SplitMix64(synth.SEED + 78)
+    eng.set_ref(0, synth.make_planes(rng, W4, H4, "B"), W4, H4)
+    dev_cmd = eng.upload(cmd)
+
+    def once():
+        eng.input_from_slot(0)
+        eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_WAVE, 0)
+    for _ in range(3):
+        once()
+    eng.sync()
+    eng.set_profiling(True)
+    for _ in range(reps * 4):
+        once()
+    ms, calls = eng.stage_times()
+    eng.close()
+    per = ms["wave"] / max(calls["wave"], 1) * 1e-3
+    return {"us_per_frame": per * 1e6, "ops": int(hdr.n_ops), "superblocks": int(hdr.n_sb), "mops_per_s": hdr.n_ops / per / 1e6,
+            "mpix_per_s": W4 * H4 / per / 1e6}
+
+
 def itx_leg(device, reps=3):
     """Inverse-transform throughput on a synthetic 3840x2160 frame of transform blocks."""
     import av1dec_b200 as pkg
@@ -516,7 +549,7 @@ def run_ours(args, rank, world, local_rank):
         r.engine.close()
 
     post, roofline = postfilter_leg(device, dev)
-    kernels_4k = {"itx": itx_leg(device), "inter": inter_leg(device)} if rank == 0 else None
+    kernels_4k = {"itx": itx_leg(device), "inter": inter_leg(device), "wave": wave_leg(device)} if rank == 0 else None
 
     if rank != 0:
         return 0
@@ -569,7 +602,7 @@ def main():
     if args.only == "postfilter":
         import torch
         post, roofline = postfilter_leg(0, torch.device("cuda", 0), reps=max(args.steps, 1))
-        print(json.dumps({"postfilter_4k": post, "itx_4k": itx_leg(0), "inter_4k": inter_leg(0), "roofline": roofline}))
+        print(json.dumps({"postfilter_4k": post, "itx_4k": itx_leg(0), "inter_4k": inter_leg(0), "wave_4k": wave_leg(0), "roofline": roofline}))
         return 0
     # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on
     # stdout, so everything but our final print goes to stderr.
