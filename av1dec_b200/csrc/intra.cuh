@@ -162,6 +162,12 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
     if (a.plane_idx == 0 && a.filter_intra) {
         // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront
         const int w4 = w >> 2, h2 = h >> 1;
+        // a lane keeps the same position inside the 4x2 sub-block on every step when the group
+        // size is a multiple of 8: its seven taps are loaded once, not on every diagonal
+        const bool fixed_k = (nt & 7) == 0;
+        int taps[7];
+        AV1B_UNROLL
+        for (int i = 0; i < 7; i++) taps[i] = k_intra_filter_taps[a.fi_mode][tid & 7][i];
         for (int d = 0; d < w4 + h2 - 1; d++) {
             int j_lo = max(0, d - (h2 - 1)), j_hi = min(w4 - 1, d);
             int nsb = j_hi - j_lo + 1;
@@ -183,7 +189,7 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
                 }
                 int pr = 0;
                 AV1B_UNROLL
-                for (int i = 0; i < 7; i++) pr += k_intra_filter_taps[a.fi_mode][k][i] * p[i];
+                for (int i = 0; i < 7; i++) pr += (fixed_k ? taps[i] : (int)k_intra_filter_taps[a.fi_mode][k][i]) * p[i];
                 P[((i2 << 1) + i1) * pp + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
             }
             block_sync(nt);
