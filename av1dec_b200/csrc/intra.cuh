@@ -82,40 +82,70 @@ AV1B_DEV unsigned warp_sum(unsigned v, int nt)
 #endif
 }
 
-// In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter)
+// In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter), for
+// the above edge (A, szA, strength sA) and the left edge (L, szL, sL) in one pass over both: they
+// are independent, and a pass costs a staging copy and two group barriers whatever its length.
+// A strength of 0 skips that edge.  tmp: EDGE_LEN bytes, the left edge uses its second half.
 template <int NTC>
-AV1B_DEV void filter_edge(uint8_t* edge, uint8_t* tmp, int sz, int strength, int tid, int nt_rt)
+AV1B_DEV void filter_edges(uint8_t* A, int szA, int sA, uint8_t* L, int szL, int sL, uint8_t* tmp, int tid, int nt_rt)
 {
     const int nt = NTC ? NTC : nt_rt;
-    if (!strength) return;
+    if (!sA) szA = 0;
+    if (!sL) szL = 0;
+    if (!(szA | szL)) return;
+    uint8_t* const tA = tmp;
+    uint8_t* const tL = tmp + EDGE_LEN / 2;
     AV1B_NOUNROLL
-    for (int k = tid; k < sz; k += nt) tmp[k] = edge[k - 1];
+    for (int k = tid; k < szA + szL; k += nt) {
+        if (k < szA) tA[k] = A[k - 1];
+        else tL[k - szA] = L[k - szA - 1];
+    }
     block_sync(nt);
     AV1B_NOUNROLL
-    for (int i = 1 + tid; i < sz; i += nt) {
+    for (int k = tid; k < szA + szL; k += nt) {
+        const bool above = k < szA;
+        const int i = above ? k : k - szA, sz = above ? szA : szL;
+        if (i < 1) continue;
+        const uint8_t* t = above ? tA : tL;
+        const uint8_t* kern = k_intra_edge_kernel[(above ? sA : sL) - 1];
         int s = 0;
         AV1B_UNROLL
-        for (int j = 0; j < 5; j++) s += k_intra_edge_kernel[strength - 1][j] * tmp[clip3(0, sz - 1, i - 2 + j)];
-        edge[i - 1] = (uint8_t)((s + 8) >> 4);
+        for (int j = 0; j < 5; j++) s += kern[j] * t[clip3(0, sz - 1, i - 2 + j)];
+        (above ? A : L)[i - 1] = (uint8_t)((s + 8) >> 4);
     }
     block_sync(nt);
 }
 
-// 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample)
+// 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample), above edge
+// (nA samples) and left edge (nL samples) in one pass; n = 0 skips that edge.
 template <int NTC>
-AV1B_DEV void upsample_edge(uint8_t* edge, uint8_t* tmp, int n, int tid, int nt_rt)
+AV1B_DEV void upsample_edges(uint8_t* A, int nA, uint8_t* L, int nL, uint8_t* tmp, int tid, int nt_rt)
 {
     const int nt = NTC ? NTC : nt_rt;
-    // tmp[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
+    if (!(nA | nL)) return;
+    uint8_t* const tA = tmp;
+    uint8_t* const tL = tmp + EDGE_LEN / 2;
+    const int cA = nA ? nA + 3 : 0, cL = nL ? nL + 3 : 0;
+    // t[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
     AV1B_NOUNROLL
-    for (int k = tid; k < n + 3; k += nt) tmp[k] = edge[clip3(-1, n - 1, k - 2)];
+    for (int k = tid; k < cA + cL; k += nt) {
+        if (k < cA) tA[k] = A[clip3(-1, nA - 1, k - 2)];
+        else tL[k - cA] = L[clip3(-1, nL - 1, k - cA - 2)];
+    }
     block_sync(nt);
-    if (tid == 0) edge[-2] = tmp[0];
+    if (tid == 0) {
+        if (nA) A[-2] = tA[0];
+        if (nL) L[-2] = tL[0];
+    }
     AV1B_NOUNROLL
-    for (int i = tid; i < n; i += nt) {
-        int s = -tmp[i] + 9 * tmp[i + 1] + 9 * tmp[i + 2] - tmp[i + 3];
+    for (int k = tid; k < nA + nL; k += nt) {
+        const bool above = k < nA;
+        const int i = above ? k : k - nA;
+        const uint8_t* t = above ? tA : tL;
+        uint8_t* edge = above ? A : L;
+        const int s = -t[i] + 9 * t[i + 1] + 9 * t[i + 2] - t[i + 3];
         edge[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
-        edge[2 * i] = tmp[i + 2];
+        edge[2 * i] = t[i + 2];
     }
     block_sync(nt);
 }
@@ -211,20 +241,19 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
                 block_sync(nt);
             }
             const int maxx_q = a.max_x + 1, maxy_q = a.max_y + 1; // quirk: no -1
+            int sA = 0, numA = 0, sL = 0, numL = 0;
             if (a.have_above) {
-                int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
-                int num = min(w, maxx_q - x + 1) + (p_angle < 90 ? h : 0) + 1;
-                filter_edge<NTC>(A, S.tmp, num, strength, tid, nt);
+                sA = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
+                numA = min(w, maxx_q - x + 1) + (p_angle < 90 ? h : 0) + 1;
             }
             if (a.have_left) {
-                int strength = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
-                int num = min(h, maxy_q - y + 1) + (p_angle > 180 ? w : 0) + 1;
-                filter_edge<NTC>(L, S.tmp, num, strength, tid, nt);
+                sL = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
+                numL = min(h, maxy_q - y + 1) + (p_angle > 180 ? w : 0) + 1;
             }
+            filter_edges<NTC>(A, numA, sA, L, numL, sL, S.tmp, tid, nt);
             up_above = edge_upsample(w, h, a.edge_smooth, p_angle - 90);
-            if (up_above) upsample_edge<NTC>(A, S.tmp, w + (p_angle < 90 ? h : 0), tid, nt);
             up_left = edge_upsample(w, h, a.edge_smooth, p_angle - 180);
-            if (up_left) upsample_edge<NTC>(L, S.tmp, h + (p_angle > 180 ? w : 0), tid, nt);
+            upsample_edges<NTC>(A, up_above ? w + (p_angle < 90 ? h : 0) : 0, L, up_left ? h + (p_angle > 180 ? w : 0) : 0, S.tmp, tid, nt);
         }
         if (p_angle < 90) {
             const int dx = k_dr_intra_derivative[p_angle];
