@@ -238,9 +238,11 @@ def record_stream(pkg, eng_mod, name, data, want_md5, device):
     return rs
 
 
-def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
-    """Roofline leg: deblock + CDEF + LR on synthetic 3840x2160 frames resident in HBM, each kernel
-    timed by the engine with CUDA events on its stream; 256 MiB L2 flush between iterations."""
+def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True, size=(3840, 2160), dist="B"):
+    """Roofline leg: deblock + CDEF + LR on synthetic frames (3840x2160, blocky-smooth pixels by
+    default; SURVEY.md 8d also asks for 1920x1080 and for uniform-random pixels) resident in HBM,
+    each kernel timed by the engine with CUDA events on its stream; 256 MiB L2 flush between
+    iterations."""
     import torch
     import av1dec_b200 as pkg
     from av1dec_b200 import format as F
@@ -252,13 +254,13 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    W4, H4 = 3840, 2160
+    W4, H4 = size
     S = W4 * H4 * 3 // 2
     eng = Engine(W4, H4, device=device, stream=None)
     eng.set_lanes(1)  # per-kernel timing: one frame on the device at a time
     frames4k = []
     for i in range(n_in):
-        sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist="B", lr_unit=64)
+        sf = synth.make_postfilter_frame(W4, H4, seed=synth.SEED + i, dist=dist, lr_unit=64)
         eng.set_ref(i, sf.planes, sf.mi_cols * 4, sf.mi_rows * 4)
         frames4k.append((eng.upload(sf.cmd), sf.cmd[:hdr_size]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -294,7 +296,7 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True):
     roofline = {"bound": "hbm", "kernel": {"deblock": "deblock_kernel (V+H passes)", "cdef": "cdef_kernel", "lr": "lr_kernel"}[dom],
                 "achieved": post[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": post[dom]["gbs"] / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "workload": "synthetic 3840x2160 4:2:0 8-bit, blocky-smooth pixels, random partition/levels/CDEF presets/LR units (configs[3])"}
+                "workload": f"synthetic {W4}x{H4} 4:2:0 8-bit, pixel distribution {dist} (B = blocky-smooth, U = uniform), random partition/levels/CDEF presets/LR units (configs[3])"}
 
     return post, roofline
 
@@ -549,6 +551,13 @@ def run_ours(args, rank, world, local_rank):
         r.engine.close()
 
     post, roofline = postfilter_leg(device, dev)
+    # the other cases SURVEY.md 8d lists, chain time only (fewer frames: they are side figures)
+    variants = {}
+    if rank == 0:
+        for key, kw in (("1080p_B", dict(size=(1920, 1080), dist="B")), ("4k_U", dict(size=(3840, 2160), dist="U"))):
+            pv, _ = postfilter_leg(device, dev, n_in=3, reps=2, **kw)
+            variants[key] = {k: round(v["us_per_frame"], 1) for k, v in pv.items()}
+            variants[key]["chain_gbs"] = pv["chain"]["gbs"]
     kernels_4k = {"itx": itx_leg(device), "inter": inter_leg(device), "wave": wave_leg(device)} if rank == 0 else None
 
     if rank != 0:
@@ -575,6 +584,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": roofline,
         "postfilter_4k": post,
+        "postfilter_variants_us": variants,
         "recon_4k": kernels_4k,
         "cpu_baseline": cpu,
     }
