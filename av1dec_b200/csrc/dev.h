@@ -59,6 +59,7 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 #define AV1B_NOINLINE
 #define AV1B_ASSUME_SHARED(p) ((void)0)

@@ -133,101 +133,158 @@ AV1B_DEV int lf_line(int* v, int plane, int limit, int blimit, int thresh, int f
 
 }  // namespace
 
-// One thread per 4-sample edge unit.  PASS 0: vertical edges (filter along x), PASS 1: horizontal.
-template <int PASS> __global__ void __launch_bounds__(256) deblock_kernel(PostCtx c)
+// Deblocking, one pass per launch (PASS 0: vertical edges, filter along x; PASS 1: horizontal).
+// The work item is a 4-sample EDGE UNIT.  Only units that lie on a transform edge with a non-zero
+// level do anything (one in two for 8x8 transforms, one in sixteen for 64x64), so a thread per
+// unit would leave most lanes idle through the filter arithmetic.  Each warp therefore first TESTS
+// 128 consecutive units (a thread per unit, four rounds: cheap, mostly metadata loads), queues the
+// live ones in shared memory, and then FILTERS the queue 32 units at a time with full warps.
+namespace {
+
+enum { LF_WARPS = 4, LF_CHUNK = 128 };
+
+struct LfJob {
+    uint32_t unit;   // edge unit index inside the plane
+    uint32_t params; // limit | blimit << 8 | thresh << 16 | filter_size << 24
+};
+
+// Is unit t of `plane` a live edge?  Fills the job.
+template <int PASS>
+AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int t, LfJob& job)
 {
+    const int sub = plane ? 1 : 0;
+    const int mi_cols = hdr->mi_cols;
+    const int ucols = mi_cols >> sub;
+    const int ur = t / ucols, uc = t - ur * ucols;
+    int row = ur << sub, col = uc << sub;
+    const int x = col * 4, y = row * 4;
+    if (x >= hdr->frame_w || y >= hdr->frame_h) return false;
+    if (PASS == 0 ? (x == 0) : (y == 0)) return false;
+    row |= sub;
+    col |= sub;
+    const int xp = x >> sub, yp = y >> sub;
+    const Av1bLfMi mi = mis[row * mi_cols + col];
+    const int tx = (mi.tx >> (5 * plane)) & 31;
+    // Tx_Width / Block_Width are powers of two: edge tests are masks
+    if (PASS == 0 ? (xp & (k_tx_w[tx] - 1)) : (yp & (k_tx_h[tx] - 1))) return false;
+    const int bw = max(4, k_block_w[mi.mi_size] >> sub), bh = max(4, k_block_h[mi.mi_size] >> sub);
+    const bool skip = mi.flags & 1;
+    const bool is_intra = ((mi.flags >> 2) & 7) == 0;
+    const bool block_edge = PASS == 0 ? !(xp & (bw - 1)) : !(yp & (bh - 1));
+    if (!(block_edge || !skip || is_intra)) return false;
+    const int prev_row = row - (PASS == 1 ? (1 << sub) : 0);
+    const int prev_col = col - (PASS == 0 ? (1 << sub) : 0);
+    const Av1bLfMi pm = mis[prev_row * mi_cols + prev_col];
+    const int ptx = (pm.tx >> (5 * plane)) & 31;
+    const int base = PASS == 0 ? min(k_tx_w[ptx], k_tx_w[tx]) : min(k_tx_h[ptx], k_tx_h[tx]);
+    const int filter_size = plane ? min(8, base) : min(16, base);
+    LfLevel L = lf_strength(lf, mi, plane, PASS);
+    if (!L.lvl) L = lf_strength(lf, pm, plane, PASS);
+    if (L.lvl <= 0) return false;
+    job.unit = (uint32_t)t;
+    job.params = (uint32_t)L.limit | ((uint32_t)L.blimit << 8) | ((uint32_t)L.thresh << 16) | ((uint32_t)filter_size << 24);
+    return true;
+}
+
+// Filter the four sample lines of one live edge unit.
+template <int PASS>
+AV1B_DEV void lf_apply(const PlaneView& pv, int plane, int ucols, const LfJob& job)
+{
+    const int ur = (int)job.unit / ucols, uc = (int)job.unit - ur * ucols;
+    const int xp = uc * 4, yp = ur * 4;
+    const int limit = job.params & 0xFF, blimit = (job.params >> 8) & 0xFF, thresh = (job.params >> 16) & 0xFF;
+    const int filter_size = job.params >> 24;
+    uint8_t* p = pv.p + (size_t)yp * pv.stride + xp;
+    if (PASS == 0) {
+        // rows yp..yp+3; per row the 16 samples x-8 .. x+7 come in as four aligned words
+        AV1B_UNROLL
+        for (int i = 0; i < 4; i++) {
+            uint8_t* r = p + (size_t)i * pv.stride;
+            int v[16];
+            const uint32_t w1 = *(const uint32_t*)(r - 4), w2 = *(const uint32_t*)r;
+            uint32_t w0 = 0, w3 = 0;
+            if (filter_size == 16) {
+                w0 = *(const uint32_t*)(r - 8);
+                w3 = *(const uint32_t*)(r + 4);
+            }
+            AV1B_UNROLL
+            for (int k = 0; k < 4; k++) {
+                v[k] = (w0 >> (8 * k)) & 0xFF;
+                v[4 + k] = (w1 >> (8 * k)) & 0xFF;
+                v[8 + k] = (w2 >> (8 * k)) & 0xFF;
+                v[12 + k] = (w3 >> (8 * k)) & 0xFF;
+            }
+            const int n = lf_line(v, plane, limit, blimit, thresh, filter_size);
+            // byte stores: the neighbouring edge units own the other bytes of these words
+            AV1B_UNROLL
+            for (int k = 1; k <= 6; k++) {
+                if (k <= n) {
+                    r[-k] = (uint8_t)v[8 - k];
+                    r[k - 1] = (uint8_t)v[7 + k];
+                }
+            }
+        }
+    } else {
+        // columns xp..xp+3 live in the byte lanes of one word per row; rows yp-8 .. yp+7
+        uint32_t w[16];
+        const int lo = filter_size == 16 ? 0 : 4, hi = filter_size == 16 ? 16 : 12;
+        AV1B_UNROLL
+        for (int k = 0; k < 16; k++) w[k] = (k >= lo && k < hi) ? *(const uint32_t*)(p + (ptrdiff_t)(k - 8) * pv.stride) : 0u;
+        int nmax = 0;
+        AV1B_UNROLL
+        for (int cidx = 0; cidx < 4; cidx++) {
+            int v[16];
+            AV1B_UNROLL
+            for (int k = 0; k < 16; k++) v[k] = (w[k] >> (8 * cidx)) & 0xFF;
+            const int n = lf_line(v, plane, limit, blimit, thresh, filter_size);
+            nmax = max(nmax, n);
+            AV1B_UNROLL
+            for (int k = 2; k < 14; k++) w[k] = (w[k] & ~(0xFFu << (8 * cidx))) | ((uint32_t)v[k] << (8 * cidx));
+        }
+        AV1B_UNROLL
+        for (int k = 1; k <= 6; k++) {
+            if (k <= nmax) {
+                *(uint32_t*)(p - (ptrdiff_t)k * pv.stride) = w[8 - k];
+                *(uint32_t*)(p + (ptrdiff_t)(k - 1) * pv.stride) = w[7 + k];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+template <int PASS> __global__ void __launch_bounds__(LF_WARPS * 32) deblock_kernel(PostCtx c)
+{
+    __shared__ LfJob queue[LF_WARPS][LF_CHUNK];
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bLfMi* mis = (const Av1bLfMi*)(c.cmd + hdr->off_lfmi);
     const Av1bLoopFilterParams lf = hdr->lf;
     const int plane = blockIdx.z;
     if (plane > 0 && !lf.level[1 + plane]) return;
     const int sub = plane ? 1 : 0;
-    const int mi_cols = hdr->mi_cols, mi_rows = hdr->mi_rows;
-    const int ucols = mi_cols >> sub, urows = mi_rows >> sub; // edge units of this plane
+    const int ucols = hdr->mi_cols >> sub, urows = hdr->mi_rows >> sub; // edge units of this plane
     const int total = ucols * urows;
     const PlaneView pv = c.src.pl[plane];
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        const int ur = t / ucols, uc = t - ur * ucols;
-        int row = ur << sub, col = uc << sub;
-        const int x = col * 4, y = row * 4;
-        if (x >= hdr->frame_w || y >= hdr->frame_h) continue;
-        if (PASS == 0 ? (x == 0) : (y == 0)) continue;
-        row |= sub;
-        col |= sub;
-        const int xp = x >> sub, yp = y >> sub;
-        const Av1bLfMi mi = mis[row * mi_cols + col];
-        const int tx = (mi.tx >> (5 * plane)) & 31;
-        // Tx_Width / Block_Width are powers of two: edge tests are masks
-        if (PASS == 0 ? (xp & (k_tx_w[tx] - 1)) : (yp & (k_tx_h[tx] - 1))) continue;
-        const int bw = max(4, k_block_w[mi.mi_size] >> sub), bh = max(4, k_block_h[mi.mi_size] >> sub);
-        const bool skip = mi.flags & 1;
-        const bool is_intra = ((mi.flags >> 2) & 7) == 0;
-        const bool block_edge = PASS == 0 ? !(xp & (bw - 1)) : !(yp & (bh - 1));
-        if (!(block_edge || !skip || is_intra)) continue;
-        const int prev_row = row - (PASS == 1 ? (1 << sub) : 0);
-        const int prev_col = col - (PASS == 0 ? (1 << sub) : 0);
-        const Av1bLfMi pm = mis[prev_row * mi_cols + prev_col];
-        const int ptx = (pm.tx >> (5 * plane)) & 31;
-        const int base = PASS == 0 ? min(k_tx_w[ptx], k_tx_w[tx]) : min(k_tx_h[ptx], k_tx_h[tx]);
-        const int filter_size = plane ? min(8, base) : min(16, base);
-        LfLevel L = lf_strength(lf, mi, plane, PASS);
-        if (!L.lvl) L = lf_strength(lf, pm, plane, PASS);
-        if (L.lvl <= 0) continue;
-        uint8_t* p = pv.p + (size_t)yp * pv.stride + xp;
-        if (PASS == 0) {
-            // rows yp..yp+3; per row the 16 samples x-8 .. x+7 come in as four aligned words
-            AV1B_UNROLL
-            for (int i = 0; i < 4; i++) {
-                uint8_t* r = p + (size_t)i * pv.stride;
-                int v[16];
-                const uint32_t w1 = *(const uint32_t*)(r - 4), w2 = *(const uint32_t*)r;
-                uint32_t w0 = 0, w3 = 0;
-                if (filter_size == 16) {
-                    w0 = *(const uint32_t*)(r - 8);
-                    w3 = *(const uint32_t*)(r + 4);
-                }
-                AV1B_UNROLL
-                for (int k = 0; k < 4; k++) {
-                    v[k] = (w0 >> (8 * k)) & 0xFF;
-                    v[4 + k] = (w1 >> (8 * k)) & 0xFF;
-                    v[8 + k] = (w2 >> (8 * k)) & 0xFF;
-                    v[12 + k] = (w3 >> (8 * k)) & 0xFF;
-                }
-                const int n = lf_line(v, plane, L.limit, L.blimit, L.thresh, filter_size);
-                // byte stores: the neighbouring edge units own the other bytes of these words
-                AV1B_UNROLL
-                for (int k = 1; k <= 6; k++) {
-                    if (k <= n) {
-                        r[-k] = (uint8_t)v[8 - k];
-                        r[k - 1] = (uint8_t)v[7 + k];
-                    }
-                }
-            }
-        } else {
-            // columns xp..xp+3 live in the byte lanes of one word per row; rows yp-8 .. yp+7
-            uint32_t w[16];
-            const int lo = filter_size == 16 ? 0 : 4, hi = filter_size == 16 ? 16 : 12;
-            AV1B_UNROLL
-            for (int k = 0; k < 16; k++) w[k] = (k >= lo && k < hi) ? *(const uint32_t*)(p + (ptrdiff_t)(k - 8) * pv.stride) : 0u;
-            int nmax = 0;
-            AV1B_UNROLL
-            for (int cidx = 0; cidx < 4; cidx++) {
-                int v[16];
-                AV1B_UNROLL
-                for (int k = 0; k < 16; k++) v[k] = (w[k] >> (8 * cidx)) & 0xFF;
-                const int n = lf_line(v, plane, L.limit, L.blimit, L.thresh, filter_size);
-                nmax = max(nmax, n);
-                AV1B_UNROLL
-                for (int k = 2; k < 14; k++) w[k] = (w[k] & ~(0xFFu << (8 * cidx))) | ((uint32_t)v[k] << (8 * cidx));
-            }
-            AV1B_UNROLL
-            for (int k = 1; k <= 6; k++) {
-                if (k <= nmax) {
-                    *(uint32_t*)(p - (ptrdiff_t)k * pv.stride) = w[8 - k];
-                    *(uint32_t*)(p + (ptrdiff_t)(k - 1) * pv.stride) = w[7 + k];
-                }
-            }
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
+    LfJob* q = queue[warp];
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (int t0 = (blockIdx.x * nw + warp) * LF_CHUNK; t0 < total; t0 += gridDim.x * nw * LF_CHUNK) {
+        // ---- test LF_CHUNK units, queue the live ones (order inside the queue does not matter:
+        // within a pass no two edges touch the same samples)
+        int n = 0;
+        for (int r = 0; r < LF_CHUNK; r += nl) {
+            const int t = t0 + r + lane;
+            LfJob job;
+            const bool live = t < total && lf_test<PASS>(hdr, mis, lf, plane, t, job);
+            const unsigned m = __ballot_sync(FULL, live);
+            if (live) q[n + __popc(m & ((1u << lane) - 1))] = job;
+            n += __popc(m);
         }
+        __syncwarp();
+        // ---- filter them, a full warp at a time
+        for (int k = lane; k < n; k += nl) lf_apply<PASS>(pv, plane, ucols, q[k]);
+        __syncwarp();
     }
 }
 
@@ -795,7 +852,8 @@ void launch_deblock(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.lf.level[0] && !h.lf.level[1]) return;
     const long long total = (long long)h.mi_cols * h.mi_rows;
-    int grid = (int)((total + 127) / 128);
+    const int per_cta = 4 * 128; // LF_WARPS warps x LF_CHUNK units
+    int grid = (int)((total + per_cta - 1) / per_cta);
     if (grid > 148 * 64) grid = 148 * 64;
     AV1B_LAUNCH(deblock_kernel<0>, (grid, 1, 3), (128), st, c);
     AV1B_LAUNCH(deblock_kernel<1>, (grid, 1, 3), (128), st, c);
