@@ -196,23 +196,31 @@ AV1B_DEV void lf_apply(const PlaneView& pv, int plane, int ucols, const LfJob& j
     const int filter_size = job.params >> 24;
     uint8_t* p = pv.p + (size_t)yp * pv.stride + xp;
     if (PASS == 0) {
-        // rows yp..yp+3; per row the 16 samples x-8 .. x+7 come in as four aligned words
+        // rows yp..yp+3; per row the 16 samples x-8 .. x+7 come in as four aligned words.  All
+        // four rows are requested before the first is filtered: the stores below may alias the
+        // loads as far as the compiler knows, so it would not hoist them itself.
+        uint32_t wa[4][4];
+        AV1B_UNROLL
+        for (int i = 0; i < 4; i++) {
+            const uint8_t* r = p + (size_t)i * pv.stride;
+            wa[i][1] = *(const uint32_t*)(r - 4);
+            wa[i][2] = *(const uint32_t*)r;
+            wa[i][0] = wa[i][3] = 0;
+            if (filter_size == 16) {
+                wa[i][0] = *(const uint32_t*)(r - 8);
+                wa[i][3] = *(const uint32_t*)(r + 4);
+            }
+        }
         AV1B_UNROLL
         for (int i = 0; i < 4; i++) {
             uint8_t* r = p + (size_t)i * pv.stride;
             int v[16];
-            const uint32_t w1 = *(const uint32_t*)(r - 4), w2 = *(const uint32_t*)r;
-            uint32_t w0 = 0, w3 = 0;
-            if (filter_size == 16) {
-                w0 = *(const uint32_t*)(r - 8);
-                w3 = *(const uint32_t*)(r + 4);
-            }
             AV1B_UNROLL
             for (int k = 0; k < 4; k++) {
-                v[k] = (w0 >> (8 * k)) & 0xFF;
-                v[4 + k] = (w1 >> (8 * k)) & 0xFF;
-                v[8 + k] = (w2 >> (8 * k)) & 0xFF;
-                v[12 + k] = (w3 >> (8 * k)) & 0xFF;
+                v[k] = (wa[i][0] >> (8 * k)) & 0xFF;
+                v[4 + k] = (wa[i][1] >> (8 * k)) & 0xFF;
+                v[8 + k] = (wa[i][2] >> (8 * k)) & 0xFF;
+                v[12 + k] = (wa[i][3] >> (8 * k)) & 0xFF;
             }
             const int n = lf_line(v, plane, limit, blimit, thresh, filter_size);
             // byte stores: the neighbouring edge units own the other bytes of these words
