@@ -509,9 +509,10 @@ def run_ours(args, rank, world, local_rank):
             yuv, frames, px = pkg.decode_ivf(s[1], device=device)
             return px, len(yuv)
         t0 = time.perf_counter()
-        # every decoder runs two host threads (parser, command emitter) and a stream of closed
-        # segments adds workers of its own: cores / 2 callers keep the cores busy without thrashing
-        with cf.ThreadPoolExecutor(args.e2e_threads or max(1, host_threads // 2)) as ex:
+        # a stream of closed segments adds workers of its own and every context has driver threads:
+        # 3/4 of the cores as callers keeps the cores busy without thrashing (16 callers on 16
+        # cores: 270-480 ms per set and unstable; 12: a steady 240 ms; 8: 268 ms)
+        with cf.ThreadPoolExecutor(args.e2e_threads or max(1, host_threads * 3 // 4)) as ex:
             res = list(ex.map(one, sorted(mine, key=lambda s: -len(s[1]))))
         return time.perf_counter() - t0, sum(p for p, _ in res)
     # untimed: fill the context / pinned / command-slot pools until a pass allocates nothing new
@@ -574,7 +575,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "bits/ conformance streams (committed fixtures); synthetic 4K frames for the roofline leg",
         "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams), "lanes_per_context": args.lanes,
-                   "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads // 2), "host_cores": cores,
+                   "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads * 3 // 4), "host_cores": cores,
                    "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
                    "stage_share_ms": share},
         "clocks": clocks,
@@ -599,7 +600,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
-    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = this rank's share of the cores)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = 3/4 of this rank's share of the cores)")
     ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter", "replay"], help="run a single leg (development aid)")
