@@ -869,6 +869,51 @@ int av1b_frame_download(av1b_ctx* c, int frame_id, uint8_t* const dst[3], const 
     return AV1B_OK;
 }
 
+int av1b_frame_device_view(av1b_ctx* c, int frame_id, const uint8_t* planes[3], int pitches[3])
+{
+    if (!c || !planes || !pitches || frame_id < 0 || frame_id >= (int)c->frames.size()) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (frame_read(c, frame_id, MAIN_LANE)) return fail(c, AV1B_ECUDA, "stream wait");
+    // the caller reads on the context stream: whoever reuses the buffer waits for that stream's tail
+    if (rt_event_record(c->frames[frame_id].copied, c->stream)) return fail(c, AV1B_ECUDA, "event record");
+    for (int p = 0; p < 3; p++) {
+        planes[p] = c->frames[frame_id].v.pl[p].p;
+        pitches[p] = c->frames[frame_id].v.pl[p].stride;
+    }
+    return AV1B_OK;
+}
+
+int av1b_frame_retain(av1b_ctx* c, int frame_id)
+{
+    if (!c || frame_id < 0 || frame_id >= (int)c->frames.size()) return AV1B_EINVAL;
+    c->frames[frame_id].refcnt++;
+    return AV1B_OK;
+}
+
+int av1b_frame_release(av1b_ctx* c, int frame_id)
+{
+    if (!c || frame_id < 0 || frame_id >= (int)c->frames.size() || c->frames[frame_id].refcnt <= 0) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    // the holder read it on the context stream up to now
+    c->frames[frame_id].readers |= 1u << MAIN_LANE;
+    if (rt_event_record(c->frames[frame_id].copied, c->stream)) return fail(c, AV1B_ECUDA, "event record");
+    c->frames[frame_id].refcnt--;
+    return AV1B_OK;
+}
+
+int av1b_frame_to_nv12(av1b_ctx* c, int frame_id, uint8_t* dst_y, int pitch_y, uint8_t* dst_uv, int pitch_uv, int w, int h)
+{
+    if (!c || !dst_y || !dst_uv || frame_id < 0 || frame_id >= (int)c->frames.size() || w <= 0 || h <= 0 || w > c->aw || h > c->ah
+        || pitch_y < w || pitch_uv < ((w >> 1) << 1))
+        return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (frame_read(c, frame_id, MAIN_LANE)) return fail(c, AV1B_ECUDA, "stream wait");
+    launch_to_nv12(c->frames[frame_id].v, dst_y, pitch_y, dst_uv, pitch_uv, w, h, c->stream);
+    c->launches++;
+    if (rt_check() || rt_event_record(c->frames[frame_id].copied, c->stream)) return fail(c, AV1B_ECUDA, "nv12");
+    return AV1B_OK;
+}
+
 int av1b_sync(av1b_ctx* c)
 {
     if (!c) return AV1B_EINVAL;
@@ -966,6 +1011,14 @@ int av1b_dev_upload(av1b_ctx* c, void* dev_dst, const void* host_src, size_t byt
     if (!c) return AV1B_EINVAL;
     rt_set_device(c->device);
     if (rt_h2d(dev_dst, host_src, bytes, c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "upload");
+    return AV1B_OK;
+}
+
+int av1b_dev_download(av1b_ctx* c, void* host_dst, const void* dev_src, size_t bytes)
+{
+    if (!c) return AV1B_EINVAL;
+    rt_set_device(c->device);
+    if (rt_d2h(host_dst, dev_src, bytes, c->stream) || rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "download");
     return AV1B_OK;
 }
 

@@ -76,6 +76,33 @@ class Engine:
         self.sync()
         return out
 
+    def device_view(self, frame_id):
+        """([device pointers], [pitches]) of the frame's planes; valid on the context stream."""
+        ptrs = (C.c_void_p * 3)()
+        pitches = (C.c_int * 3)()
+        self._check(self.lib.av1b_frame_device_view(self.ctx, frame_id, ptrs, pitches), "av1b_frame_device_view")
+        return [int(p) for p in ptrs], [int(p) for p in pitches]
+
+    def read_device(self, dev_ptr, nbytes):
+        buf = np.empty(nbytes, np.uint8)
+        self._check(self.lib.av1b_dev_download(self.ctx, buf.ctypes.data_as(C.c_void_p), C.c_void_p(dev_ptr), nbytes), "av1b_dev_download")
+        return buf
+
+    def to_nv12(self, frame_id, w, h):
+        """The frame as NV12: (luma (h, w), interleaved chroma (h/2, 2*(w/2))), converted on the device."""
+        cw = (w >> 1) * 2
+        self.lib.av1b_dev_alloc.restype = C.c_void_p
+        dy = self.lib.av1b_dev_alloc(C.c_size_t(w * h))
+        duv = self.lib.av1b_dev_alloc(C.c_size_t(max(cw, 1) * max(h >> 1, 1)))
+        try:
+            self._check(self.lib.av1b_frame_to_nv12(self.ctx, frame_id, C.c_void_p(dy), w, C.c_void_p(duv), cw, w, h), "av1b_frame_to_nv12")
+            y = self.read_device(dy, w * h).reshape(h, w)
+            uv = self.read_device(duv, cw * (h >> 1)).reshape(h >> 1, cw)
+        finally:
+            self.lib.av1b_dev_free(C.c_void_p(dy))
+            self.lib.av1b_dev_free(C.c_void_p(duv))
+        return y, uv
+
     def residual(self, n):
         out = np.empty(n, np.int16)
         self._check(self.lib.av1b_debug_get_residual(self.ctx, out.ctypes.data_as(C.POINTER(C.c_int16)), n), "av1b_debug_get_residual")

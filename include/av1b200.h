@@ -84,6 +84,19 @@ int av1b_show_existing(av1b_ctx* ctx, int slot, uint32_t refresh_mask, int* fram
 /* Asynchronous copy of the visible w x h (and chroma) area of a device frame to host planes
  * (pinned memory from av1b_host_alloc gives a true async copy).  Decoder::getOutput(). */
 int av1b_frame_download(av1b_ctx* ctx, int frame_id, uint8_t* const dst[3], const int dst_stride[3], int w, int h);
+/* Zero-copy output for a GPU consumer (the reference's VideoFrame.surface hook,
+ * interface/VideoCommonDefs.h:257-283): device pointers and pitches of the three planes of a frame.
+ * The context stream is made to wait for the frame; work the caller enqueues on that stream (the
+ * one passed to av1b_ctx_create) afterwards sees finished samples.  The planes stay valid until the
+ * frame leaves the reference store and the pool reuses it: hold it with av1b_frame_retain /
+ * av1b_frame_release for longer. */
+int av1b_frame_device_view(av1b_ctx* ctx, int frame_id, const uint8_t* planes[3], int pitches[3]);
+int av1b_frame_retain(av1b_ctx* ctx, int frame_id);
+int av1b_frame_release(av1b_ctx* ctx, int frame_id);
+/* The visible area as NV12 (luma plane, then interleaved U/V rows) into device memory the caller
+ * owns: dst_y / dst_uv with their pitches, on the context stream.  For consumers (encoders,
+ * display surfaces) that take semi-planar input. */
+int av1b_frame_to_nv12(av1b_ctx* ctx, int frame_id, uint8_t* dst_y, int pitch_y, uint8_t* dst_uv, int pitch_uv, int w, int h);
 /* Block until everything enqueued so far (kernels and copies) has finished. */
 int av1b_sync(av1b_ctx* ctx);
 /* Frames are reconstructed on internal streams ("lanes", AV1B200_LANES, default 4) so that frames
@@ -108,6 +121,8 @@ void av1b_host_free(void* p);
 void* av1b_dev_alloc(size_t bytes);
 void av1b_dev_free(void* p);
 int av1b_dev_upload(av1b_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+/* Synchronous copy of device memory (context stream order) to the host: NV12 / device-view tests. */
+int av1b_dev_download(av1b_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 
 /* Test / stage-level entry points --------------------------------------------------------- */
 /* Load host planes (MI-aligned area: w x h luma samples given) into the frame that the next

@@ -144,6 +144,30 @@ def check_wave(lib, w, h, sb_log2, ref_lib=None):
     return lev
 
 
+def check_output_paths(lib, w, h):
+    """Zero-copy device view and NV12 conversion of a frame equal its planar download."""
+    import ctypes as C
+    from av1dec_b200 import format as F
+    rng = synth.SplitMix64(synth.SEED + 21)
+    planes = synth.make_planes(rng, w, h, "U")
+    hdr = F.FrameHdr()
+    hdr.frame_w, hdr.frame_h = w, h
+    hdr.mi_cols, hdr.mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
+    hdr.sb_log2, hdr.sb_cols, hdr.sb_rows = 6, (hdr.mi_cols + 15) // 16, (hdr.mi_rows + 15) // 16
+    eng = Engine(w, h, lib=lib)
+    eng.set_input(planes, w, h)
+    fid = eng.submit(F.build(hdr, {}), stages=0)  # no stage: the input picture is the frame
+    ptrs, pitches = eng.device_view(fid)
+    for p in range(3):
+        ph, pw = (h, w) if p == 0 else (h >> 1, w >> 1)
+        got = eng.read_device(ptrs[p], pitches[p] * ph).reshape(ph, pitches[p])[:, :pw]
+        assert np.array_equal(got, planes[p][:ph, :pw]), f"device view plane {p}"
+    y, uv = eng.to_nv12(fid, w, h)
+    assert np.array_equal(y, planes[0][:h, :w])
+    assert np.array_equal(uv[:, 0::2], planes[1][:h >> 1, :w >> 1]) and np.array_equal(uv[:, 1::2], planes[2][:h >> 1, :w >> 1])
+    eng.close()
+
+
 def check_postfilter(lib, w, h, stages, **kw):
     s = synth.make_postfilter_frame(w, h, **kw)
     got = run_postfilter(lib, s, stages)

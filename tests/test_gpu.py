@@ -171,3 +171,8 @@ def test_wavefront_full_frames_vs_sequential_emulation(eng, w, h, sb_log2):
     """The wavefront kernel at sizes no conformance stream reaches (up to 60x34 superblocks in
     flight): GPU level-scheduled execution against the emulation's sequential one."""
     checks.check_wave(eng, w, h, sb_log2, ref_lib=checks.emu_engine())
+
+
+@pytest.mark.parametrize("w,h", [(178, 94), (3840, 2160)])
+def test_device_view_and_nv12(eng, w, h):
+    checks.check_output_paths(eng, w, h)

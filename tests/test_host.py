@@ -104,6 +104,11 @@ def test_wavefront_level_schedule_under_emulation(w, h, sb_log2):
 
 
 @need_emu
+def test_device_view_and_nv12_under_emulation():
+    checks.check_output_paths(checks.emu_engine(), 178, 94)
+
+
+@need_emu
 def test_inter_prediction_properties_under_emulation():
     checks.check_inter_properties(checks.emu_engine(), 192, 128)
 
