@@ -1,13 +1,17 @@
 // recon.cu -- block reconstruction kernels for sm_100a.
 //
-//   itx_kernel    batched inverse transform: dequantised int16 coefficients -> int16 residual
-//                 arena, one warp per transform block (independent, fully parallel).
-//   inter_kernel  motion compensation for every inter block of the frame (independent of the
-//                 current frame's pixels; one CTA per block).
-//   wave_kernel   the dependent pass: intra prediction (+CfL, filter-intra, palette), inter-intra
-//                 blend, intrabc and residual add, scheduled as a superblock wavefront with the
-//                 classic 2-SB lag.  CTAs take superblocks from an atomic ticket counter in
-//                 raster order, so a CTA only ever waits for CTAs that are already running.
+//   itx_kernel<CLS>    batched inverse transform, one launch per size class: dequantised int16
+//                      coefficients -> int16 residual planes (frame layout), 32/max(w,h) transform
+//                      blocks per warp, independent and fully parallel.
+//   inter_fast_kernel  motion compensation of plain translational blocks (the bulk): walks the
+//                      prediction-unit list, lane-parallel set-up, (unit, tile) jobs per warp,
+//                      residual add fused into the store.
+//   inter_kernel       every other inter block (warp, OBMC, masks, frame-edge windows), a warp per
+//                      block.
+//   wave_kernel        the dependent pass: intra prediction (+CfL, filter-intra, palette), inter-
+//                      intra blend and residual add on a shared-memory superblock tile, ops sorted by
+//                      dependency level, superblocks in wavefront order with the classic 2-SB lag.
+//   wave_kernel_global the same ops on global memory for frames with intrabc.
 //
 // Reference for the behaviour: decoder/TransformBlock.cpp:2376-2456 (TransformBlock::decode),
 // decoder/Block.cpp:100-174,1600-1608 (compute_prediction / Block::decode),
@@ -27,24 +31,6 @@
 namespace {
 
 enum { ITX_WARPS = 4, ITX_TMP_STRIDE = 66, ITX_TMP_ROWS = 32 };
-
-template <int n>
-AV1B_DEV void itx_rows(const int16_t* coef, int tw, int nz_rows, int16_t* tmp, int kind, bool rect, int row_shift,
-    int lane, int nl)
-{
-    for (int i = lane; i < nz_rows; i += nl)
-        itx::row_pass<n>(coef + i * tw, tw, tmp + i * ITX_TMP_STRIDE, kind, rect, row_shift);
-}
-
-template <int n>
-AV1B_DEV void itx_cols(const int16_t* tmp, int nz_rows, int16_t* out, int out_stride, int w, bool fud, bool flr, int kind,
-    int col_shift, int lane, int nl)
-{
-    for (int j = lane; j < w; j += nl) {
-        int jo = flr ? (w - 1 - j) : j;
-        itx::col_pass<n>(tmp + j, ITX_TMP_STRIDE, nz_rows, out + jo, out_stride, fud, kind, col_shift);
-    }
-}
 
 }  // namespace
 
@@ -682,6 +668,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     const FrameConst fc = frame_const(hdr);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    (void)nw;
     const int lane = tid % nl, warp = tid / nl;
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     const int sbs_y = 1 << hdr->sb_log2;
