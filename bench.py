@@ -295,7 +295,8 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True, size=(3840, 2160), d
         traffic = json.load(open(tr_path)).get(dom)
     roofline = {"bound": "hbm", "kernel": {"deblock": "deblock_kernel (V+H passes)", "cdef": "cdef_kernel", "lr": "lr_kernel"}[dom],
                 "achieved": post[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": post[dom]["gbs"] / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)",
+                "algorithmic_bytes_per_launch": alg[dom], "chain_frac": post["chain"]["frac_of_peak"], "peak_source": peak_src,
                 "workload": f"synthetic {W4}x{H4} 4:2:0 8-bit, pixel distribution {dist} (B = blocky-smooth, U = uniform), random partition/levels/CDEF presets/LR units (configs[3])"}
 
     return post, roofline
