@@ -1,3 +1,7 @@
+"""Single-stream end-to-end latency: av1b_decode_ivf on one conformance stream, three times.
+
+    python tools/e2e_one.py av1-1-b8-02-allintra.ivf      (AV1B200_TIMING=1 prints the host phase timers)
+"""
 import sys, os, time
 sys.path.insert(0,'/root/repo')
 import av1dec_b200 as pkg
