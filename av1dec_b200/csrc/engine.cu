@@ -165,6 +165,7 @@ struct DevFrame {
     rt_event_t copied;        // recorded on the context stream after the last download / copy out of it
     int writer = MAIN_LANE;   // lane of that submit
     uint32_t readers = 0;     // lanes that read it since (bit MAIN_LANE = the context stream)
+    bool settled = true;      // nothing recorded since the last full av1b_sync: no event to wait for
 };
 
 // Per-lane scratch: nothing here is shared between frames in flight on different lanes.
@@ -205,6 +206,7 @@ struct av1b_ctx {
     uint8_t* slab = nullptr; // one allocation holding the lanes' working set of frame buffers
     uint64_t frame_seq = 0;
     bool joined = true;     // no lane work outstanding relative to the context stream
+    bool capturing = false; // the caller is capturing the context stream into a CUDA graph: no event queries
     rt_event_t main_mark;
     uint8_t* wedge = nullptr;
     int pending_input = -1;
@@ -313,10 +315,11 @@ static int frame_alloc(av1b_ctx* c, int lane = MAIN_LANE)
         const DevFrame& f = c->frames[i];
         if (f.refcnt) continue;
         if (f.writer == lane && !(f.readers & ~(1u << lane))) return (int)i;
-        if (idle < 0 && !(f.readers & ~mine) && rt_event_done(f.ready)) idle = (int)i;
+        if (idle < 0 && !(f.readers & ~mine) && (f.settled || (!c->capturing && rt_event_done(f.ready)))) idle = (int)i;
         if (any < 0) any = (int)i;
     }
     if (idle >= 0) return idle;
+    if (c->capturing && any >= 0) return any; // no allocation while a graph is being captured
     // growing the pool costs a cudaMalloc (device-wide synchronisation): past the working set of
     // the lanes (3 buffers per frame in flight + 8 references + 1 pending output) reuse instead
     const size_t soft_cap = pool_soft_cap(c);
@@ -336,7 +339,7 @@ static int frame_claim(av1b_ctx* c, int f, int lane)
     DevFrame& fr = c->frames[f];
     av1b_stream_t st = lane_stream(c, lane);
     // exact: the submit that last wrote it, the last copy out of it on the context stream
-    if (fr.writer != lane && rt_stream_wait(st, fr.ready)) return 1;
+    if (!fr.settled && fr.writer != lane && rt_stream_wait(st, fr.ready)) return 1;
     if ((fr.readers & (1u << MAIN_LANE)) && lane != MAIN_LANE && rt_stream_wait(st, fr.copied)) return 1;
     // conservative: everything queued so far on the other lanes that read it as a reference
     const uint32_t others = fr.readers & ~((1u << lane) | (1u << MAIN_LANE));
@@ -346,6 +349,7 @@ static int frame_claim(av1b_ctx* c, int f, int lane)
     }
     fr.readers = 0;
     fr.writer = lane;
+    fr.settled = false; // the claimer records `ready` when its submit ends
     return 0;
 }
 
@@ -353,7 +357,7 @@ static int frame_claim(av1b_ctx* c, int f, int lane)
 static int frame_read(av1b_ctx* c, int f, int lane)
 {
     DevFrame& fr = c->frames[f];
-    if (fr.writer != lane && rt_stream_wait(lane_stream(c, lane), fr.ready)) return 1;
+    if (!fr.settled && fr.writer != lane && rt_stream_wait(lane_stream(c, lane), fr.ready)) return 1;
     fr.readers |= 1u << lane;
     return 0;
 }
@@ -544,8 +548,10 @@ void av1b_ctx_destroy(av1b_ctx* c)
         for (auto& f : c->frames) {
             f.refcnt = 0;
             f.readers = 0;
+            f.settled = true;
         }
         c->joined = true;
+        c->capturing = false;
         for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
         for (int i = 0; i < N_SLOTS; i++) c->slots[i].pending = false;
         c->cur_slot = -1; // the next stream starts on the slots that already own a buffer
@@ -641,8 +647,9 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     // writes residuals into frame-layout int16 planes that the inter and dependent passes read.
     const bool arena_mode = (stages & AV1B_STAGE_RECON) == AV1B_STAGE_ITX;
     const size_t plane_elems = (size_t)c->aw * c->ah * 3 / 2;
-    if (!arena_mode && h.n_itx && !L.res_planes) {
-        // first coded residual of the stream: every lane gets its planes now (no cudaMalloc later)
+    if (!arena_mode && h.n_itx) {
+        // first coded residual of the stream: every lane gets its planes now (no cudaMalloc later,
+        // whichever lane a frame lands on)
         for (int m = 0; m < c->n_lanes; m++) {
             void* p = nullptr;
             if (c->lanes[m].res_planes) continue;
@@ -669,15 +676,17 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
                 return fail(c, AV1B_ECUDA, "stream wait");
     }
     const size_t sync_need = 1 + (size_t)h.sb_rows;
-    if (sync_need > L.sync_cap) {
-        rt_stream_sync(st);
-        rt_free(L.sync);
-        L.sync = nullptr;
-        L.sync_cap = 0;
+    for (int m = 0; m < c->n_lanes; m++) { // all lanes together, like the residual planes
+        Lane& Lm = c->lanes[m];
+        if (sync_need <= Lm.sync_cap) continue;
+        rt_stream_sync(Lm.stream);
+        rt_free(Lm.sync);
+        Lm.sync = nullptr;
+        Lm.sync_cap = 0;
         void* p = nullptr;
         if (rt_malloc(&p, (sync_need + 64) * sizeof(int))) return fail(c, AV1B_ENOMEM, "sync buffer");
-        L.sync = (int*)p;
-        L.sync_cap = sync_need + 64;
+        Lm.sync = (int*)p;
+        Lm.sync_cap = sync_need + 64;
     }
     // frames: the one being written, then the references it reads
     int cur = c->pending_input;
@@ -690,6 +699,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         if (frame_read(c, cur, lane)) return fail(c, AV1B_ECUDA, "stream wait");
         c->frames[cur].readers = 0;
         c->frames[cur].writer = lane;
+        c->frames[cur].settled = false;
     } else if (frame_claim(c, cur, lane)) return fail(c, AV1B_ECUDA, "stream wait");
     ReconCtx rc;
     memset(&rc, 0, sizeof(rc));
@@ -717,7 +727,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         }
     }
     if (h.n_iblk && (stages & AV1B_STAGE_INTER)) {
-        if (!L.mask_plane) {
+        {
             for (int m = 0; m < c->n_lanes; m++) {
                 void* p = nullptr;
                 if (c->lanes[m].mask_plane) continue;
@@ -922,6 +932,27 @@ int av1b_sync(av1b_ctx* c)
         if (rt_stream_sync(c->lanes[m].stream)) return fail(c, AV1B_ECUDA, "sync");
     if (rt_stream_sync(c->stream)) return fail(c, AV1B_ECUDA, "sync");
     c->joined = true;
+    // everything is finished: no recorded event has to be waited for any more
+    for (auto& f : c->frames) {
+        f.readers = 0;
+        f.settled = true;
+    }
+    return AV1B_OK;
+}
+
+int av1b_set_capture(av1b_ctx* c, int on)
+{
+    if (!c) return AV1B_EINVAL;
+    c->capturing = on != 0;
+    // on: start from a settled context, nothing recorded outside the capture has to be waited for.
+    // off: events recorded during the capture belong to the graph and must not be waited for by
+    // later work -- nothing ran yet, so everything counts as settled again.
+    if (on) return av1b_sync(c);
+    for (auto& f : c->frames) {
+        f.readers = 0;
+        f.settled = true;
+    }
+    c->joined = true;
     return AV1B_OK;
 }
 
@@ -935,6 +966,15 @@ int av1b_set_lanes(av1b_ctx* c, int n)
         c->lanes_made = m + 1;
     }
     c->n_lanes = n;
+    // the working set of the new lane count, allocated now rather than in the middle of a decode
+    while (c->frames.size() < pool_soft_cap(c)) {
+        void* p = nullptr;
+        if (rt_malloc(&p, c->frame_bytes)) return fail(c, AV1B_ENOMEM, "frame pool");
+        if (frame_add(c, (uint8_t*)p, true, MAIN_LANE)) {
+            rt_free(p);
+            return fail(c, AV1B_ECUDA, "cudaEventCreate");
+        }
+    }
     return AV1B_OK;
 }
 

@@ -115,6 +115,10 @@ class Engine:
         """Frames in flight on the device at once (1 = strictly one after the other)."""
         self._check(self.lib.av1b_set_lanes(self.ctx, n), "av1b_set_lanes")
 
+    def set_capture(self, on):
+        """Bracket a CUDA-graph capture of submits on the context's (caller-supplied) stream."""
+        self._check(self.lib.av1b_set_capture(self.ctx, 1 if on else 0), "av1b_set_capture")
+
     def join(self):
         """Make the context stream wait (device-side) for every frame submitted so far."""
         self._check(self.lib.av1b_join(self.ctx), "av1b_join")

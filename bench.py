@@ -450,8 +450,58 @@ def run_ours(args, rank, world, local_rank):
         for r in group:
             r.engine.join()  # the side stream waits for the frames in flight on the context's lanes
 
-    def replay_once():
+    def replay_direct():
         list(submit_pool.map(replay_group, groups))
+
+    # The replay of a stream is a fixed sequence of launches: capture it once per stream into a CUDA
+    # graph (the lanes fork from and join into the captured side stream through events, so the graph
+    # keeps the frame-level concurrency) and replay the graphs -- a dozen driver calls per frame
+    # become one launch per stream, which is what keeps the GPU fed when the host cores are split
+    # over several ranks.  --no-graphs replays through the API instead.
+    graphs = []
+
+    def stream_once(r):
+        last = -1
+        for ptr, hdr, refresh, slot in r.frames:
+            last = r.engine.show_existing(slot, refresh) if ptr is None else r.engine.submit_resident(ptr, hdr, pkg.STAGE_ALL, refresh)
+        r.engine.join()
+        return last
+
+    def build_graphs():
+        checked = 0
+        for r in recs:
+            # what the plain API replay leaves in the last frame
+            fid = stream_once(r)
+            r.engine.sync()
+            want = r.engine.download(fid, r.max_w, r.max_h) if fid >= 0 else None
+            r.engine.set_capture(True)
+            g = torch.cuda.CUDAGraph()
+            l0 = r.engine.launches()
+            with torch.cuda.graph(g, stream=r.side, capture_error_mode="thread_local"):
+                fid_g = stream_once(r)
+            r.kernels_per_replay = r.engine.launches() - l0  # kernel nodes of the graph
+            r.engine.set_capture(False)
+            with torch.cuda.stream(r.side):
+                g.replay()
+            r.side.synchronize()
+            if want is not None:
+                got = r.engine.download(fid_g, r.max_w, r.max_h)
+                if any(not (a == b).all() for a, b in zip(want, got)):
+                    raise RuntimeError(f"{r.name}: CUDA-graph replay differs from the API replay")
+                checked += 1
+            graphs.append((g, r.side))
+        print(f"graphs: {len(graphs)} streams captured, {checked} checked against the API replay", file=sys.stderr)
+
+    def replay_graphs():
+        for g, side in graphs:
+            with torch.cuda.stream(side):
+                g.replay()
+
+    def replay_once():
+        if graphs:
+            replay_graphs()
+        else:
+            replay_direct()
 
     main = torch.cuda.current_stream(dev)
 
@@ -477,6 +527,11 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         timed_replay(1)
+    if not args.no_graphs:
+        torch.cuda.synchronize()
+        build_graphs()
+        for _ in range(max(args.warmup, 3)):
+            timed_replay(1)
     launches0 = sum(r.engine.launches() for r in recs)
     sampler = ClockSampler(device)
     barrier()
@@ -484,6 +539,8 @@ def run_ours(args, rank, world, local_rank):
     secs = timed_replay(args.steps)
     barrier()
     launches = sum(r.engine.launches() for r in recs) - launches0
+    if graphs:  # graph replays do not pass through the engine's launch counter: count the graphs' kernel nodes
+        launches = args.steps * sum(r.kernels_per_replay for r in recs)
     if os.environ.get("BENCH_TRACE"):  # development aid: spread of single-step times inside one process
         print("trace ms/step:", [round(1e3 * timed_replay(1), 1) for _ in range(12)], file=sys.stderr)
     total_px, tmax = reduce_result(float(pixels_step * args.steps), secs, dev)
@@ -576,6 +633,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "bits/ conformance streams (committed fixtures); synthetic 4K frames for the roofline leg",
         "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "cuda_streams": len(side_streams), "lanes_per_context": args.lanes,
+                   "replay": "submit API" if args.no_graphs else "one CUDA graph per stream (captured from the submit API, checked against it)",
                    "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads * 3 // 4), "host_cores": cores,
                    "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
                    "stage_share_ms": share},
@@ -602,6 +660,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cuda-streams", type=int, default=64)
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = 3/4 of this rank's share of the cores)")
+    ap.add_argument("--no-graphs", action="store_true", help="resident replay through the submit API instead of captured CUDA graphs")
     ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter", "replay"], help="run a single leg (development aid)")

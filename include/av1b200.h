@@ -109,6 +109,14 @@ int av1b_join(av1b_ctx* ctx);
 /* Number of lanes of this context from now on (1..16; waits for the context to go idle first).
  * 1 makes every frame run alone on the device -- what a per-kernel timing wants. */
 int av1b_set_lanes(av1b_ctx* ctx, int n);
+/* CUDA-graph capture of a resident replay: with a stream of the caller's passed to av1b_ctx_create,
+ * call av1b_set_capture(ctx, 1) (synchronises, so that nothing recorded earlier has to be waited
+ * for), begin the capture on that stream, submit the frames (av1b_frame_submit_resident /
+ * av1b_show_existing), av1b_join, end the capture, av1b_set_capture(ctx, 0).  While it is on the
+ * engine issues no call that is illegal during capture (no event query, no allocation: run the
+ * same sequence once before so that every buffer exists).  The lanes fork from and join back into
+ * the captured stream through events, so the graph keeps the frame-level concurrency. */
+int av1b_set_capture(av1b_ctx* ctx, int on);
 /* Mark a fence after the work enqueued so far / wait for it: lets a caller overlap parsing of
  * the next frame with this frame's device work. */
 int av1b_fence_record(av1b_ctx* ctx, uint64_t* fence);
