@@ -176,3 +176,48 @@ def test_wavefront_full_frames_vs_sequential_emulation(eng, w, h, sb_log2):
 @pytest.mark.parametrize("w,h", [(178, 94), (3840, 2160)])
 def test_device_view_and_nv12(eng, w, h):
     checks.check_output_paths(eng, w, h)
+
+
+@pytest.mark.parametrize("name", ["av1-1-b8-06-mfmv.ivf", "av1-1-b8-02-allintra.ivf"])
+def test_resident_replay_captured_as_cuda_graph(name, md5_table):
+    """A stream's resident replay captured into a CUDA graph (av1b_set_capture) leaves the same
+    last frame as the same submits made directly -- with eight lanes forking and joining inside
+    the capture."""
+    import ctypes as C
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from av1dec_b200 import format as F
+    from av1dec_b200.engine import Engine
+    data = open(os.path.join(BITS, name), "rb").read()
+    rs = bench.record_stream(pkg, None, name, data, md5_table[name], 0)
+    side = torch.cuda.Stream()
+    eng = Engine(rs.max_w, rs.max_h, device=0, stream=side.cuda_stream)
+    eng.set_lanes(8)
+    hdr_size = C.sizeof(F.FrameHdr)
+    frames = [(None, None, r, n) if b is None else (eng.upload(b), b[:hdr_size], r, -1) for b, n, r, s in rs.host_frames]
+
+    def once():
+        last = -1
+        for ptr, hdr, refresh, slot in frames:
+            last = eng.show_existing(slot, refresh) if ptr is None else eng.submit_resident(ptr, hdr, pkg.STAGE_ALL, refresh)
+        eng.join()
+        return last
+    for _ in range(5):  # every lane gets used, every buffer exists
+        fid = once()
+    eng.sync()
+    want = eng.download(fid, rs.max_w, rs.max_h)
+    eng.set_capture(True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+        fid_g = once()
+    eng.set_capture(False)
+    for _ in range(2):
+        with torch.cuda.stream(side):
+            g.replay()
+    side.synchronize()
+    got = eng.download(fid_g, rs.max_w, rs.max_h)
+    for p in range(3):
+        assert np.array_equal(want[p], got[p]), (name, p)
+    eng.close()
