@@ -492,10 +492,15 @@ def run_ours(args, rank, world, local_rank):
             graphs.append((g, r.side))
         print(f"graphs: {len(graphs)} streams captured, {checked} checked against the API replay", file=sys.stderr)
 
-    def replay_graphs():
-        for g, side in graphs:
+    def launch_graphs(part):
+        for g, side in part:
             with torch.cuda.stream(side):
                 g.replay()
+
+    def replay_graphs():
+        # launching a graph of a few hundred nodes still costs the host tens of microseconds:
+        # the streams' graphs are launched from the submitter threads in parallel
+        list(submit_pool.map(launch_graphs, [graphs[i::n_sub] for i in range(n_sub)]))
 
     def replay_once():
         if graphs:
