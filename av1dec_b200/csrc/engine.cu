@@ -147,7 +147,7 @@ void build_wedge_table(uint8_t* out)
 // context
 // ------------------------------------------------------------------------------------------
 namespace {
-enum { N_SLOTS = 8, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = AV1B_MAX_FRAME_IDS, MAX_LANES = 16, MAIN_LANE = MAX_LANES };
+enum { N_SLOTS = 8, N_FENCES = 64, PAD_X = 128, PAD_Y = 16, POOL_MAX = AV1B_MAX_FRAME_IDS, MAX_LANES = 24, MAIN_LANE = MAX_LANES };
 
 // Frames are reconstructed on LANES: internal streams a context deals its frames to round-robin,
 // so that frames with no dependency between them (intra-only frames, frames of different

@@ -666,7 +666,7 @@ def main():
     ap.add_argument("--cuda-streams", type=int, default=64)
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads calling av1b_decode_ivf (0 = 3/4 of this rank's share of the cores)")
     ap.add_argument("--no-graphs", action="store_true", help="resident replay through the submit API instead of captured CUDA graphs")
-    ap.add_argument("--lanes", type=int, default=8, help="frames in flight per decoder context in the resident replay")
+    ap.add_argument("--lanes", type=int, default=16, help="frames in flight per decoder context in the resident replay")
     ap.add_argument("--submit-threads", type=int, default=0, help="host threads submitting the resident replay (0 = min(4, this rank's host threads))")
     ap.add_argument("--only", default="", choices=["", "postfilter", "replay"], help="run a single leg (development aid)")
     args = ap.parse_args()

@@ -79,7 +79,7 @@ int av1b_frame_submit_resident(av1b_ctx* ctx, const void* dev_cmd, const Av1bFra
 int av1b_show_existing(av1b_ctx* ctx, int slot, uint32_t refresh_mask, int* frame_id);
 
 /* Frame ids returned by submit / show_existing are pool indices below this bound. */
-#define AV1B_MAX_FRAME_IDS 64
+#define AV1B_MAX_FRAME_IDS 96
 
 /* Asynchronous copy of the visible w x h (and chroma) area of a device frame to host planes
  * (pinned memory from av1b_host_alloc gives a true async copy).  Decoder::getOutput(). */
@@ -106,7 +106,7 @@ int av1b_sync(av1b_ctx* ctx);
  * whatever the caller enqueues on that stream afterwards: call it before recording your own event
  * on a stream passed to av1b_ctx_create. */
 int av1b_join(av1b_ctx* ctx);
-/* Number of lanes of this context from now on (1..16; waits for the context to go idle first).
+/* Number of lanes of this context from now on (1..24; waits for the context to go idle first).
  * 1 makes every frame run alone on the device -- what a per-kernel timing wants. */
 int av1b_set_lanes(av1b_ctx* ctx, int n);
 /* CUDA-graph capture of a resident replay: with a stream of the caller's passed to av1b_ctx_create,
