@@ -177,6 +177,15 @@ static __device__ __forceinline__ int av1b_dp2a_hi(uint32_t a, uint32_t b, int c
 AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 AV1B_DEV int round2(int x, int n) { return n == 0 ? x : ((x + (1 << (n - 1))) >> n); }
+// Four packed samples plus four int16 residuals, each clipped to 8 bits.
+AV1B_DEV uint32_t add_res4(uint32_t px, uint2 r)
+{
+    const int o0 = clip_u8((int)(px & 0xFF) + (int)(int16_t)(r.x & 0xFFFF));
+    const int o1 = clip_u8((int)((px >> 8) & 0xFF) + ((int)r.x >> 16));
+    const int o2 = clip_u8((int)((px >> 16) & 0xFF) + (int)(int16_t)(r.y & 0xFFFF));
+    const int o3 = clip_u8((int)(px >> 24) + ((int)r.y >> 16));
+    return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+}
 AV1B_DEV int round2s(int x, int n) { return x >= 0 ? round2(x, n) : -round2(-x, n); }
 AV1B_DEV int iabs(int v) { return v < 0 ? -v : v; }
 AV1B_DEV int floor_log2(unsigned x)

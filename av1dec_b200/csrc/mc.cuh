@@ -72,6 +72,8 @@ struct Params {
     uint8_t* mask;           // luma-resolution mask of the block (diff-weighted compound): address of
     int mask_pitch;          //   the block's top-left sample, bytes per row
     PlaneView dst;           // destination plane of the current frame
+    const int16_t* res;      // residual plane to add while writing (independent units), or null
+    int rpitch;
     RefPlane ref[2];
 };
 
@@ -371,7 +373,9 @@ AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, in
                     const int o1 = clip_u8(round2(w0 * ((int)a.x >> 16) + w1 * ((int)b.x >> 16), sh));
                     const int o2 = clip_u8(round2(w0 * (int)(int16_t)(a.y & 0xFFFF) + w1 * (int)(int16_t)(b.y & 0xFFFF), sh));
                     const int o3 = clip_u8(round2(w0 * ((int)a.y >> 16) + w1 * ((int)b.y >> 16), sh));
-                    *(uint32_t*)(P.dst.p + (size_t)(u.y + ty + r) * P.dst.stride + (u.x + tx + 4 * q)) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+                    uint32_t out = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+                    if (P.res) out = add_res4(out, *(const uint2*)(P.res + (size_t)(u.y + ty + r) * P.rpitch + (u.x + tx + 4 * q)));
+                    *(uint32_t*)(P.dst.p + (size_t)(u.y + ty + r) * P.dst.stride + (u.x + tx + 4 * q)) = out;
                 }
                 block_sync(nt);
                 continue;
@@ -424,6 +428,7 @@ AV1B_DEV void run_ipu(const Params& P, const Av1bIpu& u, Scratch& s, int tid, in
                         out = clip_u8(round2(m * p0 + (64 - m) * p1, 10));
                     }
                 }
+                if (P.res) out = clip_u8(out + P.res[(size_t)(u.y + i) * P.rpitch + (u.x + j)]);
                 *d = (uint8_t)out;
             }
             block_sync(nt);

@@ -133,6 +133,8 @@ AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const 
     P.mask = c.mask ? c.mask + (size_t)(u.y << sub) * c.mask_pitch + (u.x << sub) : nullptr;
     P.mask_pitch = c.mask_pitch;
     P.dst = c.cur.pl[plane];
+    P.res = ((u.flags & AV1B_IPUF_ADD_RES) && c.rp[0]) ? c.rp[plane] : nullptr;
+    P.rpitch = c.rpitch[plane];
     const int nl = (u.flags & AV1B_IPUF_COMPOUND) ? 2 : 1;
     for (int l = 0; l < nl; l++) {
         mc::RefPlane& R = P.ref[l];
@@ -158,16 +160,15 @@ AV1B_DEV void setup_mc_params(const ReconCtx& c, const Av1bFrameHdr* hdr, const 
 // __syncwarp, each warp owns a private scratch area, and 8x8 blocks do not idle a whole CTA.
 enum { INTER_WARPS = 8 };
 
-__global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
+static __device__ void inter_block_body(const ReconCtx& c, mc::Scratch* M, unsigned bx, unsigned gx)
 {
-    __shared__ mc::Scratch M[INTER_WARPS];
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bInterBlk* blks = (const Av1bInterBlk*)(c.cmd + hdr->off_iblk);
     const Av1bIpu* ipus = (const Av1bIpu*)(c.cmd + hdr->off_ipu);
     const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
     const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
     mc::Scratch& S = M[warp];
-    for (unsigned b = blockIdx.x * nw + warp; b < hdr->n_iblk; b += gridDim.x * nw) {
+    for (unsigned b = bx * nw + warp; b < hdr->n_iblk; b += gx * nw) {
         const Av1bInterBlk blk = blks[b];
         if (blk.flags & AV1B_IBF_FAST) continue; // inter_fast_kernel's
         for (unsigned k = 0; k < blk.n_ipu; k++) {
@@ -200,14 +201,34 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c)
     }
 }
 
-// Four packed samples plus four int16 residuals, each clipped to 8 bits.
-AV1B_DEV uint32_t add_res4(uint32_t px, uint2 r)
+// Units of blocks whose units are independent of each other (no OBMC strips, no diff-weighted mask
+// shared between planes) but need the general predictor -- warped motion, wedge masks, 2-sample-wide
+// chroma, inter-intra's inter half: one WARP PER UNIT instead of per block (three times the
+// parallelism, a third of the serial chain), residual added in the same store.
+static __device__ void inter_unit_body(const ReconCtx& c, mc::Scratch* M, unsigned bx, unsigned gx)
 {
-    const int o0 = clip_u8((int)(px & 0xFF) + (int)(int16_t)(r.x & 0xFFFF));
-    const int o1 = clip_u8((int)((px >> 8) & 0xFF) + ((int)r.x >> 16));
-    const int o2 = clip_u8((int)((px >> 16) & 0xFF) + (int)(int16_t)(r.y & 0xFFFF));
-    const int o3 = clip_u8((int)(px >> 24) + ((int)r.y >> 16));
-    return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const Av1bIpu* ipus = (const Av1bIpu*)(c.cmd + hdr->off_ipu);
+    const unsigned n_ipu = hdr->n_ipu;
+    const int nl = min(32u, blockDim.x), nw = max(1u, blockDim.x / 32);
+    const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
+    mc::Scratch& S = M[warp];
+    // a CTA takes 32 consecutive units; every warp scans them (a lane per unit) and the flagged
+    // ones are dealt round-robin to the warps
+    for (unsigned chunk = bx * nl; chunk < n_ipu; chunk += gx * nl) {
+        const unsigned idx = chunk + lane;
+        const bool mine = idx < n_ipu && (ipus[idx].flags & AV1B_IPUF_INDEP);
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, mine);
+        for (int turn = 0; todo; turn++) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (turn % nw != warp) continue;
+            const Av1bIpu u = ipus[chunk + j];
+            mc::Params P;
+            setup_mc_params(c, hdr, u, P);
+            mc::run_ipu(P, u, S, lane, nl);
+        }
+    }
 }
 
 // Fast path for the units of AV1B_IBF_FAST blocks (plain translational prediction, the bulk of
@@ -223,9 +244,8 @@ enum { FAST_WARPS = 4, FAST_SLICES = 4, FAST_JOBS_PER_SLICE = 2 }; // one unit p
 enum { FAST_WARPS = 4, FAST_SLICES = 4, FAST_JOBS_PER_SLICE = 48 };
 #endif
 
-__global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx c)
+static __device__ void inter_fast_body(const ReconCtx& c, mc::Scratch* M, unsigned bx, unsigned gx, unsigned by, unsigned gy)
 {
-    __shared__ mc::Scratch M[FAST_WARPS];
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const uint4* ipus = (const uint4*)(c.cmd + hdr->off_ipu);
     const unsigned n_ipu = hdr->n_ipu;
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
     const int lane = threadIdx.x % nl, warp = threadIdx.x / nl;
     const unsigned FULL = 0xFFFFFFFFu;
     mc::Scratch& S = M[warp];
-    for (unsigned chunk = blockIdx.x * nl; chunk < n_ipu; chunk += gridDim.x * nl) {
+    for (unsigned chunk = bx * nl; chunk < n_ipu; chunk += gx * nl) {
         // ---- lane-parallel set-up: lane i <-> unit chunk + i
         const unsigned idx = chunk + lane;
         uint32_t u_xy = 0, u_dim = 0, u_fl = 0;   // x|y<<16, w|h<<8|plane<<16|kind<<24, flags|comp|fwd|bck
@@ -249,7 +269,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
             fast = (u_fl & AV1B_IPUF_FAST) != 0;
         }
         // ---- jobs = (unit, tile) pairs in unit order.  A chunk of large units holds up to 8x the
-        // jobs of a chunk of small ones: it is shared by up to FAST_SLICES CTAs (blockIdx.y), each
+        // jobs of a chunk of small ones: it is shared by up to FAST_SLICES CTAs (by), each
         // repeating the set-up and taking every n_slices-th group of jobs; the CTAs a light chunk
         // does not need leave here.
         const int my_w = u_dim & 0xFF, my_h = (u_dim >> 8) & 0xFF;
@@ -261,8 +281,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
         }
         const int excl = incl - my_tiles;
         const int total = __shfl_sync(FULL, incl, nl - 1);
-        const int n_slices = min((int)gridDim.y, (total + FAST_JOBS_PER_SLICE - 1) / FAST_JOBS_PER_SLICE);
-        if ((int)blockIdx.y >= n_slices) continue;
+        const int n_slices = min((int)gy, (total + FAST_JOBS_PER_SLICE - 1) / FAST_JOBS_PER_SLICE);
+        if ((int)by >= n_slices) continue;
         {
             if (fast) {
                 const int x = u_xy & 0xFFFF, y = u_xy >> 16, w = u_dim & 0xFF, h = (u_dim >> 8) & 0xFF;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
             }
         }
         // the slice's jobs, dealt round-robin to its warps; parameters are broadcast from the unit's lane
-        for (int job = (int)blockIdx.y * nw + warp; job < total; job += n_slices * nw) {
+        for (int job = (int)by * nw + warp; job < total; job += n_slices * nw) {
             const int j = 31 - __clz(__ballot_sync(FULL, excl <= job));
             const int tile = job - __shfl_sync(FULL, excl, j);
             const uint32_t xy = __shfl_sync(FULL, u_xy, j), dim = __shfl_sync(FULL, u_dim, j), fl = __shfl_sync(FULL, u_fl, j);
@@ -395,6 +415,26 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 6) inter_fast_kernel(ReconCtx
             }
         }
     }
+}
+
+// One launch for the whole inter pass: the three kinds of work touch disjoint blocks, so their CTAs
+// run side by side instead of one kernel after the other (each of them alone is a set of serial
+// chains that leaves most of the GPU idle).  The CTAs with the long chains come first.
+__global__ void __launch_bounds__(INTER_WARPS * 32, 3) inter_kernel(ReconCtx c, unsigned g_block, unsigned g_unit, unsigned g_fast)
+{
+    __shared__ mc::Scratch M[INTER_WARPS];
+    unsigned b = blockIdx.x;
+    if (b < g_block) {
+        inter_block_body(c, M, b, g_block);
+        return;
+    }
+    b -= g_block;
+    if (b < g_unit) {
+        inter_unit_body(c, M, b, g_unit);
+        return;
+    }
+    b -= g_unit;
+    inter_fast_body(c, M, b % g_fast, g_fast, b / g_fast, FAST_SLICES);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -913,12 +953,14 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.n_iblk) return;
-    int grid = (int)((h.n_iblk + INTER_WARPS - 1) / INTER_WARPS);
-    if (grid > 148 * 6) grid = 148 * 6;
-    AV1B_LAUNCH(inter_kernel, (grid), (INTER_WARPS * 32), st, c);
-    int fgrid = (int)((h.n_ipu + 31) / 32); // one 32-unit chunk per CTA pass
-    if (fgrid > 148 * 48) fgrid = 148 * 48;
-    if (fgrid) AV1B_LAUNCH(inter_fast_kernel, (fgrid, FAST_SLICES), (FAST_WARPS * 32), st, c);
+    unsigned g_block = (h.n_iblk + INTER_WARPS - 1) / INTER_WARPS;   // a warp per block
+    if (g_block > 148 * 6) g_block = 148 * 6;
+    unsigned g_unit = (h.n_ipu + 31) / 32;                            // a 32-unit chunk per CTA pass
+    if (g_unit > 148 * 6) g_unit = 148 * 6;
+    unsigned g_fast = (h.n_ipu + 31) / 32;
+    if (g_fast > 148 * 24) g_fast = 148 * 24;
+    if (!g_fast) g_fast = 1;
+    AV1B_LAUNCH(inter_kernel, (g_block + g_unit + g_fast * FAST_SLICES), (INTER_WARPS * 32), st, c, g_block, g_unit, g_fast);
 }
 
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)

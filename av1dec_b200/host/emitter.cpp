@@ -446,18 +446,23 @@ void FrameEmitter::emitInter(Block& b)
     }
     ib.n_ipu = (uint16_t)(m_ipu.size() - ib.first_ipu);
     if (!intrabc && ib.n_ipu) {
-        // plain translational blocks: independent units, fast kernel
-        bool fast = true;
-        for (size_t k = ib.first_ipu; k < m_ipu.size() && fast; k++) {
+        // blocks whose units do not depend on each other are handled unit by unit: by the fast
+        // translational kernel where a unit qualifies, by the general predictor otherwise
+        bool indep = true;
+        for (size_t k = ib.first_ipu; k < m_ipu.size() && indep; k++) {
             const Av1bIpu& u = m_ipu[k];
-            const bool big = u.w >= 8 && u.h >= 8;
-            fast = u.kind == AV1B_IPU_PRED && u.w >= 4 && !(big && (u.warp[0] || u.warp[1]))
-                && (!(u.flags & AV1B_IPUF_COMPOUND) || u.comp_type == AV1B_COMP_AVERAGE || u.comp_type == AV1B_COMP_DISTANCE);
+            indep = u.kind == AV1B_IPU_PRED && !((u.flags & AV1B_IPUF_COMPOUND) && u.comp_type == AV1B_COMP_DIFFWTD);
         }
-        if (fast) {
+        if (indep) {
             ib.flags |= AV1B_IBF_FAST;
             const uint8_t add = (ib.flags & AV1B_IBF_ADD_RESIDUAL) ? AV1B_IPUF_ADD_RES : 0;
-            for (size_t k = ib.first_ipu; k < m_ipu.size(); k++) m_ipu[k].flags |= AV1B_IPUF_FAST | add;
+            for (size_t k = ib.first_ipu; k < m_ipu.size(); k++) {
+                Av1bIpu& u = m_ipu[k];
+                const bool big = u.w >= 8 && u.h >= 8;
+                const bool simple = u.w >= 4 && !(big && (u.warp[0] || u.warp[1]))
+                    && (!(u.flags & AV1B_IPUF_COMPOUND) || u.comp_type == AV1B_COMP_AVERAGE || u.comp_type == AV1B_COMP_DISTANCE);
+                u.flags |= (simple ? AV1B_IPUF_FAST : AV1B_IPUF_INDEP) | add;
+            }
         }
         m_iblk.push_back(ib);
     }

@@ -95,7 +95,8 @@ enum {
 #define AV1B_IPUF_INTERINTRA 0x02 /* block is inter-intra: write Clip1(pred) only           */
 #define AV1B_IPUF_INTRABC 0x04    /* reference is the current frame (run inside wavefront)  */
 #define AV1B_IPUF_FAST 0x08       /* unit of an AV1B_IBF_FAST block                          */
-#define AV1B_IPUF_ADD_RES 0x10    /* fast unit: add the residual planes while writing        */
+#define AV1B_IPUF_ADD_RES 0x10    /* fast / independent unit: add the residual planes while writing */
+#define AV1B_IPUF_INDEP 0x20      /* unit of an AV1B_IBF_FAST block that needs the general predictor */
 
 /* One predict_inter() call (reference decoder/InterPredict.cpp:962) or one OBMC strip. 32 B */
 typedef struct Av1bIpu {
@@ -116,10 +117,12 @@ typedef struct Av1bIpu {
 
 #define AV1B_IBF_HAS_CHROMA 0x01   /* the block carries chroma (Block::HasChroma)                   */
 #define AV1B_IBF_ADD_RESIDUAL 0x02 /* add the residual planes over the block after prediction        */
-/* Every unit of the block is a plain translational prediction (kind PRED, no warp, no mask, w >= 4,
- * compound average / distance at most): its units are independent of each other and go to the
- * fast kernel, which also adds the residual (AV1B_IPUF_ADD_RES).  Optional: a producer that never
- * sets it gets the general kernel for every block. */
+/* The units of the block are independent of each other (all of kind PRED: no OBMC strips; no
+ * diff-weighted compound mask shared between the planes): they are handled one by one, by the fast
+ * translational kernel (AV1B_IPUF_FAST: no warp, no mask, w >= 4, compound average / distance at
+ * most) or by the general predictor with a warp per unit (AV1B_IPUF_INDEP), either of which also
+ * adds the residual (AV1B_IPUF_ADD_RES).  Optional: a producer that never sets it gets the
+ * block-at-a-time kernel for every block. */
 #define AV1B_IBF_FAST 0x04
 
 /* One inter block = one CTA work item of the independent inter pass. 24 B */
