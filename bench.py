@@ -534,7 +534,19 @@ def run_ours(args, rank, world, local_rank):
         timed_replay(1)
     if not args.no_graphs:
         torch.cuda.synchronize()
-        build_graphs()
+        try:
+            build_graphs()
+        except Exception as exc:  # capture refused (driver / torch build): measure through the submit API instead
+            print(f"graph capture failed ({type(exc).__name__}: {exc}); replaying through the submit API", file=sys.stderr)
+            graphs.clear()
+            args.no_graphs = True
+            for r in recs:
+                try:
+                    r.engine.set_capture(False)
+                    r.engine.sync()
+                except Exception:
+                    pass
+            torch.cuda.synchronize()
         for _ in range(max(args.warmup, 3)):
             timed_replay(1)
     launches0 = sum(r.engine.launches() for r in recs)
