@@ -579,9 +579,12 @@ def run_ours(args, rank, world, local_rank):
         r.engine.set_profiling(False)
 
     # ---------------- e2e: public decoder call, host buffers in and out, all host cores
-    def e2e_pass():
+    def e2e_pass(check=False):
         def one(s):
             yuv, frames, px = pkg.decode_ivf(s[1], device=device)
+            # the first (untimed) pass re-checks every stream's MD5 with all callers running at once
+            if check and hashlib.md5(yuv).hexdigest() != s[2]:
+                raise RuntimeError(f"{s[0]}: MD5 mismatch in the concurrent end-to-end pass")
             return px, len(yuv)
         t0 = time.perf_counter()
         # a stream of closed segments adds workers of its own and every context has driver threads:
@@ -595,7 +598,7 @@ def run_ours(args, rank, world, local_rank):
     warm_passes = 0
     for _ in range(8):
         c0 = pkg.alloc_counters()
-        e2e_pass()
+        e2e_pass(check=warm_passes == 0)
         warm_passes += 1
         c1 = pkg.alloc_counters()
         if warm_passes >= 2 and c1[0] == c0[0] and c1[2] == c0[2] and c1[3] == c0[3]:
