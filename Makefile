@@ -25,7 +25,7 @@ HOSTFLAGS:= -std=c++17 -O2 -fno-aggressive-loop-optimizations -fPIC -Wall -Wno-u
 REFINC   := -I$(REF)/aom -I$(REF)/common -I$(REF)/interface -I$(REF)/decoder
 
 CSRC     := $(PKG)/csrc
-KERNELS  := recon postfilter engine
+KERNELS  := recon postfilter deblock cdef lr engine
 KHDRS    := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/av1b200.h include/av1b200_format.h
 
 # reference front-end translation units (parse side). NOT included: Av1Decoder, IntraPredict,

@@ -81,6 +81,57 @@ static inline uint32_t __vminu2(uint32_t a, uint32_t b)
     uint32_t lo = std::min(a & 0xFFFFu, b & 0xFFFFu), hi = std::min(a >> 16, b >> 16);
     return lo | (hi << 16);
 }
+// ---- packed 16x2 / 8x4 SIMD intrinsics used by the CDEF kernel (single SASS instructions on
+// sm_100a: VABSDIFF4, VIADD.16x2, VIMNMX[3].x16x2, VIADDMNMX.S16x2[.RELU])
+static inline uint32_t emu_map2s(uint32_t a, uint32_t b, uint32_t c, int (*f)(int, int, int))
+{
+    const int lo = f((int16_t)(a & 0xFFFF), (int16_t)(b & 0xFFFF), (int16_t)(c & 0xFFFF));
+    const int hi = f((int16_t)(a >> 16), (int16_t)(b >> 16), (int16_t)(c >> 16));
+    return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+}
+static inline uint32_t emu_map2u(uint32_t a, uint32_t b, uint32_t c, int (*f)(int, int, int))
+{
+    const int lo = f((int)(a & 0xFFFF), (int)(b & 0xFFFF), (int)(c & 0xFFFF));
+    const int hi = f((int)(a >> 16), (int)(b >> 16), (int)(c >> 16));
+    return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+}
+static inline uint32_t __vabsdiffu4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF;
+        r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
+}
+static inline uint32_t __vadd2(uint32_t a, uint32_t b) { return emu_map2s(a, b, 0, [](int x, int y, int) { return x + y; }); }
+static inline uint32_t __vmaxs2(uint32_t a, uint32_t b) { return emu_map2s(a, b, 0, [](int x, int y, int) { return x > y ? x : y; }); }
+static inline uint32_t __vmins2(uint32_t a, uint32_t b) { return emu_map2s(a, b, 0, [](int x, int y, int) { return x < y ? x : y; }); }
+static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_map2s(a, b, c, [](int x, int y, int z) { const int s = (int16_t)(x + y); return s < z ? s : z; });
+}
+static inline uint32_t __viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_map2s(a, b, c, [](int x, int y, int z) { const int s = (int16_t)(x + y); return s > z ? s : z; });
+}
+static inline uint32_t __viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_map2s(a, b, c, [](int x, int y, int z) { const int s = (int16_t)(x + y); const int m = s < z ? s : z; return m > 0 ? m : 0; });
+}
+static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_map2u(a, b, c, [](int x, int y, int z) { return std::max(x, std::max(y, z)); });
+}
+static inline uint32_t __vimin3_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return emu_map2u(a, b, c, [](int x, int y, int z) { return std::min(x, std::min(y, z)); });
+}
+static inline int av1b_dp4a_ss(uint32_t a, uint32_t b, int c)
+{
+    for (int i = 0; i < 4; i++) c += (int)(int8_t)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
+    return c;
+}
 typedef void* av1b_stream_t;
 template <class F> static inline void emu_launch(dim3 grid, F f)
 {
@@ -153,11 +204,41 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
     sh &= 31;
     return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
 }
+static inline uint32_t av1b_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+    return c;
+}
+// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)   (PTX cvt.pack.sat.u8.s32.b32)
+static inline uint32_t av1b_pack_sat_u8(int a, int b, uint32_t c)
+{
+    const uint32_t ta = a < 0 ? 0 : (a > 255 ? 255 : a), tb = b < 0 ? 0 : (b > 255 ? 255 : b);
+    return (c << 16) | (ta << 8) | tb;
+}
 #else
 static __device__ __forceinline__ int av1b_dp4a_us(uint32_t a, uint32_t b, int c)
 {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+static __device__ __forceinline__ int av1b_dp4a_ss(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+static __device__ __forceinline__ uint32_t av1b_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)   (I2IP.U8.S32.SAT)
+static __device__ __forceinline__ uint32_t av1b_pack_sat_u8(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 static __device__ __forceinline__ int av1b_dp2a_lo(uint32_t a, uint32_t b, int c)
@@ -173,6 +254,9 @@ static __device__ __forceinline__ int av1b_dp2a_hi(uint32_t a, uint32_t b, int c
     return d;
 }
 #endif
+
+// Four values, each saturated to 8 bits, packed little-endian (v0 in the low byte).
+AV1B_DEV uint32_t pack_u8x4(int v0, int v1, int v2, int v3) { return av1b_pack_sat_u8(v1, v0, av1b_pack_sat_u8(v3, v2, 0u)); }
 
 AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }

@@ -273,8 +273,8 @@ static int fail(av1b_ctx* c, int code, const char* what)
     return code;
 }
 
-// Working set of the lanes: 3 buffers per frame in flight + 8 references + 1 pending output.
-static size_t pool_soft_cap(const av1b_ctx* c) { return std::min<size_t>(POOL_MAX, (size_t)3 * c->n_lanes + 9); }
+// Working set of the lanes: 4 buffers per frame in flight (reconstruction, deblocked, CDEF, LR) + 8 references + 1 pending output.
+static size_t pool_soft_cap(const av1b_ctx* c) { return std::min<size_t>(POOL_MAX, (size_t)4 * c->n_lanes + 9); }
 
 // Register one frame buffer (planes laid out inside `base`) with the pool.
 static int frame_add(av1b_ctx* c, uint8_t* base, bool owned, int lane)
@@ -760,13 +760,21 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     memset(&pc, 0, sizeof(pc));
     pc.cmd = dev_cmd;
     pc.src = c->frames[cur].v;
-    int final_frame = cur, cdef = -1, lr = -1;
+    int final_frame = cur, deb = -1, cdef = -1, lr = -1;
+    pc.deb = pc.src;
     if ((stages & AV1B_STAGE_DEBLOCK) && (h.lf.level[0] || h.lf.level[1])) {
+        // out of place: both edge passes read the reconstruction and write the deblocked frame
+        deb = frame_alloc(c, lane);
+        if (deb < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
+        c->frames[deb].refcnt++;
+        if (frame_claim(c, deb, lane)) return fail(c, AV1B_ECUDA, "stream wait");
+        pc.deb = c->frames[deb].v;
         StageTimer t(c, 3, true, st);
         launch_deblock(pc, h, st);
-        c->launches += 2;
+        c->launches += 1;
+        final_frame = deb;
     }
-    pc.cdef = pc.src;
+    pc.cdef = pc.deb;
     if ((stages & AV1B_STAGE_CDEF) && h.cdef.enabled) {
         cdef = frame_alloc(c, lane);
         if (cdef < 0) return fail(c, AV1B_ENOMEM, "frame pool exhausted");
@@ -791,9 +799,11 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     }
     if (rt_check()) return fail(c, AV1B_ECUDA, "kernel launch");
     // one completion point for every buffer this submit wrote or used as an intermediate
-    if (rt_event_record(c->frames[final_frame].ready, st) || (cur != final_frame && rt_event_record(c->frames[cur].ready, st))
-        || (cdef >= 0 && cdef != final_frame && rt_event_record(c->frames[cdef].ready, st)))
-        return fail(c, AV1B_ECUDA, "event record");
+    {
+        const int used[4] = { cur, deb, cdef, lr };
+        for (int k = 0; k < 4; k++)
+            if (used[k] >= 0 && rt_event_record(c->frames[used[k]].ready, st)) return fail(c, AV1B_ECUDA, "event record");
+    }
     c->joined = false;
     // reference refresh (Decoder::updateFrameStore)
     for (int i = 0; i < 8; i++) {
@@ -804,6 +814,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         }
     }
     c->frames[cur].refcnt--;
+    if (deb >= 0) c->frames[deb].refcnt--;
     if (cdef >= 0) c->frames[cdef].refcnt--;
     if (lr >= 0) c->frames[lr].refcnt--;
     if (frame_id) *frame_id = final_frame;

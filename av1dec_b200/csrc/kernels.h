@@ -20,7 +20,8 @@ struct ReconCtx {
 // In-loop filter context.
 struct PostCtx {
     const uint8_t* cmd;
-    FrameView src;  // reconstructed frame; deblocked in place
+    FrameView src;  // reconstructed frame (never modified by the filters)
+    FrameView deb;  // deblocked frame (== src when the deblocking stage does not run)
     FrameView cdef; // CDEF output
     FrameView lr;   // loop-restoration output
 };
