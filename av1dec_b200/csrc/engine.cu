@@ -73,7 +73,10 @@ static int rt_stream_create(av1b_stream_t* s) { return cudaStreamCreateWithFlags
 static void rt_stream_destroy(av1b_stream_t s) { cudaStreamDestroy(s); }
 static int rt_stream_sync(av1b_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
 static int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess; }
-static void rt_event_destroy(rt_event_t e) { cudaEventDestroy(e); }
+static void rt_event_destroy(rt_event_t e)
+{
+    if (e) cudaEventDestroy(e);
+}
 static int rt_event_record(rt_event_t e, av1b_stream_t s) { return cudaEventRecord(e, s) != cudaSuccess; }
 static int rt_event_sync(rt_event_t e) { return cudaEventSynchronize(e) != cudaSuccess; }
 static int rt_stream_wait(av1b_stream_t s, rt_event_t e) { return cudaStreamWaitEvent(s, e, 0) != cudaSuccess; }
@@ -161,8 +164,8 @@ struct DevFrame {
     bool owned = true;        // own cudaMalloc (false: carved out of the context's slab)
     FrameView v;
     int refcnt = 0;
-    rt_event_t ready;         // recorded after the last kernel of the submit that wrote (or used) the frame
-    rt_event_t copied;        // recorded on the context stream after the last download / copy out of it
+    rt_event_t ready = rt_event_t(); // recorded after the last kernel of the submit that wrote (or used) the frame
+    rt_event_t copied = rt_event_t(); // recorded on the context stream after the last download / copy out of it
     int writer = MAIN_LANE;   // lane of that submit
     uint32_t readers = 0;     // lanes that read it since (bit MAIN_LANE = the context stream)
     bool settled = true;      // nothing recorded since the last full av1b_sync: no event to wait for
@@ -171,7 +174,7 @@ struct DevFrame {
 // Per-lane scratch: nothing here is shared between frames in flight on different lanes.
 struct Lane {
     av1b_stream_t stream = nullptr;
-    rt_event_t mark;               // scratch event for cross-lane ordering
+    rt_event_t mark = rt_event_t(); // scratch event for cross-lane ordering
     int16_t* res_planes = nullptr; // frame-layout residual planes (luma aw x ah, chroma aw/2 x ah/2 each)
     uint8_t* mask_plane = nullptr; // luma-resolution compound-mask scratch (aw x ah)
     int* sync = nullptr;
@@ -182,7 +185,7 @@ struct CmdSlot {
     uint8_t* host = nullptr;
     uint8_t* dev = nullptr;
     size_t cap = 0;
-    rt_event_t done;
+    rt_event_t done = rt_event_t();
     bool pending = false;
 };
 }  // namespace
@@ -207,11 +210,11 @@ struct av1b_ctx {
     uint64_t frame_seq = 0;
     bool joined = true;     // no lane work outstanding relative to the context stream
     bool capturing = false; // the caller is capturing the context stream into a CUDA graph: no event queries
-    rt_event_t main_mark;
+    rt_event_t main_mark = rt_event_t();
     uint8_t* wedge = nullptr;
     int pending_input = -1;
-    rt_event_t fences[N_FENCES];
-    uint64_t fence_next = 1;
+    rt_event_t fences[N_FENCES] = {};
+    std::atomic<uint64_t> fence_next{ 1 }; // read by the caller's thread while the emit worker records
     uint64_t launches = 0;
     std::string err;
     // optional per-stage device timing (CUDA events around each launch group)
@@ -425,7 +428,7 @@ void av1b_host_free(void* p);
 static void ctx_free(av1b_ctx* c)
 {
     rt_set_device(c->device);
-    rt_stream_sync(c->stream);
+    if (c->stream) rt_stream_sync(c->stream);
     for (int m = 0; m < c->lanes_made; m++) rt_stream_sync(c->lanes[m].stream);
     for (auto& f : c->frames) {
         if (f.owned) rt_free(f.base);
@@ -450,36 +453,15 @@ static void ctx_free(av1b_ctx* c)
     for (int i = 0; i < N_FENCES; i++) rt_event_destroy(c->fences[i]);
     for (auto e : c->event_pool) rt_event_destroy(e);
     rt_free(c->res);
-    if (c->own_stream) rt_stream_destroy(c->stream);
+    if (c->own_stream && c->stream) rt_stream_destroy(c->stream);
     delete c;
 }
 
-int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream)
+void av1b_pool_purge(void);
+static std::string g_last_create_error;
+
+static int ctx_init(av1b_ctx* c, int device, int max_w, int max_h, int aw, int ah, void* stream)
 {
-    if (!out || max_w <= 0 || max_h <= 0 || max_w > 16384 || max_h > 16384) return AV1B_EINVAL;
-#ifndef AV1B_EMU
-    // Many short streams with event waits between them: with the default 8 hardware work queues
-    // a wait at the head of a queue stalls unrelated streams behind it.  Only effective when the
-    // CUDA context does not exist yet; hosts that initialise CUDA first set it themselves.
-    static const int once = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
-    (void)once;
-#endif
-    const int aw = (max_w + 127) & ~127, ah = (max_h + 127) & ~127;
-    if (!stream) {
-        std::lock_guard<std::mutex> lk(g_mu);
-        for (size_t i = 0; i < g_ctx_pool.size(); i++) {
-            av1b_ctx* c = g_ctx_pool[i];
-            if (c->device == device && c->aw >= aw && c->ah >= ah && (size_t)c->aw * c->ah <= 2 * (size_t)aw * ah) {
-                g_ctx_pool.erase(g_ctx_pool.begin() + i);
-                g_n_ctx_reused++;
-                *out = c;
-                return AV1B_OK;
-            }
-        }
-    }
-    av1b_ctx* c = new av1b_ctx;
-    g_n_ctx_new++;
-    *out = c;
     c->device = device;
     for (int i = 0; i < 8; i++) c->ref_slot[i] = -1;
     if (rt_set_device(device)) return fail(c, AV1B_ECUDA, "cudaSetDevice");
@@ -535,6 +517,50 @@ int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stre
         c->wedge = it->second;
     }
     return AV1B_OK;
+}
+
+int av1b_ctx_create(av1b_ctx** out, int device, int max_w, int max_h, void* stream)
+{
+    if (!out || max_w <= 0 || max_h <= 0 || max_w > 16384 || max_h > 16384) return AV1B_EINVAL;
+#ifndef AV1B_EMU
+    // Many short streams with event waits between them: with the default 8 hardware work queues
+    // a wait at the head of a queue stalls unrelated streams behind it.  Only effective when the
+    // CUDA context does not exist yet; hosts that initialise CUDA first set it themselves.
+    static const int once = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    (void)once;
+#endif
+    const int aw = (max_w + 127) & ~127, ah = (max_h + 127) & ~127;
+    if (!stream) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < g_ctx_pool.size(); i++) {
+            av1b_ctx* c = g_ctx_pool[i];
+            if (c->device == device && c->aw >= aw && c->ah >= ah && (size_t)c->aw * c->ah <= 2 * (size_t)aw * ah) {
+                g_ctx_pool.erase(g_ctx_pool.begin() + i);
+                g_n_ctx_reused++;
+                *out = c;
+                return AV1B_OK;
+            }
+        }
+    }
+    // A context is either fully built or not handed out at all: on failure the partial one is
+    // freed (its handles are value-initialised, so ctx_free only destroys what exists) and *out
+    // stays null.  Out of device memory: idle pooled contexts hold frame slabs -- purge them and
+    // try once more before giving up.
+    *out = nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        av1b_ctx* c = new av1b_ctx;
+        g_n_ctx_new++;
+        const int rc = ctx_init(c, device, max_w, max_h, aw, ah, stream);
+        if (rc == AV1B_OK) {
+            *out = c;
+            return AV1B_OK;
+        }
+        g_last_create_error = c->err;
+        ctx_free(c);
+        if (rc != AV1B_ENOMEM || attempt) return rc;
+        av1b_pool_purge();
+    }
+    return AV1B_ENOMEM;
 }
 
 void av1b_ctx_destroy(av1b_ctx* c)
@@ -1011,16 +1037,19 @@ int av1b_fence_record(av1b_ctx* c, uint64_t* fence)
 int av1b_fence_done(av1b_ctx* c, uint64_t fence)
 {
     if (!c) return 1;
-    if (fence == 0 || fence + N_FENCES <= c->fence_next) return 1;
+    if (fence == 0) return 1;
     rt_set_device(c->device);
+    // a slot that has been re-recorded since holds a LATER point of the same stream: its
+    // completion implies the older fence's, so query it rather than assuming "long retired"
     return rt_event_done(c->fences[fence % N_FENCES]);
 }
 
 int av1b_fence_wait(av1b_ctx* c, uint64_t fence)
 {
     if (!c) return AV1B_EINVAL;
-    if (fence == 0 || fence + N_FENCES <= c->fence_next) return AV1B_OK; // long retired
+    if (fence == 0) return AV1B_OK;
     rt_set_device(c->device);
+    // (a re-recorded slot is a later point of the same stream: waiting on it covers this fence)
     if (rt_event_sync(c->fences[fence % N_FENCES])) return fail(c, AV1B_ECUDA, "fence wait");
     return AV1B_OK;
 }

@@ -22,6 +22,7 @@
 #include "intra.cuh"
 #include "mc.cuh"
 #include "kernels.h"
+#include <mutex>
 #include <algorithm>
 #include <cstdlib>
 
@@ -984,11 +985,18 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     const int warps = (wenv && atoi(wenv) == 8) ? 8 : 16;
     const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * warps;
 #ifndef AV1B_EMU
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 16);
-        cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 8);
-        configured = true;
+    {
+        // the attribute is per DEVICE: a process may run decoders on several GPUs
+        static std::mutex mu;
+        static uint64_t done[4] = { 0, 0, 0, 0 }; // bit per device ordinal (<= 256 devices)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (!(done[(dev >> 6) & 3] & (1ull << (dev & 63)))) {
+            cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 16);
+            cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 8);
+            done[(dev >> 6) & 3] |= 1ull << (dev & 63);
+        }
     }
     if (warps == 16) wave_kernel<16, 1><<<dim3(grid), dim3(512), smem, st>>>(c);
     else wave_kernel<8, 3><<<dim3(grid), dim3(256), smem, st>>>(c);

@@ -30,7 +30,10 @@ struct HostFrame : public YuvFrame {
     size_t cap = 0;
 };
 
+// Returned frames come back on whatever thread drops the last reference (the caller's), while the
+// emit worker takes frames out: every access to free_list holds mu.
 struct HostPool {
+    std::mutex mu;
     std::vector<HostFrame*> free_list;
     ~HostPool()
     {
@@ -46,11 +49,14 @@ std::shared_ptr<YuvFrame> acquireHostFrame(const std::shared_ptr<HostPool>& pool
     const int sy = (w + 63) & ~63, sc = ((w >> 1) + 63) & ~63;
     const size_t need = (size_t)sy * h + 2 * (size_t)sc * (h >> 1);
     HostFrame* f = nullptr;
-    for (size_t i = 0; i < pool->free_list.size(); i++) {
-        if (pool->free_list[i]->cap >= need) {
-            f = pool->free_list[i];
-            pool->free_list.erase(pool->free_list.begin() + i);
-            break;
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        for (size_t i = 0; i < pool->free_list.size(); i++) {
+            if (pool->free_list[i]->cap >= need) {
+                f = pool->free_list[i];
+                pool->free_list.erase(pool->free_list.begin() + i);
+                break;
+            }
         }
     }
     if (!f) {
@@ -76,7 +82,10 @@ std::shared_ptr<YuvFrame> acquireHostFrame(const std::shared_ptr<HostPool>& pool
     f->widths[1] = f->widths[2] = w / 2;
     f->heights[1] = f->heights[2] = h / 2;
     std::shared_ptr<HostPool> keep = pool;
-    return std::shared_ptr<YuvFrame>(static_cast<YuvFrame*>(f), [keep](YuvFrame* y) { keep->free_list.push_back(static_cast<HostFrame*>(y)); });
+    return std::shared_ptr<YuvFrame>(static_cast<YuvFrame*>(f), [keep](YuvFrame* y) {
+        std::lock_guard<std::mutex> lk(keep->mu);
+        keep->free_list.push_back(static_cast<HostFrame*>(y));
+    });
 }
 
 }  // namespace
@@ -86,6 +95,7 @@ struct Decoder::Impl {
     FramePtr frame;
     TileGroup tiles;
     av1b_ctx* ctx = nullptr;
+    int ctx_w = 0, ctx_h = 0; // size the device context was created for
     av1b200::FrameEmitter emitter;
     std::shared_ptr<HostPool> pool = std::make_shared<HostPool>();
     struct Pending {
@@ -117,7 +127,12 @@ struct Decoder::Impl {
         if (ctx) return true;
         const int mw = s.max_frame_width_minus_1 + 1, mh = s.max_frame_height_minus_1 + 1;
         if (s.BitDepth != 8 || !s.subsampling_x || !s.subsampling_y || s.mono_chrome) return fail("only 8-bit 4:2:0 streams are supported (same envelope as the reference)");
-        if (av1b_ctx_create(&ctx, opt.device, mw, mh, nullptr) != AV1B_OK) return fail("av1b_ctx_create");
+        if (av1b_ctx_create(&ctx, opt.device, mw, mh, nullptr) != AV1B_OK) {
+            ctx = nullptr; // av1b_ctx_create leaves *out null on failure; never keep a half-built context
+            return fail("av1b_ctx_create");
+        }
+        ctx_w = mw;
+        ctx_h = mh;
         return true;
     }
 
@@ -143,6 +158,21 @@ struct Decoder::Impl {
     {
         FrameHeader& h = *fr;
         if (!ensureCtx(*seq)) return false;
+        // outside the envelope (the reference asserts: Av1Decoder.cpp:194-200, InterPredict.cpp:395):
+        // refuse loudly instead of decoding as if unscaled
+        if (h.use_superres) return fail("super-resolution is not supported (same envelope as the reference)");
+        if (!h.FrameIsIntra)
+            for (int rf = LAST_FRAME; rf <= ALTREF_FRAME; rf++)
+                if (h.is_scaled(rf)) return fail("scaled reference frames are not supported (same envelope as the reference)");
+        if (h.MiCols * 4 > ((ctx_w + 7) & ~7) + 128 || (int)h.FrameWidth > ctx_w || (int)h.FrameHeight > ctx_h) {
+            // a later, larger sequence header: rebuild the device context (references are lost, as
+            // they would be useless at a new size anyway -- the new sequence starts with a key frame)
+            if (av1b_sync(ctx) != AV1B_OK) return fail("av1b_sync");
+            av1b_ctx_destroy(ctx);
+            ctx = nullptr;
+            if (!ensureCtx(*seq)) return false;
+            if ((int)h.FrameWidth > ctx_w || (int)h.FrameHeight > ctx_h) return fail("frame larger than the sequence's maximum size");
+        }
         const double t0 = now();
         emitter.begin(h, *seq);
         for (auto& t : ts) {

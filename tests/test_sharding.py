@@ -38,3 +38,29 @@ def test_streams_are_dealt_without_overlap_and_reduced():
     want_total = float(sum(1000 + 37 * i for i in range(23)))
     for r in res:
         assert r[2] == want_total and r[3] == 2.0
+
+
+def test_every_rank_decodes_the_full_set():
+    """The headline (weak-scaling) job: at world 2 / 4 / 8 every rank holds all 172 distinct
+    streams exactly once.  (Round 1 dealt `world` concatenated copies round-robin, which gives a
+    rank 172 / world distinct streams `world` times each whenever world divides 172.)"""
+    import bench
+    streams = bench.load_streams()
+    assert len(streams) == 172
+    for world in (1, 2, 4, 8):
+        for rank in range(world):
+            mine = bench.rank_job(streams, rank, world)
+            names = [n for n, _, _ in mine]
+            assert len(names) == 172 and len(set(names)) == 172
+            assert sum(len(d) for _, d, _ in mine) == sum(len(d) for _, d, _ in streams)
+
+
+def test_strong_scaling_batch_is_a_partition():
+    """shard_streams(): a 64-stream batch (BASELINE configs[4]) split over 1 / 2 / 4 / 8 ranks is a
+    partition: nothing dropped, nothing duplicated."""
+    import bench
+    batch = [f"s{i}" for i in range(64)]
+    for world in (1, 2, 4, 8):
+        parts = [bench.shard_streams(batch, r, world) for r in range(world)]
+        assert sorted(x for p in parts for x in p) == sorted(batch)
+        assert all(len(p) == 64 // world for p in parts)
