@@ -4,6 +4,14 @@
 // symbols of them that the mixed parse/decode translation units still reference are defined
 // here as traps: if anything ever tried to reconstruct a pixel on the host, the process
 // aborts instead of silently falling back to the CPU.
+//
+// The mixed translation units also DEFINE the reference's decode() tree walk (Tile / SuperBlock /
+// Partition / Block ::decode, Tile.cpp:172, SuperBlock.cpp:46, Partition.cpp:207, Block.cpp:1600),
+// kept alive by the BlockTree vtables.  The Makefile weakens those four symbols in the front-end
+// objects; the strong definitions below replace them, and with them gone nothing references
+// TransformBlock::decode / inverseTransform, Block::compute_prediction, InterPredict::predict_inter,
+// blockWarp, Palette::predict_palette ... so the linker (--gc-sections) drops that code.
+// tests/test_host.py checks with nm that none of it is left in the product.
 #include "ref_access.h"
 #include "IntraPredict.h"
 
@@ -38,6 +46,11 @@ Block::IntraPredict::IntraPredict(const Block& block, const std::shared_ptr<YuvF
 {
     trap("IntraPredict");
 }
+
+bool Tile::decode(std::shared_ptr<Yami::YuvFrame>&, const FrameStore&) { trap("Tile::decode"); }
+bool SuperBlock::decode(std::shared_ptr<Yami::YuvFrame>&, const FrameStore&) { trap("SuperBlock::decode"); }
+bool Partition::decode(std::shared_ptr<Yami::YuvFrame>&, const FrameStore&) { trap("Partition::decode"); }
+bool Block::decode(std::shared_ptr<YuvFrame>&, const FrameStore&) { trap("Block::decode"); }
 
 void Block::IntraPredict::predict_intra(int, int, bool, bool, int) { trap("predict_intra"); }
 void Block::IntraPredict::predict_chroma_from_luma(TX_SIZE) { trap("predict_chroma_from_luma"); }

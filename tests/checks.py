@@ -195,3 +195,19 @@ def stage_frames(dec_lib, data, stages):
     """Shown frames (visible area, concatenated) from the engine with a restricted stage mask."""
     yuv, frames, _ = pkg.decode_ivf(data, stages=stages, lib=dec_lib)
     return yuv, frames
+
+
+IVD_DRIVE = os.path.join(ROOT, "tests", "native", "ivd_drive")
+
+
+def drive_ivideodecoder(decoder_so, name, mode, tmp_path):
+    """Run the libyami-style client (tests/native/ivd_drive.cpp: dlopen + createVideoDecoder +
+    start / decode / getOutput / flush / reset / stop through the IVideoDecoder vtable).
+    Returns (md5 of the written I420, frames)."""
+    import subprocess
+    out = os.path.join(str(tmp_path), f"ivd_{mode}.yuv")
+    r = subprocess.run([IVD_DRIVE, decoder_so, os.path.join(ROOT, "tests", "golden", "bits", name), out, mode],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, f"ivd_drive {mode}: rc={r.returncode} {r.stderr[-400:]}"
+    frames = int([l for l in r.stdout.splitlines() if l.startswith("frames")][0].split()[1])
+    return hashlib.md5(open(out, "rb").read()).hexdigest(), frames, open(out, "rb").read()

