@@ -149,24 +149,23 @@ enum {
     LF_THREADS = 256,
 };
 
-struct LfJob {
-    uint16_t pos;    // byte offset in LfSmem::px of q0 of the unit's first line
-    uint8_t limit, blimit;
-    uint8_t thresh, filter_size;
-    uint16_t pad;
-};
+// A live edge unit, queued by filter-size class (4 / 8 / 16) so that the lanes of a warp run
+// the same filter: bits 0..13 byte offset in LfSmem::px of q0 of the unit's first line,
+// 14..19 limit, 20..25 level (blimit = 2 * (level + 2) + limit, thresh = level >> 4).
+typedef uint32_t LfJob;
 
 struct LfSmem {
     alignas(16) uint8_t px[LF_ROWS * LF_PITCH]; // px[(r + 8) * LF_PITCH + (c + 8)] = tile sample (r, c)
-    LfJob vq[LF_VCOLS * LF_VROWS];
-    LfJob hq[LF_HCOLS * LF_HROWS];
-    int nv, nh;
+    LfJob vq[3][LF_VCOLS * LF_VROWS];
+    LfJob hq[3][LF_VCOLS * LF_VROWS]; // (same capacity as vq so that one lf_run_pass serves both)
+    int nv[3], nh[3];
+    Av1bLoopFilterParams lf; // frame parameters (indexed by reference / plane: kept out of local memory)
 };
 
 // Is the edge unit at plane unit coordinates (uc, ur) (4-sample units) live in PASS?  Fills the
 // filter parameters.  (loop_filter_edge, LoopFilter.cpp:85-126)
 template <int PASS>
-AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc, int ur, LfJob& job)
+AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc, int ur, LfJob& job, int& cls)
 {
     const int sub = plane ? 1 : 0;
     const int mi_cols = hdr->mi_cols;
@@ -195,69 +194,75 @@ AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLo
     LfLevel L = lf_strength(lf, mi, plane, PASS);
     if (!L.lvl) L = lf_strength(lf, pm, plane, PASS);
     if (L.lvl <= 0) return false;
-    job.limit = (uint8_t)L.limit;
-    job.blimit = (uint8_t)L.blimit;
-    job.thresh = (uint8_t)L.thresh;
-    job.filter_size = (uint8_t)filter_size;
+    job = ((uint32_t)L.limit << 14) | ((uint32_t)L.lvl << 20);
+    cls = filter_size == 4 ? 0 : (filter_size == 8 ? 1 : 2);
     return true;
 }
 
-// Append the live units of one pass to its queue: a thread per unit, one shared-memory atomic per
-// warp (ballot-compacted).  Units are (col, row) in the ncols x nrows window starting at unit
-// (uc0, ur0) of the plane; tile-relative sample position of unit (i, j) is (4*(uc0+i) - x0, ...).
-template <int PASS>
+// Append the live units of one pass to the queue of their filter-size class: a thread per unit,
+// one shared-memory atomic per warp and class (ballot-compacted).  Units are (col, row) in the
+// ncols x nrows window starting at unit (uc0, ur0) of the plane.
+template <int PASS, int QCAP>
 AV1B_DEV void lf_collect(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc0, int ur0, int ncols,
-    int nrows, int x0, int y0, LfJob* queue, int* count, int tid, int nt)
+    int nrows, int x0, int y0, LfJob (*queue)[QCAP], int* count, int tid, int nt)
 {
     const int sub = plane ? 1 : 0;
     const int ucols = hdr->mi_cols >> sub, urows = hdr->mi_rows >> sub;
     const int total = ncols * nrows;
+    const int lane = tid & 31;
     for (int e0 = 0; e0 < total; e0 += nt) {
         const int e = e0 + tid;
-        LfJob job;
-        bool live = false;
+        LfJob job = 0;
+        int cls = -1;
         if (e < total) {
             const int j = e / ncols, i = e - j * ncols;
             const int uc = uc0 + i, ur = ur0 + j;
-            if (uc >= 0 && ur >= 0 && uc < ucols && ur < urows && lf_test<PASS>(hdr, mis, lf, plane, uc, ur, job)) {
-                live = true;
-                job.pos = (uint16_t)((4 * ur - y0 + LF_HALO) * LF_PITCH + (4 * uc - x0 + LF_HALO));
-            }
+            if (uc >= 0 && ur >= 0 && uc < ucols && ur < urows && lf_test<PASS>(hdr, mis, lf, plane, uc, ur, job, cls))
+                job |= (uint32_t)((4 * ur - y0 + LF_HALO) * LF_PITCH + (4 * uc - x0 + LF_HALO));
+            else cls = -1;
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-        if (!m) continue;
-        const int lane = tid & 31;
-        int base = 0;
-        if (lane == (__ffs(m) - 1)) base = atomicAdd(count, __popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-        if (live) queue[base + __popc(m & ((1u << lane) - 1))] = job;
+        AV1B_UNROLL
+        for (int k = 0; k < 3; k++) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == k);
+            if (!m) continue;
+            int base = 0;
+            if (lane == (__ffs(m) - 1)) base = atomicAdd(count + k, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+            if (cls == k) queue[k][base + __popc(m & ((1u << lane) - 1))] = job;
+        }
     }
 }
 
-// Filter the sample lines of the queued units: a thread per line.  `step` = distance between the
-// samples of a line (1: vertical edge, LF_PITCH: horizontal edge), `next` = distance between the
-// four lines of a unit.
-AV1B_DEV void lf_run(uint8_t* px, const LfJob* queue, int n, int plane, int step, int next, int tid, int nt)
+// Filter the sample lines of the queued units of one size class: a thread per line.  `step` =
+// distance between the samples of a line (1: vertical edge, LF_PITCH: horizontal edge), `next` =
+// distance between the four lines of a unit.
+template <int FS, bool CHROMA> AV1B_DEV void lf_run(uint8_t* px, const LfJob* queue, int n, int step, int next, int tid, int nt)
 {
+    // samples the masks and filters of this size read: 2 / 3 (chroma 6-tap) / 4 / 7 each side
+    const int reach = FS == 4 ? 2 : (FS == 8 ? (CHROMA ? 3 : 4) : 7);
     for (int e = tid; e < 4 * n; e += nt) {
         const LfJob job = queue[e >> 2];
-        uint8_t* q0 = px + job.pos + (e & 3) * next;
-        const int fs = job.filter_size;
-        // samples the masks and filters of this size read: 2 / 3 (chroma 6-tap) / 4 / 7 each side
-        const int reach = fs == 4 ? 2 : (fs == 8 ? (plane ? 3 : 4) : (plane ? 3 : 7));
+        uint8_t* q0 = px + (job & 0x3FFF) + (e & 3) * next;
+        const int limit = (job >> 14) & 63, lvl = (job >> 20) & 63;
         int v[16];
         AV1B_UNROLL
-        for (int k = 1; k < 15; k++) v[k] = (k >= 8 - reach && k < 8 + reach) ? q0[(k - 8) * step] : 0;
-        v[0] = v[15] = 0;
-        const int nmod = lf_line(v, plane, job.limit, job.blimit, job.thresh, fs);
+        for (int k = 0; k < 16; k++) v[k] = (k >= 8 - reach && k < 8 + reach) ? q0[(k - 8) * step] : 0;
+        const int nmod = lf_line(v, CHROMA ? 1 : 0, limit, 2 * (lvl + 2) + limit, lvl >> 4, FS);
         AV1B_UNROLL
-        for (int k = 1; k <= 6; k++) {
+        for (int k = 1; k <= (FS == 4 ? 2 : (FS == 8 ? 3 : 6)); k++) {
             if (k <= nmod) {
                 q0[-k * step] = (uint8_t)v[8 - k];
                 q0[(k - 1) * step] = (uint8_t)v[7 + k];
             }
         }
     }
+}
+
+template <bool CHROMA> AV1B_DEV void lf_run_pass(uint8_t* px, LfJob (*queue)[LF_VCOLS * LF_VROWS], const int* n, int step, int next, int tid, int nt)
+{
+    lf_run<4, CHROMA>(px, queue[0], n[0], step, next, tid, nt);
+    lf_run<8, CHROMA>(px, queue[1], n[1], step, next, tid, nt);
+    if (!CHROMA) lf_run<16, false>(px, queue[2], n[2], step, next, tid, nt);
 }
 
 }  // namespace
@@ -268,14 +273,15 @@ __global__ void __launch_bounds__(LF_THREADS) deblock_kernel(PostCtx c)
     __shared__ LfSmem S;
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
     const Av1bLfMi* mis = (const Av1bLfMi*)(c.cmd + hdr->off_lfmi);
-    const Av1bLoopFilterParams lf = hdr->lf;
     const int plane = blockIdx.z, sub = plane ? 1 : 0;
     const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub; // MI-aligned plane
     const int x0 = blockIdx.x * LF_TW, y0 = blockIdx.y * LF_THGT;
     if (x0 >= pw || y0 >= ph) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     const PlaneView src = c.src.pl[plane], dst = c.deb.pl[plane];
-    if (tid == 0) S.nv = S.nh = 0;
+    for (int k = tid; k < 3; k += nt) S.nv[k] = S.nh[k] = 0;
+    for (int k = tid; k < (int)(sizeof(Av1bLoopFilterParams) / 4); k += nt) ((uint32_t*)&S.lf)[k] = ((const uint32_t*)&hdr->lf)[k];
+    const Av1bLoopFilterParams& lf = S.lf;
     // ---- 1. stage rows y0-8 .. y0+71, columns x0-8 .. x0+135 (rows clamped into the padded plane)
     const int chunks = (LF_TW + 2 * LF_HALO) / 8;
     for (int e = tid; e < LF_ROWS * chunks; e += nt) {
@@ -284,16 +290,22 @@ __global__ void __launch_bounds__(LF_THREADS) deblock_kernel(PostCtx c)
         *(uint2*)(S.px + r * LF_PITCH + 8 * k) = __ldg((const uint2*)(src.p + (ptrdiff_t)y * src.stride + x0 - LF_HALO) + k);
     }
     __syncthreads();
-    const bool filtered = plane == 0 || lf.level[1 + plane];
+    const bool filtered = plane == 0 || hdr->lf.level[1 + plane];
     if (filtered) {
         // ---- 2. collect the live edge units of both passes
-        lf_collect<0>(hdr, mis, lf, plane, x0 / 4, (y0 - LF_HALO) / 4, LF_VCOLS, LF_VROWS, x0, y0, S.vq, &S.nv, tid, nt);
-        lf_collect<1>(hdr, mis, lf, plane, x0 / 4, y0 / 4, LF_HCOLS, LF_HROWS, x0, y0, S.hq, &S.nh, tid, nt);
+        lf_collect<0>(hdr, mis, lf, plane, x0 / 4, (y0 - LF_HALO) / 4, LF_VCOLS, LF_VROWS, x0, y0, S.vq, S.nv, tid, nt);
+        lf_collect<1>(hdr, mis, lf, plane, x0 / 4, y0 / 4, LF_HCOLS, LF_HROWS, x0, y0, S.hq, S.nh, tid, nt);
         __syncthreads();
         // ---- 3. vertical edges, then horizontal edges on the result
-        lf_run(S.px, S.vq, S.nv, plane, 1, LF_PITCH, tid, nt);
-        __syncthreads();
-        lf_run(S.px, S.hq, S.nh, plane, LF_PITCH, 1, tid, nt);
+        if (plane) {
+            lf_run_pass<true>(S.px, S.vq, S.nv, 1, LF_PITCH, tid, nt);
+            __syncthreads();
+            lf_run_pass<true>(S.px, S.hq, S.nh, LF_PITCH, 1, tid, nt);
+        } else {
+            lf_run_pass<false>(S.px, S.vq, S.nv, 1, LF_PITCH, tid, nt);
+            __syncthreads();
+            lf_run_pass<false>(S.px, S.hq, S.nh, LF_PITCH, 1, tid, nt);
+        }
         __syncthreads();
     }
     // ---- 4. write the tile's own samples
