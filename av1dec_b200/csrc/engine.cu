@@ -819,8 +819,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         if (frame_claim(c, lr, lane)) return fail(c, AV1B_ECUDA, "stream wait");
         pc.lr = c->frames[lr].v;
         StageTimer t(c, 5, true, st);
-        launch_lr(pc, h, st);
-        c->launches += 1;
+        c->launches += launch_lr(pc, h, st);
         final_frame = lr;
     }
     if (rt_check()) return fail(c, AV1B_ECUDA, "kernel launch");

@@ -32,7 +32,7 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 
 void launch_deblock(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 void launch_cdef(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
-void launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+int launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st); // returns the number of kernels launched
 // planar 4:2:0 -> NV12 (device to device), visible w x h
 void launch_to_nv12(const FrameView& src, uint8_t* dst_y, int pitch_y, uint8_t* dst_uv, int pitch_uv, int w, int h, av1b_stream_t st);
 

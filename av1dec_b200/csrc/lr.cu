@@ -20,6 +20,8 @@
 #include "dev.h"
 #include "av1_tables.h"
 #include "kernels.h"
+#include <algorithm>
+#include <cstring>
 
 namespace {
 
@@ -263,9 +265,8 @@ template <int TW, int PASS> AV1B_DEV void sgr_out(LrSmem<TW>& S, int h, const Sg
 }
 
 struct LrGrid {
-    int first[3]; // first linear CTA index of each plane (planes outside `mask` own no CTA)
-    int tx[3];    // tiles per row
-    int n;        // total CTAs
+    uint8_t plane_of[3]; // blockIdx.z -> plane
+    uint8_t pad;
 };
 
 }  // namespace
@@ -276,18 +277,16 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
     typedef LrGeom<TW> G;
     __shared__ LrSmem<TW> S;
     const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
-    const Av1bLrParams lp = hdr->lr;
-    const int bid = blockIdx.x;
-    const int plane = bid >= grid.first[2] ? 2 : (bid >= grid.first[1] ? 1 : 0);
+    const Av1bLrParams& lp = hdr->lr;
+    // grid = (tiles per row, tile rows, planes of this launch); everything below is shifts: unit
+    // sizes are powers of two and a stripe holds one (chroma) or two (luma) tile rows
+    const int plane = grid.plane_of[blockIdx.z];
     const int sub = plane ? 1 : 0;
-    const int t = bid - grid.first[plane];
-    const int ty = t / grid.tx[plane], tx = t - ty * grid.tx[plane];
     const int pw = (hdr->frame_w + sub) >> sub, ph = (hdr->frame_h + sub) >> sub;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int x0 = tx * TW;
-    // stripes of 64 luma rows offset by 8; a tile is 32 rows of one stripe
-    const int per_stripe = (64 >> sub) / LR_TH;
-    const int stripe = ty / per_stripe, part = ty - stripe * per_stripe;
+    const int x0 = blockIdx.x * TW;
+    const int ty = blockIdx.y;
+    const int stripe = sub ? ty : ty >> 1, part = sub ? 0 : ty & 1;
     const int start = (-8 + stripe * 64) >> sub, end = start + (64 >> sub);
     const int ya = start + part * LR_TH;
     const int y0 = max(ya, 0), y1 = min(min(ya + LR_TH, end), ph);
@@ -295,14 +294,20 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
     const int w = min((int)TW, pw - x0), h = y1 - y0;
     const PlaneView cdef = c.cdef.pl[plane], deb = c.deb.pl[plane], out = c.lr.pl[plane];
     int type = 0;
-    Av1bLrUnit unit;
+    uint32_t uw0 = 0, uw1 = 0, uw2 = 0; // the unit record as three words (kept in registers)
     if (lp.frame_type[plane]) {
-        const int us = lp.unit_size[plane];
-        const int urow = min((int)lp.unit_rows[plane] - 1, (y0 + (8 >> sub)) / us);
-        const int ucol = min((int)lp.unit_cols[plane] - 1, x0 / us);
-        unit = ((const Av1bLrUnit*)(c.cmd + hdr->off_lru))[lp.unit_first[plane] + urow * lp.unit_cols[plane] + ucol];
-        type = unit.type;
+        const int ush = 31 - __clz((int)lp.unit_size[plane]);
+        const int urow = min((int)lp.unit_rows[plane] - 1, (y0 + (8 >> sub)) >> ush);
+        const int ucol = min((int)lp.unit_cols[plane] - 1, x0 >> ush);
+        const uint32_t* up = (const uint32_t*)((const Av1bLrUnit*)(c.cmd + hdr->off_lru) + lp.unit_first[plane] + urow * lp.unit_cols[plane] + ucol);
+        uw0 = __ldg(up), uw1 = __ldg(up + 1), uw2 = __ldg(up + 2);
+        type = (int)(uw0 & 0xFF);
     }
+    // Av1bLrUnit: type, sgr_set, sgr_xqd[2] | wiener[0][0..2], wiener[1][0] | wiener[1][1..2], pad
+    const int sgr_set = (int)((uw0 >> 8) & 0xFF);
+    const int xqd0 = (int)(int8_t)(uw0 >> 16), xqd1 = (int)(int8_t)(uw0 >> 24);
+    const int wv[3] = { (int)(int8_t)uw1, (int)(int8_t)(uw1 >> 8), (int)(int8_t)(uw1 >> 16) };
+    const int wh[3] = { (int)(int8_t)(uw1 >> 24), (int)(int8_t)uw2, (int)(int8_t)(uw2 >> 8) };
     uint8_t* dst = out.p + (size_t)y0 * out.stride + x0;
     if (type == 0) {
         // RESTORE_NONE: the LR frame is a copy of the CDEF frame.  128-bit copies (rows are 16-byte
@@ -316,12 +321,14 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
         }
         return;
     }
-    // ---- stage source: tile rows -3 .. h+2, columns -8 .. TW+7 as 64-bit chunks
+    // ---- stage source: tile rows -3 .. h+2, columns -8 .. TW+7 as 64-bit chunks.  A group of 16 (8)
+    //      lanes takes one row: the row's source (stripe rule) is resolved once per lane and row
     {
         const bool interior = x0 >= 8 && x0 + TW + 8 <= pw;
-        const int nch = G::SP / 8;
-        for (int e = tid; e < (h + 6) * nch; e += nt) {
-            const int r = e / nch, k = e - r * nch;
+        const int nch = G::SP / 8, lpr = TW == 64 ? 16 : 8; // chunks per row, lanes per row
+        for (int e = tid; e < (h + 6) * lpr; e += nt) {
+            const int r = e / lpr, k = e & (lpr - 1);
+            if (k >= nch) continue;
             bool fd;
             const int sy = lr_source_row(y0 - 3 + r, start, end, ph, &fd);
             const uint8_t* rowp = (fd ? deb.p : cdef.p) + (size_t)sy * (fd ? deb.stride : cdef.stride);
@@ -345,15 +352,8 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
     }
     __syncthreads();
     if (type == 1) {
-        int vf[4], hf[4];
-        vf[3] = 128;
-        hf[3] = 128;
-        for (int k = 0; k < 3; k++) {
-            vf[k] = unit.wiener[0][k];
-            hf[k] = unit.wiener[1][k];
-            vf[3] -= 2 * unit.wiener[0][k];
-            hf[3] -= 2 * unit.wiener[1][k];
-        }
+        const int vf[4] = { wv[0], wv[1], wv[2], 128 - 2 * (wv[0] + wv[1] + wv[2]) };
+        const int hf[4] = { wh[0], wh[1], wh[2], 128 - 2 * (wh[0] + wh[1] + wh[2]) };
         // horizontal: s = sum hf[t] * x[c - 3 + t]; the centre tap (0..218) is split in two so that
         // both 4-tap groups fit signed bytes: (h0,h1,h2,c3a) . x[c-3..c] + (c3b,h2,h1,h0) . x[c..c+3]
         const int c3a = hf[3] >> 1, c3b = hf[3] - c3a;
@@ -401,11 +401,11 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
             }
         }
     } else {
-        const int set = unit.sgr_set;
+        const int set = sgr_set;
         const int r0 = k_sgr_params[set][0], r1 = k_sgr_params[set][2];
         SgrOut o;
-        o.w0 = unit.sgr_xqd[0];
-        o.w1 = unit.sgr_xqd[1];
+        o.w0 = xqd0;
+        o.w1 = xqd1;
         o.w2 = 128 - o.w0 - o.w1;
         o.dst = dst;
         o.stride = out.stride;
@@ -433,26 +433,29 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
 
 // Planes whose restoration units are at least 64 samples wide use 64-wide tiles, the others
 // (chroma of a 64-unit luma with lr_uv_shift) 32-wide ones: at most two launches.
-void launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
+int launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
-    if (!h.lr.uses_lr) return;
+    if (!h.lr.uses_lr) return 0;
+    int launches = 0;
     for (int cls = 0; cls < 2; cls++) {
         const int tw = cls == 0 ? 64 : 32;
         LrGrid g;
-        g.n = 0;
+        memset(&g, 0, sizeof(g));
+        int np = 0, gx = 0, gy = 0;
         for (int p = 0; p < 3; p++) {
             const int sub = p ? 1 : 0;
             const int pw = (h.frame_w + sub) >> sub, ph = (h.frame_h + sub) >> sub;
             const bool narrow = h.lr.frame_type[p] && h.lr.unit_size[p] < 64;
-            g.first[p] = g.n;
-            g.tx[p] = (pw + tw - 1) / tw;
             if (narrow != (cls == 1)) continue;
+            g.plane_of[np++] = (uint8_t)p;
             const int stripes = (ph + (8 >> sub) + (64 >> sub) - 1) / (64 >> sub);
-            g.n += g.tx[p] * stripes * ((64 >> sub) / LR_TH);
+            gx = std::max(gx, (pw + tw - 1) / tw);
+            gy = std::max(gy, stripes * ((64 >> sub) / LR_TH));
         }
-        if (!g.n) continue;
-        // a plane that owns no CTA of this launch gets first[] == the next plane's first: never selected
-        if (cls == 0) AV1B_LAUNCH(lr_kernel<64>, (g.n), (LR_THREADS), st, c, g);
-        else AV1B_LAUNCH(lr_kernel<32>, (g.n), (LR_THREADS), st, c, g);
+        if (!np) continue;
+        if (cls == 0) AV1B_LAUNCH(lr_kernel<64>, (gx, gy, np), (LR_THREADS), st, c, g);
+        else AV1B_LAUNCH(lr_kernel<32>, (gx, gy, np), (LR_THREADS), st, c, g);
+        launches++;
     }
+    return launches;
 }
