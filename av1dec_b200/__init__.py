@@ -35,7 +35,7 @@ ENGINE_SYMBOLS = [
     "av1b_dev_download", "av1b_frame_device_view", "av1b_frame_retain", "av1b_frame_release", "av1b_frame_to_nv12", "av1b_sync", "av1b_fence_record", "av1b_fence_wait", "av1b_fence_done", "av1b_pool_purge", "av1b_host_alloc", "av1b_host_free",
     "av1b_dev_alloc", "av1b_dev_free", "av1b_dev_upload", "av1b_debug_set_input", "av1b_debug_set_ref",
     "av1b_debug_get_residual", "av1b_debug_counters", "av1b_join", "av1b_set_lanes", "av1b_set_capture", "av1b_launch_count", "av1b_set_profiling", "av1b_get_stage_times",
-    "av1b_debug_input_from_slot", "av1b_struct_size",
+    "av1b_debug_input_from_slot", "av1b_struct_size", "av1b_debug_wave_trace", "av1b_debug_wave_trace_read",
 ]
 STAGE_NAMES = ["itx", "inter", "wave", "deblock", "cdef", "lr"]
 DECODER_SYMBOLS = [

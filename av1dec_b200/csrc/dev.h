@@ -51,6 +51,9 @@ static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
 static inline int av1b_ld_acquire(const int* p) { return *p; }
 static inline void av1b_st_release(int* p, int v) { *p = v; }
 static inline void av1b_nanosleep(unsigned) {}
+static inline int av1b_ld_relaxed(const int* p) { return *p; }
+static inline unsigned long long av1b_gtime() { return 0; }
+static inline unsigned av1b_smid() { return 0; }
 using std::max;
 using std::min;
 // single-lane "warp": shuffles and votes see only lane 0
@@ -170,6 +173,25 @@ static __device__ __forceinline__ void av1b_st_release(int* p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 static __device__ __forceinline__ void av1b_nanosleep(unsigned ns) { __nanosleep(ns); }
+// polling load: served by L2 every time, no L1 invalidation (the acquire follows once the value is there)
+static __device__ __forceinline__ int av1b_ld_relaxed(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+static __device__ __forceinline__ unsigned long long av1b_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ __forceinline__ unsigned av1b_smid()
+{
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
 #endif
 
 // ------------------------------------------------------------------ shared helpers

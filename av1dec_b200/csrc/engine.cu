@@ -19,6 +19,8 @@
 #include <vector>
 
 // allocation counters (av1b_debug_counters): a steady-state decode service should stop moving them
+static unsigned long long* g_wave_trace = nullptr; // av1b_debug_wave_trace
+static size_t g_wave_trace_cap = 0;
 static std::atomic<uint64_t> g_n_ctx_new{ 0 }, g_n_ctx_reused{ 0 }, g_n_dev_alloc{ 0 }, g_n_pinned_alloc{ 0 };
 
 // ------------------------------------------------------------------------------------------
@@ -54,6 +56,8 @@ static int rt_check() { return 0; }
 static int rt_tevent_create(rt_event_t* e) { *e = 0; return 0; }
 static float rt_event_ms(rt_event_t, rt_event_t) { return 0.f; }
 static int rt_d2d(void* d, const void* s, size_t n, av1b_stream_t) { memcpy(d, s, n); return 0; }
+static int rt_device_sync() { return 0; }
+static int rt_d2h_sync(void* d, const void* s, size_t n) { memcpy(d, s, n); return 0; }
 const char* av1b_backend(void) { return "emu"; }
 #else
 typedef cudaEvent_t rt_event_t;
@@ -91,6 +95,8 @@ static float rt_event_ms(rt_event_t a, rt_event_t b)
     return ms;
 }
 static int rt_d2d(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess; }
+static int rt_device_sync() { return cudaDeviceSynchronize() != cudaSuccess; }
+static int rt_d2h_sync(void* d, const void* s, size_t n) { return cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost) != cudaSuccess; }
 const char* av1b_backend(void) { return "cuda-sm_100a"; }
 #endif
 
@@ -766,6 +772,8 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     }
     rc.wedge = c->wedge;
     rc.sync = L.sync;
+    rc.trace = g_wave_trace;
+    rc.trace_cap = (unsigned)g_wave_trace_cap;
     if (stages & AV1B_STAGE_ITX) {
         StageTimer t(c, 0, h.n_itx != 0, st);
         launch_itx(rc, h, st);
@@ -1145,6 +1153,29 @@ int av1b_debug_get_residual(av1b_ctx* c, int16_t* dst, size_t n)
 }
 
 uint64_t av1b_launch_count(av1b_ctx* c) { return c ? c->launches : 0; }
+
+int av1b_debug_wave_trace(size_t n)
+{
+    if (g_wave_trace) {
+        rt_device_sync();
+        rt_free(g_wave_trace);
+        g_wave_trace = nullptr;
+        g_wave_trace_cap = 0;
+    }
+    if (!n) return AV1B_OK;
+    void* p = nullptr;
+    if (rt_malloc(&p, n * 64)) return AV1B_ENOMEM;
+    g_wave_trace = (unsigned long long*)p;
+    g_wave_trace_cap = n;
+    return AV1B_OK;
+}
+
+int av1b_debug_wave_trace_read(uint64_t* out, size_t n)
+{
+    if (!g_wave_trace || n > g_wave_trace_cap) return AV1B_EINVAL;
+    rt_device_sync();
+    return rt_d2h_sync(out, g_wave_trace, n * 64) ? AV1B_ECUDA : AV1B_OK;
+}
 
 void av1b_debug_counters(uint64_t out[4])
 {

@@ -1,10 +1,19 @@
-// intra.cuh -- AV1 intra prediction for one transform block, executed by one CTA.
+// intra.cuh -- AV1 intra prediction for one transform block, executed by one group of lanes (a
+// warp in the superblock wavefront, a CTA on the global-memory path).
 //
-// Restates decoder/IntraPredict.cpp of the reference (edge assembly :563-611, DC :485,
-// Paeth :151, smooth :526-561, directional with edge filter / upsample :269-469,
-// recursive filter-intra :112-149, chroma-from-luma :632-667) with the CTA's threads
-// striding over samples.  The prediction lands in shared memory (`pred`, pitch = w) so the
-// caller can add the residual / blend and store once.
+// Behaviour restated from decoder/IntraPredict.cpp of the reference (edge assembly :563-611,
+// DC :485, Paeth :151, smooth :526-561, directional with edge filter / upsample :269-469,
+// recursive filter-intra :112-149, chroma-from-luma :632-667).
+//
+// Shape of the computation (what makes the dependent pass fast is the LENGTH of this chain):
+//   phase 1  both edges are assembled word-wise into the group's scratch (aligned 32-bit loads of
+//            the row above, four gathered bytes per word of the left column);
+//   phase 2  directional modes only: corner filter + 5-tap edge filter in ONE step, written to a
+//            second pair of arrays (no staging copy), every tap read straight from phase 1;
+//   phase 3  only where the spec upsamples an edge: second pair -> first pair;
+//   phase 4  the prediction, FOUR horizontally adjacent samples per work item, with the residual
+//            add, the CfL term and the clip fused, one aligned 32-bit store per item.
+// DC / smooth / Paeth / V / H blocks run phases 1 and 4 only.
 //
 // Reference quirks that are reproduced on purpose:
 //   * directional numPx uses maxX WITHOUT the -1 (IntraPredict.cpp:385,401)
@@ -15,35 +24,69 @@
 
 namespace intra {
 
-enum { EDGE_OFF = 32, EDGE_LEN = 320 };
+enum { EDGE_OFF = 32, EDGE_LEN = 192 };
 
 struct Scratch {
-    uint8_t above[EDGE_LEN]; // AboveRow[i] at above[EDGE_OFF + i]
-    uint8_t left[EDGE_LEN];
-    uint8_t tmp[EDGE_LEN];   // filter / upsample staging
-    uint8_t pred[32 * 32];   // inter-intra only: the intra half of the blend (<= 32x32)
-    int acc;                 // CfL sum
+    // edge[0] above / edge[1] left as assembled (AboveRow[i] at edge[0][EDGE_OFF + i]);
+    // edge[2] / edge[3] the same after the edge filter
+    alignas(16) uint8_t edge[4][EDGE_LEN];
+    alignas(16) uint8_t pred[32 * 32]; // inter-intra only: the intra half of the blend (<= 32x32)
+    int acc;                           // CfL sum (groups larger than a warp)
 };
 
 struct Args {
-    const uint8_t* plane; // current-frame plane, sample (0,0)
-    int stride;
-    int x, y, log2w, log2h;
-    int max_x, max_y; // ((MiCols*4)>>subX)-1, ((MiRows*4)>>subY)-1
+    int x, y, log2w, log2h; // block position / size in plane samples
+    int max_x, max_y;       // ((MiCols*4)>>subX)-1, ((MiRows*4)>>subY)-1
     int plane_idx;
-    int mode;         // PREDICTION_MODE (0..12)
+    int mode;               // PREDICTION_MODE (0..12)
     int angle_delta;
     bool have_left, have_above, have_above_right, have_below_left;
     bool edge_filter_enabled; // sequence enable_intra_edge_filter
     bool edge_smooth;         // get_filter_type()
     bool filter_intra;
     int fi_mode;
+    bool cfl;                 // chroma-from-luma on top of the DC prediction
+    int cfl_alpha;
+    int max_luma_w, max_luma_h;
 };
 
-// The plane pointer may address the superblock tile in shared memory (wave_kernel) or the frame
-// in global memory (legacy path for intrabc frames): a volatile generic load is correct for both
-// (it is never served from a stale L1 line).
-AV1B_DEV int px(const Args& a, int x, int y) { return *(const volatile uint8_t*)(a.plane + (ptrdiff_t)y * a.stride + x); }
+enum { K_DC = 0, K_V, K_H, K_PAETH, K_SMOOTH, K_SMOOTH_V, K_SMOOTH_H, K_DIR_LT90, K_DIR_MID, K_DIR_GT180, K_FILTER_INTRA };
+
+// Everything about one block's prediction that does NOT depend on sample values: derived once,
+// off the dependency chain (the wavefront decodes a superblock's ops lane-parallel while it still
+// waits for its neighbours and keeps them bit-packed in shared memory), so that the chain itself
+// is only loads, arithmetic and stores.
+struct Prep {
+    int lw, lh;
+    bool have_left, have_above;
+    int above_n, left_n; // samples of the row above from x / of the left column from y that exist (then replicate)
+    int kind;            // K_*
+    // directional
+    int dx, dy, up_above, up_left;
+    bool filt, corner;   // phase 2 needed; the corner sample is filtered too
+    int sA, sL, szA, szL;
+    int fi_mode;
+    bool cfl;
+    int alpha, lim_w, lim_h; // CfL: luma clamp limits relative to the block's luma origin
+};
+
+// Where the block lives.
+struct Io {
+    const uint8_t* blk;   // block origin in the plane (edges: blk - stride, blk - 1)
+    int stride;
+    uint8_t* P;           // where the prediction goes (== blk for in-place), rows 4-byte aligned
+    int pp;
+    const int16_t* res;   // residual of this block (sample (0,0) of the block) added on the way, or null
+    int rpitch;
+    const uint8_t* luma;  // CfL: luma sample under the block origin
+    int luma_stride;
+};
+
+// Plane samples live in the superblock tile in shared memory (SMEM) or in the frame in global
+// memory (frames with intrabc): there they were written by other CTAs moments ago, so the loads
+// bypass L1.
+template <bool SMEM> AV1B_DEV int ld8(const uint8_t* p) { return SMEM ? (int)*p : (int)__ldcg(p); }
+template <bool SMEM> AV1B_DEV uint32_t ld32(const uint8_t* p) { return SMEM ? *(const uint32_t*)p : __ldcg((const uint32_t*)p); }
 
 AV1B_DEV int edge_filter_strength(int w, int h, bool smooth, int delta)
 {
@@ -82,122 +125,196 @@ AV1B_DEV unsigned warp_sum(unsigned v, int nt)
 #endif
 }
 
-// In-place 5-tap smoothing of edge[-1 .. sz-2] -> edge[0 .. sz-2] (reference intraEdgeFilter), for
-// the above edge (A, szA, strength sA) and the left edge (L, szL, sL) in one pass over both: they
-// are independent, and a pass costs a staging copy and two group barriers whatever its length.
-// A strength of 0 skips that edge.  tmp: EDGE_LEN bytes, the left edge uses its second half.
-template <int NTC>
-AV1B_DEV void filter_edges(uint8_t* A, int szA, int sA, uint8_t* L, int szL, int sL, uint8_t* tmp, int tid, int nt_rt)
+// Four predicted samples (packed, sample j in byte j) of row i, columns 4q .. 4q+3: residual add
+// and clip fused, one aligned 32-bit store.
+AV1B_DEV void put4(const Io& o, int i, int q, uint32_t v)
 {
-    const int nt = NTC ? NTC : nt_rt;
-    if (!sA) szA = 0;
-    if (!sL) szL = 0;
-    if (!(szA | szL)) return;
-    uint8_t* const tA = tmp;
-    uint8_t* const tL = tmp + EDGE_LEN / 2;
-    AV1B_NOUNROLL
-    for (int k = tid; k < szA + szL; k += nt) {
-        if (k < szA) tA[k] = A[k - 1];
-        else tL[k - szA] = L[k - szA - 1];
-    }
-    block_sync(nt);
-    AV1B_NOUNROLL
-    for (int k = tid; k < szA + szL; k += nt) {
-        const bool above = k < szA;
-        const int i = above ? k : k - szA, sz = above ? szA : szL;
-        if (i < 1) continue;
-        const uint8_t* t = above ? tA : tL;
-        const uint8_t* kern = k_intra_edge_kernel[(above ? sA : sL) - 1];
-        int s = 0;
-        AV1B_UNROLL
-        for (int j = 0; j < 5; j++) s += kern[j] * t[clip3(0, sz - 1, i - 2 + j)];
-        (above ? A : L)[i - 1] = (uint8_t)((s + 8) >> 4);
-    }
-    block_sync(nt);
+    if (o.res) v = add_res4(v, *(const uint2*)(o.res + i * o.rpitch + 4 * q));
+    *(uint32_t*)(o.P + i * o.pp + 4 * q) = v;
 }
 
-// 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference intraEdgeUpsample), above edge
-// (nA samples) and left edge (nL samples) in one pass; n = 0 skips that edge.
-template <int NTC>
-AV1B_DEV void upsample_edges(uint8_t* A, int nA, uint8_t* L, int nL, uint8_t* tmp, int tid, int nt_rt)
+AV1B_DEV uint32_t pack4(int v0, int v1, int v2, int v3) { return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24); }
+
+// Sub-sampled luma under four chroma samples (row i, columns j0 .. j0+3 of the block), each the
+// sum of a 2x2 luma quad times two (IntraPredict.cpp:640-650), as two packed 16x2 words.
+template <bool SMEM> AV1B_DEV uint2 cfl_luma4(const Prep& p, const Io& o, int i, int j0)
 {
-    const int nt = NTC ? NTC : nt_rt;
-    if (!(nA | nL)) return;
-    uint8_t* const tA = tmp;
-    uint8_t* const tL = tmp + EDGE_LEN / 2;
-    const int cA = nA ? nA + 3 : 0, cL = nL ? nL + 3 : 0;
-    // t[k] = dup[k] = edge[clip(-1, n-1, k-2)], k = 0 .. n+2
-    AV1B_NOUNROLL
-    for (int k = tid; k < cA + cL; k += nt) {
-        if (k < cA) tA[k] = A[clip3(-1, nA - 1, k - 2)];
-        else tL[k - cA] = L[clip3(-1, nL - 1, k - cA - 2)];
+    const int ly = min(2 * i, p.lim_h);
+    const int lx0 = 2 * j0;
+    const uint8_t* q = o.luma + (ptrdiff_t)ly * o.luma_stride;
+    if (lx0 + 6 <= p.lim_w) {
+        const uint32_t a0 = ld32<SMEM>(q + lx0), a1 = ld32<SMEM>(q + lx0 + 4);
+        const uint32_t b0 = ld32<SMEM>(q + o.luma_stride + lx0), b1 = ld32<SMEM>(q + o.luma_stride + lx0 + 4);
+        // bytes (0,1) and (2,3) of a word are the quads of two adjacent chroma samples
+        const uint32_t s0 = (a0 & 0x00FF00FFu) + ((a0 >> 8) & 0x00FF00FFu) + (b0 & 0x00FF00FFu) + ((b0 >> 8) & 0x00FF00FFu);
+        const uint32_t s1 = (a1 & 0x00FF00FFu) + ((a1 >> 8) & 0x00FF00FFu) + (b1 & 0x00FF00FFu) + ((b1 >> 8) & 0x00FF00FFu);
+        return make_uint2(s0 << 1, s1 << 1);
     }
-    block_sync(nt);
-    if (tid == 0) {
-        if (nA) A[-2] = tA[0];
-        if (nL) L[-2] = tL[0];
+    uint32_t v[4];
+    AV1B_UNROLL
+    for (int m = 0; m < 4; m++) {
+        const int lx = min(lx0 + 2 * m, p.lim_w);
+        v[m] = (uint32_t)(ld8<SMEM>(q + lx) + ld8<SMEM>(q + lx + 1) + ld8<SMEM>(q + o.luma_stride + lx) + ld8<SMEM>(q + o.luma_stride + lx + 1)) << 1;
     }
-    AV1B_NOUNROLL
-    for (int k = tid; k < nA + nL; k += nt) {
-        const bool above = k < nA;
-        const int i = above ? k : k - nA;
-        const uint8_t* t = above ? tA : tL;
-        uint8_t* edge = above ? A : L;
-        const int s = -t[i] + 9 * t[i + 1] + 9 * t[i + 2] - t[i + 3];
-        edge[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
-        edge[2 * i] = t[i + 2];
-    }
-    block_sync(nt);
+    return make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
 }
 
-// Predict one block into P (row pitch pp).  P may be the block's own position in the plane: the
-// edges are copied out first and nothing else of the plane is read afterwards.  All threads of
-// the group must call it.
-// NTC: the group size when it is a compile-time constant (32 = one warp per op), 0 = use nt_rt.
-template <int NTC>
-AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, int nt_rt)
+// The sample-independent part (IntraPredict.cpp:379-411 for the directional set-up).
+AV1B_DEV Prep prepare(const Args& a)
 {
-    const int nt = NTC ? NTC : nt_rt;
+    Prep p;
     const int w = 1 << a.log2w, h = 1 << a.log2h;
-    uint8_t* A = S.above + EDGE_OFF;
-    uint8_t* L = S.left + EDGE_OFF;
-    const int x = a.x, y = a.y;
-    // ---- edge assembly (IntraPredict.cpp:579-611)
-    {
-        const bool hl = a.have_left, ha = a.have_above;
-        int above_const = -1, left_const = -1;
-        if (!ha && hl) above_const = px(a, x - 1, y);
-        else if (!ha && !hl) above_const = 127;
-        if (!hl && ha) left_const = px(a, x, y - 1);
-        else if (!ha && !hl) left_const = 129;
-        const int above_limit = min(a.max_x, x + (a.have_above_right ? 2 * w : w) - 1);
-        const int left_limit = min(a.max_y, y + (a.have_below_left ? 2 * h : h) - 1);
-        AV1B_NOUNROLL
-        for (int i = tid; i < w + h; i += nt) {
-            A[i] = (uint8_t)(above_const >= 0 ? above_const : px(a, min(above_limit, x + i), y - 1));
-            L[i] = (uint8_t)(left_const >= 0 ? left_const : px(a, x - 1, min(left_limit, y + i)));
+    p.lw = a.log2w, p.lh = a.log2h;
+    p.have_left = a.have_left, p.have_above = a.have_above;
+    p.above_n = min(w + h, min(a.max_x, a.x + (a.have_above_right ? 2 * w : w) - 1) - a.x + 1);
+    p.left_n = min(w + h, min(a.max_y, a.y + (a.have_below_left ? 2 * h : h) - 1) - a.y + 1);
+    p.dx = p.dy = p.up_above = p.up_left = 0;
+    p.filt = p.corner = false;
+    p.sA = p.sL = p.szA = p.szL = 0;
+    p.fi_mode = a.fi_mode;
+    p.cfl = a.cfl;
+    p.alpha = a.cfl_alpha;
+    p.lim_w = min(255, max(0, a.max_luma_w - 2 - 2 * a.x));
+    p.lim_h = min(255, max(0, a.max_luma_h - 2 - 2 * a.y));
+    const int mode = a.mode;
+    if (a.plane_idx == 0 && a.filter_intra) p.kind = K_FILTER_INTRA;
+    else if (mode >= 1 && mode <= 8) {
+        const int p_angle = k_mode_to_angle[mode] + a.angle_delta * 3;
+        if (p_angle == 90) p.kind = K_V;
+        else if (p_angle == 180) p.kind = K_H;
+        else {
+            if (a.edge_filter_enabled) {
+                p.corner = p_angle > 90 && p_angle < 180 && (w + h) >= 24;
+                const int maxx_q = a.max_x + 1, maxy_q = a.max_y + 1; // quirk: no -1
+                if (a.have_above) {
+                    p.sA = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
+                    p.szA = min(w, maxx_q - a.x + 1) + (p_angle < 90 ? h : 0) + 1;
+                }
+                if (a.have_left) {
+                    p.sL = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
+                    p.szL = min(h, maxy_q - a.y + 1) + (p_angle > 180 ? w : 0) + 1;
+                }
+                p.up_above = edge_upsample(w, h, a.edge_smooth, p_angle - 90);
+                p.up_left = edge_upsample(w, h, a.edge_smooth, p_angle - 180);
+                p.filt = p.corner || p.sA || p.sL || p.up_above || p.up_left;
+            }
+            if (p_angle < 90) {
+                p.kind = K_DIR_LT90;
+                p.dx = k_dr_intra_derivative[p_angle];
+            } else if (p_angle < 180) {
+                p.kind = K_DIR_MID;
+                p.dx = k_dr_intra_derivative[180 - p_angle];
+                p.dy = k_dr_intra_derivative[p_angle - 90];
+            } else {
+                p.kind = K_DIR_GT180;
+                p.dy = k_dr_intra_derivative[270 - p_angle];
+            }
         }
-        if (tid == 0) {
-            int c;
-            if (ha && hl) c = px(a, x - 1, y - 1);
-            else if (ha) c = px(a, x, y - 1);
-            else if (hl) c = px(a, x - 1, y);
-            else c = 128;
-            A[-1] = (uint8_t)c;
-            L[-1] = (uint8_t)c;
+    } else p.kind = mode == 0 ? K_DC : (mode == 12 ? K_PAETH : (mode == 9 ? K_SMOOTH : (mode == 10 ? K_SMOOTH_V : K_SMOOTH_H)));
+    return p;
+}
+
+// Bit-packed Prep: seven words (w[1] only in its high half).
+struct Packed {
+    uint32_t w[5];
+};
+AV1B_DEV Packed pack(const Prep& p)
+{
+    Packed k;
+    k.w[0] = (uint32_t)p.lw | ((uint32_t)p.lh << 3) | ((uint32_t)p.have_left << 6) | ((uint32_t)p.have_above << 7) | ((uint32_t)p.kind << 8)
+        | ((uint32_t)p.cfl << 12) | ((uint32_t)p.up_above << 13) | ((uint32_t)p.up_left << 14) | ((uint32_t)p.corner << 15) | ((uint32_t)p.filt << 16)
+        | ((uint32_t)p.fi_mode << 17) | ((uint32_t)p.sA << 20) | ((uint32_t)p.sL << 22) | ((uint32_t)p.above_n << 24);
+    k.w[1] = (uint32_t)p.left_n | ((uint32_t)p.szA << 8) | ((uint32_t)p.szL << 16) | ((uint32_t)(p.alpha & 0xFF) << 24);
+    k.w[2] = (uint32_t)p.dx | ((uint32_t)p.dy << 11);
+    k.w[3] = (uint32_t)p.lim_w | ((uint32_t)p.lim_h << 8);
+    k.w[4] = 0;
+    return k;
+}
+AV1B_DEV Prep unpack(const Packed& k)
+{
+    Prep p;
+    p.lw = (int)(k.w[0] & 7), p.lh = (int)((k.w[0] >> 3) & 7);
+    p.have_left = (k.w[0] >> 6) & 1, p.have_above = (k.w[0] >> 7) & 1;
+    p.kind = (int)((k.w[0] >> 8) & 15);
+    p.cfl = (k.w[0] >> 12) & 1;
+    p.up_above = (int)((k.w[0] >> 13) & 1), p.up_left = (int)((k.w[0] >> 14) & 1);
+    p.corner = (k.w[0] >> 15) & 1, p.filt = (k.w[0] >> 16) & 1;
+    p.fi_mode = (int)((k.w[0] >> 17) & 7);
+    p.sA = (int)((k.w[0] >> 20) & 3), p.sL = (int)((k.w[0] >> 22) & 3);
+    p.above_n = (int)(k.w[0] >> 24);
+    p.left_n = (int)(k.w[1] & 0xFF), p.szA = (int)((k.w[1] >> 8) & 0xFF), p.szL = (int)((k.w[1] >> 16) & 0xFF);
+    p.alpha = (int)(int8_t)(k.w[1] >> 24);
+    p.dx = (int)(k.w[2] & 0x7FF), p.dy = (int)((k.w[2] >> 11) & 0x7FF);
+    p.lim_w = (int)(k.w[3] & 0xFF), p.lim_h = (int)((k.w[3] >> 8) & 0xFF);
+    return p;
+}
+
+// Predict one block into o.P (rows 4-byte aligned) and add the residual / CfL term on the way.
+// o.P may be the block's own position in the plane: the edges are copied out first and nothing
+// else of the plane is read afterwards (CfL reads the LUMA plane).  All threads of the group must
+// call it.
+// NTC: the group size when it is a compile-time constant (32 = one warp per op), 0 = use nt_rt.
+template <bool SMEM, int NTC>
+AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
+{
+    const int nt = NTC ? NTC : nt_rt;
+    const int lw = p.lw, lh = p.lh;
+    const int w = 1 << lw, h = 1 << lh;
+    const int lq = lw - 2, nq = w >> 2;  // groups of four columns
+    const int items = h << lq;
+    uint8_t* const A = S.edge[0] + EDGE_OFF;
+    uint8_t* const L = S.edge[1] + EDGE_OFF;
+    uint8_t* const P = o.P;
+    const int pp = o.pp;
+    // ---- phase 1: edge assembly (IntraPredict.cpp:579-611)
+    {
+        const bool hl = p.have_left, ha = p.have_above;
+        const uint8_t* const row_above = o.blk - o.stride;
+        const uint8_t* const col_left = o.blk - 1;
+        const int an = p.above_n, ln = p.left_n;
+        const int nw4 = (w + h) >> 2;
+        AV1B_NOUNROLL
+        for (int e = tid; e <= 2 * nw4; e += nt) {
+            if (e < nw4) {
+                const int xi = 4 * e;
+                uint32_t v;
+                if (!ha) v = hl ? (uint32_t)ld8<SMEM>(col_left) * 0x01010101u : 0x7F7F7F7Fu;
+                else if (xi + 3 < an) v = ld32<SMEM>(row_above + xi);
+                else
+                    v = pack4(ld8<SMEM>(row_above + min(an - 1, xi)), ld8<SMEM>(row_above + min(an - 1, xi + 1)),
+                        ld8<SMEM>(row_above + min(an - 1, xi + 2)), ld8<SMEM>(row_above + min(an - 1, xi + 3)));
+                *(uint32_t*)(A + xi) = v;
+            } else if (e < 2 * nw4) {
+                const int yi = 4 * (e - nw4);
+                uint32_t v;
+                if (!hl) v = ha ? (uint32_t)ld8<SMEM>(row_above) * 0x01010101u : 0x81818181u;
+                else
+                    v = pack4(ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi) * o.stride), ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 1) * o.stride),
+                        ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 2) * o.stride), ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 3) * o.stride));
+                *(uint32_t*)(L + yi) = v;
+            } else {
+                int c;
+                if (ha && hl) c = ld8<SMEM>(row_above - 1);
+                else if (ha) c = ld8<SMEM>(row_above);
+                else if (hl) c = ld8<SMEM>(col_left);
+                else c = 128;
+                A[-1] = (uint8_t)c;
+                L[-1] = (uint8_t)c;
+            }
         }
         block_sync(nt);
     }
-    const int lw = a.log2w;
-    if (a.plane_idx == 0 && a.filter_intra) {
-        // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront
+    const int kind = p.kind;
+    if (kind == K_FILTER_INTRA) {
+        // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront.  The recursion
+        // feeds on PREDICTED samples, so the residual is added in a pass of its own afterwards.
         const int w4 = w >> 2, h2 = h >> 1;
         // a lane keeps the same position inside the 4x2 sub-block on every step when the group
         // size is a multiple of 8: its seven taps are loaded once, not on every diagonal
         const bool fixed_k = (nt & 7) == 0;
         int taps[7];
         AV1B_UNROLL
-        for (int i = 0; i < 7; i++) taps[i] = k_intra_filter_taps[a.fi_mode][tid & 7][i];
+        for (int i = 0; i < 7; i++) taps[i] = k_intra_filter_taps[p.fi_mode][tid & 7][i];
         for (int d = 0; d < w4 + h2 - 1; d++) {
             int j_lo = max(0, d - (h2 - 1)), j_hi = min(w4 - 1, d);
             int nsb = j_hi - j_lo + 1;
@@ -205,125 +322,190 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
             for (int e = tid; e < nsb * 8; e += nt) {
                 int j4 = j_lo + (e >> 3), i2 = d - j4, k = e & 7;
                 int i1 = k >> 2, j1 = k & 3;
-                int p[7];
+                int px[7];
                 AV1B_UNROLL
                 for (int i = 0; i < 5; i++) {
-                    if (!i2) p[i] = A[(j4 << 2) + i - 1];
-                    else if (!j4 && !i) p[i] = L[(i2 << 1) - 1];
-                    else p[i] = P[((i2 << 1) - 1) * pp + (j4 << 2) + i - 1];
+                    if (!i2) px[i] = A[(j4 << 2) + i - 1];
+                    else if (!j4 && !i) px[i] = L[(i2 << 1) - 1];
+                    else px[i] = P[((i2 << 1) - 1) * pp + (j4 << 2) + i - 1];
                 }
                 AV1B_UNROLL
                 for (int i = 5; i < 7; i++) {
-                    if (!j4) p[i] = L[(i2 << 1) + i - 5];
-                    else p[i] = P[((i2 << 1) + i - 5) * pp + (j4 << 2) - 1];
+                    if (!j4) px[i] = L[(i2 << 1) + i - 5];
+                    else px[i] = P[((i2 << 1) + i - 5) * pp + (j4 << 2) - 1];
                 }
                 int pr = 0;
                 AV1B_UNROLL
-                for (int i = 0; i < 7; i++) pr += (fixed_k ? taps[i] : (int)k_intra_filter_taps[a.fi_mode][k][i]) * p[i];
+                for (int i = 0; i < 7; i++) pr += (fixed_k ? taps[i] : (int)k_intra_filter_taps[p.fi_mode][k][i]) * px[i];
                 P[((i2 << 1) + i1) * pp + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
+            }
+            block_sync(nt);
+        }
+        if (o.res) {
+            AV1B_NOUNROLL
+            for (int e = tid; e < items; e += nt) {
+                const int i = e >> lq, q = e & (nq - 1);
+                put4(o, i, q, *(const uint32_t*)(P + i * pp + 4 * q));
             }
             block_sync(nt);
         }
         return;
     }
-    const int mode = a.mode;
-    if (mode >= 1 && mode <= 8) {
+    if (kind >= K_DIR_LT90 && kind <= K_DIR_GT180) {
         // ---- directional (IntraPredict.cpp:379-469)
-        const int p_angle = k_mode_to_angle[mode] + a.angle_delta * 3;
-        int up_above = 0, up_left = 0;
-        if (a.edge_filter_enabled && p_angle != 90 && p_angle != 180) {
-            if (p_angle > 90 && p_angle < 180 && (w + h) >= 24) {
-                if (tid == 0) {
-                    int s = (L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4;
-                    L[-1] = (uint8_t)s;
-                    A[-1] = (uint8_t)s;
+        const int up_above = p.up_above, up_left = p.up_left;
+        const uint8_t* EA = A;
+        const uint8_t* EL = L;
+        if (p.filt) {
+            uint8_t* const A2 = S.edge[2] + EDGE_OFF;
+            uint8_t* const L2 = S.edge[3] + EDGE_OFF;
+            // phase 2: new[m] = sum_j kern[j] * old[clip(-1, sz-2, m-2+j)] for m = 0 .. sz-2 (the
+            // reference filters a copy that starts at the corner), old[-1] being the FILTERED
+            // corner where the spec filters it; other entries are carried over
+            const int n = w + h;
+            const int cf = p.corner ? ((L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4) : (int)A[-1];
+            AV1B_NOUNROLL
+            for (int e = tid; e < 2 * n; e += nt) {
+                const bool above = e < n;
+                const int m = above ? e : e - n;
+                const uint8_t* old = above ? A : L;
+                const int s = above ? p.sA : p.sL, sz = above ? p.szA : p.szL;
+                int v;
+                if (s && m <= sz - 2) {
+                    // taps {0,4,8,4,0}, {0,5,6,5,0}, {2,4,4,4,2}
+                    const int k0 = s == 3 ? 2 : 0, k1 = s == 2 ? 5 : 4, k2 = s == 1 ? 8 : (s == 2 ? 6 : 4);
+                    const int hi = sz - 2;
+                    const int t0 = max(m - 2, -1), t1 = m - 1, t3 = min(m + 1, hi), t4 = min(m + 2, hi);
+                    const int v0 = t0 < 0 ? cf : (int)old[t0], v1 = t1 < 0 ? cf : (int)old[t1];
+                    v = (k0 * (v0 + (int)old[t4]) + k1 * (v1 + (int)old[t3]) + k2 * (int)old[m] + 8) >> 4;
+                } else v = old[m];
+                uint8_t* nw = above ? A2 : L2;
+                nw[m] = (uint8_t)v;
+                if (m == 0) nw[-1] = (uint8_t)cf;
+            }
+            block_sync(nt);
+            EA = A2;
+            EL = L2;
+            if (up_above | up_left) {
+                // phase 3: 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference
+                // intraEdgeUpsample), second pair -> first pair
+                const int nA = up_above ? w + (kind == K_DIR_LT90 ? h : 0) : 0;
+                const int nL = up_left ? h + (kind == K_DIR_GT180 ? w : 0) : 0;
+                AV1B_NOUNROLL
+                for (int e = tid; e < nA + nL; e += nt) {
+                    const bool above = e < nA;
+                    const int i = above ? e : e - nA, nn = above ? nA : nL;
+                    const uint8_t* old = above ? A2 : L2;
+                    uint8_t* nw = above ? A : L;
+                    const int s = -(int)old[max(i - 2, -1)] + 9 * (int)old[i - 1] + 9 * (int)old[i] - (int)old[min(i + 1, nn - 1)];
+                    nw[2 * i - 1] = (uint8_t)clip_u8((s + 8) >> 4);
+                    nw[2 * i] = old[i];
+                    if (i == 0) nw[-2] = old[-1];
                 }
                 block_sync(nt);
+                if (up_above) EA = A;
+                if (up_left) EL = L;
             }
-            const int maxx_q = a.max_x + 1, maxy_q = a.max_y + 1; // quirk: no -1
-            int sA = 0, numA = 0, sL = 0, numL = 0;
-            if (a.have_above) {
-                sA = edge_filter_strength(w, h, a.edge_smooth, p_angle - 90);
-                numA = min(w, maxx_q - x + 1) + (p_angle < 90 ? h : 0) + 1;
-            }
-            if (a.have_left) {
-                sL = edge_filter_strength(w, h, a.edge_smooth, p_angle - 180);
-                numL = min(h, maxy_q - y + 1) + (p_angle > 180 ? w : 0) + 1;
-            }
-            filter_edges<NTC>(A, numA, sA, L, numL, sL, S.tmp, tid, nt);
-            up_above = edge_upsample(w, h, a.edge_smooth, p_angle - 90);
-            up_left = edge_upsample(w, h, a.edge_smooth, p_angle - 180);
-            upsample_edges<NTC>(A, up_above ? w + (p_angle < 90 ? h : 0) : 0, L, up_left ? h + (p_angle > 180 ? w : 0) : 0, S.tmp, tid, nt);
         }
-        if (p_angle < 90) {
-            const int dx = k_dr_intra_derivative[p_angle];
+        if (kind == K_DIR_LT90) {
+            const int dx = p.dx;
             const int max_base = (w + h - 1) << up_above;
+            const int top = EA[max_base];
             AV1B_NOUNROLL
-            for (int e = tid; e < w * h; e += nt) {
-                int i = e >> a.log2w, j = e & (w - 1);
-                int idx = (i + 1) * dx;
-                int base = (idx >> (6 - up_above)) + (j << up_above);
-                int shift = ((idx << up_above) >> 1) & 31;
-                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)(base < max_base ? ((A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5) : A[max_base]);
-            }
-        } else if (p_angle > 90 && p_angle < 180) {
-            const int dx = k_dr_intra_derivative[180 - p_angle];
-            const int dy = k_dr_intra_derivative[p_angle - 90];
-            AV1B_NOUNROLL
-            for (int e = tid; e < w * h; e += nt) {
-                int i = e >> a.log2w, j = e & (w - 1);
-                int idx = (j << 6) - (i + 1) * dx;
-                int base = idx >> (6 - up_above);
-                int v;
-                if (base >= -(1 << up_above)) {
-                    int shift = ((idx << up_above) >> 1) & 31;
-                    v = (A[base] * (32 - shift) + A[base + 1] * shift + 16) >> 5;
-                } else {
-                    idx = (i << 6) - (j + 1) * dy;
-                    base = idx >> (6 - up_left);
-                    int shift = ((idx << up_left) >> 1) & 31;
-                    v = (L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5;
+            for (int e = tid; e < items; e += nt) {
+                const int i = e >> lq, q = e & (nq - 1);
+                const int idx = (i + 1) * dx;
+                const int shift = ((idx << up_above) >> 1) & 31;
+                const int b0 = (idx >> (6 - up_above)) + ((4 * q) << up_above);
+                int v[4];
+                AV1B_UNROLL
+                for (int m = 0; m < 4; m++) {
+                    const int base = b0 + (m << up_above);
+                    v[m] = base < max_base ? ((EA[base] * (32 - shift) + EA[base + 1] * shift + 16) >> 5) : top;
                 }
-                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)v;
+                put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
-        } else if (p_angle > 180) {
-            const int dy = k_dr_intra_derivative[270 - p_angle];
+        } else if (kind == K_DIR_MID) {
+            const int dx = p.dx, dy = p.dy;
             AV1B_NOUNROLL
-            for (int e = tid; e < w * h; e += nt) {
-                int i = e >> a.log2w, j = e & (w - 1);
-                int idx = (j + 1) * dy;
-                int base = (idx >> (6 - up_left)) + (i << up_left);
-                int shift = ((idx << up_left) >> 1) & 31;
-                P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((L[base] * (32 - shift) + L[base + 1] * shift + 16) >> 5);
+            for (int e = tid; e < items; e += nt) {
+                const int i = e >> lq, q = e & (nq - 1);
+                int v[4];
+                AV1B_UNROLL
+                for (int m = 0; m < 4; m++) {
+                    const int j = 4 * q + m;
+                    int idx = (j << 6) - (i + 1) * dx;
+                    int base = idx >> (6 - up_above);
+                    if (base >= -(1 << up_above)) {
+                        const int shift = ((idx << up_above) >> 1) & 31;
+                        v[m] = (EA[base] * (32 - shift) + EA[base + 1] * shift + 16) >> 5;
+                    } else {
+                        idx = (i << 6) - (j + 1) * dy;
+                        base = idx >> (6 - up_left);
+                        const int shift = ((idx << up_left) >> 1) & 31;
+                        v[m] = (EL[base] * (32 - shift) + EL[base + 1] * shift + 16) >> 5;
+                    }
+                }
+                put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
-        } else if (p_angle == 90) {
-            AV1B_NOUNROLL
-            for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = A[e & (w - 1)];
         } else {
+            const int dy = p.dy;
             AV1B_NOUNROLL
-            for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = L[e >> a.log2w];
+            for (int e = tid; e < items; e += nt) {
+                const int i = e >> lq, q = e & (nq - 1);
+                int v[4];
+                AV1B_UNROLL
+                for (int m = 0; m < 4; m++) {
+                    const int idx = (4 * q + m + 1) * dy;
+                    const int base = (idx >> (6 - up_left)) + (i << up_left);
+                    const int shift = ((idx << up_left) >> 1) & 31;
+                    v[m] = (EL[base] * (32 - shift) + EL[base + 1] * shift + 16) >> 5;
+                }
+                put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
+            }
         }
-    } else if (mode == 12) {
-        // ---- Paeth
+    } else if (kind == K_V) {
+        AV1B_NOUNROLL
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            put4(o, i, q, *(const uint32_t*)(A + 4 * q));
+        }
+    } else if (kind == K_H) {
+        AV1B_NOUNROLL
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            put4(o, i, q, (uint32_t)L[i] * 0x01010101u);
+        }
+    } else if (kind == K_PAETH) {
         const int tl = A[-1];
         AV1B_NOUNROLL
-        for (int e = tid; e < w * h; e += nt) {
-            int i = e >> a.log2w, j = e & (w - 1);
-            int base = A[j] + L[i] - tl;
-            int pl = iabs(base - L[i]), pt = iabs(base - A[j]), ptl = iabs(base - tl);
-            P[(e >> lw) * pp + (e & (w - 1))] = (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : (uint8_t)tl);
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
+            const int l = L[i];
+            int v[4];
+            AV1B_UNROLL
+            for (int m = 0; m < 4; m++) {
+                const int t = (int)((aw >> (8 * m)) & 0xFF);
+                const int base = t + l - tl;
+                const int pl = iabs(base - l), pt = iabs(base - t), ptl = iabs(base - tl);
+                v[m] = (pl <= pt && pl <= ptl) ? l : (pt <= ptl ? t : tl);
+            }
+            put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
         }
-    } else if (mode == 0) {
+    } else if (kind == K_DC) {
         // ---- DC.  Both edge sums travel in one word (each <= 64 * 255) through one warp
         // reduction; the divisor w + h is 2^k, 3 * 2^k or 5 * 2^k, so the division is a shift and
         // an exact multiply-high.
         int sl = 0, sa = 0;
         if (nt <= 32) {
             unsigned part = 0;
+            const int wq = w >> 2, hq = h >> 2;
             AV1B_NOUNROLL
-            for (int k = tid; k < h; k += nt) part += (unsigned)L[k] << 16;
-            AV1B_NOUNROLL
-            for (int k = tid; k < w; k += nt) part += A[k];
+            for (int k = tid; k < wq + hq; k += nt) {
+                if (k < wq) part = av1b_dp4a_uu(*(const uint32_t*)(A + 4 * k), 0x01010101u, part);
+                else part += av1b_dp4a_uu(*(const uint32_t*)(L + 4 * (k - wq)), 0x01010101u, 0u) << 16;
+            }
             part = warp_sum(part, nt);
             sl = (int)(part >> 16);
             sa = (int)(part & 0xFFFF);
@@ -332,76 +514,95 @@ AV1B_DEV void predict(const Args& a, Scratch& S, uint8_t* P, int pp, int tid, in
             for (int k = 0; k < w; k++) sa += A[k];
         }
         int avg;
-        if (a.have_left && a.have_above) {
-            const int lmin = min(a.log2w, a.log2h), ratio = iabs(a.log2w - a.log2h); // w + h = (1 + 2^ratio) << lmin
+        if (p.have_left && p.have_above) {
+            const int lmin = min(lw, lh), ratio = iabs(lw - lh); // w + h = (1 + 2^ratio) << lmin
             const unsigned q = (unsigned)(sl + sa + ((w + h) >> 1)) >> lmin;
             avg = ratio == 0 ? (int)(q >> 1) : (ratio == 1 ? (int)(__umulhi(q, 0xAAAAAAABu) >> 1) : (int)(__umulhi(q, 0xCCCCCCCDu) >> 2));
-        } else if (a.have_left) avg = clip_u8((sl + (h >> 1)) >> a.log2h);
-        else if (a.have_above) avg = clip_u8((sa + (w >> 1)) >> a.log2w);
+        } else if (p.have_left) avg = clip_u8((sl + (h >> 1)) >> lh);
+        else if (p.have_above) avg = clip_u8((sa + (w >> 1)) >> lw);
         else avg = 128;
-        AV1B_NOUNROLL
-        for (int e = tid; e < w * h; e += nt) P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)avg;
-    } else if (mode == 9) {
+        if (!p.cfl) {
+            const uint32_t word = (uint32_t)avg * 0x01010101u;
+            AV1B_NOUNROLL
+            for (int e = tid; e < items; e += nt) put4(o, e >> lq, e & (nq - 1), word);
+        } else {
+            // ---- chroma-from-luma on top of the DC value (IntraPredict.cpp:632-667): two passes over
+            // the sub-sampled luma (sum, then apply) instead of a staging buffer
+            int local = 0;
+            AV1B_NOUNROLL
+            for (int e = tid; e < items; e += nt) {
+                const uint2 l4 = cfl_luma4<SMEM>(p, o, e >> lq, 4 * (e & (nq - 1)));
+                local += (int)((l4.x & 0xFFFF) + (l4.x >> 16) + (l4.y & 0xFFFF) + (l4.y >> 16));
+            }
+            int total;
+            if (nt <= 32) total = (int)warp_sum((unsigned)local, nt);
+            else {
+                if (tid == 0) S.acc = 0;
+                block_sync(nt);
+                atomicAdd(&S.acc, local);
+                block_sync(nt);
+                total = S.acc;
+            }
+            const int lavg = round2(total, lw + lh);
+            const int alpha = p.alpha;
+            AV1B_NOUNROLL
+            for (int e = tid; e < items; e += nt) {
+                const int i = e >> lq, q = e & (nq - 1);
+                const uint2 l4 = cfl_luma4<SMEM>(p, o, i, 4 * q);
+                const int v0 = clip_u8(avg + round2s(alpha * ((int)(l4.x & 0xFFFF) - lavg), 6));
+                const int v1 = clip_u8(avg + round2s(alpha * ((int)(l4.x >> 16) - lavg), 6));
+                const int v2 = clip_u8(avg + round2s(alpha * ((int)(l4.y & 0xFFFF) - lavg), 6));
+                const int v3 = clip_u8(avg + round2s(alpha * ((int)(l4.y >> 16) - lavg), 6));
+                put4(o, i, q, pack4(v0, v1, v2, v3));
+            }
+        }
+    } else if (kind == K_SMOOTH) {
         const uint8_t* wx = k_sm_weights + (w - 4);
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = L[h - 1], tr = A[w - 1];
         AV1B_NOUNROLL
-        for (int e = tid; e < w * h; e += nt) {
-            int i = e >> a.log2w, j = e & (w - 1);
-            int v = wy[i] * A[j] + (256 - wy[i]) * bl + wx[j] * L[i] + (256 - wx[j]) * tr;
-            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((v + 256) >> 9);
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
+            const int l = L[i], wyi = wy[i];
+            const int rowc = (256 - wyi) * bl + 256;
+            int v[4];
+            AV1B_UNROLL
+            for (int m = 0; m < 4; m++) {
+                const int wxj = wx[4 * q + m];
+                v[m] = (wyi * (int)((aw >> (8 * m)) & 0xFF) + rowc + wxj * l + (256 - wxj) * tr) >> 9;
+            }
+            put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
         }
-    } else if (mode == 10) {
+    } else if (kind == K_SMOOTH_V) {
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = L[h - 1];
         AV1B_NOUNROLL
-        for (int e = tid; e < w * h; e += nt) {
-            int i = e >> a.log2w, j = e & (w - 1);
-            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wy[i] * A[j] + (256 - wy[i]) * bl + 128) >> 8);
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
+            const int wyi = wy[i];
+            const int rowc = (256 - wyi) * bl + 128;
+            int v[4];
+            AV1B_UNROLL
+            for (int m = 0; m < 4; m++) v[m] = (wyi * (int)((aw >> (8 * m)) & 0xFF) + rowc) >> 8;
+            put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
         }
-    } else { // mode == 11, SMOOTH_H
+    } else { // K_SMOOTH_H
         const uint8_t* wx = k_sm_weights + (w - 4);
         const int tr = A[w - 1];
         AV1B_NOUNROLL
-        for (int e = tid; e < w * h; e += nt) {
-            int i = e >> a.log2w, j = e & (w - 1);
-            P[(e >> lw) * pp + (e & (w - 1))] = (uint8_t)((wx[j] * L[i] + (256 - wx[j]) * tr + 128) >> 8);
+        for (int e = tid; e < items; e += nt) {
+            const int i = e >> lq, q = e & (nq - 1);
+            const int l = L[i];
+            int v[4];
+            AV1B_UNROLL
+            for (int m = 0; m < 4; m++) {
+                const int wxj = wx[4 * q + m];
+                v[m] = (wxj * l + (256 - wxj) * tr + 128) >> 8;
+            }
+            put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
         }
-    }
-    block_sync(nt);
-}
-
-// Chroma-from-luma on top of the DC prediction already in P (IntraPredict.cpp:632-667).
-// `luma` is plane 0 of the current frame (already reconstructed for this block).  Two passes over
-// the sub-sampled luma (sum, then apply) instead of a staging buffer.
-AV1B_DEV int cfl_luma(const Args& a, const uint8_t* luma, int luma_stride, int max_luma_w, int max_luma_h, int i, int j)
-{
-    const int ly = min((a.y + i) << 1, max_luma_h - 2);
-    const int lx = min((a.x + j) << 1, max_luma_w - 2);
-    const volatile uint8_t* q = luma + (ptrdiff_t)ly * luma_stride + lx;
-    return (q[0] + q[1] + q[luma_stride] + q[luma_stride + 1]) << 1;
-}
-
-template <int NTC>
-AV1B_DEV void apply_cfl(const Args& a, const uint8_t* luma, int luma_stride, int alpha, int max_luma_w, int max_luma_h,
-    Scratch& S, uint8_t* P, int pp, int tid, int nt_rt)
-{
-    const int nt = NTC ? NTC : nt_rt;
-    const int w = 1 << a.log2w, h = 1 << a.log2h;
-    if (tid == 0) S.acc = 0;
-    block_sync(nt);
-    int local = 0;
-    AV1B_NOUNROLL
-    for (int e = tid; e < w * h; e += nt) local += cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, e >> a.log2w, e & (w - 1));
-    atomicAdd(&S.acc, local);
-    block_sync(nt);
-    const int avg = round2(S.acc, a.log2w + a.log2h);
-    AV1B_NOUNROLL
-    for (int e = tid; e < w * h; e += nt) {
-        const int i = e >> a.log2w, j = e & (w - 1);
-        const int scaled = round2s(alpha * (cfl_luma(a, luma, luma_stride, max_luma_w, max_luma_h, i, j) - avg), 6);
-        uint8_t* d = P + i * pp + j;
-        *d = (uint8_t)clip_u8(*d + scaled);
     }
     block_sync(nt);
 }

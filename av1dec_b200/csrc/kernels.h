@@ -15,6 +15,8 @@ struct ReconCtx {
     int mask_pitch;
     const uint8_t* wedge; // wedge mask table [9][2][16][32*32]
     int* sync;            // [0] = SB ticket counter, [1 + r] = finished SBs of SB row r
+    unsigned long long* trace; // profiling aid (av1b_debug_wave_trace), normally null
+    unsigned trace_cap;
 };
 
 // In-loop filter context.

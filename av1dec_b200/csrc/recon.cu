@@ -461,7 +461,7 @@ struct PlaneSet {
     int rpitch0, rpitch12;
 };
 
-enum { WAVE_OP_CHUNK = 64 };
+enum { WAVE_OP_CHUNK = 128 };
 #ifdef AV1B_EMU
 enum { WAVE_NT = 0 }; // the emulation runs every group with one thread
 #else
@@ -489,6 +489,75 @@ AV1B_DEV FrameConst frame_const(const Av1bFrameHdr* hdr)
     return f;
 }
 
+// The reference's view of an intra transform block, from the op record.
+AV1B_DEV intra::Args intra_args(const Av1bOp& op, const FrameConst& fc, int lw, int lh)
+{
+    const int sub = op.plane ? 1 : 0;
+    intra::Args a;
+    a.x = op.x;
+    a.y = op.y;
+    a.log2w = lw;
+    a.log2h = lh;
+    a.max_x = sub ? fc.max_x[1] : fc.max_x[0];
+    a.max_y = sub ? fc.max_y[1] : fc.max_y[0];
+    a.plane_idx = op.plane;
+    a.mode = op.mode;
+    a.angle_delta = op.angle_delta;
+    a.have_left = (op.flags & AV1B_OPF_HAVE_LEFT) != 0;
+    a.have_above = (op.flags & AV1B_OPF_HAVE_ABOVE) != 0;
+    a.have_above_right = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) != 0;
+    a.have_below_left = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) != 0;
+    a.edge_filter_enabled = fc.edge_filter;
+    a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
+    a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
+    a.fi_mode = op.fi_mode;
+    a.cfl = op.kind == AV1B_OP_INTRA && (op.flags & AV1B_OPF_CFL) != 0;
+    a.cfl_alpha = op.cfl_alpha;
+    a.max_luma_w = op.max_luma_w;
+    a.max_luma_h = op.max_luma_h;
+    return a;
+}
+
+// Intra ops of the superblock wavefront are DECODED in shared memory ahead of their turn (lane-
+// parallel, while the CTA still waits for its neighbours): the 32-byte record keeps x, y, plane
+// and the level word and carries intra::Packed in place of the raw fields; kind gets bit 7.
+enum { WAVE_OP_DECODED = 0x80 };
+AV1B_DEV void decode_intra_op(Av1bOp* slot, const FrameConst& fc)
+{
+    const Av1bOp op = *slot;
+    if (op.kind != AV1B_OP_INTRA) return;
+    const int lw = (int)((AV1T_TX_WLOG2_PACKED >> (3 * op.tx_size)) & 7), lh = (int)((AV1T_TX_HLOG2_PACKED >> (3 * op.tx_size)) & 7);
+    const intra::Packed k = intra::pack(intra::prepare(intra_args(op, fc, lw, lh)));
+    uint32_t* w = (uint32_t*)slot;
+    w[1] = (uint32_t)op.plane | ((uint32_t)(AV1B_OP_INTRA | WAVE_OP_DECODED) << 8);
+    w[2] = k.w[0];
+    w[3] = k.w[1];
+    w[4] = k.w[2];
+    w[6] = k.w[3] | ((op.flags & AV1B_OPF_HAS_RESID) ? 0x10000u : 0u);
+}
+
+template <int NTC>
+AV1B_DEV void exec_decoded_intra(const uint4 a, const uint4 b, const PlaneSet& io, OpScratch& S, int tid, int nt_rt)
+{
+    intra::Packed k;
+    k.w[0] = a.z, k.w[1] = a.w, k.w[2] = b.x, k.w[3] = b.z;
+    const intra::Prep p = intra::unpack(k);
+    const int x = (int)(a.x & 0xFFFF), y = (int)(a.x >> 16), plane = (int)(a.y & 0xFF);
+    uint8_t* const pix = plane == 0 ? io.pix0 : (plane == 1 ? io.pix1 : io.pix2);
+    const int pitch = plane == 0 ? io.pitch0 : io.pitch12;
+    const int16_t* const rbase = plane == 0 ? io.res0 : (plane == 1 ? io.res1 : io.res2);
+    const int rpitch = plane == 0 ? io.rpitch0 : io.rpitch12;
+    intra::Io o;
+    o.P = pix + (ptrdiff_t)y * pitch + x;
+    o.blk = o.P;
+    o.stride = o.pp = pitch;
+    o.res = ((b.z & 0x10000u) && rbase) ? rbase + (ptrdiff_t)y * rpitch + x : nullptr;
+    o.rpitch = rpitch;
+    o.luma = io.pix0 + (ptrdiff_t)(2 * y) * io.pitch0 + 2 * x;
+    o.luma_stride = io.pitch0;
+    intra::run<true, NTC>(p, o, S.I, tid, nt_rt);
+}
+
 // SMEM: the planes in `io` are the superblock tile in shared memory (wave_kernel) -- said to the
 // compiler so that sample accesses become shared-memory instructions instead of generic ones.
 // NTC: compile-time group size (32: one warp per op) or 0 = runtime nt_rt.
@@ -497,7 +566,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     mc::Scratch* M, int tid, int nt_rt)
 {
     const int nt = NTC ? NTC : nt_rt;
-    const int plane = op.plane, sub = plane ? 1 : 0;
+    const int plane = op.plane;
     PlaneIo D;
     D.pix = plane == 0 ? io.pix0 : (plane == 1 ? io.pix1 : io.pix2);
     D.pitch = plane == 0 ? io.pitch0 : io.pitch12;
@@ -520,61 +589,31 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
     switch (op.kind) {
     case AV1B_OP_INTER_RES: {
         if (!res) break;
-        for (int e = tid; e < w * h; e += nt) {
-            const int i = e >> lw, j = e & (w - 1);
-            volatile uint8_t* d = dst + i * D.pitch + j;
-            *d = (uint8_t)clip_u8((int)*d + res[i * D.rpitch + j]);
+        const int lq = lw - 2;
+        for (int e = tid; e < (h << lq); e += nt) {
+            const int i = e >> lq, q = e & ((1 << lq) - 1);
+            uint32_t* d = (uint32_t*)(dst + i * D.pitch + 4 * q);
+            *d = add_res4(SMEM ? *d : __ldcg(d), *(const uint2*)(res + i * D.rpitch + 4 * q));
         }
         break;
     }
     case AV1B_OP_INTRA:
     case AV1B_OP_INTERINTRA: {
-        intra::Args a;
-        a.plane = pix;
-        a.stride = D.pitch;
-        a.x = op.x;
-        a.y = op.y;
-        a.log2w = lw;
-        a.log2h = lh;
-        a.max_x = sub ? fc.max_x[1] : fc.max_x[0];
-        a.max_y = sub ? fc.max_y[1] : fc.max_y[0];
-        a.plane_idx = plane;
-        a.mode = op.mode;
-        a.angle_delta = op.angle_delta;
-        a.have_left = (op.flags & AV1B_OPF_HAVE_LEFT) != 0;
-        a.have_above = (op.flags & AV1B_OPF_HAVE_ABOVE) != 0;
-        a.have_above_right = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) != 0;
-        a.have_below_left = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) != 0;
-        a.edge_filter_enabled = fc.edge_filter;
-        a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
-        a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
-        a.fi_mode = op.fi_mode;
-        // Intra blocks are predicted straight into their place and the residual is added over it;
-        // the first residual words are requested before the prediction so their latency hides
-        // behind it.  Inter-intra blocks predict into scratch (the place holds the inter half).
+        // Intra blocks are predicted straight into their place, residual and CfL fused into the
+        // store.  Inter-intra blocks predict into scratch (the place holds the inter half).
         const bool in_place = op.kind == AV1B_OP_INTRA;
-        const int lw2 = lw - 1, n2 = (w * h) >> 1; // pairs of samples
-        uint32_t r0 = 0, r1 = 0;
-        if (in_place && res) {
-            if (tid < n2) r0 = *(const uint32_t*)(res + (tid >> lw2) * D.rpitch + 2 * (tid & ((1 << lw2) - 1)));
-            if (tid + nt < n2) r1 = *(const uint32_t*)(res + ((tid + nt) >> lw2) * D.rpitch + 2 * ((tid + nt) & ((1 << lw2) - 1)));
-        }
-        intra::predict<NTC>(a, S.I, in_place ? dst : S.I.pred, in_place ? D.pitch : w, tid, nt);
-        if (in_place) {
-            if (op.flags & AV1B_OPF_CFL)
-                intra::apply_cfl<NTC>(a, luma_pix, io.pitch0, op.cfl_alpha, op.max_luma_w, op.max_luma_h, S.I, dst, D.pitch, tid, nt);
-            if (res) {
-                int k = 0;
-                AV1B_NOUNROLL
-                for (int e = tid; e < n2; e += nt, k++) {
-                    const int i = e >> lw2, j = 2 * (e & ((1 << lw2) - 1));
-                    const uint32_t rr = k == 0 ? r0 : (k == 1 ? r1 : *(const uint32_t*)(res + i * D.rpitch + j));
-                    uint8_t* d = dst + i * D.pitch + j;
-                    d[0] = (uint8_t)clip_u8((int)d[0] + (int)(int16_t)(rr & 0xFFFF));
-                    d[1] = (uint8_t)clip_u8((int)d[1] + ((int)rr >> 16));
-                }
-            }
-        } else {
+        const intra::Prep p = intra::prepare(intra_args(op, fc, lw, lh));
+        intra::Io o;
+        o.blk = dst;
+        o.stride = D.pitch;
+        o.P = in_place ? dst : S.I.pred;
+        o.pp = in_place ? D.pitch : w;
+        o.res = in_place ? res : nullptr;
+        o.rpitch = D.rpitch;
+        o.luma = luma_pix + (ptrdiff_t)(2 * op.y) * io.pitch0 + 2 * op.x;
+        o.luma_stride = io.pitch0;
+        intra::run<SMEM, NTC>(p, o, S.I, tid, nt);
+        if (!in_place) {
             // inter-intra blend over the inter prediction already in place
             // (reference maskBlend, InterPredict.cpp:584-609; masks :555-582, :888-899)
             const Av1bBlkAux* aux = (const Av1bBlkAux*)(c.cmd + hdr->off_aux) + op.aux;
@@ -658,48 +697,55 @@ AV1B_DEV void sb_from_ticket(int t, int rows, int cols, int lag, int& r, int& c)
 AV1B_DEV void wave_wait(int* progress, int r, int col, int sb_cols, int lag, int tid, int nt)
 {
     if (tid == 0) {
+        // poll with plain L2 reads; one acquire (which also drops this SM's L1 lines) once the
+        // counters are there
         if (r > 0) {
             const int need = min(col + lag, sb_cols);
-            while (av1b_ld_acquire(progress + r - 1) < need) av1b_nanosleep(64);
+            while (av1b_ld_relaxed(progress + r - 1) < need) av1b_nanosleep(32);
         }
         if (col > 0) {
-            while (av1b_ld_acquire(progress + r) < col) av1b_nanosleep(64);
+            while (av1b_ld_relaxed(progress + r) < col) av1b_nanosleep(32);
         }
-        __threadfence();
+        if (r > 0 || col > 0) (void)av1b_ld_acquire(progress + r - (r > 0 ? 1 : 0));
     }
     block_sync(nt);
 }
 
+// The CTA barrier orders every thread's stores before thread 0's release (the pattern of a
+// cooperative grid barrier): one fence by one thread instead of one per thread.
 AV1B_DEV void wave_signal(int* progress, int r, int col, int tid, int nt)
 {
-    __threadfence(); // every thread's tile stores are visible device-wide before the flag moves
     block_sync(nt);
     if (tid == 0) av1b_st_release(progress + r, col + 1);
-    block_sync(nt);
 }
 
 
-// Shared-memory footprint of one superblock tile (bytes) for SB size `sb` (64 or 128):
-// luma (sb+1) x (2sb+8) samples with a one-sample halo row/column, and two chroma planes.
-#define WAVE_TILE_BYTES(sb) (((sb) + 1) * (2 * (sb) + 8) + 2 * ((sb) / 2 + 1) * ((sb) + 8))
+// Shared-memory footprint of one superblock (bytes) for SB size `sb` (64 or 128): the sample tile
+// -- luma (sb+1) rows of 2sb+8 bytes (a halo row above, long enough for above-right reads, and a
+// halo column to the left; sample (x0, y0) sits at byte 4 of row 1 so that every block row is
+// word aligned), two chroma planes likewise -- and the int16 residuals of the superblock.
+#define WAVE_TILE_BYTES(sb) (((((sb) + 1) * (2 * (sb) + 8) + 2 * ((sb) / 2 + 1) * ((sb) + 8)) + 15) & ~15)
+#define WAVE_RES_BYTES(sb) (3 * (sb) * (sb))
+#define WAVE_SMEM_BYTES(sb, warps) (WAVE_TILE_BYTES(sb) + WAVE_RES_BYTES(sb) + (int)sizeof(OpScratch) * (warps))
 
 }  // namespace
 
 int wave_tile_bytes(int sb) { return WAVE_TILE_BYTES(sb); }
 
 // Superblock-in-shared-memory wavefront: the SB's samples (all planes) live in a smem tile with a
-// one-sample halo row above (long enough for above-right reads) and halo column to the left, so
-// the chain of intra predictions never waits on L2.  Inside the SB the ops come sorted by
-// dependency level (host/emitter.cpp scheduleSb): all ops of one level are independent, each is
-// executed by ONE warp, and the CTA only synchronises between levels -- a 128x128 SB of 4x4
-// blocks needs ~100 level steps instead of ~650 sequential ops.  Frames without intrabc only.
+// one-sample halo row above (long enough for above-right reads) and halo column to the left, and
+// so do its residuals, so the chain of intra predictions never waits on L2.  Inside the SB the ops
+// come sorted by dependency level (host/emitter.cpp scheduleSb): all ops of one level are
+// independent, each is executed by ONE warp, and the CTA only synchronises between levels -- a
+// 128x128 SB of 4x4 blocks needs ~100 level steps instead of ~650 sequential ops.  Frames without
+// intrabc only.
 template <int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 {
     alignas(16) __shared__ Av1bOp s_ops[2][WAVE_OP_CHUNK];
     __shared__ int s_sb;
 #ifdef AV1B_EMU
-    static uint8_t dyn[WAVE_TILE_BYTES(128) + 64 + sizeof(OpScratch) * WARPS];
+    alignas(16) static uint8_t dyn[WAVE_SMEM_BYTES(128, WARPS)];
 #else
     extern __shared__ __align__(16) uint8_t dyn[];
 #endif
@@ -717,14 +763,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     const bool have_res = c.rp[0] != nullptr && hdr->n_itx != 0;
     int* ticket = c.sync;
     int* progress = c.sync + 1;
-    // tile geometry: luma n0 x n0 with pitch 2*n0 + 8 (one halo row long enough for above-right
-    // reads, one halo column), chroma likewise
     const int n0 = sbs_y, n1 = sbs_y >> 1;
     const int pitch0 = 2 * n0 + 8, pitch1 = 2 * n1 + 8;
     uint8_t* const t0 = dyn;
     uint8_t* const t1 = t0 + (n0 + 1) * pitch0;
     uint8_t* const t2 = t1 + (n1 + 1) * pitch1;
-    OpScratch* const scratch = (OpScratch*)(dyn + (((n0 + 1) * pitch0 + 2 * (n1 + 1) * pitch1 + 15) & ~15)) + warp;
+    int16_t* const q0 = (int16_t*)(dyn + WAVE_TILE_BYTES(n0));
+    int16_t* const q1 = q0 + n0 * n0;
+    int16_t* const q2 = q1 + n1 * n1;
+    OpScratch* const scratch = (OpScratch*)(dyn + WAVE_TILE_BYTES(n0) + WAVE_RES_BYTES(n0)) + warp;
     for (;;) {
         block_sync(nt);
         if (tid == 0) {
@@ -738,76 +785,108 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         if (sb >= n_sb) break;
         const int r = sb / sb_cols, col = sb - r * sb_cols;
         const Av1bSb e = sbs[sb];
+        unsigned long long* const tr = (c.trace && tid == 0 && (unsigned)sb < c.trace_cap) ? c.trace + 8 * (size_t)sb : nullptr;
+        if (tr) tr[0] = (unsigned long long)sb, tr[1] = av1b_smid(), tr[2] = av1b_gtime();
         if (e.n_ops == 0) {
             wave_wait(progress, r, col, sb_cols, 2, tid, nt);
             wave_signal(progress, r, col, tid, nt);
+            if (tr) tr[3] = tr[4] = tr[5] = tr[6] = tr[7] = av1b_gtime();
             continue;
         }
         // ---- everything that does not depend on the neighbours is requested BEFORE the wait (a
         // CTA standing by on the next diagonal has it done when its dependencies finish): the first
-        // chunk of the op list and, for inter frames, the superblock's own samples.
+        // chunk of the op list, the superblock's residuals and, for inter frames, its own samples.
         {
             const uint4* src = (const uint4*)(ops + e.first_op);
             const unsigned n0c = min((unsigned)WAVE_OP_CHUNK, e.n_ops);
             uint4* dstv = (uint4*)s_ops[0];
             for (unsigned q = tid; q < n0c * 2; q += nt) dstv[q] = __ldg(src + q);
         }
-        auto load_own = [&](int pl, uint8_t* t, int n, int pitch) {
-            // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 1)]
+        const int lg0 = mc::ilog2_pow2(n0); // 6 or 7
+        auto load_own = [&](int pl, uint8_t* t, int n, int lg, int pitch) {
+            // tile sample (x, y) in frame coordinates lives at t[(y - y0 + 1) * pitch + (x - x0 + 4)]
             const int x0 = col * n, y0 = r * n;
             const PlaneView g = c.cur.pl[pl];
-            const int lwords = mc::ilog2_pow2(n) - 2; // n is 32, 64 or 128
+            const int lwords = lg - 2;
             AV1B_NOUNROLL
             for (int k = tid; k < (n << lwords); k += nt) {
                 const int i = k >> lwords, j = k & ((1 << lwords) - 1);
-                const uint32_t v = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
-                uint8_t* d = t + (i + 1) * pitch + 1 + 4 * j;
-                d[0] = (uint8_t)v;
-                d[1] = (uint8_t)(v >> 8);
-                d[2] = (uint8_t)(v >> 16);
-                d[3] = (uint8_t)(v >> 24);
+                *(uint32_t*)(t + (i + 1) * pitch + 4 + 4 * j) = __ldcg((const uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j);
             }
         };
-        if (load_pred) {
-            load_own(0, t0, n0, pitch0);
-            load_own(1, t1, n1, pitch1);
-            load_own(2, t2, n1, pitch1);
+        auto load_res = [&](int pl, int16_t* q, int n, int lg) {
+            const int x0 = col * n, y0 = r * n;
+            const int16_t* g = c.rp[pl] + (size_t)y0 * c.rpitch[pl] + x0;
+            const int lch = lg - 3; // 16-byte chunks per row
+            AV1B_NOUNROLL
+            for (int k = tid; k < (n << lch); k += nt) {
+                const int i = k >> lch, j = k & ((1 << lch) - 1);
+                *((uint4*)(q + i * n) + j) = __ldcg((const uint4*)(g + (size_t)i * c.rpitch[pl]) + j);
+            }
+        };
+        if (have_res) {
+            load_res(0, q0, n0, lg0);
+            load_res(1, q1, n1, lg0 - 1);
+            load_res(2, q2, n1, lg0 - 1);
         }
+        if (load_pred) {
+            load_own(0, t0, n0, lg0, pitch0);
+            load_own(1, t1, n1, lg0 - 1, pitch1);
+            load_own(2, t2, n1, lg0 - 1, pitch1);
+        }
+        // the sample-independent half of every intra op of the chunk, one op per thread
+        block_sync(nt);
+        for (unsigned q = tid; q < min((unsigned)WAVE_OP_CHUNK, e.n_ops); q += nt) decode_intra_op(&s_ops[0][q], fc);
         wave_wait(progress, r, col, sb_cols, 2, tid, nt);
-        // ---- halo: the row above (long enough for above-right reads) and the column to the left
+        if (tr) tr[3] = av1b_gtime();
+        // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and the column to the left
         auto load_halo = [&](int pl, uint8_t* t, int n, int pitch) {
             const int x0 = col * n, y0 = r * n;
             const PlaneView g = c.cur.pl[pl];
-            if (r > 0) { // above row: x0-1 .. x0+2n-1
-                const uint8_t* src = g.p + (size_t)(y0 - 1) * g.stride + x0 - 1;
+            if (r > 0) {
+                const uint32_t* src = (const uint32_t*)(g.p + (size_t)(y0 - 1) * g.stride + x0 - 4);
                 AV1B_NOUNROLL
-                for (int k = tid; k < 2 * n + 1; k += nt) t[k] = __ldcg(src + k);
+                for (int k = tid; k < (n >> 1) + 1; k += nt) ((uint32_t*)t)[k] = __ldcg(src + k);
             }
-            if (col > 0) { // left column
+            if (col > 0) {
                 const uint8_t* src = g.p + (size_t)y0 * g.stride + x0 - 1;
                 AV1B_NOUNROLL
-                for (int k = tid; k < n; k += nt) t[(k + 1) * pitch] = __ldcg(src + (size_t)k * g.stride);
+                for (int k = tid; k < n; k += nt) t[(k + 1) * pitch + 3] = __ldcg(src + (size_t)k * g.stride);
             }
         };
         load_halo(0, t0, n0, pitch0);
         load_halo(1, t1, n1, pitch1);
         load_halo(2, t2, n1, pitch1);
         PlaneSet io;
-        io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (1 - col * n0);
-        io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (1 - col * n1);
-        io.pix2 = t2 + (ptrdiff_t)(1 - r * n1) * pitch1 + (1 - col * n1);
+        io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (4 - col * n0);
+        io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (4 - col * n1);
+        io.pix2 = t2 + (ptrdiff_t)(1 - r * n1) * pitch1 + (4 - col * n1);
         io.pitch0 = pitch0;
         io.pitch12 = pitch1;
-        // residuals stay in the frame-layout planes (L2): exec_op requests them ahead of use
-        io.res0 = have_res ? c.rp[0] : nullptr;
-        io.res1 = have_res ? c.rp[1] : nullptr;
-        io.res2 = have_res ? c.rp[2] : nullptr;
-        io.rpitch0 = c.rpitch[0];
-        io.rpitch12 = c.rpitch[1];
+        // residual (x, y) in frame coordinates lives at q[(y - y0) * n + (x - x0)]
+        io.res0 = have_res ? q0 - (ptrdiff_t)(r * n0) * n0 - col * n0 : nullptr;
+        io.res1 = have_res ? q1 - (ptrdiff_t)(r * n1) * n1 - col * n1 : nullptr;
+        io.res2 = have_res ? q2 - (ptrdiff_t)(r * n1) * n1 - col * n1 : nullptr;
+        io.rpitch0 = n0;
+        io.rpitch12 = n1;
         // ---- the ops of this superblock, level by level, one warp per op.  The op list streams
         // through a double buffer: the next chunk is requested before the current one runs, so
         // its L2 latency hides behind the levels in between.
         block_sync(nt);
+        if (tr) tr[4] = av1b_gtime();
+        auto run_one = [&](const Av1bOp* slot) {
+            const uint4 wa = ((const uint4*)slot)[0], wb = ((const uint4*)slot)[1];
+            if (wa.y & (WAVE_OP_DECODED << 8)) {
+                exec_decoded_intra<WAVE_NT>(wa, wb, io, *scratch, lane, nl);
+                return;
+            }
+            union {
+                uint4 v[2];
+                Av1bOp op;
+            } u;
+            u.v[0] = wa, u.v[1] = wb;
+            exec_op<true, WAVE_NT>(c, hdr, fc, u.op, io, *scratch, nullptr, lane, nl);
+        };
         int buf = 0;
         for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK, buf ^= 1) {
             const unsigned nk = min((unsigned)WAVE_OP_CHUNK, e.n_ops - k0);
@@ -825,15 +904,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 #ifdef AV1B_EMU
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
-                for (unsigned k = g1; k-- > g0;) {
-                    const Av1bOp op = cur_ops[k];
-                    exec_op<true, WAVE_NT>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
-                }
+                for (unsigned k = g1; k-- > g0;) run_one(cur_ops + k);
 #else
-                for (unsigned k = g0 + warp; k < g1; k += nw) {
-                    const Av1bOp op = cur_ops[k];
-                    exec_op<true, WAVE_NT>(c, hdr, fc, op, io, *scratch, nullptr, lane, nl);
-                }
+                for (unsigned k = g0 + warp; k < g1; k += nw) run_one(cur_ops + k);
 #endif
                 block_sync(nt);
                 g0 = g1;
@@ -845,8 +918,36 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 if ((unsigned)tid < nn * 2) ((uint4*)s_ops[buf ^ 1])[tid] = pre;
 #endif
                 block_sync(nt);
+                for (unsigned q = tid; q < nn; q += nt) decode_intra_op(&s_ops[buf ^ 1][q], fc);
+                block_sync(nt);
             }
         }
+        if (tr) tr[5] = av1b_gtime();
+        // ---- hand-off first: the neighbours only read this superblock's bottom row (as their row
+        // above / above-right) and right column, so those go out ahead of the rest of the tile and
+        // the progress counter moves as soon as they are on their way
+        auto flush_border = [&](int pl, const uint8_t* t, int n, int pitch) {
+            const int sub = pl ? 1 : 0;
+            const int x0 = col * n, y0 = r * n;
+            const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub;
+            const int cw = min(n, pw - x0), chh = min(n, ph - y0);
+            const PlaneView g = c.cur.pl[pl];
+            if (chh == n) { // a superblock row below exists
+                uint32_t* d = (uint32_t*)(g.p + (size_t)(y0 + n - 1) * g.stride + x0);
+                AV1B_NOUNROLL
+                for (int k = tid; k < (cw >> 2); k += nt) d[k] = *(const uint32_t*)(t + n * pitch + 4 + 4 * k);
+            }
+            if (cw == n) { // a superblock to the right exists
+                uint8_t* d = g.p + (size_t)y0 * g.stride + x0 + n - 1;
+                AV1B_NOUNROLL
+                for (int k = tid; k < chh; k += nt) d[(size_t)k * g.stride] = t[(k + 1) * pitch + 4 + n - 1];
+            }
+        };
+        flush_border(0, t0, n0, pitch0);
+        flush_border(1, t1, n1, pitch1);
+        flush_border(2, t2, n1, pitch1);
+        wave_signal(progress, r, col, tid, nt);
+        if (tr) tr[6] = av1b_gtime();
         // ---- flush the tile (MI-aligned area only)
         auto flush_plane = [&](int pl, const uint8_t* t, int n, int pitch) {
             const int sub = pl ? 1 : 0;
@@ -855,18 +956,25 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             const int cw = min(n, pw - x0), chh = min(n, ph - y0);
             const PlaneView g = c.cur.pl[pl];
             const int words = cw >> 2; // MI-aligned widths are multiples of 4 in every plane
-            AV1B_NOUNROLL
-            for (int k = tid; k < chh * words; k += nt) {
-                const int i = k / words, j = k - i * words;
-                const uint8_t* s = t + (i + 1) * pitch + 1 + 4 * j;
-                const uint32_t v = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
-                *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = v;
+            if (words == (n >> 2)) {
+                const int lwords = mc::ilog2_pow2(n) - 2;
+                AV1B_NOUNROLL
+                for (int k = tid; k < (chh << lwords); k += nt) {
+                    const int i = k >> lwords, j = k & ((1 << lwords) - 1);
+                    *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = *(const uint32_t*)(t + (i + 1) * pitch + 4 + 4 * j);
+                }
+            } else {
+                AV1B_NOUNROLL
+                for (int k = tid; k < chh * words; k += nt) {
+                    const int i = k / words, j = k - i * words;
+                    *((uint32_t*)(g.p + (size_t)(y0 + i) * g.stride + x0) + j) = *(const uint32_t*)(t + (i + 1) * pitch + 4 + 4 * j);
+                }
             }
         };
         flush_plane(0, t0, n0, pitch0);
         flush_plane(1, t1, n1, pitch1);
         flush_plane(2, t2, n1, pitch1);
-        wave_signal(progress, r, col, tid, nt);
+        if (tr) tr[7] = av1b_gtime();
     }
 }
 
@@ -983,7 +1091,7 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     // wavefront of one superblock keeps a warp scheduler mostly idle).  AV1B200_WAVE_WARPS picks.
     const char* wenv = getenv("AV1B200_WAVE_WARPS");
     const int warps = (wenv && atoi(wenv) == 8) ? 8 : 16;
-    const int smem = wave_tile_bytes(1 << h.sb_log2) + 64 + (int)sizeof(OpScratch) * warps;
+    const int smem = WAVE_SMEM_BYTES(1 << h.sb_log2, warps);
 #ifndef AV1B_EMU
     {
         // the attribute is per DEVICE: a process may run decoders on several GPUs
@@ -993,8 +1101,8 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lk(mu);
         if (!(done[(dev >> 6) & 3] & (1ull << (dev & 63)))) {
-            cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 16);
-            cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_tile_bytes(128) + 64 + (int)sizeof(OpScratch) * 8);
+            cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 16));
+            cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 8));
             done[(dev >> 6) & 3] |= 1ull << (dev & 63);
         }
     }

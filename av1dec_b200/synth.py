@@ -403,7 +403,7 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512, fixed_mv=N
     return cmd, nb, algo
 
 
-def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
+def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, sizes=(8, 16, 32), mode_set=None, fi=True, cfl=True):
     """A frame for the superblock wavefront (prediction only): a random `intra_frac` of the blocks
     of a non-intra frame are intra-predicted over whatever the frame already holds (the caller
     supplies it as the input picture, standing for the inter prediction), so every edge carries
@@ -415,7 +415,8 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
     overwrites, and the dependency levels (level | run length << 16 in res_off, ops stably sorted
     by level inside each superblock) are computed the way the host emitter does (4x4-cell map).
     `levelled=False` keeps the ops in decoding order, one per step (res_off = 0): the reference
-    the level analysis is checked against.  Returns the command buffer."""
+    the level analysis is checked against.  `sizes` / `mode_set` / `fi` / `cfl` narrow the mix
+    (profiling aid: tools/wave_prof.py).  Returns the command buffer."""
     rng = SplitMix64(seed)
     sb = 1 << sb_log2
     mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
@@ -429,9 +430,10 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
     all_ops, sbs = [], []
     sq_tx = {4: 0, 8: 1, 16: 2, 32: 3}
     size_pick = rng.randint(0, 2, (sb_rows, sb_cols))
+    sizes = tuple(sizes) if len(sizes) == 3 else tuple(sizes[i % len(sizes)] for i in range(3))
     for r in range(sb_rows):
         for c in range(sb_cols):
-            bs = (8, 16, 32)[int(size_pick[r, c])]
+            bs = sizes[int(size_pick[r, c])]
             x0, y0 = c * sb, r * sb
             nbx, nby = min(sb, fw - x0) // bs, min(sb, fh - y0) // bs
             n_blk = nbx * nby
@@ -462,6 +464,8 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
                         if bx == 0 and c > 0 and by + 1 < nby and y + 2 * s <= ph:
                             fl |= F.OPF_HAVE_BELOW_LEFT
                         mode = int(modes[k, 1 if pl else 0])
+                        if mode_set is not None:
+                            mode = mode_set[mode % len(mode_set)]
                         o = np.zeros((), op_t)
                         o["x"], o["y"], o["plane"], o["kind"], o["tx_size"] = x, y, pl, F.OP_INTRA, sq_tx[s]
                         o["mode"] = mode
@@ -469,10 +473,10 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True):
                             o["angle"] = int(deltas[k, 1 if pl else 0])
                             if misc[k, 0] & 1:
                                 fl |= F.OPF_EDGE_SMOOTH
-                        if pl == 0 and s <= 32 and misc[k, 1] < 48:
+                        if fi and pl == 0 and s <= 32 and misc[k, 1] < 48:
                             o["mode"], o["angle"], o["fi"] = 0, 0, int(misc[k, 2]) % 5
                             fl |= F.OPF_FILTER_INTRA
-                        if pl > 0 and misc[k, 3] < 64:
+                        if cfl and pl > 0 and misc[k, 3] < 64:
                             o["mode"], o["angle"] = 0, 0
                             o["cfl"] = int(misc[k, 2 if pl == 1 else 1]) % 31 - 15
                             o["mlw"], o["mlh"] = x0 + bx * bs + bs, y0 + by * bs + bs

@@ -155,6 +155,13 @@ int av1b_get_stage_times(av1b_ctx* ctx, double ms[AV1B_N_STAGES], uint64_t calls
 /* Device-to-device: make a copy of reference slot `slot` the "current" frame of the next submit
  * (benchmark: re-run the in-place post-filter chain on pristine, HBM-resident input). */
 int av1b_debug_input_from_slot(av1b_ctx* ctx, int slot);
+/* Wavefront trace (profiling aid).  av1b_debug_wave_trace(n) makes every later wavefront launch of
+ * the process record, per superblock, eight 64-bit words into a device buffer of n entries
+ * (n = 0 turns it off): superblock index, SM id, and %globaltimer nanoseconds at ticket taken,
+ * dependencies satisfied, first level started, last level finished, neighbours signalled, tile
+ * flushed.  av1b_debug_wave_trace_read copies the first n entries to the host (device-synchronous). */
+int av1b_debug_wave_trace(size_t n_entries);
+int av1b_debug_wave_trace_read(uint64_t* out, size_t n_entries);
 /* sizeof() of the command-format structs (0 FrameHdr, 1 Op, 2 Sb, 3 Ipu, 4 InterBlk, 5 BlkAux,
  * 6 LfMi, 7 LrUnit): lets a foreign-language binding verify its mirror of av1b200_format.h. */
 size_t av1b_struct_size(int which);
