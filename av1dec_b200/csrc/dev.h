@@ -196,6 +196,7 @@ static __device__ __forceinline__ unsigned av1b_smid()
 
 // ------------------------------------------------------------------ shared helpers
 #define AV1B_DEV static __device__ __forceinline__
+#define AV1B_DEV_M __device__ __forceinline__ // member functions
 
 // Barrier for a CTA of nt threads: a single-warp CTA (the latency-critical intra wavefront runs
 // one warp per superblock) only needs warp-level ordering.
@@ -283,14 +284,14 @@ AV1B_DEV uint32_t pack_u8x4(int v0, int v1, int v2, int v3) { return av1b_pack_s
 AV1B_DEV int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 AV1B_DEV int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 AV1B_DEV int round2(int x, int n) { return n == 0 ? x : ((x + (1 << (n - 1))) >> n); }
-// Four packed samples plus four int16 residuals, each clipped to 8 bits.
+// Four packed samples plus four int16 residuals, each clipped to 8 bits: bytes widened to 16x2,
+// add + min(255) + max(0) per pair in one instruction (VIADDMNMX.S16x2.RELU), bytes gathered back.
+// (Residuals of a conformant stream are 8 + BitDepth bits at most: the 16-bit add cannot wrap.)
 AV1B_DEV uint32_t add_res4(uint32_t px, uint2 r)
 {
-    const int o0 = clip_u8((int)(px & 0xFF) + (int)(int16_t)(r.x & 0xFFFF));
-    const int o1 = clip_u8((int)((px >> 8) & 0xFF) + ((int)r.x >> 16));
-    const int o2 = clip_u8((int)((px >> 16) & 0xFF) + (int)(int16_t)(r.y & 0xFFFF));
-    const int o3 = clip_u8((int)(px >> 24) + ((int)r.y >> 16));
-    return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+    const uint32_t p01 = __byte_perm(px, 0u, 0x4140), p23 = __byte_perm(px, 0u, 0x4342);
+    const uint32_t s01 = __viaddmin_s16x2_relu(p01, r.x, 0x00FF00FFu), s23 = __viaddmin_s16x2_relu(p23, r.y, 0x00FF00FFu);
+    return __byte_perm(s01, s23, 0x6420);
 }
 AV1B_DEV int round2s(int x, int n) { return x >= 0 ? round2(x, n) : -round2(-x, n); }
 AV1B_DEV int iabs(int v) { return v < 0 ? -v : v; }

@@ -137,12 +137,12 @@ AV1B_DEV uint32_t pack4(int v0, int v1, int v2, int v3) { return (uint32_t)v0 | 
 
 // Sub-sampled luma under four chroma samples (row i, columns j0 .. j0+3 of the block), each the
 // sum of a 2x2 luma quad times two (IntraPredict.cpp:640-650), as two packed 16x2 words.
-template <bool SMEM> AV1B_DEV uint2 cfl_luma4(const Prep& p, const Io& o, int i, int j0)
+template <bool SMEM> AV1B_DEV uint2 cfl_luma4(int lim_w, int lim_h, const Io& o, int i, int j0)
 {
-    const int ly = min(2 * i, p.lim_h);
+    const int ly = min(2 * i, lim_h);
     const int lx0 = 2 * j0;
     const uint8_t* q = o.luma + (ptrdiff_t)ly * o.luma_stride;
-    if (lx0 + 6 <= p.lim_w) {
+    if (lx0 + 6 <= lim_w) {
         const uint32_t a0 = ld32<SMEM>(q + lx0), a1 = ld32<SMEM>(q + lx0 + 4);
         const uint32_t b0 = ld32<SMEM>(q + o.luma_stride + lx0), b1 = ld32<SMEM>(q + o.luma_stride + lx0 + 4);
         // bytes (0,1) and (2,3) of a word are the quads of two adjacent chroma samples
@@ -153,7 +153,7 @@ template <bool SMEM> AV1B_DEV uint2 cfl_luma4(const Prep& p, const Io& o, int i,
     uint32_t v[4];
     AV1B_UNROLL
     for (int m = 0; m < 4; m++) {
-        const int lx = min(lx0 + 2 * m, p.lim_w);
+        const int lx = min(lx0 + 2 * m, lim_w);
         v[m] = (uint32_t)(ld8<SMEM>(q + lx) + ld8<SMEM>(q + lx + 1) + ld8<SMEM>(q + o.luma_stride + lx) + ld8<SMEM>(q + o.luma_stride + lx + 1)) << 1;
     }
     return make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
@@ -214,9 +214,32 @@ AV1B_DEV Prep prepare(const Args& a)
     return p;
 }
 
-// Bit-packed Prep: seven words (w[1] only in its high half).
+// Bit-packed Prep (four words).  run() works from this form and extracts a field where it needs
+// it, so a block only pays for the fields of its own mode.
 struct Packed {
-    uint32_t w[5];
+    uint32_t w[4];
+    AV1B_DEV_M int lw() const { return (int)(w[0] & 7); }
+    AV1B_DEV_M int lh() const { return (int)((w[0] >> 3) & 7); }
+    AV1B_DEV_M bool have_left() const { return (w[0] >> 6) & 1; }
+    AV1B_DEV_M bool have_above() const { return (w[0] >> 7) & 1; }
+    AV1B_DEV_M int kind() const { return (int)((w[0] >> 8) & 15); }
+    AV1B_DEV_M bool cfl() const { return (w[0] >> 12) & 1; }
+    AV1B_DEV_M int up_above() const { return (int)((w[0] >> 13) & 1); }
+    AV1B_DEV_M int up_left() const { return (int)((w[0] >> 14) & 1); }
+    AV1B_DEV_M bool corner() const { return (w[0] >> 15) & 1; }
+    AV1B_DEV_M bool filt() const { return (w[0] >> 16) & 1; }
+    AV1B_DEV_M int fi_mode() const { return (int)((w[0] >> 17) & 7); }
+    AV1B_DEV_M int sA() const { return (int)((w[0] >> 20) & 3); }
+    AV1B_DEV_M int sL() const { return (int)((w[0] >> 22) & 3); }
+    AV1B_DEV_M int above_n() const { return (int)(w[0] >> 24); }
+    AV1B_DEV_M int left_n() const { return (int)(w[1] & 0xFF); }
+    AV1B_DEV_M int szA() const { return (int)((w[1] >> 8) & 0xFF); }
+    AV1B_DEV_M int szL() const { return (int)((w[1] >> 16) & 0xFF); }
+    AV1B_DEV_M int alpha() const { return (int)(int8_t)(w[1] >> 24); }
+    AV1B_DEV_M int dx() const { return (int)(w[2] & 0x7FF); }
+    AV1B_DEV_M int dy() const { return (int)((w[2] >> 11) & 0x7FF); }
+    AV1B_DEV_M int lim_w() const { return (int)(w[3] & 0xFF); }
+    AV1B_DEV_M int lim_h() const { return (int)((w[3] >> 8) & 0xFF); }
 };
 AV1B_DEV Packed pack(const Prep& p)
 {
@@ -227,26 +250,7 @@ AV1B_DEV Packed pack(const Prep& p)
     k.w[1] = (uint32_t)p.left_n | ((uint32_t)p.szA << 8) | ((uint32_t)p.szL << 16) | ((uint32_t)(p.alpha & 0xFF) << 24);
     k.w[2] = (uint32_t)p.dx | ((uint32_t)p.dy << 11);
     k.w[3] = (uint32_t)p.lim_w | ((uint32_t)p.lim_h << 8);
-    k.w[4] = 0;
     return k;
-}
-AV1B_DEV Prep unpack(const Packed& k)
-{
-    Prep p;
-    p.lw = (int)(k.w[0] & 7), p.lh = (int)((k.w[0] >> 3) & 7);
-    p.have_left = (k.w[0] >> 6) & 1, p.have_above = (k.w[0] >> 7) & 1;
-    p.kind = (int)((k.w[0] >> 8) & 15);
-    p.cfl = (k.w[0] >> 12) & 1;
-    p.up_above = (int)((k.w[0] >> 13) & 1), p.up_left = (int)((k.w[0] >> 14) & 1);
-    p.corner = (k.w[0] >> 15) & 1, p.filt = (k.w[0] >> 16) & 1;
-    p.fi_mode = (int)((k.w[0] >> 17) & 7);
-    p.sA = (int)((k.w[0] >> 20) & 3), p.sL = (int)((k.w[0] >> 22) & 3);
-    p.above_n = (int)(k.w[0] >> 24);
-    p.left_n = (int)(k.w[1] & 0xFF), p.szA = (int)((k.w[1] >> 8) & 0xFF), p.szL = (int)((k.w[1] >> 16) & 0xFF);
-    p.alpha = (int)(int8_t)(k.w[1] >> 24);
-    p.dx = (int)(k.w[2] & 0x7FF), p.dy = (int)((k.w[2] >> 11) & 0x7FF);
-    p.lim_w = (int)(k.w[3] & 0xFF), p.lim_h = (int)((k.w[3] >> 8) & 0xFF);
-    return p;
 }
 
 // Predict one block into o.P (rows 4-byte aligned) and add the residual / CfL term on the way.
@@ -255,10 +259,10 @@ AV1B_DEV Prep unpack(const Packed& k)
 // call it.
 // NTC: the group size when it is a compile-time constant (32 = one warp per op), 0 = use nt_rt.
 template <bool SMEM, int NTC>
-AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
+AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
 {
     const int nt = NTC ? NTC : nt_rt;
-    const int lw = p.lw, lh = p.lh;
+    const int lw = p.lw(), lh = p.lh();
     const int w = 1 << lw, h = 1 << lh;
     const int lq = lw - 2, nq = w >> 2;  // groups of four columns
     const int items = h << lq;
@@ -268,10 +272,10 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
     const int pp = o.pp;
     // ---- phase 1: edge assembly (IntraPredict.cpp:579-611)
     {
-        const bool hl = p.have_left, ha = p.have_above;
+        const bool hl = p.have_left(), ha = p.have_above();
         const uint8_t* const row_above = o.blk - o.stride;
         const uint8_t* const col_left = o.blk - 1;
-        const int an = p.above_n, ln = p.left_n;
+        const int an = p.above_n(), ln = p.left_n();
         const int nw4 = (w + h) >> 2;
         AV1B_NOUNROLL
         for (int e = tid; e <= 2 * nw4; e += nt) {
@@ -304,7 +308,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
         }
         block_sync(nt);
     }
-    const int kind = p.kind;
+    const int kind = p.kind();
     if (kind == K_FILTER_INTRA) {
         // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront.  The recursion
         // feeds on PREDICTED samples, so the residual is added in a pass of its own afterwards.
@@ -314,7 +318,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
         const bool fixed_k = (nt & 7) == 0;
         int taps[7];
         AV1B_UNROLL
-        for (int i = 0; i < 7; i++) taps[i] = k_intra_filter_taps[p.fi_mode][tid & 7][i];
+        for (int i = 0; i < 7; i++) taps[i] = k_intra_filter_taps[p.fi_mode()][tid & 7][i];
         for (int d = 0; d < w4 + h2 - 1; d++) {
             int j_lo = max(0, d - (h2 - 1)), j_hi = min(w4 - 1, d);
             int nsb = j_hi - j_lo + 1;
@@ -336,7 +340,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 }
                 int pr = 0;
                 AV1B_UNROLL
-                for (int i = 0; i < 7; i++) pr += (fixed_k ? taps[i] : (int)k_intra_filter_taps[p.fi_mode][k][i]) * px[i];
+                for (int i = 0; i < 7; i++) pr += (fixed_k ? taps[i] : (int)k_intra_filter_taps[p.fi_mode()][k][i]) * px[i];
                 P[((i2 << 1) + i1) * pp + (j4 << 2) + j1] = (uint8_t)clip_u8(round2s(pr, 4));
             }
             block_sync(nt);
@@ -353,23 +357,23 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
     }
     if (kind >= K_DIR_LT90 && kind <= K_DIR_GT180) {
         // ---- directional (IntraPredict.cpp:379-469)
-        const int up_above = p.up_above, up_left = p.up_left;
+        const int up_above = p.up_above(), up_left = p.up_left();
         const uint8_t* EA = A;
         const uint8_t* EL = L;
-        if (p.filt) {
+        if (p.filt()) {
             uint8_t* const A2 = S.edge[2] + EDGE_OFF;
             uint8_t* const L2 = S.edge[3] + EDGE_OFF;
             // phase 2: new[m] = sum_j kern[j] * old[clip(-1, sz-2, m-2+j)] for m = 0 .. sz-2 (the
             // reference filters a copy that starts at the corner), old[-1] being the FILTERED
             // corner where the spec filters it; other entries are carried over
             const int n = w + h;
-            const int cf = p.corner ? ((L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4) : (int)A[-1];
+            const int cf = p.corner() ? ((L[0] * 5 + A[-1] * 6 + A[0] * 5 + 8) >> 4) : (int)A[-1];
             AV1B_NOUNROLL
             for (int e = tid; e < 2 * n; e += nt) {
                 const bool above = e < n;
                 const int m = above ? e : e - n;
                 const uint8_t* old = above ? A : L;
-                const int s = above ? p.sA : p.sL, sz = above ? p.szA : p.szL;
+                const int s = above ? p.sA() : p.sL(), sz = above ? p.szA() : p.szL();
                 int v;
                 if (s && m <= sz - 2) {
                     // taps {0,4,8,4,0}, {0,5,6,5,0}, {2,4,4,4,2}
@@ -408,7 +412,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
             }
         }
         if (kind == K_DIR_LT90) {
-            const int dx = p.dx;
+            const int dx = p.dx();
             const int max_base = (w + h - 1) << up_above;
             const int top = EA[max_base];
             AV1B_NOUNROLL
@@ -426,7 +430,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
         } else if (kind == K_DIR_MID) {
-            const int dx = p.dx, dy = p.dy;
+            const int dx = p.dx(), dy = p.dy();
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
@@ -449,7 +453,7 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
         } else {
-            const int dy = p.dy;
+            const int dy = p.dy();
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
@@ -514,24 +518,25 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
             for (int k = 0; k < w; k++) sa += A[k];
         }
         int avg;
-        if (p.have_left && p.have_above) {
+        if (p.have_left() && p.have_above()) {
             const int lmin = min(lw, lh), ratio = iabs(lw - lh); // w + h = (1 + 2^ratio) << lmin
             const unsigned q = (unsigned)(sl + sa + ((w + h) >> 1)) >> lmin;
             avg = ratio == 0 ? (int)(q >> 1) : (ratio == 1 ? (int)(__umulhi(q, 0xAAAAAAABu) >> 1) : (int)(__umulhi(q, 0xCCCCCCCDu) >> 2));
-        } else if (p.have_left) avg = clip_u8((sl + (h >> 1)) >> lh);
-        else if (p.have_above) avg = clip_u8((sa + (w >> 1)) >> lw);
+        } else if (p.have_left()) avg = clip_u8((sl + (h >> 1)) >> lh);
+        else if (p.have_above()) avg = clip_u8((sa + (w >> 1)) >> lw);
         else avg = 128;
-        if (!p.cfl) {
+        if (!p.cfl()) {
             const uint32_t word = (uint32_t)avg * 0x01010101u;
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) put4(o, e >> lq, e & (nq - 1), word);
         } else {
             // ---- chroma-from-luma on top of the DC value (IntraPredict.cpp:632-667): two passes over
             // the sub-sampled luma (sum, then apply) instead of a staging buffer
+            const int lim_w = p.lim_w(), lim_h = p.lim_h();
             int local = 0;
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) {
-                const uint2 l4 = cfl_luma4<SMEM>(p, o, e >> lq, 4 * (e & (nq - 1)));
+                const uint2 l4 = cfl_luma4<SMEM>(lim_w, lim_h, o, e >> lq, 4 * (e & (nq - 1)));
                 local += (int)((l4.x & 0xFFFF) + (l4.x >> 16) + (l4.y & 0xFFFF) + (l4.y >> 16));
             }
             int total;
@@ -544,11 +549,11 @@ AV1B_DEV void run(const Prep& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 total = S.acc;
             }
             const int lavg = round2(total, lw + lh);
-            const int alpha = p.alpha;
+            const int alpha = p.alpha();
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
-                const uint2 l4 = cfl_luma4<SMEM>(p, o, i, 4 * q);
+                const uint2 l4 = cfl_luma4<SMEM>(lim_w, lim_h, o, i, 4 * q);
                 const int v0 = clip_u8(avg + round2s(alpha * ((int)(l4.x & 0xFFFF) - lavg), 6));
                 const int v1 = clip_u8(avg + round2s(alpha * ((int)(l4.x >> 16) - lavg), 6));
                 const int v2 = clip_u8(avg + round2s(alpha * ((int)(l4.y & 0xFFFF) - lavg), 6));

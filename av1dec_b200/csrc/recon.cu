@@ -533,29 +533,38 @@ AV1B_DEV void decode_intra_op(Av1bOp* slot, const FrameConst& fc)
     w[2] = k.w[0];
     w[3] = k.w[1];
     w[4] = k.w[2];
-    w[6] = k.w[3] | ((op.flags & AV1B_OPF_HAS_RESID) ? 0x10000u : 0u);
+    w[6] = k.w[3] | ((op.flags & AV1B_OPF_HAS_RESID) ? 0x10000u : 0u); // lim_w, lim_h in the low half
 }
 
-template <int NTC>
-AV1B_DEV void exec_decoded_intra(const uint4 a, const uint4 b, const PlaneSet& io, OpScratch& S, int tid, int nt_rt)
-{
-    intra::Packed k;
-    k.w[0] = a.z, k.w[1] = a.w, k.w[2] = b.x, k.w[3] = b.z;
-    const intra::Prep p = intra::unpack(k);
-    const int x = (int)(a.x & 0xFFFF), y = (int)(a.x >> 16), plane = (int)(a.y & 0xFF);
-    uint8_t* const pix = plane == 0 ? io.pix0 : (plane == 1 ? io.pix1 : io.pix2);
-    const int pitch = plane == 0 ? io.pitch0 : io.pitch12;
-    const int16_t* const rbase = plane == 0 ? io.res0 : (plane == 1 ? io.res1 : io.res2);
-    const int rpitch = plane == 0 ? io.rpitch0 : io.rpitch12;
+// An op fetched from shared memory and, for decoded intra ops, the addresses it works on -- all a
+// warp can know about its NEXT op before the level barrier opens.
+struct StagedOp {
+    uint4 wa, wb;
     intra::Io o;
-    o.P = pix + (ptrdiff_t)y * pitch + x;
-    o.blk = o.P;
-    o.stride = o.pp = pitch;
-    o.res = ((b.z & 0x10000u) && rbase) ? rbase + (ptrdiff_t)y * rpitch + x : nullptr;
-    o.rpitch = rpitch;
-    o.luma = io.pix0 + (ptrdiff_t)(2 * y) * io.pitch0 + 2 * x;
-    o.luma_stride = io.pitch0;
-    intra::run<true, NTC>(p, o, S.I, tid, nt_rt);
+    int state; // 0 none, 1 decoded intra op (o is valid), 2 any other op
+};
+AV1B_DEV StagedOp stage_op(const Av1bOp* slot, const PlaneSet& io)
+{
+    StagedOp s;
+    s.wa = ((const uint4*)slot)[0];
+    s.wb = ((const uint4*)slot)[1];
+    s.state = 2;
+    if (s.wa.y & (WAVE_OP_DECODED << 8)) {
+        const int x = (int)(s.wa.x & 0xFFFF), y = (int)(s.wa.x >> 16), plane = (int)(s.wa.y & 0xFF);
+        uint8_t* const pix = plane == 0 ? io.pix0 : (plane == 1 ? io.pix1 : io.pix2);
+        const int pitch = plane == 0 ? io.pitch0 : io.pitch12;
+        const int16_t* const rbase = plane == 0 ? io.res0 : (plane == 1 ? io.res1 : io.res2);
+        const int rpitch = plane == 0 ? io.rpitch0 : io.rpitch12;
+        s.o.P = pix + (ptrdiff_t)y * pitch + x;
+        s.o.blk = s.o.P;
+        s.o.stride = s.o.pp = pitch;
+        s.o.res = ((s.wb.z & 0x10000u) && rbase) ? rbase + (ptrdiff_t)y * rpitch + x : nullptr;
+        s.o.rpitch = rpitch;
+        s.o.luma = io.pix0 + (ptrdiff_t)(2 * y) * io.pitch0 + 2 * x;
+        s.o.luma_stride = io.pitch0;
+        s.state = 1;
+    }
+    return s;
 }
 
 // SMEM: the planes in `io` are the superblock tile in shared memory (wave_kernel) -- said to the
@@ -602,7 +611,7 @@ AV1B_DEV void exec_op(const ReconCtx& c, const Av1bFrameHdr* hdr, const FrameCon
         // Intra blocks are predicted straight into their place, residual and CfL fused into the
         // store.  Inter-intra blocks predict into scratch (the place holds the inter half).
         const bool in_place = op.kind == AV1B_OP_INTRA;
-        const intra::Prep p = intra::prepare(intra_args(op, fc, lw, lh));
+        const intra::Packed p = intra::pack(intra::prepare(intra_args(op, fc, lw, lh)));
         intra::Io o;
         o.blk = dst;
         o.stride = D.pitch;
@@ -839,24 +848,52 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         for (unsigned q = tid; q < min((unsigned)WAVE_OP_CHUNK, e.n_ops); q += nt) decode_intra_op(&s_ops[0][q], fc);
         wave_wait(progress, r, col, sb_cols, 2, tid, nt);
         if (tr) tr[3] = av1b_gtime();
-        // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and the column to the left
-        auto load_halo = [&](int pl, uint8_t* t, int n, int pitch) {
-            const int x0 = col * n, y0 = r * n;
-            const PlaneView g = c.cur.pl[pl];
-            if (r > 0) {
-                const uint32_t* src = (const uint32_t*)(g.p + (size_t)(y0 - 1) * g.stride + x0 - 4);
-                AV1B_NOUNROLL
-                for (int k = tid; k < (n >> 1) + 1; k += nt) ((uint32_t*)t)[k] = __ldcg(src + k);
+        // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and the column to the left, of all three
+        // planes as ONE list of items so that every load is in flight before the first store waits
+        {
+            const int aw0 = (n0 >> 1) + 1, aw1 = (n1 >> 1) + 1; // words of a row above
+            const int n_above = r > 0 ? aw0 + 2 * aw1 : 0;
+            const int n_left = col > 0 ? n0 + 2 * n1 : 0;
+            AV1B_NOUNROLL
+            for (int b0 = 0; b0 < n_above + n_left; b0 += 2 * nt) {
+                uint32_t v[2];
+                uint8_t* dsts[2];
+                bool word[2];
+                AV1B_UNROLL
+                for (int u = 0; u < 2; u++) {
+                    int k = b0 + u * nt + tid;
+                    dsts[u] = nullptr;
+                    word[u] = false;
+                    v[u] = 0;
+                    if (k >= n_above + n_left) continue;
+                    if (k < n_above) {
+                        const int pl = k < aw0 ? 0 : (k < aw0 + aw1 ? 1 : 2);
+                        k -= pl == 0 ? 0 : (pl == 1 ? aw0 : aw0 + aw1);
+                        const int n = pl ? n1 : n0;
+                        const PlaneView g = c.cur.pl[pl];
+                        uint8_t* t = pl == 0 ? t0 : (pl == 1 ? t1 : t2);
+                        v[u] = __ldcg((const uint32_t*)(g.p + (size_t)(r * n - 1) * g.stride + col * n - 4) + k);
+                        dsts[u] = t + 4 * k;
+                        word[u] = true;
+                    } else {
+                        k -= n_above;
+                        const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2);
+                        k -= pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1);
+                        const int n = pl ? n1 : n0, pitch = pl ? pitch1 : pitch0;
+                        const PlaneView g = c.cur.pl[pl];
+                        uint8_t* t = pl == 0 ? t0 : (pl == 1 ? t1 : t2);
+                        v[u] = __ldcg(g.p + (size_t)(r * n + k) * g.stride + col * n - 1);
+                        dsts[u] = t + (k + 1) * pitch + 3;
+                    }
+                }
+                AV1B_UNROLL
+                for (int u = 0; u < 2; u++) {
+                    if (!dsts[u]) continue;
+                    if (word[u]) *(uint32_t*)dsts[u] = v[u];
+                    else *dsts[u] = (uint8_t)v[u];
+                }
             }
-            if (col > 0) {
-                const uint8_t* src = g.p + (size_t)y0 * g.stride + x0 - 1;
-                AV1B_NOUNROLL
-                for (int k = tid; k < n; k += nt) t[(k + 1) * pitch + 3] = __ldcg(src + (size_t)k * g.stride);
-            }
-        };
-        load_halo(0, t0, n0, pitch0);
-        load_halo(1, t1, n1, pitch1);
-        load_halo(2, t2, n1, pitch1);
+        }
         PlaneSet io;
         io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (4 - col * n0);
         io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (4 - col * n1);
@@ -874,17 +911,18 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         // its L2 latency hides behind the levels in between.
         block_sync(nt);
         if (tr) tr[4] = av1b_gtime();
-        auto run_one = [&](const Av1bOp* slot) {
-            const uint4 wa = ((const uint4*)slot)[0], wb = ((const uint4*)slot)[1];
-            if (wa.y & (WAVE_OP_DECODED << 8)) {
-                exec_decoded_intra<WAVE_NT>(wa, wb, io, *scratch, lane, nl);
+        auto exec_staged = [&](const StagedOp& st) {
+            if (st.state == 1) {
+                intra::Packed k;
+                k.w[0] = st.wa.z, k.w[1] = st.wa.w, k.w[2] = st.wb.x, k.w[3] = st.wb.z;
+                intra::run<true, WAVE_NT>(k, st.o, scratch->I, lane, nl);
                 return;
             }
             union {
                 uint4 v[2];
                 Av1bOp op;
             } u;
-            u.v[0] = wa, u.v[1] = wb;
+            u.v[0] = st.wa, u.v[1] = st.wb;
             exec_op<true, WAVE_NT>(c, hdr, fc, u.op, io, *scratch, nullptr, lane, nl);
         };
         int buf = 0;
@@ -896,21 +934,43 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             uint4 pre = make_uint4(0, 0, 0, 0);
             static_assert(WAVE_OP_CHUNK * 2 <= 256, "one uint4 of the next chunk per thread");
             if ((unsigned)tid < nn * 2) pre = __ldg((const uint4*)(ops + e.first_op + k1) + tid);
-            unsigned g0 = 0;
-            while (g0 < nk) {
-                // res_off >> 16 = ops left in this level (emitter scheduleSb); 0 from a producer
-                // that does not fill it: one op per step, still a valid order
-                const unsigned g1 = min(nk, g0 + max(1u, cur_ops[g0].res_off >> 16));
+            // res_off >> 16 = ops left in this level (emitter scheduleSb); 0 from a producer that
+            // does not fill it: one op per step, still a valid order
+            auto level_end = [&](unsigned g) { return min(nk, g + max(1u, cur_ops[g].res_off >> 16)); };
+            unsigned g0 = 0, g1 = level_end(0);
 #ifdef AV1B_EMU
+            while (g0 < nk) {
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
-                for (unsigned k = g1; k-- > g0;) run_one(cur_ops + k);
+                for (unsigned k = g1; k-- > g0;) exec_staged(stage_op(cur_ops + k, io));
+                g0 = g1;
+                if (g0 < nk) g1 = level_end(g0);
+            }
 #else
-                for (unsigned k = g0 + warp; k < g1; k += nw) run_one(cur_ops + k);
-#endif
+            // Op j of a level goes to warp (j + parity * nw/2) mod nw, the parity flipping with
+            // every level: a level rarely has more than nw/2 ops, so the warps that work in one
+            // level idle in the next and have fetched their next op and worked out its addresses
+            // BEFORE the barrier opens -- the chain between two barriers is loads, arithmetic,
+            // stores.
+            unsigned par = 0;
+            unsigned mine = g0 + ((warp + par * (nw >> 1)) & (nw - 1));
+            StagedOp st;
+            st.state = 0;
+            if (mine < g1) st = stage_op(cur_ops + mine, io);
+            while (g0 < nk) {
+                if (mine < g1) {
+                    exec_staged(st);
+                    for (unsigned k = mine + nw; k < g1; k += nw) exec_staged(stage_op(cur_ops + k, io));
+                }
+                const unsigned g2 = g1 < nk ? level_end(g1) : g1;
+                par ^= 1;
+                mine = g1 + ((warp + par * (nw >> 1)) & (nw - 1));
+                if (mine < g2) st = stage_op(cur_ops + mine, io);
                 block_sync(nt);
                 g0 = g1;
+                g1 = g2;
             }
+#endif
             if (nn) {
 #ifdef AV1B_EMU
                 for (unsigned q = 0; q < nn * 2; q++) ((uint4*)s_ops[buf ^ 1])[q] = ((const uint4*)(ops + e.first_op + k1))[q];
@@ -1087,7 +1147,7 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         return;
     }
     // Two builds: 16 warps, one CTA per SM (lowest latency for a lone stream), and 8 warps at
-    // <= 80 registers, three CTAs per SM (a busy multi-stream device is bound by CTA slots: the
+    // two CTAs per SM (a busy multi-stream device is bound by CTA slots: the
     // wavefront of one superblock keeps a warp scheduler mostly idle).  AV1B200_WAVE_WARPS picks.
     const char* wenv = getenv("AV1B200_WAVE_WARPS");
     const int warps = (wenv && atoi(wenv) == 8) ? 8 : 16;
@@ -1102,14 +1162,14 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         std::lock_guard<std::mutex> lk(mu);
         if (!(done[(dev >> 6) & 3] & (1ull << (dev & 63)))) {
             cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 16));
-            cudaFuncSetAttribute(wave_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 8));
+            cudaFuncSetAttribute(wave_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 8));
             done[(dev >> 6) & 3] |= 1ull << (dev & 63);
         }
     }
     if (warps == 16) wave_kernel<16, 1><<<dim3(grid), dim3(512), smem, st>>>(c);
-    else wave_kernel<8, 3><<<dim3(grid), dim3(256), smem, st>>>(c);
+    else wave_kernel<8, 2><<<dim3(grid), dim3(256), smem, st>>>(c);
 #else
     (void)smem;
-    AV1B_LAUNCH((wave_kernel<8, 3>), (grid), (256), st, c);
+    AV1B_LAUNCH((wave_kernel<8, 2>), (grid), (256), st, c);
 #endif
 }
