@@ -270,45 +270,42 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
     uint8_t* const L = S.edge[1] + EDGE_OFF;
     uint8_t* const P = o.P;
     const int pp = o.pp;
-    // ---- phase 1: edge assembly (IntraPredict.cpp:579-611)
-    {
-        const bool hl = p.have_left(), ha = p.have_above();
-        const uint8_t* const row_above = o.blk - o.stride;
-        const uint8_t* const col_left = o.blk - 1;
+    const int kind = p.kind();
+    const bool hl = p.have_left(), ha = p.have_above();
+    const uint8_t* const row_above = o.blk - o.stride;
+    const uint8_t* const col_left = o.blk - 1;
+    // DC / V / H / Paeth / smooth blocks whose edges all exist read them where they lie (tile in
+    // shared memory): no assembly, no barrier.  EA[i] = AboveRow[i], EL[i * es] = LeftCol[i].
+    const bool direct = SMEM && kind <= K_SMOOTH_H && ha && hl && p.above_n() >= w && p.left_n() >= h;
+    const uint8_t* const EA = direct ? row_above : A;
+    const uint8_t* const EL = direct ? col_left : L;
+    const int es = direct ? o.stride : 1;
+    // ---- phase 1: edge assembly (IntraPredict.cpp:579-611).  Every item gathers four bytes at
+    // base + min(n - 1, i) * step; the three kinds of item (word of the row above, word of the
+    // left column, corner) differ only in those operands, so the lanes do not diverge.
+    if (!direct) {
         const int an = p.above_n(), ln = p.left_n();
         const int nw4 = (w + h) >> 2;
+        const bool none = !ha && !hl;
         AV1B_NOUNROLL
         for (int e = tid; e <= 2 * nw4; e += nt) {
-            if (e < nw4) {
-                const int xi = 4 * e;
-                uint32_t v;
-                if (!ha) v = hl ? (uint32_t)ld8<SMEM>(col_left) * 0x01010101u : 0x7F7F7F7Fu;
-                else if (xi + 3 < an) v = ld32<SMEM>(row_above + xi);
-                else
-                    v = pack4(ld8<SMEM>(row_above + min(an - 1, xi)), ld8<SMEM>(row_above + min(an - 1, xi + 1)),
-                        ld8<SMEM>(row_above + min(an - 1, xi + 2)), ld8<SMEM>(row_above + min(an - 1, xi + 3)));
-                *(uint32_t*)(A + xi) = v;
-            } else if (e < 2 * nw4) {
-                const int yi = 4 * (e - nw4);
-                uint32_t v;
-                if (!hl) v = ha ? (uint32_t)ld8<SMEM>(row_above) * 0x01010101u : 0x81818181u;
-                else
-                    v = pack4(ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi) * o.stride), ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 1) * o.stride),
-                        ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 2) * o.stride), ld8<SMEM>(col_left + (ptrdiff_t)min(ln - 1, yi + 3) * o.stride));
-                *(uint32_t*)(L + yi) = v;
-            } else {
-                int c;
-                if (ha && hl) c = ld8<SMEM>(row_above - 1);
-                else if (ha) c = ld8<SMEM>(row_above);
-                else if (hl) c = ld8<SMEM>(col_left);
-                else c = 128;
-                A[-1] = (uint8_t)c;
-                L[-1] = (uint8_t)c;
-            }
+            const bool is_a = e < nw4, is_c = e == 2 * nw4;
+            const int i0 = is_a ? 4 * e : 4 * (e - nw4);
+            const uint8_t* base;
+            int n, step;
+            if (is_c) base = ha ? (hl ? row_above - 1 : row_above) : col_left, n = 1, step = 0; // (x-1,y-1) | (x,y-1) | (x-1,y)
+            else if (is_a) base = ha ? row_above : col_left, n = ha ? an : 1, step = 1;            // row above | (x-1,y) replicated
+            else base = hl ? col_left : row_above, n = hl ? ln : 1, step = o.stride;              // left column | (x,y-1) replicated
+            uint32_t v = pack4(ld8<SMEM>(base + (ptrdiff_t)min(n - 1, i0) * step), ld8<SMEM>(base + (ptrdiff_t)min(n - 1, i0 + 1) * step),
+                ld8<SMEM>(base + (ptrdiff_t)min(n - 1, i0 + 2) * step), ld8<SMEM>(base + (ptrdiff_t)min(n - 1, i0 + 3) * step));
+            if (none) v = is_c ? 0x80808080u : (is_a ? 0x7F7F7F7Fu : 0x81818181u);
+            if (is_c) {
+                A[-1] = (uint8_t)v;
+                L[-1] = (uint8_t)v;
+            } else *(uint32_t*)((is_a ? A : L) + i0) = v;
         }
         block_sync(nt);
     }
-    const int kind = p.kind();
     if (kind == K_FILTER_INTRA) {
         // ---- recursive filter-intra: 4x2 sub-blocks, anti-diagonal wavefront.  The recursion
         // feeds on PREDICTED samples, so the residual is added in a pass of its own afterwards.
@@ -358,8 +355,8 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
     if (kind >= K_DIR_LT90 && kind <= K_DIR_GT180) {
         // ---- directional (IntraPredict.cpp:379-469)
         const int up_above = p.up_above(), up_left = p.up_left();
-        const uint8_t* EA = A;
-        const uint8_t* EL = L;
+        const uint8_t* DA = A;
+        const uint8_t* DL = L;
         if (p.filt()) {
             uint8_t* const A2 = S.edge[2] + EDGE_OFF;
             uint8_t* const L2 = S.edge[3] + EDGE_OFF;
@@ -388,8 +385,8 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 if (m == 0) nw[-1] = (uint8_t)cf;
             }
             block_sync(nt);
-            EA = A2;
-            EL = L2;
+            DA = A2;
+            DL = L2;
             if (up_above | up_left) {
                 // phase 3: 2x upsampling of edge[-1 .. n-1] into edge[-2 .. 2n-2] (reference
                 // intraEdgeUpsample), second pair -> first pair
@@ -407,14 +404,14 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                     if (i == 0) nw[-2] = old[-1];
                 }
                 block_sync(nt);
-                if (up_above) EA = A;
-                if (up_left) EL = L;
+                if (up_above) DA = A;
+                if (up_left) DL = L;
             }
         }
         if (kind == K_DIR_LT90) {
             const int dx = p.dx();
             const int max_base = (w + h - 1) << up_above;
-            const int top = EA[max_base];
+            const int top = DA[max_base];
             AV1B_NOUNROLL
             for (int e = tid; e < items; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
@@ -425,7 +422,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 AV1B_UNROLL
                 for (int m = 0; m < 4; m++) {
                     const int base = b0 + (m << up_above);
-                    v[m] = base < max_base ? ((EA[base] * (32 - shift) + EA[base + 1] * shift + 16) >> 5) : top;
+                    v[m] = base < max_base ? ((DA[base] * (32 - shift) + DA[base + 1] * shift + 16) >> 5) : top;
                 }
                 put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
@@ -442,12 +439,12 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                     int base = idx >> (6 - up_above);
                     if (base >= -(1 << up_above)) {
                         const int shift = ((idx << up_above) >> 1) & 31;
-                        v[m] = (EA[base] * (32 - shift) + EA[base + 1] * shift + 16) >> 5;
+                        v[m] = (DA[base] * (32 - shift) + DA[base + 1] * shift + 16) >> 5;
                     } else {
                         idx = (i << 6) - (j + 1) * dy;
                         base = idx >> (6 - up_left);
                         const int shift = ((idx << up_left) >> 1) & 31;
-                        v[m] = (EL[base] * (32 - shift) + EL[base + 1] * shift + 16) >> 5;
+                        v[m] = (DL[base] * (32 - shift) + DL[base + 1] * shift + 16) >> 5;
                     }
                 }
                 put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
@@ -463,7 +460,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                     const int idx = (4 * q + m + 1) * dy;
                     const int base = (idx >> (6 - up_left)) + (i << up_left);
                     const int shift = ((idx << up_left) >> 1) & 31;
-                    v[m] = (EL[base] * (32 - shift) + EL[base + 1] * shift + 16) >> 5;
+                    v[m] = (DL[base] * (32 - shift) + DL[base + 1] * shift + 16) >> 5;
                 }
                 put4(o, i, q, pack4(v[0], v[1], v[2], v[3]));
             }
@@ -472,21 +469,21 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            put4(o, i, q, *(const uint32_t*)(A + 4 * q));
+            put4(o, i, q, *(const uint32_t*)(EA + 4 * q));
         }
     } else if (kind == K_H) {
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            put4(o, i, q, (uint32_t)L[i] * 0x01010101u);
+            put4(o, i, q, (uint32_t)EL[i * es] * 0x01010101u);
         }
     } else if (kind == K_PAETH) {
-        const int tl = A[-1];
+        const int tl = EA[-1];
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
-            const int l = L[i];
+            const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
+            const int l = EL[i * es];
             int v[4];
             AV1B_UNROLL
             for (int m = 0; m < 4; m++) {
@@ -507,23 +504,26 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
             const int wq = w >> 2, hq = h >> 2;
             AV1B_NOUNROLL
             for (int k = tid; k < wq + hq; k += nt) {
-                if (k < wq) part = av1b_dp4a_uu(*(const uint32_t*)(A + 4 * k), 0x01010101u, part);
-                else part += av1b_dp4a_uu(*(const uint32_t*)(L + 4 * (k - wq)), 0x01010101u, 0u) << 16;
+                if (k < wq) part = av1b_dp4a_uu(*(const uint32_t*)(EA + 4 * k), 0x01010101u, part);
+                else {
+                    const uint8_t* l4 = EL + 4 * (k - wq) * es;
+                    part += (uint32_t)(l4[0] + l4[es] + l4[2 * es] + l4[3 * es]) << 16;
+                }
             }
             part = warp_sum(part, nt);
             sl = (int)(part >> 16);
             sa = (int)(part & 0xFFFF);
         } else {
-            for (int k = 0; k < h; k++) sl += L[k];
-            for (int k = 0; k < w; k++) sa += A[k];
+            for (int k = 0; k < h; k++) sl += EL[k * es];
+            for (int k = 0; k < w; k++) sa += EA[k];
         }
         int avg;
-        if (p.have_left() && p.have_above()) {
+        if (hl && ha) {
             const int lmin = min(lw, lh), ratio = iabs(lw - lh); // w + h = (1 + 2^ratio) << lmin
             const unsigned q = (unsigned)(sl + sa + ((w + h) >> 1)) >> lmin;
             avg = ratio == 0 ? (int)(q >> 1) : (ratio == 1 ? (int)(__umulhi(q, 0xAAAAAAABu) >> 1) : (int)(__umulhi(q, 0xCCCCCCCDu) >> 2));
-        } else if (p.have_left()) avg = clip_u8((sl + (h >> 1)) >> lh);
-        else if (p.have_above()) avg = clip_u8((sa + (w >> 1)) >> lw);
+        } else if (hl) avg = clip_u8((sl + (h >> 1)) >> lh);
+        else if (ha) avg = clip_u8((sa + (w >> 1)) >> lw);
         else avg = 128;
         if (!p.cfl()) {
             const uint32_t word = (uint32_t)avg * 0x01010101u;
@@ -564,12 +564,12 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
     } else if (kind == K_SMOOTH) {
         const uint8_t* wx = k_sm_weights + (w - 4);
         const uint8_t* wy = k_sm_weights + (h - 4);
-        const int bl = L[h - 1], tr = A[w - 1];
+        const int bl = EL[(h - 1) * es], tr = EA[w - 1];
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
-            const int l = L[i], wyi = wy[i];
+            const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
+            const int l = EL[i * es], wyi = wy[i];
             const int rowc = (256 - wyi) * bl + 256;
             int v[4];
             AV1B_UNROLL
@@ -581,11 +581,11 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         }
     } else if (kind == K_SMOOTH_V) {
         const uint8_t* wy = k_sm_weights + (h - 4);
-        const int bl = L[h - 1];
+        const int bl = EL[(h - 1) * es];
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            const uint32_t aw = *(const uint32_t*)(A + 4 * q);
+            const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
             const int wyi = wy[i];
             const int rowc = (256 - wyi) * bl + 128;
             int v[4];
@@ -595,11 +595,11 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         }
     } else { // K_SMOOTH_H
         const uint8_t* wx = k_sm_weights + (w - 4);
-        const int tr = A[w - 1];
+        const int tr = EA[w - 1];
         AV1B_NOUNROLL
         for (int e = tid; e < items; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
-            const int l = L[i];
+            const int l = EL[i * es];
             int v[4];
             AV1B_UNROLL
             for (int m = 0; m < 4; m++) {
