@@ -284,7 +284,7 @@ AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int ph, int rows,
 __global__ void __launch_bounds__(CD_THREADS) cdef_kernel(PostCtx c)
 {
     __shared__ CdefSmem S;
-    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const PostHdr* hdr = &c.h;
     const uint8_t* cdef8 = c.cmd + hdr->off_cdef8;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int c8 = hdr->mi_cols >> 1, r8 = hdr->mi_rows >> 1; // 8x8 blocks in the frame

@@ -165,7 +165,7 @@ struct LfSmem {
 // Is the edge unit at plane unit coordinates (uc, ur) (4-sample units) live in PASS?  Fills the
 // filter parameters.  (loop_filter_edge, LoopFilter.cpp:85-126)
 template <int PASS>
-AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc, int ur, LfJob& job, int& cls)
+AV1B_DEV bool lf_test(const PostHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc, int ur, LfJob& job, int& cls)
 {
     const int sub = plane ? 1 : 0;
     const int mi_cols = hdr->mi_cols;
@@ -203,7 +203,7 @@ AV1B_DEV bool lf_test(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLo
 // one shared-memory atomic per warp and class (ballot-compacted).  Units are (col, row) in the
 // ncols x nrows window starting at unit (uc0, ur0) of the plane.
 template <int PASS, int QCAP>
-AV1B_DEV void lf_collect(const Av1bFrameHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc0, int ur0, int ncols,
+AV1B_DEV void lf_collect(const PostHdr* hdr, const Av1bLfMi* mis, const Av1bLoopFilterParams& lf, int plane, int uc0, int ur0, int ncols,
     int nrows, int x0, int y0, LfJob (*queue)[QCAP], int* count, int tid, int nt)
 {
     const int sub = plane ? 1 : 0;
@@ -271,7 +271,7 @@ template <bool CHROMA> AV1B_DEV void lf_run_pass(uint8_t* px, LfJob (*queue)[LF_
 __global__ void __launch_bounds__(LF_THREADS) deblock_kernel(PostCtx c)
 {
     __shared__ LfSmem S;
-    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const PostHdr* hdr = &c.h;
     const Av1bLfMi* mis = (const Av1bLfMi*)(c.cmd + hdr->off_lfmi);
     const int plane = blockIdx.z, sub = plane ? 1 : 0;
     const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub; // MI-aligned plane

@@ -793,6 +793,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     PostCtx pc;
     memset(&pc, 0, sizeof(pc));
     pc.cmd = dev_cmd;
+    pc.h = make_post_hdr(h);
     pc.src = c->frames[cur].v;
     int final_frame = cur, deb = -1, cdef = -1, lr = -1;
     pc.deb = pc.src;

@@ -19,8 +19,27 @@ struct ReconCtx {
     unsigned trace_cap;
 };
 
+// The frame-header fields the filter kernels read, BY VALUE: a kernel argument lives in the constant
+// bank, so a CTA starts on its tile without a dependent global load of the header first.
+struct PostHdr {
+    uint16_t frame_w, frame_h, mi_cols, mi_rows;
+    uint32_t off_lfmi, off_cdef8, off_lru;
+    Av1bLoopFilterParams lf;
+    Av1bCdefParams cdef;
+    Av1bLrParams lr;
+};
+inline PostHdr make_post_hdr(const Av1bFrameHdr& h)
+{
+    PostHdr p;
+    p.frame_w = h.frame_w, p.frame_h = h.frame_h, p.mi_cols = h.mi_cols, p.mi_rows = h.mi_rows;
+    p.off_lfmi = h.off_lfmi, p.off_cdef8 = h.off_cdef8, p.off_lru = h.off_lru;
+    p.lf = h.lf, p.cdef = h.cdef, p.lr = h.lr;
+    return p;
+}
+
 // In-loop filter context.
 struct PostCtx {
+    PostHdr h;
     const uint8_t* cmd;
     FrameView src;  // reconstructed frame (never modified by the filters)
     FrameView deb;  // deblocked frame (== src when the deblocking stage does not run)

@@ -276,7 +276,7 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
 {
     typedef LrGeom<TW> G;
     __shared__ LrSmem<TW> S;
-    const Av1bFrameHdr* hdr = (const Av1bFrameHdr*)c.cmd;
+    const PostHdr* hdr = &c.h;
     const Av1bLrParams& lp = hdr->lr;
     // grid = (tiles per row, tile rows, planes of this launch); everything below is shifts: unit
     // sizes are powers of two and a stripe holds one (chroma) or two (luma) tile rows

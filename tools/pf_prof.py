@@ -19,7 +19,8 @@ eng = Engine(W, H, device=0, stream=None)
 eng.set_lanes(1)
 frames = []
 for i in range(n):
-    sf = synth.make_postfilter_frame(W, H, seed=synth.SEED + i, dist="B", lr_unit=64)
+    sf = synth.make_postfilter_frame(W, H, seed=synth.SEED + i, dist="B", lr_unit=int(os.environ.get("PF_LR_UNIT", "64")),
+                                     lr_types=tuple(int(t) for t in os.environ.get("PF_LR_TYPES", "0,1,2").split(",")))
     eng.set_ref(i, sf.planes, sf.mi_cols * 4, sf.mi_rows * 4)
     frames.append((eng.upload(sf.cmd), sf.cmd[:hdr_size]))
 eng.set_profiling(True)
