@@ -281,7 +281,7 @@ AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int ph, int rows,
 
 }  // namespace
 
-__global__ void __launch_bounds__(CD_THREADS) cdef_kernel(PostCtx c)
+__global__ void __launch_bounds__(CD_THREADS, 5) cdef_kernel(PostCtx c)
 {
     __shared__ CdefSmem S;
     const PostHdr* hdr = &c.h;

@@ -265,22 +265,19 @@ template <int TW, int PASS> AV1B_DEV void sgr_out(LrSmem<TW>& S, int h, const Sg
 }
 
 struct LrGrid {
-    uint8_t plane_of[3]; // blockIdx.z -> plane
+    uint8_t narrow[3]; // plane uses 32-wide tiles (restoration units of 32 samples)
     uint8_t pad;
 };
 
-}  // namespace
-
 // One CTA = one TW x 32 tile of one plane.
-template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCtx c, LrGrid grid)
+template <int TW> AV1B_DEV void lr_tile(const PostCtx& c, const int plane, uint8_t* smem_raw)
 {
     typedef LrGeom<TW> G;
-    __shared__ LrSmem<TW> S;
+    LrSmem<TW>& S = *reinterpret_cast<LrSmem<TW>*>(smem_raw);
     const PostHdr* hdr = &c.h;
     const Av1bLrParams& lp = hdr->lr;
     // grid = (tiles per row, tile rows, planes of this launch); everything below is shifts: unit
     // sizes are powers of two and a stripe holds one (chroma) or two (luma) tile rows
-    const int plane = grid.plane_of[blockIdx.z];
     const int sub = plane ? 1 : 0;
     const int pw = (hdr->frame_w + sub) >> sub, ph = (hdr->frame_h + sub) >> sub;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -431,31 +428,35 @@ template <int TW> __global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCt
     }
 }
 
-// Planes whose restoration units are at least 64 samples wide use 64-wide tiles, the others
-// (chroma of a 64-unit luma with lr_uv_shift) 32-wide ones: at most two launches.
+}  // namespace
+
+// grid = (tiles per row, tile rows, plane), both maxima over the planes.  Planes whose restoration
+// units are at least 64 samples wide use 64-wide tiles, the others (chroma of a 64-unit luma with
+// lr_uv_shift) 32-wide ones -- in the SAME launch: at 4K a launch of a few thousand short CTAs
+// spends a third of its time ramping up and draining.
+__global__ void __launch_bounds__(LR_THREADS) lr_kernel(PostCtx c, LrGrid grid)
+{
+    alignas(16) __shared__ uint8_t smem_raw[sizeof(LrSmem<64>)];
+    const int plane = blockIdx.z;
+    if (grid.narrow[plane]) lr_tile<32>(c, plane, smem_raw);
+    else lr_tile<64>(c, plane, smem_raw);
+}
+
 int launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
     if (!h.lr.uses_lr) return 0;
-    int launches = 0;
-    for (int cls = 0; cls < 2; cls++) {
-        const int tw = cls == 0 ? 64 : 32;
-        LrGrid g;
-        memset(&g, 0, sizeof(g));
-        int np = 0, gx = 0, gy = 0;
-        for (int p = 0; p < 3; p++) {
-            const int sub = p ? 1 : 0;
-            const int pw = (h.frame_w + sub) >> sub, ph = (h.frame_h + sub) >> sub;
-            const bool narrow = h.lr.frame_type[p] && h.lr.unit_size[p] < 64;
-            if (narrow != (cls == 1)) continue;
-            g.plane_of[np++] = (uint8_t)p;
-            const int stripes = (ph + (8 >> sub) + (64 >> sub) - 1) / (64 >> sub);
-            gx = std::max(gx, (pw + tw - 1) / tw);
-            gy = std::max(gy, stripes * ((64 >> sub) / LR_TH));
-        }
-        if (!np) continue;
-        if (cls == 0) AV1B_LAUNCH(lr_kernel<64>, (gx, gy, np), (LR_THREADS), st, c, g);
-        else AV1B_LAUNCH(lr_kernel<32>, (gx, gy, np), (LR_THREADS), st, c, g);
-        launches++;
+    LrGrid g;
+    memset(&g, 0, sizeof(g));
+    int gx = 0, gy = 0;
+    for (int p = 0; p < 3; p++) {
+        const int sub = p ? 1 : 0;
+        const int pw = (h.frame_w + sub) >> sub, ph = (h.frame_h + sub) >> sub;
+        g.narrow[p] = h.lr.frame_type[p] && h.lr.unit_size[p] < 64;
+        const int tw = g.narrow[p] ? 32 : 64;
+        const int stripes = (ph + (8 >> sub) + (64 >> sub) - 1) / (64 >> sub);
+        gx = std::max(gx, (pw + tw - 1) / tw);
+        gy = std::max(gy, stripes * ((64 >> sub) / LR_TH));
     }
-    return launches;
+    AV1B_LAUNCH(lr_kernel, (gx, gy, 3), (LR_THREADS), st, c, g);
+    return 1;
 }
