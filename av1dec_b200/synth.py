@@ -403,7 +403,7 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512, fixed_mv=N
     return cmd, nb, algo
 
 
-def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, sizes=(8, 16, 32), mode_set=None, fi=True, cfl=True):
+def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, sizes=(8, 16, 32), mode_set=None, fi=True, cfl=True, rect=False):
     """A frame for the superblock wavefront (prediction only): a random `intra_frac` of the blocks
     of a non-intra frame are intra-predicted over whatever the frame already holds (the caller
     supplies it as the input picture, standing for the inter prediction), so every edge carries
@@ -416,7 +416,8 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
     by level inside each superblock) are computed the way the host emitter does (4x4-cell map).
     `levelled=False` keeps the ops in decoding order, one per step (res_off = 0): the reference
     the level analysis is checked against.  `sizes` / `mode_set` / `fi` / `cfl` narrow the mix
-    (profiling aid: tools/wave_prof.py).  Returns the command buffer."""
+    (profiling aid: tools/wave_prof.py); `rect` splits half of the blocks into two rectangular
+    transform blocks (side by side or stacked, flags per half).  Returns the command buffer."""
     rng = SplitMix64(seed)
     sb = 1 << sb_log2
     mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
@@ -428,7 +429,8 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                      ("mlw", "<u2"), ("mlh", "<u2")])
     assert op_t.itemsize == 32
     all_ops, sbs = [], []
-    sq_tx = {4: 0, 8: 1, 16: 2, 32: 3}
+    sq_tx = {4: 0, 8: 1, 16: 2, 32: 3, 64: 4}
+    rect_tx = {(4, 8): 5, (8, 4): 6, (8, 16): 7, (16, 8): 8, (16, 32): 9, (32, 16): 10, (32, 64): 11, (64, 32): 12}
     size_pick = rng.randint(0, 2, (sb_rows, sb_cols))
     sizes = tuple(sizes) if len(sizes) == 3 else tuple(sizes[i % len(sizes)] for i in range(3))
     for r in range(sb_rows):
@@ -482,7 +484,25 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                             o["mlw"], o["mlh"] = x0 + bx * bs + bs, y0 + by * bs + bs
                             fl = (fl | F.OPF_CFL) & ~F.OPF_EDGE_SMOOTH
                         o["flags"] = fl
-                        ops.append(o)
+                        split = int(misc[k, 0] >> 1) & 3 if (rect and s >= 8 and not (fl & F.OPF_FILTER_INTRA and s > 32)) else 0
+                        if split == 1:  # two transform blocks side by side (s/2 x s)
+                            a, b = o.copy(), o.copy()
+                            a["tx_size"] = b["tx_size"] = rect_tx[(s // 2, s)]
+                            fa = (fl & ~F.OPF_HAVE_ABOVE_RIGHT) | (F.OPF_HAVE_ABOVE_RIGHT if y > 0 else 0)
+                            fb = (fl | F.OPF_HAVE_LEFT) & ~F.OPF_HAVE_BELOW_LEFT
+                            a["flags"], b["flags"] = fa, fb
+                            b["x"] = x + s // 2
+                            ops.extend([a, b])
+                        elif split == 2:  # two transform blocks stacked (s x s/2)
+                            a, b = o.copy(), o.copy()
+                            a["tx_size"] = b["tx_size"] = rect_tx[(s, s // 2)]
+                            fa = (fl & ~F.OPF_HAVE_BELOW_LEFT) | (F.OPF_HAVE_BELOW_LEFT if (fl & F.OPF_HAVE_LEFT) else 0)
+                            fb = (fl | F.OPF_HAVE_ABOVE) & ~F.OPF_HAVE_ABOVE_RIGHT
+                            a["flags"], b["flags"] = fa, fb
+                            b["y"] = y + s // 2
+                            ops.extend([a, b])
+                        else:
+                            ops.append(o)
             # dependency levels: 4x4-cell map per plane, like host/emitter.cpp scheduleSb
             cell = [np.zeros((sb >> 2, sb >> 2), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64)]
             levels = []
@@ -490,7 +510,7 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                 pl = int(o["plane"])
                 sub = 1 if pl else 0
                 nc = (sb >> sub) >> 2
-                s = 4 << int(o["tx_size"])
+                tw, th = TX_W[int(o["tx_size"])], TX_H[int(o["tx_size"])]
                 x, y = int(o["x"]) - (x0 >> sub), int(o["y"]) - (y0 >> sub)
 
                 def rd(p, cxa, cxb, cya, cyb, ncp):
@@ -498,16 +518,16 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                     if cxa > cxb or cya > cyb:
                         return 0
                     return int(cell[p][cya:cyb + 1, cxa:cxb + 1].max())
-                cx0, cy0, cx1, cy1 = x >> 2, y >> 2, (x + s - 1) >> 2, (y + s - 1) >> 2
+                cx0, cy0, cx1, cy1 = x >> 2, y >> 2, (x + tw - 1) >> 2, (y + th - 1) >> 2
                 lvl = rd(pl, cx0, cx1, cy0, cy1, nc)
-                ar = 2 * s if int(o["flags"]) & F.OPF_HAVE_ABOVE_RIGHT else s
-                bl = 2 * s if int(o["flags"]) & F.OPF_HAVE_BELOW_LEFT else s
+                ar = 2 * tw if int(o["flags"]) & F.OPF_HAVE_ABOVE_RIGHT else tw
+                bl = 2 * th if int(o["flags"]) & F.OPF_HAVE_BELOW_LEFT else th
                 if y > 0:
                     lvl = max(lvl, rd(pl, (x - 1) >> 2, (x + ar - 1) >> 2, (y - 1) >> 2, (y - 1) >> 2, nc))
                 if x > 0:
                     lvl = max(lvl, rd(pl, (x - 1) >> 2, (x - 1) >> 2, (y - 1) >> 2, (y + bl - 1) >> 2, nc))
                 if int(o["flags"]) & F.OPF_CFL:
-                    lvl = max(lvl, rd(0, (2 * x) >> 2, (2 * (x + s) - 1) >> 2, (2 * y) >> 2, (2 * (y + s) - 1) >> 2, nc * 2))
+                    lvl = max(lvl, rd(0, (2 * x) >> 2, (2 * (x + tw) - 1) >> 2, (2 * y) >> 2, (2 * (y + th) - 1) >> 2, nc * 2))
                 lvl += 1
                 cell[pl][cy0:cy1 + 1, cx0:cx1 + 1] = lvl
                 levels.append(lvl)

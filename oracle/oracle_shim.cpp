@@ -12,6 +12,10 @@
 //   oracle_postfilter        LoopFilter::filter / Cdef::filter / LoopRestoration::filter on a
 //                            hand-filled FrameHeader                   LoopFilter.cpp:40 Cdef.cpp:41 LoopRestoration.cpp:191
 //   oracle_inverse_transform TransformBlock::inverseTransform          decoder/TransformBlock.cpp:2173
+//   oracle_predict_intra     Block::IntraPredict::predict_intra / predict_chroma_from_luma on the
+//                            ops of a synthetic command buffer         decoder/IntraPredict.cpp:563-667
+//   oracle_predict_inter     Block::InterPredict::predict_inter on the prediction units of a
+//                            synthetic command buffer (translational) decoder/InterPredict.cpp:962-1049
 #include <algorithm>
 #include <deque>
 #include <functional>
@@ -27,10 +31,24 @@
 
 #define private public
 #define protected public
+// Block's nested helper classes (IntraPredict, InterPredict, ...) are declared under the class's
+// DEFAULT access, which no keyword redefinition reaches: Block.h alone is read with `class` spelt
+// `struct` (its own includes come first, so nothing else is affected; same mangled names).
+#include "../aom/enums.h"
+#include "BitReader.h"
+#include "BlockTree.h"
+#include "EntropyDecoder.h"
+#include "Tile.h"
+#define class struct
+#include "Block.h"
+#undef class
 #include "Av1Decoder.h"
 #include "BitReader.h"
 #include "Block.h"
 #include "Cdef.h"
+#include "EntropyDecoder.h"
+#include "IntraPredict.h"
+#include "InterPredict.h"
 #include "LoopFilter.h"
 #include "LoopRestoration.h"
 #include "Parser.h"
@@ -311,6 +329,200 @@ int oracle_postfilter(const uint8_t* cmd, const int8_t* cdef_idx64, int sb128, u
         for (int y = 0; y < ph; y++) memcpy(out[p] + (size_t)y * out_stride[p], result->data[p] + (size_t)y * result->strides[p], pw);
     }
     return 0;
+}
+
+// Block::IntraPredict on every AV1B_OP_INTRA op of a (synthetic) command buffer, in list order, the
+// way TransformBlock::decode() drives it (TransformBlock.cpp:2392-2426): prediction, chroma-from-
+// luma, then the block is written into the frame (no residual).  The availability flags are the
+// op's; the block-level state predict_intra reads (filter-intra, angle deltas, CfL alphas and
+// MaxLumaW/H, the smooth-neighbour test behind get_filter_type) is set from the op.  `planes` is the
+// frame (MI-aligned area), updated in place.  Returns the number of ops run, < 0 on error.
+int oracle_predict_intra(const uint8_t* cmd, uint8_t* const planes[3], const int strides[3])
+{
+    const Av1bFrameHdr& hd = *(const Av1bFrameHdr*)cmd;
+    auto seq = std::make_shared<SequenceHeader>();
+    seq->BitDepth = 8;
+    seq->subsampling_x = seq->subsampling_y = 1;
+    seq->NumPlanes = 3;
+    seq->mono_chrome = false;
+    seq->use_128x128_superblock = hd.sb_log2 == 7;
+    seq->enable_intra_edge_filter = hd.enable_intra_edge_filter != 0;
+    ConstSequencePtr cseq = seq;
+    auto fh = std::make_shared<FrameHeader>(cseq);
+    FrameHeader& f = *fh;
+    f.FrameWidth = hd.frame_w;
+    f.FrameHeight = hd.frame_h;
+    f.UpscaledWidth = hd.frame_w;
+    f.compute_image_size();
+    f.initGeometry();
+    if ((int)f.MiCols != hd.mi_cols || (int)f.MiRows != hd.mi_rows) return -1;
+    f.TileCols = f.TileRows = 1;
+    f.MiColStarts.assign({ 0, (int)f.MiCols });
+    f.MiRowStarts.assign({ 0, (int)f.MiRows });
+    memset(&f.m_quant, 0, sizeof(f.m_quant));
+    Tile tile(cseq, fh, 0);
+    static const uint8_t no_bits[32] = { 0 };
+    tile.m_entropy.reset(new EntropyDecoder(no_bits, sizeof(no_bits), true, tile.m_cdfs));
+    const int aw = f.MiCols * 4, ah = f.MiRows * 4;
+    std::shared_ptr<YuvFrame> frame = YuvFrame::create(f.FrameWidth, f.FrameHeight);
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? aw / 2 : aw, ph = p ? ah / 2 : ah;
+        for (int y = 0; y < ph; y++) memcpy(frame->data[p] + (size_t)y * frame->strides[p], planes[p] + (size_t)y * strides[p], pw);
+    }
+    static const uint8_t wlog2[19] = { 2, 3, 4, 5, 6, 2, 3, 3, 4, 4, 5, 5, 6, 2, 4, 3, 5, 4, 6 };
+    static const uint8_t hlog2[19] = { 2, 3, 4, 5, 6, 3, 2, 4, 3, 5, 4, 6, 5, 4, 2, 5, 3, 6, 4 };
+    const Av1bOp* ops = (const Av1bOp*)(cmd + hd.off_ops);
+    int n = 0;
+    for (uint32_t k = 0; k < hd.n_ops; k++) {
+        const Av1bOp& op = ops[k];
+        if (op.kind != AV1B_OP_INTRA) continue;
+        const int plane = op.plane, sub = plane ? 1 : 0;
+        const int mi_row = (op.y << sub) >> 2, mi_col = (op.x << sub) >> 2;
+        Block b(tile, mi_row, mi_col, BLOCK_4X4);
+        b.use_filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
+        b.filter_intra_mode = (FILTER_INTRA_MODE)op.fi_mode;
+        b.AngleDeltaY = b.AngleDeltaUV = op.angle_delta;
+        b.CflAlphaU = b.CflAlphaV = op.cfl_alpha;
+        b.MaxLumaW = op.max_luma_w;
+        b.MaxLumaH = op.max_luma_h;
+        // get_filter_type(): a smooth neighbour above (or, on the first MI row, to the left)
+        const bool smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
+        b.AvailU = b.AvailUChroma = b.AvailL = b.AvailLChroma = false;
+        if (mi_row > 0 || (plane && mi_row > 1)) {
+            int r = mi_row - 1, c = mi_col;
+            if (plane) {
+                if (!(mi_col & 1)) c++;
+                if (mi_row & 1) r--;
+            }
+            if (r >= 0 && c < (int)f.MiCols) {
+                ModeInfoBlock& info = f.m_modeInfo[r][c];
+                info.YMode = smooth ? SMOOTH_PRED : DC_PRED;
+                info.UVMode = smooth ? UV_SMOOTH_PRED : UV_DC_PRED;
+                info.RefFrames[0] = INTRA_FRAME;
+                b.AvailU = b.AvailUChroma = true;
+            }
+        }
+        if (!b.AvailU && mi_col > 0) {
+            int r = mi_row, c = mi_col - 1;
+            if (plane) {
+                if (mi_col & 1) c--;
+                if (!(mi_row & 1)) r++;
+            }
+            if (c >= 0 && r < (int)f.MiRows) {
+                ModeInfoBlock& info = f.m_modeInfo[r][c];
+                info.YMode = smooth ? SMOOTH_PRED : DC_PRED;
+                info.UVMode = smooth ? UV_SMOOTH_PRED : UV_DC_PRED;
+                info.RefFrames[0] = INTRA_FRAME;
+                b.AvailL = b.AvailLChroma = true;
+            }
+        }
+        const int lw = wlog2[op.tx_size], lh = hlog2[op.tx_size];
+        std::vector<std::vector<uint8_t>> pred;
+        Block::IntraPredict ip(b, frame, plane, op.x, op.y, lw, lh, pred);
+        ip.predict_intra((op.flags & AV1B_OPF_HAVE_LEFT) != 0, (op.flags & AV1B_OPF_HAVE_ABOVE) != 0, (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) != 0,
+            (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) != 0, op.mode);
+        if (op.flags & AV1B_OPF_CFL) ip.predict_chroma_from_luma((TX_SIZE)op.tx_size);
+        for (int i = 0; i < (1 << lh); i++)
+            for (int j = 0; j < (1 << lw); j++) frame->setPixel(plane, op.x + j, op.y + i, pred[i][j]);
+        n++;
+    }
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? aw / 2 : aw, ph = p ? ah / 2 : ah;
+        for (int y = 0; y < ph; y++) memcpy(planes[p] + (size_t)y * strides[p], frame->data[p] + (size_t)y * frame->strides[p], pw);
+    }
+    return n;
+}
+
+// Block::InterPredict::predict_inter for every AV1B_IPU_PRED unit of a (synthetic) command buffer:
+// translational prediction, single reference or compound average / distance, from the reference
+// pictures `refs[slot][plane]` (MI-aligned, one stride set for all).  ref_frame r reads store slot
+// hd.ref_slot[r].  `out` receives the predicted picture (only samples covered by a unit change).
+// Returns the number of units run, < 0 on error.
+int oracle_predict_inter(const uint8_t* cmd, int n_refs, const uint8_t* const* refs, const int ref_strides[3], uint8_t* const out[3],
+    const int out_strides[3])
+{
+    const Av1bFrameHdr& hd = *(const Av1bFrameHdr*)cmd;
+    auto seq = std::make_shared<SequenceHeader>();
+    seq->BitDepth = 8;
+    seq->subsampling_x = seq->subsampling_y = 1;
+    seq->NumPlanes = 3;
+    seq->mono_chrome = false;
+    seq->use_128x128_superblock = hd.sb_log2 == 7;
+    ConstSequencePtr cseq = seq;
+    auto fh = std::make_shared<FrameHeader>(cseq);
+    FrameHeader& f = *fh;
+    f.FrameWidth = hd.frame_w;
+    f.FrameHeight = hd.frame_h;
+    f.UpscaledWidth = hd.frame_w;
+    f.compute_image_size();
+    f.initGeometry();
+    if ((int)f.MiCols != hd.mi_cols || (int)f.MiRows != hd.mi_rows) return -1;
+    f.TileCols = f.TileRows = 1;
+    f.MiColStarts.assign({ 0, (int)f.MiCols });
+    f.MiRowStarts.assign({ 0, (int)f.MiRows });
+    memset(&f.m_quant, 0, sizeof(f.m_quant));
+    f.force_integer_mv = false;
+    const int aw = f.MiCols * 4, ah = f.MiRows * 4;
+    FrameStore store(NUM_REF_FRAMES);
+    for (int sl = 0; sl < n_refs && sl < NUM_REF_FRAMES; sl++) {
+        store[sl] = YuvFrame::create(f.FrameWidth, f.FrameHeight);
+        for (int p = 0; p < 3; p++) {
+            const int pw = p ? aw / 2 : aw, ph = p ? ah / 2 : ah;
+            for (int y = 0; y < ph; y++) memcpy(store[sl]->data[p] + (size_t)y * store[sl]->strides[p], refs[sl * 3 + p] + (size_t)y * ref_strides[p], pw);
+        }
+        RefFrame& r = f.m_refInfo.m_refs[sl];
+        r.RefValid = true;
+        r.RefFrameWidth = r.RefUpscaledWidth = hd.frame_w;
+        r.RefFrameHeight = hd.frame_h;
+    }
+    for (int r = LAST_FRAME; r <= ALTREF_FRAME; r++) {
+        f.ref_frame_idx[r - LAST_FRAME] = hd.ref_slot[r] >= 0 ? hd.ref_slot[r] : 0;
+        f.GmType[r] = IDENTITY;
+    }
+    Tile tile(cseq, fh, 0);
+    static const uint8_t no_bits[32] = { 0 };
+    tile.m_entropy.reset(new EntropyDecoder(no_bits, sizeof(no_bits), true, tile.m_cdfs));
+    std::shared_ptr<YuvFrame> frame = YuvFrame::create(f.FrameWidth, f.FrameHeight);
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? aw / 2 : aw, ph = p ? ah / 2 : ah;
+        for (int y = 0; y < ph; y++) memcpy(frame->data[p] + (size_t)y * frame->strides[p], out[p] + (size_t)y * out_strides[p], pw);
+    }
+    const Av1bIpu* units = (const Av1bIpu*)(cmd + hd.off_ipu);
+    std::vector<std::vector<uint8_t>> mask;
+    int n = 0;
+    for (uint32_t k = 0; k < hd.n_ipu; k++) {
+        const Av1bIpu& u = units[k];
+        if (u.kind != AV1B_IPU_PRED || u.warp[0] || u.warp[1]) continue;
+        const int plane = u.plane, sub = plane ? 1 : 0;
+        const bool compound = (u.flags & AV1B_IPUF_COMPOUND) != 0;
+        if (compound && u.comp_type != AV1B_COMP_AVERAGE) continue;
+        const int mi_row = (u.y << sub) >> 2, mi_col = (u.x << sub) >> 2;
+        Block b(tile, mi_row, mi_col, BLOCK_8X8);
+        b.is_inter = true;
+        b.use_intrabc = false;
+        b.YMode = compound ? NEW_NEWMV : NEWMV;
+        b.motion_mode = SIMPLE_TRANSLATION;
+        b.compound_type = COMPOUND_AVERAGE;
+        b.interintra = false;
+        b.RefFrame[0] = u.ref_frame[0];
+        b.RefFrame[1] = compound ? u.ref_frame[1] : NONE_FRAME;
+        ModeInfoBlock& info = f.m_modeInfo[mi_row][mi_col];
+        info.RefFrames[0] = b.RefFrame[0];
+        info.RefFrames[1] = b.RefFrame[1];
+        for (int l = 0; l < 2; l++) {
+            info.Mvs[l].mv[0] = u.mv[l][0];
+            info.Mvs[l].mv[1] = u.mv[l][1];
+            info.InterpFilters[l] = (InterpFilter)u.filt[l];
+        }
+        Block::InterPredict ip(b, plane, *frame, store, mask);
+        ip.predict_inter(u.x, u.y, u.w, u.h, mi_row, mi_col);
+        n++;
+    }
+    for (int p = 0; p < 3; p++) {
+        const int pw = p ? aw / 2 : aw, ph = p ? ah / 2 : ah;
+        for (int y = 0; y < ph; y++) memcpy(out[p] + (size_t)y * out_strides[p], frame->data[p] + (size_t)y * frame->strides[p], pw);
+    }
+    return n;
 }
 
 // TransformBlock::inverseTransform() on `n` blocks.  For block i: tx_size[i], tx_type[i],

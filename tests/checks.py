@@ -115,6 +115,24 @@ def check_inter_properties(lib, w, h):
         assert np.array_equal(a[p], b[p]), f"fast vs general kernel, plane {p}"
 
 
+def check_inter_vs_oracle(lib, w, h, **kw):
+    """Motion compensation against the REFERENCE's Block::InterPredict::predict_inter
+    (oracle_predict_inter) on a synthetic frame of translational blocks: random 1/8-pel vectors
+    (windows leaving the frame included), the four interpolation filters per direction, single and
+    compound-average prediction, block sizes 8..64 -- at full frame size."""
+    import oracle
+    rng = synth.SplitMix64(synth.SEED + 5)
+    refs = [synth.make_planes(rng, w, h, "B"), synth.make_planes(rng, w, h, "B")]
+    cmd, nb, _ = synth.make_inter_frame(w, h, **kw)
+    got = run_inter(lib, w, h, refs, **kw)
+    want, n = oracle.predict_inter(cmd, refs, refs[0])
+    assert n == 3 * nb
+    for p in range(3):
+        hh, ww = got[p].shape
+        assert np.array_equal(got[p], want[p][:hh, :ww]), f"inter vs reference InterPredict: plane {p}, {int((got[p] != want[p][:hh, :ww]).sum())} samples differ"
+    return n
+
+
 def run_wave(lib, w, h, planes, cmd):
     """Superblock wavefront alone over the input picture `planes`.  Returns the planes."""
     from av1dec_b200 import STAGE_WAVE
@@ -142,6 +160,27 @@ def check_wave(lib, w, h, sb_log2, ref_lib=None):
         changed += int((lev[p] != planes[p]).sum())
     assert changed > w * h // 4  # the ops really did something
     return lev
+
+
+def check_wave_vs_oracle(lib, w, h, sb_log2, seed=0, **kw):
+    """Superblock wavefront against the REFERENCE's Block::IntraPredict (oracle_predict_intra) on a
+    synthetic frame: every mode x size the generator draws, edge filter / upsampling, filter-intra,
+    chroma-from-luma, frame-edge clamps -- at frame sizes whose coordinates run into the thousands."""
+    import oracle
+    rng = synth.SplitMix64(synth.SEED + 11 + seed)
+    planes = synth.make_planes(rng, w, h, "B")
+    cmd = synth.make_intra_frame(w, h, seed=synth.SEED + seed, sb_log2=sb_log2, levelled=True, **kw)
+    got = run_wave(lib, w, h, planes, cmd)
+    mw, mh = 2 * ((w + 7) >> 3) * 4, 2 * ((h + 7) >> 3) * 4
+    full = [np.zeros((mh >> (1 if p else 0), mw >> (1 if p else 0)), np.uint8) for p in range(3)]
+    for p in range(3):
+        full[p][:planes[p].shape[0], :planes[p].shape[1]] = planes[p]
+    want, n = oracle.predict_intra(cmd, full)
+    assert n > 0
+    for p in range(3):
+        hh, ww = got[p].shape
+        assert np.array_equal(got[p], want[p][:hh, :ww]), f"wavefront vs reference IntraPredict: plane {p}, {int((got[p] != want[p][:hh, :ww]).sum())} samples differ"
+    return n
 
 
 def check_output_paths(lib, w, h):

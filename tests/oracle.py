@@ -32,6 +32,8 @@ def lib():
                                         C.POINTER(C.c_int)]
         l.oracle_inverse_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p]
+        l.oracle_predict_intra.argtypes = [C.c_char_p, u8pp, C.POINTER(C.c_int)]
+        l.oracle_predict_inter.argtypes = [C.c_char_p, C.c_int, u8pp, C.POINTER(C.c_int), u8pp, C.POINTER(C.c_int)]
         _lib = l
     return _lib
 
@@ -92,3 +94,31 @@ def inverse_transform(batch):
                                         coef_off.ctypes.data, res.ctypes.data, res_off.ctypes.data)
     assert rc == 0
     return [res[res_off[i]:res_off[i] + TX_W[b[0]] * TX_H[b[0]]].reshape(TX_H[b[0]], TX_W[b[0]]) for i, b in enumerate(batch)]
+
+
+def predict_intra(cmd, planes):
+    """Block::IntraPredict::predict_intra (+ chroma-from-luma) for every intra op of a synthetic
+    command buffer, in list order, over the picture `planes` ([Y, U, V], MI-aligned).  Returns the
+    resulting planes."""
+    outs = [np.ascontiguousarray(p).copy() for p in planes]
+    ptrs = (C.POINTER(C.c_uint8) * 3)(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in outs])
+    strides = (C.c_int * 3)(*[a.strides[0] for a in outs])
+    n = lib().oracle_predict_intra(cmd, ptrs, strides)
+    assert n >= 0
+    return outs, n
+
+
+def predict_inter(cmd, refs, shape_like):
+    """Block::InterPredict::predict_inter for every translational prediction unit of a synthetic
+    command buffer from the reference pictures `refs` (list of [Y, U, V] per store slot).  Returns
+    ([Y, U, V] predicted picture, units run); samples no unit covers stay 0."""
+    rr = [[np.ascontiguousarray(p) for p in planes] for planes in refs]
+    flat = [a for planes in rr for a in planes]
+    rptr = (C.POINTER(C.c_uint8) * len(flat))(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in flat])
+    rstr = (C.c_int * 3)(*[a.strides[0] for a in rr[0]])
+    outs = [np.zeros_like(p) for p in shape_like]
+    optr = (C.POINTER(C.c_uint8) * 3)(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in outs])
+    ostr = (C.c_int * 3)(*[a.strides[0] for a in outs])
+    n = lib().oracle_predict_inter(cmd, len(rr), rptr, rstr, optr, ostr)
+    assert n >= 0
+    return outs, n

@@ -188,6 +188,29 @@ def test_wavefront_full_frames_vs_sequential_emulation(eng, w, h, sb_log2):
     checks.check_wave(eng, w, h, sb_log2, ref_lib=checks.emu_engine())
 
 
+@pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("w,h,kw", [(1920, 1080, dict(compound_frac=0.3)), (1920, 1080, dict(compound_frac=0.3, fast=False, max_mv=2048, seed=99)),
+                                    (3840, 2160, dict(compound_frac=0.25, max_mv=1024)), (3840, 2160, dict(compound_frac=0.5, fast=False, seed=5))])
+def test_inter_prediction_vs_reference(eng, w, h, kw):
+    """The inter pass (fast translational kernel and the general predictor) against the REFERENCE's
+    Block::InterPredict::predict_inter (oracle_predict_inter) at 1080p and 4K: random 1/8-pel
+    vectors including windows that leave the frame, every interpolation filter pair, single and
+    compound-average prediction, blocks of 8..64 samples."""
+    checks.check_inter_vs_oracle(eng, w, h, **kw)
+
+
+@pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("w,h,sb_log2,kw", [(1920, 1080, 6, {}), (1920, 1080, 7, dict(rect=True, intra_frac=1.0)),
+                                             (3840, 2160, 6, dict(rect=True, sizes=(8, 32, 64), intra_frac=0.9)),
+                                             (3840, 2160, 7, dict(rect=True, sizes=(16, 32, 64)))])
+def test_intra_prediction_vs_reference(eng, w, h, sb_log2, kw):
+    """The wavefront kernel against the REFERENCE's Block::IntraPredict::predict_intra /
+    predict_chroma_from_luma (oracle_predict_intra) at 1080p and 4K: every mode, square and
+    rectangular transform sizes up to 64, edge filter / upsampling, filter-intra, CfL -- with
+    coordinates in the thousands (16-bit packed op fields)."""
+    checks.check_wave_vs_oracle(eng, w, h, sb_log2, **kw)
+
+
 @pytest.mark.parametrize("w,h", [(178, 94), (3840, 2160)])
 def test_device_view_and_nv12(eng, w, h):
     checks.check_output_paths(eng, w, h)

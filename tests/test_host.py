@@ -133,6 +133,23 @@ def test_wavefront_level_schedule_under_emulation(w, h, sb_log2):
 
 
 @need_emu
+@pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw", [dict(compound_frac=0.3), dict(compound_frac=0.3, fast=False, seed=1234, max_mv=2048)])
+def test_inter_prediction_vs_reference_under_emulation(kw):
+    """Translational motion compensation against the reference's Block::InterPredict."""
+    checks.check_inter_vs_oracle(checks.emu_engine(), 640, 384, **kw)
+
+
+@need_emu
+@pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("w,h,sb_log2,kw", [(640, 360, 6, {}), (1280, 720, 7, dict(rect=True, sizes=(16, 32, 64))),
+                                             (1920, 1080, 6, dict(rect=True, intra_frac=1.0))])
+def test_intra_prediction_vs_reference_under_emulation(w, h, sb_log2, kw):
+    """Every intra op of a synthetic frame against the reference's Block::IntraPredict."""
+    checks.check_wave_vs_oracle(checks.emu_engine(), w, h, sb_log2, **kw)
+
+
+@need_emu
 def test_device_view_and_nv12_under_emulation():
     checks.check_output_paths(checks.emu_engine(), 178, 94)
 
