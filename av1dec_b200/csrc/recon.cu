@@ -60,6 +60,7 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
     const int row_shift = lossless ? 0 : k_tx_row_shift[txs];
     const int col_shift = lossless ? 0 : 4;
     const int nz_rows = min((int)op.nz_rows, min(h, 32));
+    const int nz_cols = lossless ? tw : min(max((int)op.nz_cols, 1), tw);
     const int16_t* c = coef + op.coef_off;
     int16_t* out;
     int out_stride;
@@ -72,11 +73,11 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
     }
     for (int i = gl; i < nz_rows; i += G) {
         int16_t* trow = tmp + i * tstride;
-        if (MAXLOG >= 6 && lw == 6) itx::row_pass<6>(c + i * tw, tw, trow, rk, rect, row_shift);
-        else if (MAXLOG >= 5 && lw == 5) itx::row_pass<5>(c + i * tw, tw, trow, rk, rect, row_shift);
-        else if (MAXLOG >= 4 && lw == 4) itx::row_pass<4>(c + i * tw, tw, trow, rk, rect, row_shift);
-        else if (MAXLOG >= 3 && lw == 3) itx::row_pass<3>(c + i * tw, tw, trow, rk, rect, row_shift);
-        else itx::row_pass<2>(c + i * tw, tw, trow, rk, rect, row_shift);
+        if (MAXLOG >= 6 && lw == 6) itx::row_pass<6>(c + i * tw, tw, nz_cols, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 5 && lw == 5) itx::row_pass<5>(c + i * tw, tw, nz_cols, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 4 && lw == 4) itx::row_pass<4>(c + i * tw, tw, nz_cols, trow, rk, rect, row_shift);
+        else if (MAXLOG >= 3 && lw == 3) itx::row_pass<3>(c + i * tw, tw, nz_cols, trow, rk, rect, row_shift);
+        else itx::row_pass<2>(c + i * tw, tw, nz_cols, trow, rk, rect, row_shift);
     }
     __syncwarp();
     const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
@@ -94,7 +95,7 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
 
 // One launch per size class CLS (0: 4x4, 1: max dim 8, 2: max dim 16, 3: 32 and 64).
 template <int CLS>
-__global__ void __launch_bounds__(ITX_WARPS * 32)
+__global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
     itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n,
         const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
 {

@@ -233,6 +233,31 @@ def make_itx_batch(n, seed=SEED, lossless_frac=0.05, sizes=None):
     return out
 
 
+def make_itx_extent_batch(seed=SEED):
+    """Transform blocks whose non-zero coefficients fill a given leading box: every transform size
+    x every legal type x a ladder of (nz_rows, nz_cols) extents -- 1x1 (DC only), a few low
+    frequencies, half, full -- so that each zero-aware variant of the generated butterflies
+    (itx_gen.h, selected by the extents) runs in the row pass and in the column pass."""
+    rng = SplitMix64(seed)
+    out = []
+    ladder = (1, 2, 4, 5, 8, 11, 16, 23, 32)
+    k = 0
+    for ts in range(19):
+        tw, th = min(TX_W[ts], 32), min(TX_H[ts], 32)
+        for tt in legal_tx_types(ts):
+            for e, nzr in enumerate(ladder):
+                if nzr > th:
+                    break
+                nzc = min(tw, ladder[(e + k) % len(ladder)])
+                k += 1
+                vals = rng.randint(-1500, 1500, (nzr, nzc))
+                vals[nzr - 1, nzc - 1] = 777  # the extents are exact
+                coef = np.zeros((th, tw), np.int64)
+                coef[:nzr, :nzc] = vals
+                out.append((ts, tt, 0, coef.reshape(-1).astype(np.int16), nzr, nzc))
+    return out
+
+
 def make_itx_cmd(batch):
     """Command buffer holding only inverse-transform work (ops + itx list + coefficient arena)."""
     ops, coefs, itx = [], [], []

@@ -40,8 +40,8 @@ def flip_residual(res, tx_type):
     return res
 
 
-def check_itx(lib, n=400, seed=synth.SEED, sizes=None):
-    batch = synth.make_itx_batch(n, seed=seed, sizes=sizes)
+def check_itx(lib, n=400, seed=synth.SEED, sizes=None, extents=False):
+    batch = synth.make_itx_extent_batch(seed=seed) if extents else synth.make_itx_batch(n, seed=seed, sizes=sizes)
     cmd, n_res = synth.make_itx_cmd(batch)
     eng = Engine(64, 64, lib=lib)
     eng.submit(cmd, stages=pkg.STAGE_ITX)

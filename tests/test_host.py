@@ -186,6 +186,7 @@ def test_decode_rejects_garbage():
 @need_oracle
 def test_itx_vs_reference_under_emulation():
     assert checks.check_itx(checks.emu_engine(), n=600) == 600
+    assert checks.check_itx(checks.emu_engine(), extents=True) > 800  # every zero-aware butterfly variant
     # every transform size on its own, so a failure names the size
     for ts in range(19):
         checks.check_itx(checks.emu_engine(), n=40, seed=1000 + ts, sizes=[ts])
