@@ -707,7 +707,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
             if (m != lane && (rt_event_record(c->lanes[m].mark, c->lanes[m].stream) || rt_stream_wait(st, c->lanes[m].mark)))
                 return fail(c, AV1B_ECUDA, "stream wait");
     }
-    const size_t sync_need = 1 + (size_t)h.sb_rows;
+    const size_t sync_need = 2 + (size_t)h.sb_rows;
     for (int m = 0; m < c->n_lanes; m++) { // all lanes together, like the residual planes
         Lane& Lm = c->lanes[m];
         if (sync_need <= Lm.sync_cap) continue;
@@ -717,6 +717,9 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         Lm.sync_cap = 0;
         void* p = nullptr;
         if (rt_malloc(&p, (sync_need + 64) * sizeof(int))) return fail(c, AV1B_ENOMEM, "sync buffer");
+        // zeroed ONCE: every wavefront launch leaves its counters at zero again (the last CTA out
+        // resets them), so a frame does not pay a memset node for them
+        if (rt_memset(p, 0, (sync_need + 64) * sizeof(int), Lm.stream) || rt_stream_sync(Lm.stream)) return fail(c, AV1B_ECUDA, "memset");
         Lm.sync = (int*)p;
         Lm.sync_cap = sync_need + 64;
     }
@@ -752,7 +755,12 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         if (stages & AV1B_STAGE_ITX) {
             // zero only the area this frame can touch (SB-aligned rows of the luma plane + chroma)
             const size_t rows = (size_t)h.sb_rows << h.sb_log2;
-            if (rt_memset(rc.rp[0], 0, rows * c->aw * sizeof(int16_t), st)
+            const size_t separate = rows * c->aw + 2 * (rows / 2) * (c->aw / 2);
+            const size_t joined = (size_t)(rc.rp[2] - rc.rp[0]) + (rows / 2) * (c->aw / 2); // the planes are contiguous
+            if (joined <= separate + separate / 4) {
+                // one node instead of three: a small frame's cost is launches, not bytes
+                if (rt_memset(rc.rp[0], 0, joined * sizeof(int16_t), st)) return fail(c, AV1B_ECUDA, "memset");
+            } else if (rt_memset(rc.rp[0], 0, rows * c->aw * sizeof(int16_t), st)
                 || rt_memset(rc.rp[1], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), st)
                 || rt_memset(rc.rp[2], 0, (rows / 2) * (c->aw / 2) * sizeof(int16_t), st))
                 return fail(c, AV1B_ECUDA, "memset");
@@ -776,8 +784,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
     rc.trace_cap = (unsigned)g_wave_trace_cap;
     if (stages & AV1B_STAGE_ITX) {
         StageTimer t(c, 0, h.n_itx != 0, st);
-        launch_itx(rc, h, st);
-        c->launches += h.n_itx ? 1 : 0;
+        c->launches += launch_itx(rc, h, st);
     }
     if (stages & AV1B_STAGE_INTER) {
         StageTimer t(c, 1, h.n_iblk != 0, st);
@@ -785,7 +792,6 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         c->launches += h.n_iblk ? 1 : 0;
     }
     if (stages & AV1B_STAGE_WAVE) {
-        if (rt_memset(L.sync, 0, sync_need * sizeof(int), st)) return fail(c, AV1B_ECUDA, "memset");
         StageTimer t(c, 2, h.n_ops != 0, st);
         launch_wave(rc, h, st);
         c->launches += h.n_ops ? 1 : 0;

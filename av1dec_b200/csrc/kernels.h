@@ -14,7 +14,8 @@ struct ReconCtx {
     uint8_t* mask;        // luma-resolution scratch plane for diff-weighted compound masks
     int mask_pitch;
     const uint8_t* wedge; // wedge mask table [9][2][16][32*32]
-    int* sync;            // [0] = SB ticket counter, [1 + r] = finished SBs of SB row r
+    int* sync;            // [0] = SB ticket counter, [1] = CTAs that left the kernel, [2 + r] = finished SBs of SB row r;
+                          // all zero between launches (the last CTA out resets them)
     unsigned long long* trace; // profiling aid (av1b_debug_wave_trace), normally null
     unsigned trace_cap;
 };
@@ -47,7 +48,7 @@ struct PostCtx {
     FrameView lr;   // loop-restoration output
 };
 
-void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+int launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st); // returns the number of kernels launched
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 

@@ -93,11 +93,11 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
 
 }  // namespace
 
-// One launch per size class CLS (0: 4x4, 1: max dim 8, 2: max dim 16, 3: 32 and 64).
+// The transform blocks of one size class CLS (0: 4x4, 1: max dim 8, 2: max dim 16, 3: 32 and 64),
+// CTA `bid` of `nblocks`.
 template <int CLS>
-__global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
-    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n,
-        const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
+AV1B_DEV void itx_cta(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n, const int16_t* __restrict__ coef,
+    int16_t* __restrict__ res, const ResPlanes& rp, unsigned bid, unsigned nblocks)
 {
     constexpr int GMAX = 4 << CLS;
     constexpr int TSTRIDE = (CLS == 3) ? (int)ITX_TMP_STRIDE : GMAX + 2;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
     const int per = max(1, nl / G); // transform blocks per warp pass
     const int gl = lane % G, grp = lane / G;
     int16_t* tmp = tmp_all[warp] + grp * REGION;
-    for (uint32_t t0 = (blockIdx.x * nw + warp) * per; t0 < n; t0 += gridDim.x * nw * per) {
+    for (uint32_t t0 = (bid * nw + warp) * per; t0 < n; t0 += nblocks * nw * per) {
         const uint32_t t = t0 + grp;
         if (t < n) {
             const Av1bOp op = ops[list[t]];
@@ -119,6 +119,32 @@ __global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
         }
         __syncwarp();
     }
+}
+
+// One launch per size class: small transforms compile to few registers and run at full occupancy.
+template <int CLS>
+__global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
+    itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n,
+        const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
+{
+    itx_cta<CLS>(ops, list, n, coef, res, rp, blockIdx.x, gridDim.x);
+}
+
+// Small frames: all four classes in ONE launch (CTA ranges per class) -- a CIF frame's inverse
+// transform is a few hundred CTAs, and four launches of a few microseconds each cost more than the
+// occupancy the per-class kernels buy.
+struct ItxPlan {
+    uint32_t first[4], cnt[4], cta_end[4];
+};
+__global__ void __launch_bounds__(ITX_WARPS * 32)
+    itx_kernel_all(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, const int16_t* __restrict__ coef,
+        int16_t* __restrict__ res, ResPlanes rp, ItxPlan p)
+{
+    const unsigned b = blockIdx.x;
+    if (b < p.cta_end[0]) itx_cta<0>(ops, list + p.first[0], p.cnt[0], coef, res, rp, b, p.cta_end[0]);
+    else if (b < p.cta_end[1]) itx_cta<1>(ops, list + p.first[1], p.cnt[1], coef, res, rp, b - p.cta_end[0], p.cta_end[1] - p.cta_end[0]);
+    else if (b < p.cta_end[2]) itx_cta<2>(ops, list + p.first[2], p.cnt[2], coef, res, rp, b - p.cta_end[1], p.cta_end[2] - p.cta_end[1]);
+    else itx_cta<3>(ops, list + p.first[3], p.cnt[3], coef, res, rp, b - p.cta_end[2], p.cta_end[3] - p.cta_end[2]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -730,6 +756,21 @@ AV1B_DEV void wave_signal(int* progress, int r, int col, int tid, int nt)
 }
 
 
+// Leaving the kernel: the last CTA out puts the counters back to zero for the next launch (every
+// other CTA has drawn a ticket past the end and polls nothing any more), so no memset node per
+// frame is needed.
+AV1B_DEV void wave_leave(int* sync, int sb_rows, int tid)
+{
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
+            for (int r = 0; r < sb_rows; r++) sync[2 + r] = 0;
+            sync[0] = 0;
+            sync[1] = 0;
+        }
+    }
+}
+
 // Shared-memory footprint of one superblock (bytes) for SB size `sb` (64 or 128): the sample tile
 // -- luma (sb+1) rows of 2sb+8 bytes (a halo row above, long enough for above-right reads, and a
 // halo column to the left; sample (x0, y0) sits at byte 4 of row 1 so that every block row is
@@ -772,7 +813,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     const bool load_pred = !hdr->frame_is_intra; // inter prediction already sits in the frame
     const bool have_res = c.rp[0] != nullptr && hdr->n_itx != 0;
     int* ticket = c.sync;
-    int* progress = c.sync + 1;
+    int* progress = c.sync + 2;
     const int n0 = sbs_y, n1 = sbs_y >> 1;
     const int pitch0 = 2 * n0 + 8, pitch1 = 2 * n1 + 8;
     uint8_t* const t0 = dyn;
@@ -1037,6 +1078,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         flush_plane(2, t2, n1, pitch1);
         if (tr) tr[7] = av1b_gtime();
     }
+    wave_leave(c.sync, hdr->sb_rows, tid);
 }
 
 // Global-memory variant (frames with allow_intrabc: block copies read arbitrary earlier parts of
@@ -1053,7 +1095,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int sb_cols = hdr->sb_cols, n_sb = hdr->n_sb;
     int* ticket = c.sync;
-    int* progress = c.sync + 1;
+    int* progress = c.sync + 2;
     // An intrabc block vector may point into the row k superblock rows above up to 5k - 4 columns
     // (64-sample units) to the right of the current one (spec 7.11.3.2 / libaom av1_is_dv_valid:
     // gradient 1 + INTRABC_DELAY_SB64 [+ 1 for 128x128]); waiting for the row above through column
@@ -1085,14 +1127,15 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         }
         wave_signal(progress, r, col, tid, nt);
     }
+    wave_leave(c.sync, hdr->sb_rows, tid);
 }
 
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
+int launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
 {
-    if (!h.n_itx) return;
+    if (!h.n_itx) return 0;
     const Av1bOp* ops = (const Av1bOp*)(c.cmd + h.off_ops);
     const uint32_t* list = (const uint32_t*)(c.cmd + h.off_itx);
     const int16_t* coef = (const int16_t*)(c.cmd + h.off_coef);
@@ -1101,16 +1144,30 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         rp.p[i] = c.rp[i];
         rp.pitch[i] = c.rpitch[i];
     }
-    uint32_t prev = 0;
+    ItxPlan plan;
+    uint32_t prev = 0, ctas = 0;
+    int classes = 0;
     for (int k = 0; k < 4; k++) {
         const uint32_t end = h.itx_class_end[k] > h.n_itx ? h.n_itx : h.itx_class_end[k];
-        const uint32_t cnt = end > prev ? end - prev : 0;
-        const uint32_t* lst = list + prev;
+        plan.first[k] = prev;
+        plan.cnt[k] = end > prev ? end - prev : 0;
         prev = end > prev ? end : prev;
-        if (!cnt) continue;
         const uint32_t per_cta = ITX_WARPS * (32 / (4 << k)); // transform blocks per CTA pass
-        int nb = (int)((cnt + per_cta - 1) / per_cta);
+        uint32_t nb = (plan.cnt[k] + per_cta - 1) / per_cta;
         if (nb > 148 * 16) nb = 148 * 16;
+        ctas += nb;
+        plan.cta_end[k] = ctas;
+        classes += plan.cnt[k] != 0;
+    }
+    if (classes > 1 && h.n_itx <= 8192) {
+        AV1B_LAUNCH(itx_kernel_all, (ctas), (ITX_WARPS * 32), st, ops, list, coef, c.res, rp, plan);
+        return 1;
+    }
+    for (int k = 0; k < 4; k++) {
+        const uint32_t cnt = plan.cnt[k];
+        if (!cnt) continue;
+        const uint32_t* lst = list + plan.first[k];
+        const int nb = (int)(plan.cta_end[k] - (k ? plan.cta_end[k - 1] : 0));
         switch (k) {
         case 0: AV1B_LAUNCH(itx_kernel<0>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
         case 1: AV1B_LAUNCH(itx_kernel<1>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
@@ -1118,6 +1175,7 @@ void launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         default: AV1B_LAUNCH(itx_kernel<3>, (nb), (ITX_WARPS * 32), st, ops, lst, cnt, coef, c.res, rp); break;
         }
     }
+    return classes;
 }
 
 void launch_inter(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)

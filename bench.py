@@ -311,6 +311,21 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True, size=(3840, 2160), d
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)",
                 "algorithmic_bytes_per_launch": alg[dom], "chain_frac": post["chain"]["frac_of_peak"], "peak_source": peak_src,
                 "workload": f"synthetic {W4}x{H4} 4:2:0 8-bit, pixel distribution {dist} (B = blocky-smooth, U = uniform), random partition/levels/CDEF presets/LR units (configs[3])"}
+    # Issue-slot roofline next to the HBM one: these kernels are exact integer filters whose DRAM
+    # traffic is already at or below the algorithmic bytes, so what bounds them is instruction issue.
+    # warp-instructions per launch come from the committed ncu capture of this same workload
+    # (profiles/issue.json: smsp__inst_executed.sum); the time is the one measured live above.
+    is_path = os.path.join(ROOT, "profiles", "issue.json")
+    if (W4, H4) == (3840, 2160) and os.path.exists(is_path):
+        insts = json.load(open(is_path))
+        slots_per_s = 148 * 4 * float(insts.get("_sm_clock_hz", 1.965e9))  # one warp-instruction per scheduler per clock
+        issue = {"unit": "warp-instructions", "slots_per_s": slots_per_s, "source": "profiles/issue.json (ncu smsp__inst_executed.sum per launch)"}
+        for k in ("deblock", "cdef", "lr"):
+            if k in insts and post[k]["us_per_frame"] > 0:
+                t = post[k]["us_per_frame"] * 1e-6
+                issue[k] = {"warp_insts_per_launch": insts[k], "thread_insts_per_sample": insts[k] * 32 / (W4 * H4 * 1.5),
+                            "issue_frac": insts[k] / (t * slots_per_s), "us_at_full_issue": insts[k] / slots_per_s * 1e6}
+        roofline["issue"] = issue
 
     return post, roofline
 
