@@ -62,8 +62,47 @@ const char* av1b_backend(void) { return "emu"; }
 #else
 typedef cudaEvent_t rt_event_t;
 static int rt_set_device(int d) { return cudaSetDevice(d) != cudaSuccess; }
-static int rt_malloc(void** p, size_t n) { g_n_dev_alloc++; return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
-static void rt_free(void* p) { if (p) cudaFree(p); }
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on a stream of its own,
+// release threshold = never): once the pool is warm an allocation in the middle of a decode is a
+// pointer bump, where cudaMalloc / cudaFree synchronise the WHOLE device and stall every other
+// decoder of the process for as long as its kernels take to drain.  The allocation stream carries
+// nothing else, so synchronising it right away makes the block usable on any stream.  Callers free
+// only what no stream uses any more (they synchronise first), as cudaFree required.
+static cudaStream_t rt_alloc_stream()
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!streams[dev]) {
+        cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return streams[dev];
+}
+static int rt_malloc(void** p, size_t n)
+{
+    g_n_dev_alloc++;
+    cudaStream_t s = rt_alloc_stream();
+    if (cudaMallocAsync(p, n ? n : 1, s) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaMalloc(p, n ? n : 1) != cudaSuccess; // pool exhausted / unsupported: the blocking path
+    }
+    return cudaStreamSynchronize(s) != cudaSuccess;
+}
+static void rt_free(void* p)
+{
+    if (p && cudaFreeAsync(p, rt_alloc_stream()) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+    }
+}
 static int rt_host_alloc(void** p, size_t n) { g_n_pinned_alloc++; return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess; }
 static void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
 static int rt_h2d(void* d, const void* s, size_t n, av1b_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) != cudaSuccess; }

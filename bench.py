@@ -624,18 +624,26 @@ def run_ours(args, rank, world, local_rank):
         return time.perf_counter() - t0, sum(p for p, _ in res)
     # untimed: fill the context / pinned / command-slot pools until a pass allocates nothing new
     # (a steady-state decode service; cudaHostAlloc of a multi-MB block costs milliseconds)
+    # The warm passes run the SAME job list as the timed one (`steps` copies, longest first): three
+    # copies of the big streams in flight at once need three times their contexts and pinned
+    # buffers, and a cudaMalloc / cudaHostAlloc in the timed region synchronises the whole device
+    # (a single-copy warm-up left ~50 of them in the timed pass: 45 instead of 85 Mpix/s one run in four).
     warm_passes = 0
     for _ in range(8):
         c0 = pkg.alloc_counters()
-        e2e_pass(check=warm_passes == 0)
+        e2e_pass(check=warm_passes == 0, copies=1 if warm_passes == 0 else args.steps)
         warm_passes += 1
         c1 = pkg.alloc_counters()
-        if warm_passes >= 2 and c1[0] == c0[0] and c1[2] == c0[2] and c1[3] == c0[3]:
+        if warm_passes >= 3 and c1[0] == c0[0] and c1[2] == c0[2] and c1[3] == c0[3]:
             break
     barrier()
     # timed: `steps` copies of the set as ONE job list, like the reference arm (callers keep pulling
     # streams across the copies: no barrier between passes)
-    e2e_t, e2e_px = e2e_pass(copies=args.steps)
+    # (the host side is 12 caller threads plus segment workers on a 16-vCPU VM: the same job runs
+    # anywhere from 220 to 350 ms per set; three timed runs, the MEDIAN is the reported one and all
+    # three are listed)
+    e2e_runs = sorted((e2e_pass(copies=args.steps) for _ in range(3)), key=lambda r: r[0])
+    e2e_t, e2e_px = e2e_runs[1]
     e2e_single = pixels_step / e2e_pass()[0] / 1e6
     if os.environ.get("BENCH_TRACE"):
         extra = []
@@ -691,7 +699,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step * world, "d2h_bytes_per_step": d2h_step * world,
                 "ms_per_step": 1e3 * e2e_tmax / args.steps, "api": "av1b_decode_ivf (include/av1b200_decoder.h)",
                 "untimed_warm_passes": warm_passes, "single_pass": e2e_single,
-                "job": f"{args.steps} copies of the set per GPU as one job list (no barrier between the copies)"},
+                "job": f"{args.steps} copies of the set per GPU as one job list (no barrier between the copies); median of 3 runs",
+                "runs_mpix_per_s": [round(px / t / 1e6, 1) for t, px in e2e_runs]},
         "gpu_launches": launches,
         "roofline": roofline,
         "postfilter_4k": post,
