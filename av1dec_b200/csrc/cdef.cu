@@ -30,9 +30,10 @@
 namespace {
 
 enum {
-    CD_YP = 80,    // bytes per luma tile row: tile columns -8 .. 71
+    CD_X0 = 16,    // the tile row starts CD_X0 columns left of the tile (16-byte aligned rows for bulk copies)
+    CD_YP = 96,    // bytes per luma tile row: tile columns -16 .. 79
     CD_YROWS = 68, // tile rows -2 .. 65
-    CD_CP = 48,    // chroma: tile columns -8 .. 39
+    CD_CP = 64,    // chroma: tile columns -16 .. 47
     CD_CROWS = 36,
     CD_K = 16,     // bias of the constrained difference (strengths are <= 15)
     CD_THREADS = 256,
@@ -50,9 +51,9 @@ struct CdefBlk {
     int8_t d[2][6][2];
 };
 
-struct CdefSmem {
-    alignas(16) uint8_t y[CD_YROWS * CD_YP];        // y[(r + 2) * CD_YP + (c + 8)] = luma tile sample (r, c)
-    alignas(16) uint8_t c[2][CD_CROWS * CD_CP];
+struct alignas(128) CdefSmem {
+    alignas(128) uint8_t y[CD_YROWS * CD_YP];        // y[(r + 2) * CD_YP + (c + CD_X0)] = luma tile sample (r, c)
+    alignas(128) uint8_t c[2][CD_CROWS * CD_CP];   // (both tile sizes are multiples of 128 bytes: TMA destinations)
     int cost[64][8];
     CdefBlk blk[64];
 };
@@ -239,7 +240,7 @@ template <bool EDGE> AV1B_DEV void cdef_filter_tile(CdefSmem& S, const PostCtx& 
         const int xg = (fbx + bx) * 8, yg = (fby + by) * 8 + r;
         if (xg >= pw || yg >= ph) continue;
         const CdefBlk& B = S.blk[b];
-        const int ctr = (by * 8 + r + 2) * CD_YP + bx * 8 + 8;
+        const int ctr = (by * 8 + r + 2) * CD_YP + bx * 8 + CD_X0;
         uint32_t out[2];
         if (B.idx != 0xFF && (B.pri[0] | B.sec[0]))
             cdef_filter_row<4, EDGE>(S.y, ctr, CD_YP, B.d[0], B.pri[0], B.sec[0], B.adjp[0], B.adjs[0], xg, yg, pw, ph, out);
@@ -258,7 +259,7 @@ template <bool EDGE> AV1B_DEV void cdef_filter_tile(CdefSmem& S, const PostCtx& 
         if (xg >= cpw || yg >= cph) continue;
         const CdefBlk& B = S.blk[b];
         const uint8_t* tile = S.c[plane - 1];
-        const int ctr = (by * 4 + r + 2) * CD_CP + bx * 4 + 8;
+        const int ctr = (by * 4 + r + 2) * CD_CP + bx * 4 + CD_X0;
         uint32_t out[1];
         if (B.idx != 0xFF && (B.pri[1] | B.sec[1]))
             cdef_filter_row<2, EDGE>(tile, ctr, CD_CP, B.d[1], B.pri[1], B.sec[1], B.adjp[1], B.adjs[1], xg, yg, cpw, cph, out);
@@ -267,21 +268,29 @@ template <bool EDGE> AV1B_DEV void cdef_filter_tile(CdefSmem& S, const PostCtx& 
     }
 }
 
-// Stage rows -2 .. rows-3 of a tile whose sample (0, 0) is plane sample (x0, y0): `chunks` 64-bit
-// words per row starting at column x0 - 8.  Rows are clamped into the plane's padded area (their
-// content is never used: taps there are unavailable).
-AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int ph, int rows, int chunks, int pitch, uint8_t* tile, int tid, int nt)
+// Load-based staging (no TMA descriptor: emulation, or a driver without the encoder): rows -2 ..
+// rows-3 of a tile whose sample (0, 0) is plane sample (x0, y0), `pitch` bytes per row from column
+// x0 - CD_X0 as 128-bit words.  Rows are clamped into the plane's padded area (their content is
+// never used: taps there are unavailable).
+AV1B_DEV void cdef_stage(const PlaneView& src, int x0, int y0, int ph, int rows, int pitch, uint8_t* tile, int tid, int nt)
 {
+    const int chunks = pitch >> 4;
     for (int e = tid; e < rows * chunks; e += nt) {
         const int r = e / chunks, k = e - r * chunks;
         const int y = clip3(-2, ph + 1, y0 - 2 + r);
-        *(uint2*)(tile + r * pitch + 8 * k) = __ldg((const uint2*)(src.p + (ptrdiff_t)y * src.stride + x0 - 8) + k);
+        *(uint4*)(tile + r * pitch + 16 * k) = __ldg((const uint4*)(src.p + (ptrdiff_t)y * src.stride + x0 - CD_X0) + k);
     }
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(CD_THREADS, 5) cdef_kernel(PostCtx c)
+void cdef_tile_box(int plane, int* box_w, int* box_h)
+{
+    *box_w = plane ? CD_CP : CD_YP;
+    *box_h = plane ? CD_CROWS : CD_YROWS;
+}
+
+__global__ void __launch_bounds__(CD_THREADS, 5) cdef_kernel(const __grid_constant__ PostCtx c)
 {
     __shared__ CdefSmem S;
     const PostHdr* hdr = &c.h;
@@ -290,15 +299,32 @@ __global__ void __launch_bounds__(CD_THREADS, 5) cdef_kernel(PostCtx c)
     const int c8 = hdr->mi_cols >> 1, r8 = hdr->mi_rows >> 1; // 8x8 blocks in the frame
     const int fbx = blockIdx.x * 8, fby = blockIdx.y * 8;      // first 8x8 block of this CTA
     const int pw = hdr->mi_cols * 4, ph = hdr->mi_rows * 4;
-    // ---- 1. stage
-    cdef_stage(c.deb.pl[0], fbx * 8, fby * 8, ph, CD_YROWS, CD_YP / 8, CD_YP, S.y, tid, nt);
-    cdef_stage(c.deb.pl[1], fbx * 4, fby * 4, ph >> 1, CD_CROWS, CD_CP / 8, CD_CP, S.c[0], tid, nt);
-    cdef_stage(c.deb.pl[2], fbx * 4, fby * 4, ph >> 1, CD_CROWS, CD_CP / 8, CD_CP, S.c[1], tid, nt);
+    // ---- 1. stage.  With TMA descriptors the three tiles (halo included) are THREE requests to the
+    // TMA unit, issued by one thread and counted in bytes on `bar`: nobody spends issue slots on
+    // moving the bytes, and the preset look-up below overlaps the copies.  Tile rows past the
+    // plane's padded area come back as zeros (never used: taps there are unavailable).
+    alignas(8) __shared__ unsigned long long bar;
+    const bool tma = c.tma_ok != 0;
+    if (tma) {
+        if (tid == 0) av1b_mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            av1b_mbar_expect_tx(&bar, CD_YROWS * CD_YP + 2 * CD_CROWS * CD_CP);
+            av1b_tma_load_2d(S.y, &c.cdef_in[0], c.tma_x0 + fbx * 8 - CD_X0, c.tma_y0 + fby * 8 - 2, &bar);
+            av1b_tma_load_2d(S.c[0], &c.cdef_in[1], c.tma_x0 + fbx * 4 - CD_X0, c.tma_y0 + fby * 4 - 2, &bar);
+            av1b_tma_load_2d(S.c[1], &c.cdef_in[2], c.tma_x0 + fbx * 4 - CD_X0, c.tma_y0 + fby * 4 - 2, &bar);
+        }
+    } else {
+        cdef_stage(c.deb.pl[0], fbx * 8, fby * 8, ph, CD_YROWS, CD_YP, S.y, tid, nt);
+        cdef_stage(c.deb.pl[1], fbx * 4, fby * 4, ph >> 1, CD_CROWS, CD_CP, S.c[0], tid, nt);
+        cdef_stage(c.deb.pl[2], fbx * 4, fby * 4, ph >> 1, CD_CROWS, CD_CP, S.c[1], tid, nt);
+    }
     const Av1bCdefParams& cp = hdr->cdef;
     for (int e = tid; e < 64; e += nt) {
         const int by = fby + (e >> 3), bx = fbx + (e & 7);
         S.blk[e].idx = (by < r8 && bx < c8) ? cdef8[by * c8 + bx] : 0xFF;
     }
+    if (tma) av1b_mbar_wait(&bar, 0);
     __syncthreads();
     // ---- 2. direction search (only blocks whose primary strengths are not both zero need one)
     for (int e = tid; e < 512; e += nt) {
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__(CD_THREADS, 5) cdef_kernel(PostCtx c)
         const int idx = S.blk[b].idx;
         if (idx == 0xFF || !(cp.y_pri[idx] | cp.uv_pri[idx])) continue;
         uint32_t w[16];
-        const uint8_t* bp = S.y + ((b >> 3) * 8 + 2) * CD_YP + (b & 7) * 8 + 8;
+        const uint8_t* bp = S.y + ((b >> 3) * 8 + 2) * CD_YP + (b & 7) * 8 + CD_X0;
         AV1B_UNROLL
         for (int i = 0; i < 8; i++) {
             const uint2 v = *(const uint2*)(bp + i * CD_YP);

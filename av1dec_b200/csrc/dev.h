@@ -35,6 +35,7 @@ extern EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __shared__ static
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __restrict__
 #define AV1B_UNROLL
 #define AV1B_UNROLL4
@@ -135,6 +136,14 @@ static inline int av1b_dp4a_ss(uint32_t a, uint32_t b, int c)
     for (int i = 0; i < 4; i++) c += (int)(int8_t)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
     return c;
 }
+// bulk asynchronous copies: the emulation copies at once, the barrier is always complete
+static inline void av1b_mbar_init(unsigned long long*, unsigned) {}
+static inline void av1b_mbar_expect_tx(unsigned long long*, unsigned) {}
+static inline void av1b_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+static inline void av1b_mbar_wait(unsigned long long*, unsigned) {}
+struct Av1bTensorMap;
+static inline void av1b_tma_load_2d(void*, const Av1bTensorMap*, int, int, unsigned long long*) {}
+struct alignas(64) Av1bTensorMap { unsigned long long opaque[16]; }; // CUtensorMap stand-in (never used by the emulation)
 typedef void* av1b_stream_t;
 template <class F> static inline void emu_launch(dim3 grid, F f)
 {
@@ -173,6 +182,42 @@ static __device__ __forceinline__ void av1b_st_release(int* p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 static __device__ __forceinline__ void av1b_nanosleep(unsigned ns) { __nanosleep(ns); }
+// ---- bulk asynchronous global -> shared copies (the TMA unit moves whole rows; SASS UBLKCP), completion
+// counted in bytes on a shared-memory mbarrier.  Source, destination and size are multiples of 16.
+static __device__ __forceinline__ void av1b_mbar_init(unsigned long long* bar, unsigned arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+static __device__ __forceinline__ void av1b_mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void av1b_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// A 2-D tile (the box the descriptor was encoded with) at element coordinates (x, y) of the tensor:
+// ONE request to the TMA unit (SASS UTMALDG), rows land packed in shared memory.
+struct alignas(64) Av1bTensorMap { unsigned long long opaque[16]; }; // same size / alignment as CUtensorMap
+static __device__ __forceinline__ void av1b_tma_load_2d(void* dst, const Av1bTensorMap* map, int x, int y, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+static __device__ __forceinline__ void av1b_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done)
+                     : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 // polling load: served by L2 every time, no L1 invalidation (the acquire follows once the value is there)
 static __device__ __forceinline__ int av1b_ld_relaxed(const int* p)
 {

@@ -140,6 +140,46 @@ const char* av1b_backend(void) { return "cuda-sm_100a"; }
 #endif
 
 // ------------------------------------------------------------------------------------------
+// TMA descriptors.  cuTensorMapEncodeTiled is a driver entry point: fetched at run time so the
+// library does not link libcuda.
+// ------------------------------------------------------------------------------------------
+#ifndef AV1B_EMU
+#include <cuda.h>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder()
+{
+    static std::once_flag once;
+    static EncodeTiledFn fn = nullptr;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("AV1B200_NO_TMA") == nullptr && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess
+            && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    });
+    return fn;
+}
+// The padded plane (rows x pitch bytes starting at `base`) as a 2-D byte tensor with a box_w x box_h box.
+static bool tma_encode_plane(Av1bTensorMap* out, uint8_t* base, size_t pitch, size_t rows, int box_w, int box_h)
+{
+    static_assert(sizeof(Av1bTensorMap) == sizeof(CUtensorMap) && alignof(Av1bTensorMap) >= alignof(CUtensorMap), "descriptor stand-in");
+    EncodeTiledFn fn = tma_encoder();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)pitch, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)pitch };
+    const cuuint32_t box[2] = { (cuuint32_t)box_w, (cuuint32_t)box_h };
+    const cuuint32_t estr[2] = { 1, 1 };
+    return fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        == CUDA_SUCCESS;
+}
+#else
+static bool tma_encode_plane(Av1bTensorMap*, uint8_t*, size_t, size_t, int, int) { return false; }
+#endif
+
+// ------------------------------------------------------------------------------------------
 // wedge mask table (spec 7.11.3.11; reference initialise_wedge_mask_table, InterPredict.cpp:835)
 // ------------------------------------------------------------------------------------------
 void build_wedge_table(uint8_t* out)
@@ -214,6 +254,8 @@ struct DevFrame {
     int writer = MAIN_LANE;   // lane of that submit
     uint32_t readers = 0;     // lanes that read it since (bit MAIN_LANE = the context stream)
     bool settled = true;      // nothing recorded since the last full av1b_sync: no event to wait for
+    Av1bTensorMap tm_cdef[3];  // TMA descriptors of the padded planes (CDEF tile boxes)
+    bool tm_ok = false;
 };
 
 // Per-lane scratch: nothing here is shared between frames in flight on different lanes.
@@ -340,6 +382,15 @@ static int frame_add(av1b_ctx* c, uint8_t* base, bool owned, int lane)
     f.v.pl[1].stride = c->stride_c;
     f.v.pl[2].p = v + (size_t)PAD_Y * c->stride_c + PAD_X;
     f.v.pl[2].stride = c->stride_c;
+    {
+        int bw, bh;
+        f.tm_ok = true;
+        uint8_t* bases[3] = { y, u, v };
+        for (int p = 0; p < 3; p++) {
+            cdef_tile_box(p, &bw, &bh);
+            f.tm_ok = f.tm_ok && tma_encode_plane(&f.tm_cdef[p], bases[p], p ? c->stride_c : c->stride_y, p ? chroma_rows : luma_rows, bw, bh);
+        }
+    }
     if (rt_event_create(&f.ready)) return 1;
     if (rt_event_create(&f.copied)) {
         rt_event_destroy(f.ready);
@@ -861,6 +912,13 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
         c->frames[cdef].refcnt++;
         if (frame_claim(c, cdef, lane)) return fail(c, AV1B_ECUDA, "stream wait");
         pc.cdef = c->frames[cdef].v;
+        {
+            const DevFrame& in = c->frames[deb >= 0 ? deb : cur]; // what the kernel reads as pc.deb
+            pc.tma_ok = in.tm_ok;
+            pc.tma_x0 = PAD_X;
+            pc.tma_y0 = PAD_Y;
+            for (int p = 0; p < 3; p++) pc.cdef_in[p] = in.tm_cdef[p];
+        }
         StageTimer t(c, 4, true, st);
         launch_cdef(pc, h, st);
         c->launches += 1;

@@ -40,6 +40,11 @@ inline PostHdr make_post_hdr(const Av1bFrameHdr& h)
 
 // In-loop filter context.
 struct PostCtx {
+    // TMA descriptors of the CDEF input planes (the whole padded plane as a 2-D byte tensor, box =
+    // the CDEF tile with its halo); tma_ok == 0: not available, the kernel stages with loads
+    Av1bTensorMap cdef_in[3];
+    int tma_ok;
+    int tma_x0, tma_y0; // tensor coordinates of plane sample (0, 0)
     PostHdr h;
     const uint8_t* cmd;
     FrameView src;  // reconstructed frame (never modified by the filters)
@@ -54,6 +59,8 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 
 void launch_deblock(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
 void launch_cdef(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st);
+// CDEF tile boxes the descriptors are encoded with: {bytes per row, rows} for luma / chroma
+void cdef_tile_box(int plane, int* box_w, int* box_h);
 int launch_lr(const PostCtx& c, const Av1bFrameHdr& h, av1b_stream_t st); // returns the number of kernels launched
 // planar 4:2:0 -> NV12 (device to device), visible w x h
 void launch_to_nv12(const FrameView& src, uint8_t* dst_y, int pitch_y, uint8_t* dst_uv, int pitch_uv, int w, int h, av1b_stream_t st);

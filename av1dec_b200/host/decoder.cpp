@@ -108,6 +108,7 @@ struct Decoder::Impl {
     std::string error;
     // AV1B200_TIMING=1: cumulative host-side phase timers, printed when the decoder is destroyed
     bool timing = getenv("AV1B200_TIMING") != nullptr;
+    double t_dbg[4] = { 0, 0, 0, 0 };
     double t_parse = 0, t_emit = 0, t_submit = 0, t_wait = 0;
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -176,11 +177,17 @@ struct Decoder::Impl {
         const double t0 = now();
         emitter.begin(h, *seq);
         for (auto& t : ts) {
+            const double ta = now();
             emitter.emitTile(*t);
+            const double tb = now();
             t->m_sbs.clear(); // the block tree is no longer needed (Tile::decode pops as it goes)
+            t_dbg[0] += tb - ta;
+            t_dbg[1] += now() - tb;
         }
+        const double tc = now();
         emitter.finish();
         const double t1 = now();
+        t_dbg[2] += t1 - tc;
         t_emit += t1 - t0;
         const size_t bytes = emitter.bytes();
         void* slot = nullptr;
@@ -326,7 +333,8 @@ Decoder::~Decoder()
 {
     m_impl->stopWorker();
     if (m_impl->timing)
-        fprintf(stderr, "av1b200 timing: parse %.3fs emit %.3fs submit %.3fs wait %.3fs\n", m_impl->t_parse, m_impl->t_emit, m_impl->t_submit, m_impl->t_wait);
+        fprintf(stderr, "av1b200 timing: parse %.3fs emit %.3fs (walk %.3f, tree free %.3f, finish %.3f) submit %.3fs wait %.3fs\n", m_impl->t_parse, m_impl->t_emit,
+            m_impl->t_dbg[0], m_impl->t_dbg[1], m_impl->t_dbg[2], m_impl->t_submit, m_impl->t_wait);
     if (m_impl->ctx) {
         av1b_sync(m_impl->ctx);
         m_impl->output.clear();
