@@ -137,4 +137,72 @@ AV1B_DEV void col_pass(const int16_t* tmp_col, int tmp_stride, int nz_rows, int1
     }
 }
 
+// ---- 32- and 64-point DCT shared by two lanes (of different warps): lane `half` 0 runs the DCT of
+// half the size on the even-indexed inputs, lane 1 the odd half of the flow graph on the odd-indexed
+// ones; the caller exchanges the results through shared memory and applies the last Hadamard stage.
+// Each lane holds N/2 values: half the registers and half the latency of the one-lane transform.
+// X: where this lane's N/2 results go (ints, before the last stage).  nz: leading inputs of the
+// N-point transform that may be non-zero (<= 32).
+template <int n> AV1B_DEV void dct_half(int* T, int half, int cnt)
+{
+    if (half == 0) {
+        if (n == 6) {
+            const int hi = 32767, lo = -32768;
+            if (cnt <= 1) idct32_k1(T, lo, hi);
+            else if (cnt <= 8) idct32_k8(T, lo, hi);
+            else idct32_k16(T, lo, hi); // a 64-point transform has at most 32 inputs, 16 of them even
+        } else idct16(T, 16, cnt);
+    } else {
+        if (n == 6) idct64_odd(T, 16, cnt);
+        else idct32_odd(T, 16, cnt);
+    }
+}
+
+template <int n> AV1B_DEV void row_half(const int16_t* coef_row, int tw_nz, bool rect, int half, int* X)
+{
+    constexpr int M = 1 << (n - 1);
+    const int cnt = (tw_nz + 1 - half) >> 1; // x[2k + half], k < cnt, may be non-zero (cnt <= 16)
+    int T[M];
+    AV1B_UNROLL
+    for (int k = 0; k < M; k++) T[k] = (k < 16 && k < cnt) ? (int)coef_row[2 * k + half] : 0;
+    if (rect) {
+        AV1B_UNROLL
+        for (int k = 0; k < 16; k++) T[k] = (T[k] * 2896 + 2048) >> 12;
+    }
+    dct_half<n>(T, half, cnt);
+    AV1B_UNROLL
+    for (int k = 0; k < M; k++) X[k] = T[k];
+}
+
+template <int n> AV1B_DEV void col_half(const int16_t* tmp_col, int tmp_stride, int nz_rows, int half, int* X)
+{
+    constexpr int M = 1 << (n - 1);
+    const int cnt = (nz_rows + 1 - half) >> 1;
+    int T[M];
+    AV1B_UNROLL
+    for (int k = 0; k < M; k++) T[k] = (k < 16 && k < cnt) ? (int)tmp_col[(2 * k + half) * tmp_stride] : 0;
+    dct_half<n>(T, half, cnt);
+    AV1B_UNROLL
+    for (int k = 0; k < M; k++) X[k] = T[k];
+}
+
+// 32-point identity row / column (the only non-DCT transform of that length)
+AV1B_DEV void row_identity32(const int16_t* coef_row, int tw_nz, int16_t* tmp_row, bool rect, int row_shift)
+{
+    AV1B_UNROLL
+    for (int j = 0; j < 32; j++) {
+        int v = (j < tw_nz) ? (int)coef_row[j] : 0;
+        if (rect) v = (v * 2896 + 2048) >> 12;
+        tmp_row[j] = (int16_t)clip3(-32768, 32767, round2(v * 4, row_shift));
+    }
+}
+AV1B_DEV void col_identity32(const int16_t* tmp_col, int tmp_stride, int nz_rows, int16_t* out_col, int out_stride, bool fud, int col_shift)
+{
+    AV1B_UNROLL
+    for (int i = 0; i < 32; i++) {
+        const int v = (i < nz_rows) ? (int)tmp_col[i * tmp_stride] * 4 : 0;
+        out_col[(fud ? (31 - i) : i) * out_stride] = (int16_t)clip3(-32768, 32767, round2(v, col_shift));
+    }
+}
+
 }  // namespace itx

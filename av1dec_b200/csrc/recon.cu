@@ -93,16 +93,110 @@ AV1B_DEV void itx_block(const Av1bOp& op, const int16_t* __restrict__ coef, int1
 
 }  // namespace
 
+// Class 3 (a dimension of 32 or 64): the whole CTA works on ONE transform block at a time.  A 32- or
+// 64-point DCT is shared by two lanes of different warps (even / odd half of the flow graph, results
+// exchanged through shared memory, last Hadamard stage in the combine step), so the row pass of a
+// 64x64 block keeps 64 lanes busy and the column pass all 128 -- the one-lane-per-transform layout
+// of the small classes would leave a handful of 250-register warps per SM to do all the work.
+AV1B_DEV void itx_cta_big(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n, const int16_t* __restrict__ coef,
+    int16_t* __restrict__ res, const ResPlanes& rp, unsigned bid, unsigned nblocks)
+{
+    enum { XP = 33, TP = 66 };
+    __shared__ int X[2][64][XP];     // [half][row | column][k]: the two halves before the last stage
+    __shared__ int16_t tmp[32][TP];  // row-pass output (rows < nz_rows)
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t t = bid; t < n; t += nblocks) {
+        const Av1bOp op = ops[list[t]];
+        const int txs = op.tx_size;
+        const int lw = (int)((AV1T_TX_WLOG2_PACKED >> (3 * txs)) & 7), lh = (int)((AV1T_TX_HLOG2_PACKED >> (3 * txs)) & 7);
+        const int w = 1 << lw, h = 1 << lh;
+        const int tw = min(w, 32);
+        const int rk = itx::row_kind(op.tx_type), ck = itx::col_kind(op.tx_type);
+        const bool rect = (lw - lh == 1) || (lh - lw == 1);
+        const int row_shift = k_tx_row_shift[txs];
+        const int col_shift = 4;
+        const int nz_rows = min(max((int)op.nz_rows, 1), min(h, 32));
+        const int nz_cols = min(max((int)op.nz_cols, 1), tw);
+        const int16_t* c = coef + op.coef_off;
+        int16_t* out;
+        int out_stride;
+        if (rp.p[0]) {
+            out = rp.p[op.plane] + (size_t)op.y * rp.pitch[op.plane] + op.x;
+            out_stride = rp.pitch[op.plane];
+        } else {
+            out = res + op.res_off;
+            out_stride = w;
+        }
+        const bool fud = itx::flip_ud(op.tx_type), flr = itx::flip_lr(op.tx_type);
+        // ---- row pass
+        if (rk == itx::K_DCT && lw >= 5) {
+            for (int e = tid; e < 64; e += nt) { // lanes 0..31: even halves of the rows, 32..63: odd halves
+                const int i = e & 31, half = e >> 5;
+                if (i >= nz_rows) continue;
+                if (lw == 6) itx::row_half<6>(c + i * tw, nz_cols, rect, half, X[half][i]);
+                else itx::row_half<5>(c + i * tw, nz_cols, rect, half, X[half][i]);
+            }
+            __syncthreads();
+            const int lm = lw - 1, M = 1 << lm;
+            for (int e = tid; e < (nz_rows << lm); e += nt) {
+                const int i = e >> lm, k = e & (M - 1);
+                const int E = X[0][i][k], O = X[1][i][M - 1 - k];
+                tmp[i][k] = (int16_t)clip3(-32768, 32767, round2(clip3(-32768, 32767, E + O), row_shift));
+                tmp[i][w - 1 - k] = (int16_t)clip3(-32768, 32767, round2(clip3(-32768, 32767, E - O), row_shift));
+            }
+        } else {
+            for (int i = tid; i < nz_rows; i += nt) {
+                if (lw == 5) itx::row_identity32(c + i * tw, nz_cols, tmp[i], rect, row_shift);
+                else if (lw == 4) itx::row_pass<4>(c + i * tw, tw, nz_cols, tmp[i], rk, rect, row_shift);
+                else itx::row_pass<3>(c + i * tw, tw, nz_cols, tmp[i], rk, rect, row_shift);
+            }
+        }
+        __syncthreads();
+        // ---- column pass
+        if (ck == itx::K_DCT && lh >= 5) {
+            for (int e = tid; e < 2 * w; e += nt) { // first w lanes: even halves of the columns, next w: odd halves
+                const int half = e >= w ? 1 : 0, j = e - half * w;
+                if (lh == 6) itx::col_half<6>(&tmp[0][j], TP, nz_rows, half, X[half][j]);
+                else itx::col_half<5>(&tmp[0][j], TP, nz_rows, half, X[half][j]);
+            }
+            __syncthreads();
+            const int M = h >> 1;
+            for (int e = tid; e < (M << lw); e += nt) {
+                const int k = e >> lw, j = e & (w - 1); // j fastest: coalesced residual stores
+                const int E = X[0][j][k], O = X[1][j][M - 1 - k];
+                const int v0 = clip3(-32768, 32767, round2(clip3(-32768, 32767, E + O), col_shift));
+                const int v1 = clip3(-32768, 32767, round2(clip3(-32768, 32767, E - O), col_shift));
+                const int jo = flr ? (w - 1 - j) : j;
+                const int r0 = fud ? (h - 1 - k) : k, r1 = fud ? k : (h - 1 - k);
+                out[(size_t)r0 * out_stride + jo] = (int16_t)v0;
+                out[(size_t)r1 * out_stride + jo] = (int16_t)v1;
+            }
+        } else {
+            for (int j = tid; j < w; j += nt) {
+                const int jo = flr ? (w - 1 - j) : j;
+                if (lh == 5) itx::col_identity32(&tmp[0][j], TP, nz_rows, out + jo, out_stride, fud, col_shift);
+                else if (lh == 4) itx::col_pass<4>(&tmp[0][j], TP, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+                else itx::col_pass<3>(&tmp[0][j], TP, nz_rows, out + jo, out_stride, fud, ck, col_shift);
+            }
+        }
+        __syncthreads(); // tmp / X are reused by the next block
+    }
+}
+
 // The transform blocks of one size class CLS (0: 4x4, 1: max dim 8, 2: max dim 16, 3: 32 and 64),
 // CTA `bid` of `nblocks`.
 template <int CLS>
 AV1B_DEV void itx_cta(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n, const int16_t* __restrict__ coef,
     int16_t* __restrict__ res, const ResPlanes& rp, unsigned bid, unsigned nblocks)
 {
-    constexpr int GMAX = 4 << CLS;
-    constexpr int TSTRIDE = (CLS == 3) ? (int)ITX_TMP_STRIDE : GMAX + 2;
-    constexpr int REGION = (CLS == 3) ? (int)ITX_TMP_ROWS * ITX_TMP_STRIDE : GMAX * (GMAX + 2);
-    __shared__ int16_t tmp_all[ITX_WARPS][(CLS == 3) ? REGION : (32 / GMAX) * REGION];
+    if (CLS == 3) {
+        itx_cta_big(ops, list, n, coef, res, rp, bid, nblocks);
+        return;
+    }
+    constexpr int GMAX = 4 << (CLS == 3 ? 2 : CLS); // (class 3 never gets here: keep its big transforms out of this code)
+    constexpr int TSTRIDE = GMAX + 2;
+    constexpr int REGION = GMAX * (GMAX + 2);
+    __shared__ int16_t tmp_all[ITX_WARPS][(32 / GMAX) * REGION];
     const int nl = min(32u, blockDim.x);
     const int nw = max(1u, blockDim.x / 32);
     const int lane = threadIdx.x % nl;
@@ -115,7 +209,7 @@ AV1B_DEV void itx_cta(const Av1bOp* __restrict__ ops, const uint32_t* __restrict
         const uint32_t t = t0 + grp;
         if (t < n) {
             const Av1bOp op = ops[list[t]];
-            itx_block<(CLS == 3) ? 6 : CLS + 2>(op, coef, res, rp, tmp, TSTRIDE, gl, G);
+            itx_block<(CLS == 3) ? 4 : CLS + 2>(op, coef, res, rp, tmp, TSTRIDE, gl, G);
         }
         __syncwarp();
     }
@@ -123,7 +217,7 @@ AV1B_DEV void itx_cta(const Av1bOp* __restrict__ ops, const uint32_t* __restrict
 
 // One launch per size class: small transforms compile to few registers and run at full occupancy.
 template <int CLS>
-__global__ void __launch_bounds__(ITX_WARPS * 32, CLS == 3 ? 3 : 1)
+__global__ void __launch_bounds__(ITX_WARPS * 32)
     itx_kernel(const Av1bOp* __restrict__ ops, const uint32_t* __restrict__ list, uint32_t n,
         const int16_t* __restrict__ coef, int16_t* __restrict__ res, ResPlanes rp)
 {
@@ -1152,7 +1246,7 @@ int launch_itx(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         plan.first[k] = prev;
         plan.cnt[k] = end > prev ? end - prev : 0;
         prev = end > prev ? end : prev;
-        const uint32_t per_cta = ITX_WARPS * (32 / (4 << k)); // transform blocks per CTA pass
+        const uint32_t per_cta = k == 3 ? 1 : ITX_WARPS * (32 / (4 << k)); // transform blocks per CTA pass (class 3: the CTA shares one)
         uint32_t nb = (plan.cnt[k] + per_cta - 1) / per_cta;
         if (nb > 148 * 16) nb = 148 * 16;
         ctas += nb;

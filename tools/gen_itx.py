@@ -123,7 +123,7 @@ class Graph:
 
 
 # ------------------------------------------------------------------------------ the flow graphs
-def dct_graph(g, T, n):
+def dct_graph(g, T, n, skip_final=False):
     """Inverse DCT of 1 << n points (AV1 spec 7.13.2.3, steps in the order the spec lists them;
     a step applies when n is large enough for the indices it names)."""
     N = 1 << n
@@ -226,6 +226,9 @@ def dct_graph(g, T, n):
             B(55 - i, 40 + i, 32, True)
         for i in range(32):
             H(i, 63 - i)
+    if skip_final:  # everything but the last Hadamard stage H(i, N-1-i): the two halves are still independent
+        last, steps = steps[-(N // 2):], steps[:-(N // 2)]
+        assert all(st == ("H", i, N - 1 - i, False) for i, st in enumerate(last))
     for st in steps:
         if st[0] == "B":
             g.rot(T, st[1], st[2], st[3], st[4])
@@ -279,12 +282,23 @@ def adst_graph(g, T, n):
 
 
 # ------------------------------------------------------------------------------ emission
-def emit(name, n, k, graph_fn):
-    """One function: T[0 .. k-1] are the inputs (the rest are zero), T[0 .. N-1] the outputs."""
+def emit(name, n, k, graph_fn, odd_half=False):
+    """One function: T[0 .. k-1] are the inputs (the rest are zero), T[0 .. N-1] the outputs.
+    odd_half: the ODD half of a DCT of 1 << n points on its own -- T[0 .. k-1] are the odd-indexed
+    inputs x[1], x[3], ..., the outputs T[0 .. N/2-1] are positions N/2 .. N-1 of the flow graph
+    before its last Hadamard stage (the even half is the DCT of half the size on the even-indexed
+    inputs; the caller combines the two: out[i] = clip(E[i] + O[N/2-1-i]), out[N-1-i] = clip(E[i] - O[N/2-1-i]))."""
     N = 1 << n
     g = Graph()
-    T = [g.inp(i) if i < k else 0 for i in range(N)]
-    graph_fn(g, T, n)
+    if odd_half:
+        T = [g.inp(i >> 1) if (i & 1) and (i >> 1) < k else 0 for i in range(N)]
+        graph_fn(g, T, n, skip_final=True)
+        assert all(t == 0 for t in T[:N // 2])
+        T = T[N // 2:]
+        N = N // 2
+    else:
+        T = [g.inp(i) if i < k else 0 for i in range(N)]
+        graph_fn(g, T, n)
     live, stack = set(), [t for t in T if t]
     while stack:
         v = stack.pop()
@@ -349,8 +363,10 @@ def main():
     parts = ["// itx_gen.h -- GENERATED by tools/gen_itx.py; do not edit.",
              "// Zero-aware straight-line AV1 inverse DCT / ADST butterflies (see the generator for the design).",
              "#pragma once", '#include "dev.h"', "", "namespace itx {", ""]
-    plan = [("idct", dct_graph, {2: [1, 4], 3: [1, 4, 8], 4: [1, 4, 8, 16], 5: [1, 4, 8, 16, 32], 6: [1, 4, 8, 16, 32]}),
-            ("iadst", adst_graph, {3: [1, 4, 8], 4: [1, 4, 8, 16]})]
+    # three variants per transform: DC only, the low-frequency quarter, everything (more variants
+    # cost instruction-cache and registers on dense blocks and buy little on sparse ones)
+    plan = [("idct", dct_graph, {2: [1, 4], 3: [1, 4, 8], 4: [1, 4, 16], 5: [1, 8, 16, 32], 6: [1, 8, 32]}),
+            ("iadst", adst_graph, {3: [1, 4, 8], 4: [1, 4, 16]})]
     for prefix, fn, sizes in plan:
         for n, ks in sizes.items():
             for k in ks:
@@ -358,6 +374,13 @@ def main():
                 parts.append("")
             parts.append(dispatcher(prefix, n, ks))
             parts.append("")
+    # the odd halves of the 32- and 64-point DCT (two lanes of different warps share one transform)
+    for n, ks in ((5, [4, 16]), (6, [4, 16])):
+        for k in ks:
+            parts.append(emit("idct%d_odd_k%d" % (1 << n, k), n, k, dct_graph, odd_half=True))
+            parts.append("")
+        parts.append(dispatcher("idct%d_odd" % (1 << n), 0, ks).replace("of 1 points", "odd half").replace("idct%d_odd1" % (1 << n), "idct%d_odd" % (1 << n)))
+        parts.append("")
     parts.append("}  // namespace itx")
     open(OUT, "w").write("\n".join(parts) + "\n")
     print("wrote", OUT, sum(p.count("\n") + 1 for p in parts), "lines")
