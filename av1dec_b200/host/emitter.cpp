@@ -587,18 +587,22 @@ void FrameEmitter::emitTb(Block& b, TransformBlock& t)
         int16_t* out = &m_coef[off];
         int nzr = 0, nzc = 0;
         const int dshift = denom == 1 ? 0 : (denom == 2 ? 1 : 2); // dqDenom is 1, 2 or 4: magnitude division by shift
+        // only the first eob positions of the scan can hold a level (TransformBlock::coeffs,
+        // TransformBlock.cpp:1678-1697): walk those, not the whole 4 KB Quant array of the block
         const auto* quant = &t.Quant[0];
-        for (int i = 0; i < th; i++) {
-            const auto* qrow = quant + i * tw;
-            for (int j = 0; j < tw; j++) {
-                const int q = qrow[j];
-                if (!q) continue;
-                const int dq = (int)((unsigned)q * (unsigned)((i | j) ? acq : dcq));
-                const int mag = (int)((((dq < 0) ? (0u - (unsigned)dq) : (unsigned)dq) & 0xffffffu) >> dshift);
-                out[i * tw + j] = (int16_t)clip3(-32768, 32767, dq < 0 ? -mag : mag);
-                if (i + 1 > nzr) nzr = i + 1;
-                if (j + 1 > nzc) nzc = j + 1;
-            }
+        const int16_t* scan = t.get_scan();
+        int ltw = 0;
+        while ((1 << ltw) < tw) ltw++;
+        for (int cidx = 0; cidx < t.m_eob; cidx++) {
+            const int pos = scan[cidx];
+            const int q = quant[pos];
+            if (!q) continue;
+            const int i = pos >> ltw, j = pos & (tw - 1);
+            const int dq = (int)((unsigned)q * (unsigned)(pos ? acq : dcq));
+            const int mag = (int)((((dq < 0) ? (0u - (unsigned)dq) : (unsigned)dq) & 0xffffffu) >> dshift);
+            out[pos] = (int16_t)clip3(-32768, 32767, dq < 0 ? -mag : mag);
+            if (i + 1 > nzr) nzr = i + 1;
+            if (j + 1 > nzc) nzc = j + 1;
         }
         op.flags |= AV1B_OPF_HAS_RESID;
         op.tx_type = (uint8_t)t.PlaneTxType;
