@@ -797,7 +797,7 @@ static int submit_impl(av1b_ctx* c, int lane, const uint8_t* dev_cmd, const Av1b
             if (m != lane && (rt_event_record(c->lanes[m].mark, c->lanes[m].stream) || rt_stream_wait(st, c->lanes[m].mark)))
                 return fail(c, AV1B_ECUDA, "stream wait");
     }
-    const size_t sync_need = 2 + (size_t)h.sb_rows;
+    const size_t sync_need = 2 + (size_t)std::max<uint32_t>(h.n_sb, h.sb_rows); // ticket, exit counter, progress per superblock
     for (int m = 0; m < c->n_lanes; m++) { // all lanes together, like the residual planes
         Lane& Lm = c->lanes[m];
         if (sync_need <= Lm.sync_cap) continue;

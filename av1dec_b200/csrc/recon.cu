@@ -24,6 +24,7 @@
 #include "kernels.h"
 #include <mutex>
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 // ------------------------------------------------------------------------------------------
@@ -853,12 +854,17 @@ AV1B_DEV void wave_signal(int* progress, int r, int col, int tid, int nt)
 // Leaving the kernel: the last CTA out puts the counters back to zero for the next launch (every
 // other CTA has drawn a ticket past the end and polls nothing any more), so no memset node per
 // frame is needed.
-AV1B_DEV void wave_leave(int* sync, int sb_rows, int tid)
+AV1B_DEV void wave_leave(int* sync, int n_progress, int tid, int nt, int* s_flag)
 {
+    block_sync(nt); // s_flag is the shared ticket word: every thread has read its last ticket before it is reused
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
-            for (int r = 0; r < sb_rows; r++) sync[2 + r] = 0;
+        *s_flag = atomicAdd(sync + 1, 1) == (int)gridDim.x - 1;
+    }
+    block_sync(nt);
+    if (*s_flag) {
+        for (int k = tid; k < n_progress; k += nt) sync[2 + k] = 0;
+        if (tid == 0) {
             sync[0] = 0;
             sync[1] = 0;
         }
@@ -917,6 +923,25 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     int16_t* const q1 = q0 + n0 * n0;
     int16_t* const q2 = q1 + n1 * n1;
     OpScratch* const scratch = (OpScratch*)(dyn + WAVE_TILE_BYTES(n0) + WAVE_RES_BYTES(n0)) + warp;
+    const int n_sb_rows = hdr->sb_rows;
+    (void)n_sb_rows;
+    // progress[sb]: bit 0 = the upper half of superblock sb's right column is final and in the frame,
+    // bit 1 = the left half of its bottom row, bit 2 = all of it
+    auto poll = [&](int idx, int mask) {
+#ifdef AV1B_WAVE_WATCHDOG
+        unsigned spins = 0;
+        while (!(av1b_ld_relaxed(progress + idx) & mask)) {
+            av1b_nanosleep(32);
+            if (++spins == (1u << 22)) {
+                printf("wave watchdog: sb %d waits for sb %d mask %d, sees %d (ticket %d, grid %d)\n", s_sb, idx, mask, av1b_ld_relaxed(progress + idx),
+                    av1b_ld_relaxed(ticket), (int)gridDim.x);
+                break;
+            }
+        }
+#else
+        while (!(av1b_ld_relaxed(progress + idx) & mask)) av1b_nanosleep(32);
+#endif
+    };
     for (;;) {
         block_sync(nt);
         if (tid == 0) {
@@ -933,8 +958,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         unsigned long long* const tr = (c.trace && tid == 0 && (unsigned)sb < c.trace_cap) ? c.trace + 8 * (size_t)sb : nullptr;
         if (tr) tr[0] = (unsigned long long)sb, tr[1] = av1b_smid(), tr[2] = av1b_gtime();
         if (e.n_ops == 0) {
-            wave_wait(progress, r, col, sb_cols, 2, tid, nt);
-            wave_signal(progress, r, col, tid, nt);
+            // nothing to reconstruct: the samples the neighbours read are in the frame already
+            if (tid == 0) av1b_st_release(progress + sb, 7);
             if (tr) tr[3] = tr[4] = tr[5] = tr[6] = tr[7] = av1b_gtime();
             continue;
         }
@@ -982,14 +1007,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         // the sample-independent half of every intra op of the chunk, one op per thread
         block_sync(nt);
         for (unsigned q = tid; q < min((unsigned)WAVE_OP_CHUNK, e.n_ops); q += nt) decode_intra_op(&s_ops[0][q], fc);
-        wave_wait(progress, r, col, sb_cols, 2, tid, nt);
-        if (tr) tr[3] = av1b_gtime();
-        // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and the column to the left, of all three
-        // planes as ONE list of items so that every load is in flight before the first store waits
-        {
+        block_sync(nt); // ops are staged (stage_op) by other threads than the ones that decoded them
+        // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and / or the column to the left, of all
+        // three planes as ONE list of items so that every load is in flight before the first store waits
+        auto load_halo = [&](bool above, bool left) {
             const int aw0 = (n0 >> 1) + 1, aw1 = (n1 >> 1) + 1; // words of a row above
-            const int n_above = r > 0 ? aw0 + 2 * aw1 : 0;
-            const int n_left = col > 0 ? n0 + 2 * n1 : 0;
+            const int n_above = (above && r > 0) ? aw0 + 2 * aw1 : 0;
+            const int n_left = (left && col > 0) ? n0 + 2 * n1 : 0;
             AV1B_NOUNROLL
             for (int b0 = 0; b0 < n_above + n_left; b0 += 2 * nt) {
                 uint32_t v[2];
@@ -1029,7 +1053,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                     else *dsts[u] = (uint8_t)v[u];
                 }
             }
-        }
+        };
         PlaneSet io;
         io.pix0 = t0 + (ptrdiff_t)(1 - r * n0) * pitch0 + (4 - col * n0);
         io.pix1 = t1 + (ptrdiff_t)(1 - r * n1) * pitch1 + (4 - col * n1);
@@ -1042,11 +1066,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         io.res2 = have_res ? q2 - (ptrdiff_t)(r * n1) * n1 - col * n1 : nullptr;
         io.rpitch0 = n0;
         io.rpitch12 = n1;
-        // ---- the ops of this superblock, level by level, one warp per op.  The op list streams
-        // through a double buffer: the next chunk is requested before the current one runs, so
-        // its L2 latency hides behind the levels in between.
-        block_sync(nt);
-        if (tr) tr[4] = av1b_gtime();
         auto exec_staged = [&](const StagedOp& st) {
             if (st.state == 1) {
                 intra::Packed k;
@@ -1061,6 +1080,68 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             u.v[0] = st.wa, u.v[1] = st.wb;
             exec_op<true, WAVE_NT>(c, hdr, fc, u.op, io, *scratch, nullptr, lane, nl);
         };
+        // ---- hand-off.  The neighbours only read this superblock's right column and bottom row, so
+        // those go out ahead of the rest of the tile -- each half as soon as no later op writes it
+        // (Av1bSb::pub_r1 / pub_b1), everything at the end -- and the progress word moves as soon as
+        // they are on their way (one fence by one thread).
+        int pubbits = 0;
+        auto publish = [&](int bits) {
+            const bool all = (bits & 4) != 0;
+            for (int pl = 0; pl < 3; pl++) {
+                const int sub = pl ? 1 : 0;
+                const int n = pl ? n1 : n0, pitch = pl ? pitch1 : pitch0;
+                const uint8_t* t = pl == 0 ? t0 : (pl == 1 ? t1 : t2);
+                const int x0 = col * n, y0 = r * n;
+                const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub;
+                const int cw = min(n, pw - x0), chh = min(n, ph - y0);
+                const PlaneView g = c.cur.pl[pl];
+                if (chh == n && (all || (bits & 2))) { // a superblock row below exists
+                    uint32_t* d = (uint32_t*)(g.p + (size_t)(y0 + n - 1) * g.stride + x0);
+                    const int words = (all ? cw : min(cw, n >> 1)) >> 2;
+                    AV1B_NOUNROLL
+                    for (int k = tid; k < words; k += nt) d[k] = *(const uint32_t*)(t + n * pitch + 4 + 4 * k);
+                }
+                if (cw == n && (all || (bits & 1))) { // a superblock to the right exists
+                    uint8_t* d = g.p + (size_t)y0 * g.stride + x0 + n - 1;
+                    const int rows = all ? chh : min(chh, n >> 1);
+                    AV1B_NOUNROLL
+                    for (int k = tid; k < rows; k += nt) d[(size_t)k * g.stride] = t[(k + 1) * pitch + 4 + n - 1];
+                }
+            }
+            pubbits |= all ? 7 : bits;
+            block_sync(nt);
+            if (tid == 0) av1b_st_release(progress + sb, pubbits);
+        };
+        // ---- waiting, level by level: before a level runs, the halves of the neighbours' borders it
+        // reads (Av1bSb::wait_*) must be final; the superblocks above and above-left always are.
+        int waited_l = -1, waited_a = -1; // -1 nothing loaded yet, 0 no wait, 1 the first half, 2 all
+        auto open_level = [&](unsigned level) {
+            const int need_l = (col == 0) ? 0 : (level >= e.wait_l2 ? 2 : (level >= e.wait_l1 ? 1 : 0));
+            const int need_a = (r == 0 || col + 1 >= sb_cols) ? 0 : (level >= e.wait_a2 ? 2 : (level >= e.wait_a1 ? 1 : 0));
+            if (need_l <= waited_l && need_a <= waited_a) return;
+            const bool first = waited_l < 0;
+            if (tid == 0) {
+                bool any = false;
+                if (first && r > 0) {
+                    poll(sb - sb_cols, 4);
+                    if (col > 0) poll(sb - sb_cols - 1, 4);
+                    any = true;
+                }
+                if (need_l > max(waited_l, 0)) poll(sb - 1, need_l == 2 ? 4 : 5), any = true;
+                if (need_a > max(waited_a, 0)) poll(sb - sb_cols + 1, need_a == 2 ? 4 : 6), any = true;
+                if (any) (void)av1b_ld_acquire(progress + sb - (col > 0 ? 1 : sb_cols));
+            }
+            block_sync(nt);
+            if (tr && first) tr[3] = av1b_gtime();
+            load_halo(first || need_a > max(waited_a, 0), first || need_l > max(waited_l, 0));
+            block_sync(nt);
+            if (tr && first) tr[4] = av1b_gtime();
+            waited_l = max(waited_l, need_l);
+            waited_a = max(waited_a, need_a);
+        };
+        // ---- the ops, level by level, one warp per op.  The op list streams through a double
+        // buffer: the next chunk is requested before the current one runs, so its L2 latency hides
+        // behind the levels in between.
         int buf = 0;
         for (unsigned k0 = 0; k0 < e.n_ops; k0 += WAVE_OP_CHUNK, buf ^= 1) {
             const unsigned nk = min((unsigned)WAVE_OP_CHUNK, e.n_ops - k0);
@@ -1070,19 +1151,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             uint4 pre = make_uint4(0, 0, 0, 0);
             static_assert(WAVE_OP_CHUNK * 2 <= 256, "one uint4 of the next chunk per thread");
             if ((unsigned)tid < nn * 2) pre = __ldg((const uint4*)(ops + e.first_op + k1) + tid);
-            // res_off >> 16 = ops left in this level (emitter scheduleSb); 0 from a producer that
-            // does not fill it: one op per step, still a valid order
+            // res_off = level | (ops left in this level) << 16 (emitter scheduleSb); a producer that
+            // leaves the count zero gets one op per step, still a valid order
             auto level_end = [&](unsigned g) { return min(nk, g + max(1u, cur_ops[g].res_off >> 16)); };
             unsigned g0 = 0, g1 = level_end(0);
-#ifdef AV1B_EMU
-            while (g0 < nk) {
-                // the emulation runs the ops of a level in REVERSE order: if the level analysis
-                // missed a dependency, the conformance MD5s under emulation break
-                for (unsigned k = g1; k-- > g0;) exec_staged(stage_op(cur_ops + k, io));
-                g0 = g1;
-                if (g0 < nk) g1 = level_end(g0);
-            }
-#else
+#ifndef AV1B_EMU
             // Op j of a level goes to warp (j + parity * nw/2) mod nw, the parity flipping with
             // every level: a level rarely has more than nw/2 ops, so the warps that work in one
             // level idle in the next and have fetched their next op and worked out its addresses
@@ -1093,7 +1166,24 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             StagedOp st;
             st.state = 0;
             if (mine < g1) st = stage_op(cur_ops + mine, io);
+#endif
             while (g0 < nk) {
+                const unsigned level = cur_ops[g0].res_off & 0xFFFFu;
+                // early hand-off of the border halves the levels before this one made final (a
+                // level may straddle two chunks, so it only counts as over once a later one starts)
+                if (k0 + g0 > 0) {
+                    int bits = 0;
+                    if (e.pub_r1 && level > e.pub_r1 && !(pubbits & 1)) bits |= 1;
+                    if (e.pub_b1 && level > e.pub_b1 && !(pubbits & 2)) bits |= 2;
+                    if (bits) publish(bits);
+                }
+                open_level(level);
+#ifdef AV1B_EMU
+                // the emulation runs the ops of a level in REVERSE order: if the level analysis
+                // missed a dependency, the conformance MD5s under emulation break
+                for (unsigned k = g1; k-- > g0;) exec_staged(stage_op(cur_ops + k, io));
+                const unsigned g2 = g1 < nk ? level_end(g1) : g1;
+#else
                 if (mine < g1) {
                     exec_staged(st);
                     for (unsigned k = mine + nw; k < g1; k += nw) exec_staged(stage_op(cur_ops + k, io));
@@ -1102,11 +1192,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 par ^= 1;
                 mine = g1 + ((warp + par * (nw >> 1)) & (nw - 1));
                 if (mine < g2) st = stage_op(cur_ops + mine, io);
+#endif
                 block_sync(nt);
                 g0 = g1;
                 g1 = g2;
             }
-#endif
             if (nn) {
 #ifdef AV1B_EMU
                 for (unsigned q = 0; q < nn * 2; q++) ((uint4*)s_ops[buf ^ 1])[q] = ((const uint4*)(ops + e.first_op + k1))[q];
@@ -1118,32 +1208,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 block_sync(nt);
             }
         }
-        if (tr) tr[5] = av1b_gtime();
-        // ---- hand-off first: the neighbours only read this superblock's bottom row (as their row
-        // above / above-right) and right column, so those go out ahead of the rest of the tile and
-        // the progress counter moves as soon as they are on their way
-        auto flush_border = [&](int pl, const uint8_t* t, int n, int pitch) {
-            const int sub = pl ? 1 : 0;
-            const int x0 = col * n, y0 = r * n;
-            const int pw = (hdr->mi_cols * 4) >> sub, ph = (hdr->mi_rows * 4) >> sub;
-            const int cw = min(n, pw - x0), chh = min(n, ph - y0);
-            const PlaneView g = c.cur.pl[pl];
-            if (chh == n) { // a superblock row below exists
-                uint32_t* d = (uint32_t*)(g.p + (size_t)(y0 + n - 1) * g.stride + x0);
-                AV1B_NOUNROLL
-                for (int k = tid; k < (cw >> 2); k += nt) d[k] = *(const uint32_t*)(t + n * pitch + 4 + 4 * k);
-            }
-            if (cw == n) { // a superblock to the right exists
-                uint8_t* d = g.p + (size_t)y0 * g.stride + x0 + n - 1;
-                AV1B_NOUNROLL
-                for (int k = tid; k < chh; k += nt) d[(size_t)k * g.stride] = t[(k + 1) * pitch + 4 + n - 1];
-            }
-        };
-        flush_border(0, t0, n0, pitch0);
-        flush_border(1, t1, n1, pitch1);
-        flush_border(2, t2, n1, pitch1);
-        wave_signal(progress, r, col, tid, nt);
-        if (tr) tr[6] = av1b_gtime();
+        publish(4);
+        if (tr) tr[5] = tr[6] = av1b_gtime();
         // ---- flush the tile (MI-aligned area only)
         auto flush_plane = [&](int pl, const uint8_t* t, int n, int pitch) {
             const int sub = pl ? 1 : 0;
@@ -1172,7 +1238,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         flush_plane(2, t2, n1, pitch1);
         if (tr) tr[7] = av1b_gtime();
     }
-    wave_leave(c.sync, hdr->sb_rows, tid);
+    wave_leave(c.sync, n_sb, tid, nt, &s_sb);
 }
 
 // Global-memory variant (frames with allow_intrabc: block copies read arbitrary earlier parts of
@@ -1221,7 +1287,7 @@ __global__ void __launch_bounds__(256) wave_kernel_global(ReconCtx c)
         }
         wave_signal(progress, r, col, tid, nt);
     }
-    wave_leave(c.sync, hdr->sb_rows, tid);
+    wave_leave(c.sync, n_sb, tid, nt, &s_sb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1295,6 +1361,13 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
     const int width = std::max(1, std::min<int>((int)h.sb_rows, ((int)h.sb_cols + lag - 1) / lag));
     int grid = std::min<int>((int)h.n_sb, width + width / 2 + 1);
     if (grid > 148 * 2) grid = 148 * 2;
+    if (!h.allow_intrabc) {
+        // quadrant-level dependencies let the superblocks of TWO consecutive diagonals run together
+        // (a superblock starts when its left neighbour is half done): twice the active set
+        const char* genv = getenv("AV1B200_WAVE_GRID");
+        grid = std::min<int>((int)h.n_sb, genv && atoi(genv) > 0 ? atoi(genv) : 2 * width + width / 2 + 1);
+        if (grid > 148) grid = 148;
+    }
     if (h.allow_intrabc) {
         AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);
         return;

@@ -7,7 +7,7 @@ Sizes are cross-checked against the C structs by tests/test_host.py (av1b_struct
 import ctypes as C
 
 MAGIC = 0x42315641
-VERSION = 3
+VERSION = 4
 
 OP_INTER_RES, OP_INTRA, OP_PALETTE, OP_INTERINTRA, OP_INTRABC = range(5)
 OPF_HAVE_LEFT, OPF_HAVE_ABOVE, OPF_HAVE_ABOVE_RIGHT, OPF_HAVE_BELOW_LEFT = 1, 2, 4, 8
@@ -23,7 +23,8 @@ class Op(C.Structure):
 
 
 class Sb(C.Structure):
-    _fields_ = [("first_op", C.c_uint32), ("n_ops", C.c_uint32)]
+    _fields_ = [("first_op", C.c_uint32), ("n_ops", C.c_uint32), ("wait_l1", C.c_uint8), ("wait_l2", C.c_uint8), ("wait_a1", C.c_uint8), ("wait_a2", C.c_uint8),
+                ("pub_r1", C.c_uint8), ("pub_b1", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
 class Ipu(C.Structure):

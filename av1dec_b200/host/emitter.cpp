@@ -48,7 +48,11 @@ void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
         }
     }
     m_gmReady = false;
-    m_sbs.assign((size_t)h.sb_cols * h.sb_rows, Av1bSb{ 0, 0 });
+    {
+        Av1bSb zero;
+        memset(&zero, 0, sizeof(zero));
+        m_sbs.assign((size_t)h.sb_cols * h.sb_rows, zero);
+    }
     m_ops.clear();
     m_itxOnly.clear();
     m_itx.clear();
@@ -61,6 +65,16 @@ void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
     m_lftx.assign((size_t)3 * frame.MiRows * frame.MiCols, 0);
     m_nRes = 0;
     m_total = 0;
+}
+
+// AV1B200_WAVE_OVERLAP=0 leaves the overlap hints zero (the classic two-superblock-lag wavefront)
+static bool getenv_overlap()
+{
+    static const bool on = [] {
+        const char* e = getenv("AV1B200_WAVE_OVERLAP");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
 }
 
 void FrameEmitter::emitTile(Tile& tile)
@@ -143,6 +157,50 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
         m_levels[k] = lvl;
         maxLevel = std::max(maxLevel, lvl);
     }
+    // ---- overlap hints (av1b200_format.h, Av1bSb): the first level that reads each half of the left
+    // superblock's right column and of the above-right superblock's bottom row (from the
+    // availability flags), and the level after which the halves of this superblock's own border
+    // that are announced early are final (the last op that writes them).
+    const uint32_t sbIdx = (uint32_t)((sby >> m_hdr.sb_log2) * m_hdr.sb_cols + (sbx >> m_hdr.sb_log2));
+    const bool haveLeftSb = sbx > 0, haveAboveSb = sby > 0;
+    uint32_t wl1 = 0xFF, wl2 = 0xFF, wa1 = 0xFF, wa2 = 0xFF, pr1 = 1, pb1 = 1;
+    bool hints = getenv_overlap() && maxLevel < 0xFF;
+    for (uint32_t k = 0; k < n && hints; k++) {
+        const Av1bOp& op = m_ops[first + k];
+        const int sub = op.plane ? 1 : 0;
+        const int np = sbPix >> sub, q = np >> 1;
+        int lw, lh;
+        if (op.kind == AV1B_OP_INTERINTRA || op.kind == AV1B_OP_INTRABC) {
+            lw = op.tx_size & 15;
+            lh = op.tx_size >> 4;
+        } else {
+            lw = hk_tx_wlog2[op.tx_size];
+            lh = hk_tx_hlog2[op.tx_size];
+        }
+        if (op.kind == AV1B_OP_INTRABC) {
+            hints = false;
+            break;
+        }
+        const int w = 1 << lw, h = 1 << lh;
+        const int x = op.x - (sbx >> sub), y = op.y - (sby >> sub);
+        const uint32_t lvl = m_levels[k];
+        if (op.kind == AV1B_OP_INTRA || op.kind == AV1B_OP_INTERINTRA) {
+            if (x <= 0 && haveLeftSb) { // the left superblock's right column, rows y-1 .. y+bl-1
+                const int bl = (op.flags & AV1B_OPF_HAVE_BELOW_LEFT) ? 2 * h : h;
+                if (y - 1 < q) wl1 = std::min(wl1, lvl);
+                if (y + bl > q) wl2 = std::min(wl2, lvl);
+            }
+            if (y <= 0 && haveAboveSb) { // the row above, columns x-1 .. x+ar-1
+                const int ar = (op.flags & AV1B_OPF_HAVE_ABOVE_RIGHT) ? 2 * w : w;
+                if (x + ar > np) {
+                    wa1 = std::min(wa1, lvl);
+                    if (x + ar - np > q) wa2 = std::min(wa2, lvl);
+                }
+            }
+        }
+        if (x + w >= np && y < q) pr1 = std::max(pr1, lvl);
+        if (y + h >= np && x < q) pb1 = std::max(pb1, lvl);
+    }
     // stable counting sort by level
     m_count.assign(maxLevel + 2, 0);
     for (uint32_t k = 0; k < n; k++) m_count[m_levels[k] + 1]++;
@@ -164,6 +222,13 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
     std::copy(m_sorted.begin(), m_sorted.end(), m_ops.begin() + first);
     for (size_t i = firstItx; i < m_itx.size(); i++)
         if (!(m_itx[i] & 0x80000000u)) m_itx[i] = first + m_perm[m_itx[i] - first];
+    Av1bSb& e = m_sbs[sbIdx];
+    if (hints) {
+        e.wait_l1 = (uint8_t)wl1, e.wait_l2 = (uint8_t)wl2, e.wait_a1 = (uint8_t)wa1, e.wait_a2 = (uint8_t)wa2;
+        e.pub_r1 = (uint8_t)pr1, e.pub_b1 = (uint8_t)pb1;
+    } else {
+        e.wait_l1 = e.wait_l2 = e.wait_a1 = e.wait_a2 = e.pub_r1 = e.pub_b1 = 0; // the classic wavefront
+    }
 }
 
 void FrameEmitter::walk(Partition& p)

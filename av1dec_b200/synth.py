@@ -428,7 +428,14 @@ def make_inter_frame(w, h, seed=SEED, compound_frac=0.25, max_mv=512, fixed_mv=N
     return cmd, nb, algo
 
 
-def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, sizes=(8, 16, 32), mode_set=None, fi=True, cfl=True, rect=False):
+def _morton(x, y):
+    z = 0
+    for b in range(8):
+        z |= ((x >> b) & 1) << (2 * b) | ((y >> b) & 1) << (2 * b + 1)
+    return z
+
+
+def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, sizes=(8, 16, 32), mode_set=None, fi=True, cfl=True, rect=False, segments=True):
     """A frame for the superblock wavefront (prediction only): a random `intra_frac` of the blocks
     of a non-intra frame are intra-predicted over whatever the frame already holds (the caller
     supplies it as the input picture, standing for the inter prediction), so every edge carries
@@ -442,7 +449,8 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
     `levelled=False` keeps the ops in decoding order, one per step (res_off = 0): the reference
     the level analysis is checked against.  `sizes` / `mode_set` / `fi` / `cfl` narrow the mix
     (profiling aid: tools/wave_prof.py); `rect` splits half of the blocks into two rectangular
-    transform blocks (side by side or stacked, flags per half).  Returns the command buffer."""
+    transform blocks (side by side or stacked, flags per half); `segments=False` leaves the overlap
+    hints of every superblock zero (the classic two-superblock-lag wavefront).  Returns the command buffer."""
     rng = SplitMix64(seed)
     sb = 1 << sb_log2
     mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
@@ -486,7 +494,9 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                         if y > 0:
                             fl |= F.OPF_HAVE_ABOVE
                         top_row = by == 0
-                        if y > 0 and x + s < pw and (top_row or x + s < (x0 >> sub) + n):
+                        # above-right: in the superblock row above, or an earlier block of this
+                        # superblock in DECODING (z) order -- what AV1's availability rule gives
+                        if y > 0 and x + s < pw and (top_row or (bx + 1 < nbx and _morton(bx + 1, by - 1) < _morton(bx, by))):
                             fl |= F.OPF_HAVE_ABOVE_RIGHT
                         if bx == 0 and c > 0 and by + 1 < nby and y + 2 * s <= ph:
                             fl |= F.OPF_HAVE_BELOW_LEFT
@@ -557,9 +567,43 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                 cell[pl][cy0:cy1 + 1, cx0:cx1 + 1] = lvl
                 levels.append(lvl)
             if not levelled:
-                sbs.append((len(all_ops), len(ops)))
+                sbs.append((len(all_ops), len(ops), 0, 0, 0, 0, 0, 0, 0))
                 all_ops.extend(ops)
                 continue
+            # overlap hints (av1b200_format.h, Av1bSb): the first level that reads each half of the
+            # left superblock's right column / the above-right superblock's bottom row, and the level
+            # after which each early-published half of the own border is final -- like
+            # host/emitter.cpp scheduleSb
+            NEVER = 0xFF
+            wl1 = wl2 = wa1 = wa2 = NEVER
+            pr1 = pb1 = 1
+            for o, lvl in zip(ops, levels):
+                sub = 1 if int(o["plane"]) else 0
+                n, q = sb >> sub, (sb >> 1) >> sub
+                tw, th = TX_W[int(o["tx_size"])], TX_H[int(o["tx_size"])]
+                xr, yr = int(o["x"]) - (x0 >> sub), int(o["y"]) - (y0 >> sub)
+                fl = int(o["flags"])
+                lv8 = min(lvl, 0xFE)
+                if xr == 0 and c > 0:  # reads the left superblock's right column, rows yr-1 .. yr+bl-1
+                    bl = 2 * th if fl & F.OPF_HAVE_BELOW_LEFT else th
+                    if yr - 1 < q:
+                        wl1 = min(wl1, lv8)
+                    if yr + bl > q:
+                        wl2 = min(wl2, lv8)
+                if yr == 0 and r > 0:  # reads the row above, columns xr-1 .. xr+ar-1
+                    ar = 2 * tw if fl & F.OPF_HAVE_ABOVE_RIGHT else tw
+                    if xr + ar > n:
+                        wa1 = min(wa1, lv8)
+                        if xr + ar - n > q:
+                            wa2 = min(wa2, lv8)
+                if xr + tw == n and yr < q:
+                    pr1 = max(pr1, lvl)
+                if yr + th == n and xr < q:
+                    pb1 = max(pb1, lvl)
+            if not segments:
+                wl1 = wl2 = wa1 = wa2 = pr1 = pb1 = 0
+            elif pr1 > 0xFE or pb1 > 0xFE:
+                pr1 = pb1 = 0
             order = np.argsort(np.asarray(levels, np.int64), kind="stable") if ops else []
             sorted_ops = [ops[i] for i in order]
             lv = [levels[i] for i in order]
@@ -567,7 +611,7 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
             for k in range(len(sorted_ops) - 1, -1, -1):
                 rem = rem + 1 if (k + 1 < len(sorted_ops) and lv[k + 1] == lv[k]) else 1
                 sorted_ops[k]["res_off"] = (lv[k] & 0xFFFF) | (min(rem, 0xFFFF) << 16)
-            sbs.append((len(all_ops), len(sorted_ops)))
+            sbs.append((len(all_ops), len(sorted_ops), wl1, wl2, wa1, wa2, pr1, pb1, 0))
             all_ops.extend(sorted_ops)
     hdr = F.FrameHdr()
     hdr.frame_w, hdr.frame_h, hdr.mi_cols, hdr.mi_rows = w, h, mi_cols, mi_rows
@@ -575,5 +619,5 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
     hdr.enable_intra_edge_filter, hdr.frame_is_intra = 1, 0
     hdr.n_sb, hdr.n_ops = len(sbs), len(all_ops)
     ops_blob = np.array(all_ops, op_t).tobytes() if all_ops else b""
-    sb_blob = np.array(sbs, np.dtype([("first", "<u4"), ("n", "<u4")])).tobytes()
+    sb_blob = np.array(sbs, np.dtype([("first", "<u4"), ("n", "<u4"), ("wl1", "u1"), ("wl2", "u1"), ("wa1", "u1"), ("wa2", "u1"), ("pr1", "u1"), ("pb1", "u1"), ("pad", "<u2")])).tobytes()
     return F.build(hdr, {"off_sb": sb_blob, "off_ops": ops_blob})

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define AV1B_MAGIC 0x42315641u /* "AV1B" */
-#define AV1B_FORMAT_VERSION 3
+#define AV1B_FORMAT_VERSION 4
 
 /* ---- Av1bOp.kind ------------------------------------------------------------------- */
 enum {
@@ -75,10 +75,28 @@ typedef struct Av1bOp {
     uint16_t max_luma_w, max_luma_h; /* CfL: Block::MaxLumaW/H at this TB                   */
 } Av1bOp;
 
-/* Superblock entry: its ops are [first_op, first_op + n_ops). Indexed by frame-raster SB. */
+/* Superblock entry: its ops are [first_op, first_op + n_ops), sorted by dependency level (levels
+ * count from 1).  Indexed by frame-raster SB.
+ *
+ * The remaining fields let neighbouring superblocks OVERLAP in the wavefront: a superblock does not
+ * wait for all of its left / above-right neighbour before its first op, only -- level by level --
+ * for the part of the neighbour's border it is about to read, and it announces the halves of its
+ * own right column / bottom row as soon as no later op writes them.  ("half" = sb/2 samples.)
+ *   wait_l1  first level that reads the left superblock's right column above its middle
+ *   wait_l2  first level that reads it below the middle
+ *   wait_a1  first level that reads the above-right superblock's bottom row left of its middle
+ *   wait_a2  first level that reads it right of the middle
+ *            (0 = before the first level, 0xFF = never)
+ *   pub_r1   level after which the upper half of this superblock's right column is final
+ *   pub_b1   level after which the left half of its bottom row is final   (0 = only at the end)
+ * The superblocks above and above-left are always complete before a superblock starts.  All zero
+ * is the conservative setting: the classic two-superblock-lag wavefront. */
 typedef struct Av1bSb {
     uint32_t first_op;
     uint32_t n_ops;
+    uint8_t wait_l1, wait_l2, wait_a1, wait_a2;
+    uint8_t pub_r1, pub_b1;
+    uint8_t pad[2];
 } Av1bSb;
 
 /* ---- inter prediction ---------------------------------------------------------------- */

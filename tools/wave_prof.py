@@ -23,6 +23,8 @@ CONFIGS = {
     "bs8_full": dict(sizes=(8,), intra_frac=1.0),
     "bs32_dc": dict(sizes=(32,), mode_set=[0], fi=False, cfl=False),
     "mix_sb128": dict(sb_log2=7),
+    "mix_noseg": dict(segments=False),
+    "bs8_dc_noseg": dict(sizes=(8,), mode_set=[0], fi=False, cfl=False, segments=False),
 }
 
 W, H = 3840, 2160
@@ -80,7 +82,7 @@ def trace(name="mix"):
     t0 = t[:, 0].min()
     t -= t0
     cols, rows = int(hdr.sb_cols), int(hdr.sb_rows)
-    ops = np.frombuffer(cmd, np.uint32, count=2 * n, offset=int(hdr.off_sb)).reshape(n, 2)[:, 1]
+    ops = np.frombuffer(cmd, np.uint32, count=4 * n, offset=int(hdr.off_sb)).reshape(n, 4)[:, 1]
     dur = {"wait": t[:, 1] - t[:, 0], "halo": t[:, 2] - t[:, 1], "ops": t[:, 3] - t[:, 2], "signal": t[:, 4] - t[:, 3], "flush": t[:, 5] - t[:, 4]}
     print(name, "total us", t[:, 5].max() / 1e3, "SMs used", len(set(buf[:, 1].tolist())))
     for k, v in dur.items():
