@@ -1010,25 +1010,32 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         block_sync(nt); // ops are staged (stage_op) by other threads than the ones that decoded them
         // ---- halo: the row above (x0-4 .. x0+2n-1 as words) and / or the column to the left, of all
         // three planes as ONE list of items so that every load is in flight before the first store waits
-        auto load_halo = [&](bool above, bool left) {
+        // `ahalf`: only the part of the row above that belongs to the above-right superblock; `lhalf`:
+        // only the lower half of the column; (id, cnt): the threads that share the work (the whole
+        // CTA, or one warp on its own while the others run ops).
+        auto load_halo = [&](bool above, bool ahalf, bool left, bool lhalf, int id, int cnt) {
             const int aw0 = (n0 >> 1) + 1, aw1 = (n1 >> 1) + 1; // words of a row above
-            const int n_above = (above && r > 0) ? aw0 + 2 * aw1 : 0;
-            const int n_left = (left && col > 0) ? n0 + 2 * n1 : 0;
+            const int a0 = ahalf ? (n0 >> 2) + 1 : 0, a1 = ahalf ? (n1 >> 2) + 1 : 0;
+            const int ca0 = (above && r > 0) ? aw0 - a0 : 0, ca1 = (above && r > 0) ? aw1 - a1 : 0;
+            const int l0 = lhalf ? n0 >> 1 : 0, l1 = lhalf ? n1 >> 1 : 0;
+            const int cl0 = (left && col > 0) ? n0 - l0 : 0, cl1 = (left && col > 0) ? n1 - l1 : 0;
+            const int n_above = ca0 + 2 * ca1, total = n_above + cl0 + 2 * cl1;
             AV1B_NOUNROLL
-            for (int b0 = 0; b0 < n_above + n_left; b0 += 2 * nt) {
+            for (int b0 = 0; b0 < total; b0 += 2 * cnt) {
                 uint32_t v[2];
                 uint8_t* dsts[2];
                 bool word[2];
                 AV1B_UNROLL
                 for (int u = 0; u < 2; u++) {
-                    int k = b0 + u * nt + tid;
+                    int k = b0 + u * cnt + id;
                     dsts[u] = nullptr;
                     word[u] = false;
                     v[u] = 0;
-                    if (k >= n_above + n_left) continue;
+                    if (k >= total) continue;
                     if (k < n_above) {
-                        const int pl = k < aw0 ? 0 : (k < aw0 + aw1 ? 1 : 2);
-                        k -= pl == 0 ? 0 : (pl == 1 ? aw0 : aw0 + aw1);
+                        const int pl = k < ca0 ? 0 : (k < ca0 + ca1 ? 1 : 2);
+                        k -= pl == 0 ? 0 : (pl == 1 ? ca0 : ca0 + ca1);
+                        k += pl ? a1 : a0;
                         const int n = pl ? n1 : n0;
                         const PlaneView g = c.cur.pl[pl];
                         uint8_t* t = pl == 0 ? t0 : (pl == 1 ? t1 : t2);
@@ -1037,8 +1044,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                         word[u] = true;
                     } else {
                         k -= n_above;
-                        const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2);
-                        k -= pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1);
+                        const int pl = k < cl0 ? 0 : (k < cl0 + cl1 ? 1 : 2);
+                        k -= pl == 0 ? 0 : (pl == 1 ? cl0 : cl0 + cl1);
+                        k += pl ? l1 : l0;
                         const int n = pl ? n1 : n0, pitch = pl ? pitch1 : pitch0;
                         const PlaneView g = c.cur.pl[pl];
                         uint8_t* t = pl == 0 ? t0 : (pl == 1 ? t1 : t2);
@@ -1084,9 +1092,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         // those go out ahead of the rest of the tile -- each half as soon as no later op writes it
         // (Av1bSb::pub_r1 / pub_b1), everything at the end -- and the progress word moves as soon as
         // they are on their way (one fence by one thread).
+        // An early hand-off is the work of ONE warp (`solo` >= 0: that warp), the others go on with
+        // the next level: what it copies is final, and its own lane 0 releases the progress word
+        // after the warp's stores (__syncwarp orders them before the release).
         int pubbits = 0;
-        auto publish = [&](int bits) {
+        auto publish = [&](int bits, int solo) {
             const bool all = (bits & 4) != 0;
+            pubbits |= all ? 7 : bits;
+            if (solo >= 0 && warp != solo) return;
+            const int id = solo >= 0 ? lane : tid, cnt = solo >= 0 ? nl : nt;
             for (int pl = 0; pl < 3; pl++) {
                 const int sub = pl ? 1 : 0;
                 const int n = pl ? n1 : n0, pitch = pl ? pitch1 : pitch0;
@@ -1099,43 +1113,63 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                     uint32_t* d = (uint32_t*)(g.p + (size_t)(y0 + n - 1) * g.stride + x0);
                     const int words = (all ? cw : min(cw, n >> 1)) >> 2;
                     AV1B_NOUNROLL
-                    for (int k = tid; k < words; k += nt) d[k] = *(const uint32_t*)(t + n * pitch + 4 + 4 * k);
+                    for (int k = id; k < words; k += cnt) d[k] = *(const uint32_t*)(t + n * pitch + 4 + 4 * k);
                 }
                 if (cw == n && (all || (bits & 1))) { // a superblock to the right exists
                     uint8_t* d = g.p + (size_t)y0 * g.stride + x0 + n - 1;
                     const int rows = all ? chh : min(chh, n >> 1);
                     AV1B_NOUNROLL
-                    for (int k = tid; k < rows; k += nt) d[(size_t)k * g.stride] = t[(k + 1) * pitch + 4 + n - 1];
+                    for (int k = id; k < rows; k += cnt) d[(size_t)k * g.stride] = t[(k + 1) * pitch + 4 + n - 1];
                 }
             }
-            pubbits |= all ? 7 : bits;
-            block_sync(nt);
-            if (tid == 0) av1b_st_release(progress + sb, pubbits);
+            if (solo >= 0) {
+                __syncwarp();
+                if (lane == 0) av1b_st_release(progress + sb, pubbits);
+            } else {
+                block_sync(nt);
+                if (tid == 0) av1b_st_release(progress + sb, pubbits);
+            }
         };
         // ---- waiting, level by level: before a level runs, the halves of the neighbours' borders it
         // reads (Av1bSb::wait_*) must be final; the superblocks above and above-left always are.
+        // The first wait of a superblock is the whole CTA's; a later one is normally done one level
+        // AHEAD by one warp on its own (`solo` >= 0) while the others run the ops of the level before
+        // -- the level barrier then makes the halo it loaded visible -- so a neighbour that is
+        // already there costs nothing.  Up to four progress words are polled by four lanes at once.
         int waited_l = -1, waited_a = -1; // -1 nothing loaded yet, 0 no wait, 1 the first half, 2 all
-        auto open_level = [&](unsigned level) {
+        auto open_level = [&](unsigned level, int solo) {
             const int need_l = (col == 0) ? 0 : (level >= e.wait_l2 ? 2 : (level >= e.wait_l1 ? 1 : 0));
             const int need_a = (r == 0 || col + 1 >= sb_cols) ? 0 : (level >= e.wait_a2 ? 2 : (level >= e.wait_a1 ? 1 : 0));
             if (need_l <= waited_l && need_a <= waited_a) return;
             const bool first = waited_l < 0;
-            if (tid == 0) {
-                bool any = false;
-                if (first && r > 0) {
-                    poll(sb - sb_cols, 4);
-                    if (col > 0) poll(sb - sb_cols - 1, 4);
-                    any = true;
+            const bool more_l = need_l > max(waited_l, 0), more_a = need_a > max(waited_a, 0);
+            const bool lhalf = waited_l >= 1; // the upper half of the column was final when it was loaded
+            if (first) solo = -1;
+            if (solo < 0 || warp == solo) {
+                const int id = solo >= 0 ? lane : tid;
+                if (id < 4) {
+                    int idx = -1, mask = 4;
+                    if (id == 0 && first && r > 0) idx = sb - sb_cols;
+                    if (id == 1 && first && r > 0 && col > 0) idx = sb - sb_cols - 1;
+                    if (id == 2 && more_l) idx = sb - 1, mask = need_l == 2 ? 4 : 5;
+                    if (id == 3 && more_a) idx = sb - sb_cols + 1, mask = need_a == 2 ? 4 : 6;
+                    if (idx >= 0) {
+                        poll(idx, mask);
+                        (void)av1b_ld_acquire(progress + idx);
+                    }
                 }
-                if (need_l > max(waited_l, 0)) poll(sb - 1, need_l == 2 ? 4 : 5), any = true;
-                if (need_a > max(waited_a, 0)) poll(sb - sb_cols + 1, need_a == 2 ? 4 : 6), any = true;
-                if (any) (void)av1b_ld_acquire(progress + sb - (col > 0 ? 1 : sb_cols));
+                if (solo >= 0) {
+                    __syncwarp();
+                    load_halo(more_a, true, more_l, lhalf, lane, nl);
+                }
             }
-            block_sync(nt);
-            if (tr && first) tr[3] = av1b_gtime();
-            load_halo(first || need_a > max(waited_a, 0), first || need_l > max(waited_l, 0));
-            block_sync(nt);
-            if (tr && first) tr[4] = av1b_gtime();
+            if (solo < 0) {
+                block_sync(nt);
+                if (tr && first) tr[3] = av1b_gtime();
+                load_halo(first || more_a, !first, first || more_l, !first && lhalf, tid, nt);
+                block_sync(nt);
+                if (tr && first) tr[4] = av1b_gtime();
+            }
             waited_l = max(waited_l, need_l);
             waited_a = max(waited_a, need_a);
         };
@@ -1148,9 +1182,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             const Av1bOp* cur_ops = s_ops[buf];
             const unsigned k1 = k0 + WAVE_OP_CHUNK;
             const unsigned nn = k1 < e.n_ops ? min((unsigned)WAVE_OP_CHUNK, e.n_ops - k1) : 0;
-            uint4 pre = make_uint4(0, 0, 0, 0);
-            static_assert(WAVE_OP_CHUNK * 2 <= 256, "one uint4 of the next chunk per thread");
-            if ((unsigned)tid < nn * 2) pre = __ldg((const uint4*)(ops + e.first_op + k1) + tid);
+            constexpr int PRE = (WAVE_OP_CHUNK * 2 + WARPS * 32 - 1) / (WARPS * 32); // uint4s of the next chunk per thread
+            uint4 pre[PRE];
+            AV1B_UNROLL
+            for (int u = 0; u < PRE; u++) {
+                pre[u] = make_uint4(0, 0, 0, 0);
+                if ((unsigned)(tid + u * nt) < nn * 2) pre[u] = __ldg((const uint4*)(ops + e.first_op + k1) + tid + u * nt);
+            }
             // res_off = level | (ops left in this level) << 16 (emitter scheduleSb); a producer that
             // leaves the count zero gets one op per step, still a valid order
             auto level_end = [&](unsigned g) { return min(nk, g + max(1u, cur_ops[g].res_off >> 16)); };
@@ -1171,13 +1209,18 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 const unsigned level = cur_ops[g0].res_off & 0xFFFFu;
                 // early hand-off of the border halves the levels before this one made final (a
                 // level may straddle two chunks, so it only counts as over once a later one starts)
+#ifdef AV1B_EMU
+                const int solo = -1;
+#else
+                const int solo = (int)((nw - 1 + par * (nw >> 1)) & (nw - 1)); // the warp least likely to hold an op of this level
+#endif
                 if (k0 + g0 > 0) {
                     int bits = 0;
                     if (e.pub_r1 && level > e.pub_r1 && !(pubbits & 1)) bits |= 1;
                     if (e.pub_b1 && level > e.pub_b1 && !(pubbits & 2)) bits |= 2;
-                    if (bits) publish(bits);
+                    if (bits) publish(bits, solo);
                 }
-                open_level(level);
+                open_level(level, -1); // (no-op when the look-ahead of the level before did it)
 #ifdef AV1B_EMU
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
@@ -1189,6 +1232,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                     for (unsigned k = mine + nw; k < g1; k += nw) exec_staged(stage_op(cur_ops + k, io));
                 }
                 const unsigned g2 = g1 < nk ? level_end(g1) : g1;
+                if (g1 < nk) open_level(cur_ops[g1].res_off & 0xFFFFu, solo);
                 par ^= 1;
                 mine = g1 + ((warp + par * (nw >> 1)) & (nw - 1));
                 if (mine < g2) st = stage_op(cur_ops + mine, io);
@@ -1201,14 +1245,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 #ifdef AV1B_EMU
                 for (unsigned q = 0; q < nn * 2; q++) ((uint4*)s_ops[buf ^ 1])[q] = ((const uint4*)(ops + e.first_op + k1))[q];
 #else
-                if ((unsigned)tid < nn * 2) ((uint4*)s_ops[buf ^ 1])[tid] = pre;
+                AV1B_UNROLL
+                for (int u = 0; u < PRE; u++)
+                    if ((unsigned)(tid + u * nt) < nn * 2) ((uint4*)s_ops[buf ^ 1])[tid + u * nt] = pre[u];
 #endif
                 block_sync(nt);
                 for (unsigned q = tid; q < nn; q += nt) decode_intra_op(&s_ops[buf ^ 1][q], fc);
                 block_sync(nt);
             }
         }
-        publish(4);
+        publish(4, -1);
         if (tr) tr[5] = tr[6] = av1b_gtime();
         // ---- flush the tile (MI-aligned area only)
         auto flush_plane = [&](int pl, const uint8_t* t, int n, int pitch) {
@@ -1365,18 +1411,23 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         // quadrant-level dependencies let the superblocks of TWO consecutive diagonals run together
         // (a superblock starts when its left neighbour is half done): twice the active set
         const char* genv = getenv("AV1B200_WAVE_GRID");
-        grid = std::min<int>((int)h.n_sb, genv && atoi(genv) > 0 ? atoi(genv) : 2 * width + width / 2 + 1);
+        const char* qenv = getenv("AV1B200_WAVE_GRIDQ"); // CTAs per superblock of the classic wavefront width, in quarters
+        const int gq = qenv && atoi(qenv) > 0 ? atoi(qenv) : 10;
+        grid = std::min<int>((int)h.n_sb, genv && atoi(genv) > 0 ? atoi(genv) : (gq * width + 3) / 4 + 1);
         if (grid > 148) grid = 148;
     }
     if (h.allow_intrabc) {
         AV1B_LAUNCH(wave_kernel_global, (grid), (256), st, c);
         return;
     }
-    // Two builds: 16 warps, one CTA per SM (lowest latency for a lone stream), and 8 warps at
-    // two CTAs per SM (a busy multi-stream device is bound by CTA slots: the
-    // wavefront of one superblock keeps a warp scheduler mostly idle).  AV1B200_WAVE_WARPS picks.
+    // Three builds.  The op code wants ~230 registers: at 16 warps per CTA it is held to 128 and pays
+    // for it in every op (spills, rematerialised addresses), so the default is 8 warps with the full
+    // register budget (a level rarely has more than 8 ops); 16 warps win only on frames of very many
+    // small, simple blocks; 4 warps at two CTAs per SM are for a device crowded with streams.
+    // AV1B200_WAVE_WARPS picks (measured: profiles/r02_wave_variants.md).
     const char* wenv = getenv("AV1B200_WAVE_WARPS");
-    const int warps = (wenv && atoi(wenv) == 8) ? 8 : 16;
+    const int wv = wenv ? atoi(wenv) : 8;
+    const int warps = (wv == 16 || wv == 4) ? wv : 8;
     const int smem = WAVE_SMEM_BYTES(1 << h.sb_log2, warps);
 #ifndef AV1B_EMU
     {
@@ -1388,14 +1439,16 @@ void launch_wave(const ReconCtx& c, const Av1bFrameHdr& h, av1b_stream_t st)
         std::lock_guard<std::mutex> lk(mu);
         if (!(done[(dev >> 6) & 3] & (1ull << (dev & 63)))) {
             cudaFuncSetAttribute(wave_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 16));
-            cudaFuncSetAttribute(wave_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 8));
+            cudaFuncSetAttribute(wave_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 8));
+            cudaFuncSetAttribute(wave_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM_BYTES(128, 4));
             done[(dev >> 6) & 3] |= 1ull << (dev & 63);
         }
     }
     if (warps == 16) wave_kernel<16, 1><<<dim3(grid), dim3(512), smem, st>>>(c);
-    else wave_kernel<8, 2><<<dim3(grid), dim3(256), smem, st>>>(c);
+    else if (warps == 8) wave_kernel<8, 1><<<dim3(grid), dim3(256), smem, st>>>(c);
+    else wave_kernel<4, 2><<<dim3(grid), dim3(128), smem, st>>>(c);
 #else
     (void)smem;
-    AV1B_LAUNCH((wave_kernel<8, 2>), (grid), (256), st, c);
+    AV1B_LAUNCH((wave_kernel<8, 1>), (grid), (256), st, c);
 #endif
 }
