@@ -49,6 +49,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline int av1b_ld_acquire(const int* p) { return *p; }
 static inline void av1b_st_release(int* p, int v) { *p = v; }
 static inline void av1b_nanosleep(unsigned) {}

@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 {
     alignas(16) __shared__ Av1bOp s_ops[2][WAVE_OP_CHUNK];
     __shared__ int s_sb;
+    __shared__ unsigned long long s_polled;
 #ifdef AV1B_EMU
     alignas(16) static uint8_t dyn[WAVE_SMEM_BYTES(128, WARPS)];
 #else
@@ -939,6 +940,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             }
         }
 #else
+        if (c.trace) { // trace: time spent polling after the first wait, summed per superblock
+            const unsigned long long t_in = av1b_gtime();
+            while (!(av1b_ld_relaxed(progress + idx) & mask)) av1b_nanosleep(32);
+            atomicAdd(&s_polled, (unsigned long long)(av1b_gtime() - t_in));
+            return;
+        }
         while (!(av1b_ld_relaxed(progress + idx) & mask)) av1b_nanosleep(32);
 #endif
     };
@@ -1168,7 +1175,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 if (tr && first) tr[3] = av1b_gtime();
                 load_halo(first || more_a, !first, first || more_l, !first && lhalf, tid, nt);
                 block_sync(nt);
-                if (tr && first) tr[4] = av1b_gtime();
+                if (tr && first) tr[4] = av1b_gtime(), s_polled = 0;
             }
             waited_l = max(waited_l, need_l);
             waited_a = max(waited_a, need_a);
@@ -1255,7 +1262,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             }
         }
         publish(4, -1);
-        if (tr) tr[5] = tr[6] = av1b_gtime();
+        if (tr) tr[5] = av1b_gtime(), tr[6] = tr[5] + s_polled; // "signal" column of the trace = mid-superblock polling
         // ---- flush the tile (MI-aligned area only)
         auto flush_plane = [&](int pl, const uint8_t* t, int n, int pitch) {
             const int sub = pl ? 1 : 0;

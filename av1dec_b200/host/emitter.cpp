@@ -4,6 +4,7 @@
 #include "emitter.h"
 #include "../csrc/av1_tables_host.h"
 
+#include <cstdio>
 #include <cstdlib>
 
 using namespace YamiAv1;
@@ -52,6 +53,7 @@ void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
         Av1bSb zero;
         memset(&zero, 0, sizeof(zero));
         m_sbs.assign((size_t)h.sb_cols * h.sb_rows, zero);
+        m_sbDepth.assign((size_t)h.sb_cols * h.sb_rows, 0);
     }
     m_ops.clear();
     m_itxOnly.clear();
@@ -68,6 +70,20 @@ void FrameEmitter::begin(FrameHeader& frame, const SequenceHeader& seq)
 }
 
 // AV1B200_WAVE_OVERLAP=0 leaves the overlap hints zero (the classic two-superblock-lag wavefront)
+// Seeds (percent of a neighbour's depth, AV1B200_WAVE_SEED="L,A1,A2"): see scheduleSb.
+struct WaveSeeds {
+    int l2, a1, a2;
+};
+static const WaveSeeds& getenv_seeds()
+{
+    static const WaveSeeds s = [] {
+        WaveSeeds v = { 50, 50, 80 };
+        if (const char* e = getenv("AV1B200_WAVE_SEED")) sscanf(e, "%d,%d,%d", &v.l2, &v.a1, &v.a2);
+        return v;
+    }();
+    return s;
+}
+
 static bool getenv_overlap()
 {
     static const bool on = [] {
@@ -111,6 +127,26 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
     memset(cell, 0, sizeof(cell));
     m_levels.resize(n);
     uint32_t maxLevel = 0;
+    // Ops that read the part of a neighbouring superblock that becomes final LATE -- the lower half
+    // of the left superblock's right column, the above-right superblock's bottom row -- are seeded
+    // with a level by which that part can be expected (the device starts a superblock when the one
+    // above is finished: the left neighbour is then about two thirds through, the above-right one a
+    // third; a level of theirs is taken to last as long as one of ours).  Without the seed such an
+    // op sits in level 1 or 2 whenever the blocks before it are not intra, and the whole superblock
+    // waits for the neighbour before its second level.  Their dependents follow by the usual rule.
+    const uint32_t sbIdx = (uint32_t)((sby >> m_hdr.sb_log2) * m_hdr.sb_cols + (sbx >> m_hdr.sb_log2));
+    const bool haveLeftSb = sbx > 0, haveAboveSb = sby > 0;
+    const bool overlap = getenv_overlap();
+    uint32_t seedL2 = 0, seedA1 = 0, seedA2 = 0; // levels BEFORE the op's own
+    if (overlap) {
+        const WaveSeeds& sd = getenv_seeds();
+        if (haveLeftSb) seedL2 = m_sbDepth[sbIdx - 1] * sd.l2 / 100;
+        if (haveAboveSb && (sbx >> m_hdr.sb_log2) + 1 < (int)m_hdr.sb_cols) {
+            const uint32_t d = m_sbDepth[sbIdx - m_hdr.sb_cols + 1];
+            seedA1 = d * sd.a1 / 100;
+            seedA2 = d * sd.a2 / 100;
+        }
+    }
     for (uint32_t k = 0; k < n; k++) {
         Av1bOp& op = m_ops[first + k];
         const int pl = op.plane, sub = pl ? 1 : 0;
@@ -150,6 +186,9 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
             if (y > 0) rd(pl, (x - 1) >> 2, (x + ar - 1) >> 2, (y - 1) >> 2, (y - 1) >> 2, nc); // above row + corner
             if (x > 0) rd(pl, (x - 1) >> 2, (x - 1) >> 2, (y - 1) >> 2, (y + bl - 1) >> 2, nc); // left column + corner
             if (op.flags & AV1B_OPF_CFL) rd(0, (2 * x) >> 2, (2 * (x + w) - 1) >> 2, (2 * y) >> 2, (2 * (y + h) - 1) >> 2, nc * 2);
+            const int np = sbPix >> sub, q = np >> 1;
+            if (x <= 0 && y + bl > q) lvl = std::max(lvl, seedL2);
+            if (y <= 0 && x + ar > np) lvl = std::max(lvl, x + ar - np > q ? seedA2 : seedA1);
         }
         lvl += 1;
         for (int cy = cy0; cy <= cy1; cy++)
@@ -161,10 +200,9 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
     // superblock's right column and of the above-right superblock's bottom row (from the
     // availability flags), and the level after which the halves of this superblock's own border
     // that are announced early are final (the last op that writes them).
-    const uint32_t sbIdx = (uint32_t)((sby >> m_hdr.sb_log2) * m_hdr.sb_cols + (sbx >> m_hdr.sb_log2));
-    const bool haveLeftSb = sbx > 0, haveAboveSb = sby > 0;
+    m_sbDepth[sbIdx] = (uint16_t)std::min<uint32_t>(maxLevel, 0xFFFF);
     uint32_t wl1 = 0xFF, wl2 = 0xFF, wa1 = 0xFF, wa2 = 0xFF, pr1 = 1, pb1 = 1;
-    bool hints = getenv_overlap() && maxLevel < 0xFF;
+    bool hints = overlap && maxLevel < 0xFF;
     for (uint32_t k = 0; k < n && hints; k++) {
         const Av1bOp& op = m_ops[first + k];
         const int sub = op.plane ? 1 : 0;

@@ -59,6 +59,7 @@ private:
     std::vector<uint8_t> m_cdef8;
     std::vector<Av1bLrUnit> m_lru;
     std::vector<uint32_t> m_levels, m_count, m_perm;
+    std::vector<uint16_t> m_sbDepth; // levels of each superblock scheduled so far (seeds of its neighbours' late ops)
     std::vector<Av1bOp> m_sorted;
     uint32_t m_nRes = 0;
     size_t m_total = 0;

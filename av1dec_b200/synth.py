@@ -462,6 +462,9 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                      ("mlw", "<u2"), ("mlh", "<u2")])
     assert op_t.itemsize == 32
     all_ops, sbs = [], []
+    import os
+    seed_pct = [int(v) for v in os.environ.get("AV1B200_WAVE_SEED", "50,50,80").split(",")]  # like host/emitter.cpp
+    depth = {}
     sq_tx = {4: 0, 8: 1, 16: 2, 32: 3, 64: 4}
     rect_tx = {(4, 8): 5, (8, 4): 6, (8, 16): 7, (16, 8): 8, (16, 32): 9, (32, 16): 10, (32, 64): 11, (64, 32): 12}
     size_pick = rng.randint(0, 2, (sb_rows, sb_cols))
@@ -541,6 +544,9 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
             # dependency levels: 4x4-cell map per plane, like host/emitter.cpp scheduleSb
             cell = [np.zeros((sb >> 2, sb >> 2), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64)]
             levels = []
+            seed_l2 = depth.get((r, c - 1), 0) * seed_pct[0] // 100 if (segments and c > 0) else 0
+            d_ar = depth.get((r - 1, c + 1), 0) if (segments and r > 0) else 0
+            seed_a1, seed_a2 = d_ar * seed_pct[1] // 100, d_ar * seed_pct[2] // 100
             for o in ops:
                 pl = int(o["plane"])
                 sub = 1 if pl else 0
@@ -563,9 +569,15 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                     lvl = max(lvl, rd(pl, (x - 1) >> 2, (x - 1) >> 2, (y - 1) >> 2, (y + bl - 1) >> 2, nc))
                 if int(o["flags"]) & F.OPF_CFL:
                     lvl = max(lvl, rd(0, (2 * x) >> 2, (2 * (x + tw) - 1) >> 2, (2 * y) >> 2, (2 * (y + th) - 1) >> 2, nc * 2))
+                n_pl, q_pl = sb >> sub, (sb >> 1) >> sub
+                if x == 0 and y + bl > q_pl:
+                    lvl = max(lvl, seed_l2)
+                if y == 0 and x + ar > n_pl:
+                    lvl = max(lvl, seed_a2 if x + ar - n_pl > q_pl else seed_a1)
                 lvl += 1
                 cell[pl][cy0:cy1 + 1, cx0:cx1 + 1] = lvl
                 levels.append(lvl)
+            depth[(r, c)] = max(levels) if levels else 0
             if not levelled:
                 sbs.append((len(all_ops), len(ops), 0, 0, 0, 0, 0, 0, 0))
                 all_ops.extend(ops)

@@ -78,6 +78,9 @@ def trace(name="mix"):
     assert lib.av1b_debug_wave_trace_read(buf.ctypes.data, n) == 0
     lib.av1b_debug_wave_trace(0)
     eng.close()
+    if os.environ.get("WAVE_TRACE_DUMP"):
+        np.save(os.path.join(os.environ["WAVE_TRACE_DUMP"], f"wave_trace_{name}.npy"), buf)
+        open(os.path.join(os.environ["WAVE_TRACE_DUMP"], f"wave_trace_{name}.cmd"), "wb").write(cmd)
     t = buf[:, 2:].astype(np.int64)
     t0 = t[:, 0].min()
     t -= t0
