@@ -46,6 +46,7 @@ static int rt_stream_create(av1b_stream_t* s) { *s = nullptr; return 0; }
 static void rt_stream_destroy(av1b_stream_t) {}
 static int rt_stream_sync(av1b_stream_t) { return 0; }
 static int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
+static int rt_event_create_host(rt_event_t* e) { *e = 0; return 0; }
 static void rt_event_destroy(rt_event_t) {}
 static int rt_event_record(rt_event_t, av1b_stream_t) { return 0; }
 static int rt_event_sync(rt_event_t) { return 0; }
@@ -116,6 +117,18 @@ static int rt_stream_create(av1b_stream_t* s) { return cudaStreamCreateWithFlags
 static void rt_stream_destroy(av1b_stream_t s) { cudaStreamDestroy(s); }
 static int rt_stream_sync(av1b_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
 static int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess; }
+// Events a HOST thread waits on (command-slot reuse, output fences): the waiter sleeps instead of
+// spinning -- a decode service runs more host threads than cores (callers, emit workers, segment
+// workers), and a core spent polling the device is taken from the parser.  AV1B200_SPIN_WAIT=1
+// restores the spinning wait (lowest wake-up latency for a lone stream).
+static int rt_event_create_host(rt_event_t* e)
+{
+    static const bool spin = [] {
+        const char* v = getenv("AV1B200_SPIN_WAIT");
+        return v && atoi(v) != 0;
+    }();
+    return cudaEventCreateWithFlags(e, cudaEventDisableTiming | (spin ? 0 : cudaEventBlockingSync)) != cudaSuccess;
+}
 static void rt_event_destroy(rt_event_t e)
 {
     if (e) cudaEventDestroy(e);
@@ -595,9 +608,9 @@ static int ctx_init(av1b_ctx* c, int device, int max_w, int max_h, int aw, int a
             if (frame_add(c, c->slab + i * c->frame_bytes, false, MAIN_LANE)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     }
     for (int i = 0; i < N_SLOTS; i++)
-        if (rt_event_create(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+        if (rt_event_create_host(&c->slots[i].done)) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     for (int i = 0; i < N_FENCES; i++)
-        if (rt_event_create(&c->fences[i])) return fail(c, AV1B_ECUDA, "cudaEventCreate");
+        if (rt_event_create_host(&c->fences[i])) return fail(c, AV1B_ECUDA, "cudaEventCreate");
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_wedge.find(device);
