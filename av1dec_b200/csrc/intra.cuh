@@ -45,6 +45,7 @@ struct Args {
     bool edge_smooth;         // get_filter_type()
     bool filter_intra;
     int fi_mode;
+    int strip;                // row strip of the block this op predicts: log2(strips) | index << 2 (0 = all of it)
     bool cfl;                 // chroma-from-luma on top of the DC prediction
     int cfl_alpha;
     int max_luma_w, max_luma_h;
@@ -66,6 +67,7 @@ struct Prep {
     bool filt, corner;   // phase 2 needed; the corner sample is filtered too
     int sA, sL, szA, szL;
     int fi_mode;
+    int strip;
     bool cfl;
     int alpha, lim_w, lim_h; // CfL: luma clamp limits relative to the block's luma origin
 };
@@ -172,6 +174,7 @@ AV1B_DEV Prep prepare(const Args& a)
     p.filt = p.corner = false;
     p.sA = p.sL = p.szA = p.szL = 0;
     p.fi_mode = a.fi_mode;
+    p.strip = a.strip;
     p.cfl = a.cfl;
     p.alpha = a.cfl_alpha;
     p.lim_w = min(255, max(0, a.max_luma_w - 2 - 2 * a.x));
@@ -240,6 +243,8 @@ struct Packed {
     AV1B_DEV_M int dy() const { return (int)((w[2] >> 11) & 0x7FF); }
     AV1B_DEV_M int lim_w() const { return (int)(w[3] & 0xFF); }
     AV1B_DEV_M int lim_h() const { return (int)((w[3] >> 8) & 0xFF); }
+    AV1B_DEV_M int strip_lg() const { return (int)((w[3] >> 24) & 3); }
+    AV1B_DEV_M int strip_idx() const { return (int)((w[3] >> 26) & 7); }
 };
 AV1B_DEV Packed pack(const Prep& p)
 {
@@ -249,7 +254,7 @@ AV1B_DEV Packed pack(const Prep& p)
         | ((uint32_t)p.fi_mode << 17) | ((uint32_t)p.sA << 20) | ((uint32_t)p.sL << 22) | ((uint32_t)p.above_n << 24);
     k.w[1] = (uint32_t)p.left_n | ((uint32_t)p.szA << 8) | ((uint32_t)p.szL << 16) | ((uint32_t)(p.alpha & 0xFF) << 24);
     k.w[2] = (uint32_t)p.dx | ((uint32_t)p.dy << 11);
-    k.w[3] = (uint32_t)p.lim_w | ((uint32_t)p.lim_h << 8);
+    k.w[3] = (uint32_t)p.lim_w | ((uint32_t)p.lim_h << 8) | ((uint32_t)p.strip << 24); // (bit 16: the wavefront's residual flag)
     return k;
 }
 
@@ -266,6 +271,11 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
     const int w = 1 << lw, h = 1 << lh;
     const int lq = lw - 2, nq = w >> 2;  // groups of four columns
     const int items = h << lq;
+    // A large block may be shared by several warps, each predicting a strip of rows (the emitter
+    // splits the op, Av1bOp::fi_mode): every warp prepares the edges for itself, the prediction
+    // of a sample depends on nothing but the edges.  (Never a filter-intra block.)
+    const int strip_rows = h >> p.strip_lg();
+    const int e_lo = (p.strip_idx() * strip_rows) << lq, e_hi = e_lo + (strip_rows << lq);
     uint8_t* const A = S.edge[0] + EDGE_OFF;
     uint8_t* const L = S.edge[1] + EDGE_OFF;
     uint8_t* const P = o.P;
@@ -413,7 +423,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
             const int max_base = (w + h - 1) << up_above;
             const int top = DA[max_base];
             AV1B_NOUNROLL
-            for (int e = tid; e < items; e += nt) {
+            for (int e = e_lo + tid; e < e_hi; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
                 const int idx = (i + 1) * dx;
                 const int shift = ((idx << up_above) >> 1) & 31;
@@ -429,7 +439,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         } else if (kind == K_DIR_MID) {
             const int dx = p.dx(), dy = p.dy();
             AV1B_NOUNROLL
-            for (int e = tid; e < items; e += nt) {
+            for (int e = e_lo + tid; e < e_hi; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
                 int v[4];
                 AV1B_UNROLL
@@ -452,7 +462,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         } else {
             const int dy = p.dy();
             AV1B_NOUNROLL
-            for (int e = tid; e < items; e += nt) {
+            for (int e = e_lo + tid; e < e_hi; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
                 int v[4];
                 AV1B_UNROLL
@@ -467,20 +477,20 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         }
     } else if (kind == K_V) {
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             put4(o, i, q, *(const uint32_t*)(EA + 4 * q));
         }
     } else if (kind == K_H) {
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             put4(o, i, q, (uint32_t)EL[i * es] * 0x01010101u);
         }
     } else if (kind == K_PAETH) {
         const int tl = EA[-1];
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
             const int l = EL[i * es];
@@ -528,7 +538,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         if (!p.cfl()) {
             const uint32_t word = (uint32_t)avg * 0x01010101u;
             AV1B_NOUNROLL
-            for (int e = tid; e < items; e += nt) put4(o, e >> lq, e & (nq - 1), word);
+            for (int e = e_lo + tid; e < e_hi; e += nt) put4(o, e >> lq, e & (nq - 1), word);
         } else {
             // ---- chroma-from-luma on top of the DC value (IntraPredict.cpp:632-667): two passes over
             // the sub-sampled luma (sum, then apply) instead of a staging buffer
@@ -551,7 +561,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
             const int lavg = round2(total, lw + lh);
             const int alpha = p.alpha();
             AV1B_NOUNROLL
-            for (int e = tid; e < items; e += nt) {
+            for (int e = e_lo + tid; e < e_hi; e += nt) {
                 const int i = e >> lq, q = e & (nq - 1);
                 const uint2 l4 = cfl_luma4<SMEM>(lim_w, lim_h, o, i, 4 * q);
                 const int v0 = clip_u8(avg + round2s(alpha * ((int)(l4.x & 0xFFFF) - lavg), 6));
@@ -566,7 +576,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = EL[(h - 1) * es], tr = EA[w - 1];
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
             const int l = EL[i * es], wyi = wy[i];
@@ -583,7 +593,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         const uint8_t* wy = k_sm_weights + (h - 4);
         const int bl = EL[(h - 1) * es];
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             const uint32_t aw = *(const uint32_t*)(EA + 4 * q);
             const int wyi = wy[i];
@@ -597,7 +607,7 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
         const uint8_t* wx = k_sm_weights + (w - 4);
         const int tr = EA[w - 1];
         AV1B_NOUNROLL
-        for (int e = tid; e < items; e += nt) {
+        for (int e = e_lo + tid; e < e_hi; e += nt) {
             const int i = e >> lq, q = e & (nq - 1);
             const int l = EL[i * es];
             int v[4];

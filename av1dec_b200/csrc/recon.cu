@@ -632,7 +632,8 @@ AV1B_DEV intra::Args intra_args(const Av1bOp& op, const FrameConst& fc, int lw, 
     a.edge_filter_enabled = fc.edge_filter;
     a.edge_smooth = (op.flags & AV1B_OPF_EDGE_SMOOTH) != 0;
     a.filter_intra = (op.flags & AV1B_OPF_FILTER_INTRA) != 0;
-    a.fi_mode = op.fi_mode;
+    a.fi_mode = op.fi_mode & 7;
+    a.strip = (op.flags & AV1B_OPF_FILTER_INTRA) ? 0 : op.fi_mode >> 3;
     a.cfl = op.kind == AV1B_OP_INTRA && (op.flags & AV1B_OPF_CFL) != 0;
     a.cfl_alpha = op.cfl_alpha;
     a.max_luma_w = op.max_luma_w;

@@ -84,6 +84,17 @@ static const WaveSeeds& getenv_seeds()
     return s;
 }
 
+// Intra blocks of at least this many samples are split into row strips of 256 samples, one op
+// (one warp) per strip (AV1B200_WAVE_SPLIT, 0 = never).
+static int getenv_split()
+{
+    static const int v = [] {
+        const char* e = getenv("AV1B200_WAVE_SPLIT");
+        return e ? atoi(e) : 512;
+    }();
+    return v;
+}
+
 static bool getenv_overlap()
 {
     static const bool on = [] {
@@ -165,6 +176,10 @@ void FrameEmitter::scheduleSb(uint32_t first, size_t firstItx, int sbx, int sby)
             while ((1 << lw) < u.w) lw++;
             lh = 0;
             while ((1 << lh) < u.h) lh++;
+        }
+        if (k > 0 && op.kind == AV1B_OP_INTRA && !(op.flags & AV1B_OPF_FILTER_INTRA) && (op.fi_mode >> 5)) {
+            m_levels[k] = m_levels[k - 1]; // a further strip of the block before: same reads, disjoint rows
+            continue;
         }
         const int w = 1 << lw, h = 1 << lh;
         const int x = op.x - (sbx >> sub), y = op.y - (sby >> sub); // tile-relative
@@ -729,6 +744,18 @@ void FrameEmitter::emitTb(Block& b, TransformBlock& t)
         }
     } else if (op.kind != AV1B_OP_INTER_RES || (op.flags & AV1B_OPF_HAS_RESID)) {
         m_ops.push_back(op);
+        // a large intra block is the work of several warps: one op per strip of rows (same block,
+        // same edges, Av1bOp::fi_mode says which rows); the inverse transform knows the first only
+        const int area = Tx_Width[txSz] * Tx_Height[txSz];
+        if (op.kind == AV1B_OP_INTRA && !(op.flags & AV1B_OPF_FILTER_INTRA) && getenv_split() > 0 && area >= std::max(512, getenv_split())) {
+            int lg = 1;
+            while (lg < 3 && (area >> (8 + lg)) > 1) lg++;
+            m_ops.back().fi_mode = (uint8_t)(lg << 3);
+            for (int i = 1; i < (1 << lg); i++) {
+                op.fi_mode = (uint8_t)((lg | (i << 2)) << 3);
+                m_ops.push_back(op);
+            }
+        }
     }
     // LoopfilterTxSizes + BlockDecoded bookkeeping (TransformBlock.cpp:2444-2454)
     const int miRows = f.MiRows, miCols = f.MiCols;

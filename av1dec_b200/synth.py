@@ -463,6 +463,7 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
     assert op_t.itemsize == 32
     all_ops, sbs = [], []
     import os
+    split_area = int(os.environ.get("AV1B200_WAVE_SPLIT", "512"))
     seed_pct = [int(v) for v in os.environ.get("AV1B200_WAVE_SEED", "50,50,80").split(",")]  # like host/emitter.cpp
     depth = {}
     sq_tx = {4: 0, 8: 1, 16: 2, 32: 3, 64: 4}
@@ -541,6 +542,22 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
                             ops.extend([a, b])
                         else:
                             ops.append(o)
+            # large blocks as row strips of 256 samples, one op each (like host/emitter.cpp)
+            if split_area > 0:
+                split_ops = []
+                for o in ops:
+                    area = TX_W[int(o["tx_size"])] * TX_H[int(o["tx_size"])]
+                    if int(o["flags"]) & F.OPF_FILTER_INTRA or area < max(512, split_area):
+                        split_ops.append(o)
+                        continue
+                    lg = 1
+                    while lg < 3 and (area >> (8 + lg)) > 1:
+                        lg += 1
+                    for i in range(1 << lg):
+                        so = o.copy()
+                        so["fi"] = (lg | (i << 2)) << 3
+                        split_ops.append(so)
+                ops = split_ops
             # dependency levels: 4x4-cell map per plane, like host/emitter.cpp scheduleSb
             cell = [np.zeros((sb >> 2, sb >> 2), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64), np.zeros((sb >> 3, sb >> 3), np.int64)]
             levels = []
@@ -548,6 +565,9 @@ def make_intra_frame(w, h, seed=SEED, sb_log2=6, intra_frac=0.6, levelled=True, 
             d_ar = depth.get((r - 1, c + 1), 0) if (segments and r > 0) else 0
             seed_a1, seed_a2 = d_ar * seed_pct[1] // 100, d_ar * seed_pct[2] // 100
             for o in ops:
+                if levels and not (int(o["flags"]) & F.OPF_FILTER_INTRA) and (int(o["fi"]) >> 5):
+                    levels.append(levels[-1])  # a further strip of the block before
+                    continue
                 pl = int(o["plane"])
                 sub = 1 if pl else 0
                 nc = (sb >> sub) >> 2

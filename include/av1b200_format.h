@@ -61,7 +61,9 @@ typedef struct Av1bOp {
     uint8_t mode;       /* intra prediction mode actually run (CfL -> DC_PRED)              */
     int8_t angle_delta; /* AngleDeltaY / AngleDeltaUV                                       */
     uint8_t flags;      /* AV1B_OPF_*                                                       */
-    uint8_t fi_mode;    /* filter_intra_mode                                                */
+    uint8_t fi_mode;    /* bits 0-2: filter_intra_mode.  Intra ops without filter-intra: bits 3-4
+                           log2 of the number of row strips the block is split into, bits 5-7 the
+                           strip this op predicts (one op per strip, consecutive; 0 = whole block) */
     int8_t cfl_alpha;   /* CflAlphaU / CflAlphaV                                            */
     uint8_t nz_rows;    /* number of leading coefficient rows that may be non-zero (<=32)  */
     uint8_t nz_cols;    /* number of leading coefficient columns that may be non-zero      */
