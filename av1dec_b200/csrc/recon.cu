@@ -1145,9 +1145,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
         // -- the level barrier then makes the halo it loaded visible -- so a neighbour that is
         // already there costs nothing.  Up to four progress words are polled by four lanes at once.
         int waited_l = -1, waited_a = -1; // -1 nothing loaded yet, 0 no wait, 1 the first half, 2 all
+        // the last level at which a wait can still come up (0xFF = never): past it, and with nothing
+        // left to announce early, a level costs none of this bookkeeping
+        auto lv_or0 = [](unsigned v) { return v == 0xFFu ? 0u : v; };
+        const unsigned busy_until = max(max(lv_or0(e.wait_l1), lv_or0(e.wait_l2)), max(lv_or0(e.wait_a1), lv_or0(e.wait_a2)));
+        const int want_bits = (e.pub_r1 ? 1 : 0) | (e.pub_b1 ? 2 : 0);
+        bool waits_done = false;
         auto open_level = [&](unsigned level, int solo) {
             const int need_l = (col == 0) ? 0 : (level >= e.wait_l2 ? 2 : (level >= e.wait_l1 ? 1 : 0));
             const int need_a = (r == 0 || col + 1 >= sb_cols) ? 0 : (level >= e.wait_a2 ? 2 : (level >= e.wait_a1 ? 1 : 0));
+            waits_done = level >= busy_until; // (the first call never returns early: waited_l is -1)
             if (need_l <= waited_l && need_a <= waited_a) return;
             const bool first = waited_l < 0;
             const bool more_l = need_l > max(waited_l, 0), more_a = need_a > max(waited_a, 0);
@@ -1199,8 +1206,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             }
             // res_off = level | (ops left in this level) << 16 (emitter scheduleSb); a producer that
             // leaves the count zero gets one op per step, still a valid order
-            auto level_end = [&](unsigned g) { return min(nk, g + max(1u, cur_ops[g].res_off >> 16)); };
-            unsigned g0 = 0, g1 = level_end(0);
+            // (the word of the group that starts the NEXT level is read before the barrier and carried
+            // over: nothing but the op itself sits between a barrier and the next)
+            unsigned ro0 = cur_ops[0].res_off;
+            unsigned g0 = 0, g1 = min(nk, max(1u, ro0 >> 16));
 #ifndef AV1B_EMU
             // Op j of a level goes to warp (j + parity * nw/2) mod nw, the parity flipping with
             // every level: a level rarely has more than nw/2 ops, so the warps that work in one
@@ -1214,7 +1223,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
             if (mine < g1) st = stage_op(cur_ops + mine, io);
 #endif
             while (g0 < nk) {
-                const unsigned level = cur_ops[g0].res_off & 0xFFFFu;
+                const unsigned level = ro0 & 0xFFFFu;
                 // early hand-off of the border halves the levels before this one made final (a
                 // level may straddle two chunks, so it only counts as over once a later one starts)
 #ifdef AV1B_EMU
@@ -1222,25 +1231,27 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 #else
                 const int solo = (int)((nw - 1 + par * (nw >> 1)) & (nw - 1)); // the warp least likely to hold an op of this level
 #endif
-                if (k0 + g0 > 0) {
+                if ((pubbits & want_bits) != want_bits && k0 + g0 > 0) {
                     int bits = 0;
                     if (e.pub_r1 && level > e.pub_r1 && !(pubbits & 1)) bits |= 1;
                     if (e.pub_b1 && level > e.pub_b1 && !(pubbits & 2)) bits |= 2;
                     if (bits) publish(bits, solo);
                 }
-                open_level(level, -1); // (no-op when the look-ahead of the level before did it)
+                if (!waits_done) open_level(level, -1); // (no-op when the look-ahead of the level before did it)
 #ifdef AV1B_EMU
                 // the emulation runs the ops of a level in REVERSE order: if the level analysis
                 // missed a dependency, the conformance MD5s under emulation break
                 for (unsigned k = g1; k-- > g0;) exec_staged(stage_op(cur_ops + k, io));
-                const unsigned g2 = g1 < nk ? level_end(g1) : g1;
+                const unsigned ro1 = g1 < nk ? cur_ops[g1].res_off : 0u;
+                const unsigned g2 = g1 < nk ? min(nk, g1 + max(1u, ro1 >> 16)) : g1;
 #else
                 if (mine < g1) {
                     exec_staged(st);
                     for (unsigned k = mine + nw; k < g1; k += nw) exec_staged(stage_op(cur_ops + k, io));
                 }
-                const unsigned g2 = g1 < nk ? level_end(g1) : g1;
-                if (g1 < nk) open_level(cur_ops[g1].res_off & 0xFFFFu, solo);
+                const unsigned ro1 = g1 < nk ? cur_ops[g1].res_off : 0u;
+                const unsigned g2 = g1 < nk ? min(nk, g1 + max(1u, ro1 >> 16)) : g1;
+                if (g1 < nk && !waits_done) open_level(ro1 & 0xFFFFu, solo);
                 par ^= 1;
                 mine = g1 + ((warp + par * (nw >> 1)) & (nw - 1));
                 if (mine < g2) st = stage_op(cur_ops + mine, io);
@@ -1248,6 +1259,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 block_sync(nt);
                 g0 = g1;
                 g1 = g2;
+                ro0 = ro1;
             }
             if (nn) {
 #ifdef AV1B_EMU
