@@ -330,15 +330,17 @@ def postfilter_leg(device, dev, n_in=8, reps=3, quiet=True, size=(3840, 2160), d
     return post, roofline
 
 
-def inter_leg(device, reps=3):
-    """Motion-compensation throughput on a synthetic 3840x2160 frame of translational inter blocks."""
+def inter_leg(device, reps=3, fast=True):
+    """Motion-compensation throughput on a synthetic 3840x2160 frame of translational inter blocks.
+    `fast=False`: the same blocks without the fast-path flags, i.e. through the general predictor
+    (the path warped / OBMC / masked blocks of real streams take)."""
     import av1dec_b200 as pkg
     from av1dec_b200 import format as F
     from av1dec_b200 import synth
     from av1dec_b200.engine import Engine
     hdr_size = C.sizeof(F.FrameHdr)
     W4, H4 = 3840, 2160
-    cmd, n_blk, algo = synth.make_inter_frame(W4, H4)
+    cmd, n_blk, algo = synth.make_inter_frame(W4, H4, fast=fast)
     eng = Engine(W4, H4, device=device)
     eng.set_lanes(1)
     rng = synth.SplitMix64(synth.SEED + 77)
@@ -670,7 +672,8 @@ def run_ours(args, rank, world, local_rank):
             pv, _ = postfilter_leg(device, dev, n_in=3, reps=2, **kw)
             variants[key] = {k: round(v["us_per_frame"], 1) for k, v in pv.items()}
             variants[key]["chain_gbs"] = pv["chain"]["gbs"]
-    kernels_4k = {"itx": itx_leg(device), "inter": inter_leg(device), "wave": wave_leg(device)} if rank == 0 else None
+    kernels_4k = ({"itx": itx_leg(device), "inter": inter_leg(device), "inter_general_path": inter_leg(device, fast=False), "wave": wave_leg(device)}
+                  if rank == 0 else None)
 
     if rank != 0:
         return 0

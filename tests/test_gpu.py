@@ -152,7 +152,8 @@ def test_postfilter_4k_is_deterministic_and_launches_kernels(eng):
 
 @pytest.mark.parametrize("env", [{"AV1B200_LANES": "1", "AV1B200_GOP_THREADS": "1"},
                                  {"AV1B200_LANES": "16", "AV1B200_GOP_THREADS": "8"},
-                                 {"AV1B200_LANES": "3", "AV1B200_WAVE_WARPS": "8"}])
+                                 {"AV1B200_LANES": "3", "AV1B200_WAVE_WARPS": "16"},
+                                 {"AV1B200_LANES": "8", "AV1B200_WAVE_WARPS": "4", "AV1B200_WAVE_GRIDQ": "4"}])
 def test_concurrency_knobs_do_not_change_pixels(dec, md5_table, env, monkeypatch):
     """Frame lanes, closed-segment workers and the wavefront build only reorder work: an
     all-intra stream (39 independent frames), an inter stream with compound / OBMC references and
@@ -201,14 +202,17 @@ def test_inter_prediction_vs_reference(eng, w, h, kw):
 
 
 @pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("w,h,sb_log2,kw", [(1920, 1080, 6, {}), (1920, 1080, 7, dict(rect=True, intra_frac=1.0)),
+@pytest.mark.parametrize("w,h,sb_log2,kw", [(1920, 1080, 6, {}), (1920, 1080, 6, dict(segments=False, intra_frac=0.9)),
+                                             (1920, 1080, 7, dict(rect=True, intra_frac=1.0)),
                                              (3840, 2160, 6, dict(rect=True, sizes=(8, 32, 64), intra_frac=0.9)),
                                              (3840, 2160, 7, dict(rect=True, sizes=(16, 32, 64)))])
 def test_intra_prediction_vs_reference(eng, w, h, sb_log2, kw):
     """The wavefront kernel against the REFERENCE's Block::IntraPredict::predict_intra /
     predict_chroma_from_luma (oracle_predict_intra) at 1080p and 4K: every mode, square and
-    rectangular transform sizes up to 64, edge filter / upsampling, filter-intra, CfL -- with
-    coordinates in the thousands (16-bit packed op fields)."""
+    rectangular transform sizes up to 64 (blocks of 512 samples and more run as row strips on
+    several warps), edge filter / upsampling, filter-intra, CfL -- with coordinates in the thousands
+    (16-bit packed op fields); overlapping superblocks (hints + seeded levels) and, with
+    `segments=False`, the classic two-superblock-lag schedule."""
     checks.check_wave_vs_oracle(eng, w, h, sb_log2, **kw)
 
 
