@@ -52,6 +52,21 @@ def test_dropin_cli_unchanged_reference_main(md5_table, tmp_path):
         assert hashlib.md5(out.read_bytes()).hexdigest() == md5_table[name], name
 
 
+@pytest.mark.parametrize("env", [{"AV1B200_WAVE_OVERLAP": "0"}, {"AV1B200_WAVE_SPLIT": "0", "AV1B200_WAVE_SEED": "0,0,0", "AV1B200_SPIN_WAIT": "1"},
+                                 {"AV1B200_WAVE_SEED": "90,90,100", "AV1B200_WAVE_WARPS": "16"}])
+def test_scheduling_knobs_read_at_start_up(md5_table, tmp_path, env):
+    """The emitter's scheduling choices (overlap hints, level seeds, row strips) and the host wait
+    mode are read once per process: each setting decodes intra-heavy and inter streams through the
+    CLI in a process of its own and must give the same pictures."""
+    cli = os.path.join(ROOT, "av1dec_b200", "bin", "av1dec")
+    for name in ("av1-1-b8-02-allintra.ivf", "av1-1-b8-06-mfmv.ivf", "av1-1-b8-00-quantizer-20.ivf", "av1-1-b8-04-cdfupdate.ivf"):
+        if name not in md5_table:
+            continue
+        out = tmp_path / "o.yuv"
+        subprocess.run([cli, "-i", os.path.join(BITS, name), str(out)], check=True, stdout=subprocess.DEVNULL, timeout=300, env={**os.environ, **env})
+        assert hashlib.md5(out.read_bytes()).hexdigest() == md5_table[name], (name, env)
+
+
 @pytest.mark.skipif(not os.path.exists(checks.IVD_DRIVE), reason="tests/native/ivd_drive not built")
 def test_ivideodecoder_vtable(md5_table, tmp_path):
     """interface/VideoDecoderInterface.h:31-68 through dlopen + createVideoDecoder on the product
