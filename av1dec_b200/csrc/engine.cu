@@ -1282,6 +1282,10 @@ int av1b_debug_wave_trace(size_t n)
     if (!n) return AV1B_OK;
     void* p = nullptr;
     if (rt_malloc(&p, n * 64)) return AV1B_ENOMEM;
+    if (rt_memset(p, 0, n * 64, nullptr) || rt_device_sync()) {
+        rt_free(p);
+        return AV1B_ECUDA;
+    }
     g_wave_trace = (unsigned long long*)p;
     g_wave_trace_cap = n;
     return AV1B_OK;

@@ -1224,6 +1224,17 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
 #endif
             while (g0 < nk) {
                 const unsigned level = ro0 & 0xFFFFu;
+                // level log of ONE superblock (trace capacity beyond the per-superblock records):
+                // per level 16 words -- barrier exit, then (start, end) of the op of warps 0..6
+                // (compiled in with -DAV1B_WAVE_LEVEL_LOG only: the test costs every level ~8 %)
+#ifdef AV1B_WAVE_LEVEL_LOG
+                unsigned long long* const lvlog = (c.trace && c.trace_cap >= (unsigned)n_sb + 64 && sb == (n_sb >> 1) + (sb_cols >> 1) && lane == 0 && level < 32)
+                    ? c.trace + 8 * (size_t)n_sb + 16 * level : nullptr;
+#else
+                unsigned long long* const lvlog = nullptr;
+#endif
+                if (lvlog && warp == 0) lvlog[0] = av1b_gtime();
+                if (lvlog && warp < 7) lvlog[1 + 2 * warp] = lvlog[2 + 2 * warp] = 0;
                 // early hand-off of the border halves the levels before this one made final (a
                 // level may straddle two chunks, so it only counts as over once a later one starts)
 #ifdef AV1B_EMU
@@ -1246,7 +1257,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 const unsigned g2 = g1 < nk ? min(nk, g1 + max(1u, ro1 >> 16)) : g1;
 #else
                 if (mine < g1) {
+                    if (lvlog && warp < 7) lvlog[1 + 2 * warp] = av1b_gtime();
                     exec_staged(st);
+                    if (lvlog && warp < 7) lvlog[2 + 2 * warp] = av1b_gtime();
                     for (unsigned k = mine + nw; k < g1; k += nw) exec_staged(stage_op(cur_ops + k, io));
                 }
                 const unsigned ro1 = g1 < nk ? cur_ops[g1].res_off : 0u;
@@ -1256,6 +1269,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
                 mine = g1 + ((warp + par * (nw >> 1)) & (nw - 1));
                 if (mine < g2) st = stage_op(cur_ops + mine, io);
 #endif
+                if (lvlog && warp == 7) lvlog[15] = av1b_gtime(); // warp 7 reaches the level barrier
                 block_sync(nt);
                 g0 = g1;
                 g1 = g2;

@@ -70,12 +70,22 @@ def trace(name="mix"):
     lib.av1b_debug_wave_trace_read.argtypes = [C.c_void_p, C.c_size_t]
     for it in range(3):
         if it == 2:
-            assert lib.av1b_debug_wave_trace(n) == 0
+            assert lib.av1b_debug_wave_trace(n + 64) == 0
         eng.input_from_slot(0)
         eng.submit_resident(dev_cmd, cmd[:hdr_size], pkg.STAGE_WAVE, 0)
         eng.sync()
-    buf = np.zeros((n, 8), np.uint64)
-    assert lib.av1b_debug_wave_trace_read(buf.ctypes.data, n) == 0
+    buf = np.zeros((n + 64, 8), np.uint64)
+    assert lib.av1b_debug_wave_trace_read(buf.ctypes.data, n + 64) == 0
+    lvlog = buf[n:].reshape(32, 16).astype(np.int64)  # level log of the middle superblock (csrc/recon.cu)
+    buf = buf[:n]
+    if os.environ.get("WAVE_LEVEL_LOG"):
+        base = lvlog[lvlog[:, 0] > 0, 0].min() if (lvlog[:, 0] > 0).any() else 0
+        print("level log (ns from the first barrier exit): level, barrier exit, [op start-end per warp 0..6], warp 7 at the barrier")
+        for lv in range(32):
+            if lvlog[lv, 0] == 0:
+                continue
+            ops = " ".join(f"w{w}:{lvlog[lv, 1 + 2 * w] - base}-{lvlog[lv, 2 + 2 * w] - base}" for w in range(7) if lvlog[lv, 1 + 2 * w])
+            print(f"  L{lv:2d} exit {lvlog[lv, 0] - base:7d}  {ops}  w7@bar {lvlog[lv, 15] - base}")
     lib.av1b_debug_wave_trace(0)
     eng.close()
     if os.environ.get("WAVE_TRACE_DUMP"):
