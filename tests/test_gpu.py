@@ -205,6 +205,23 @@ def test_wavefront_full_frames_vs_sequential_emulation(eng, w, h, sb_log2):
     checks.check_wave(eng, w, h, sb_log2, ref_lib=checks.emu_engine())
 
 
+@pytest.mark.parametrize("warps", ["8", "16", "4"])
+def test_wavefront_hand_offs_are_race_free(eng, warps, monkeypatch):
+    """The overlapping wavefront (early hand-offs by one warp, look-ahead waits, progress words)
+    run 8 times over a dense 1080p intra frame under each CTA shape: a lost ordering between a
+    border store and the progress word, or a halo read too early, shows up as a differing run."""
+    monkeypatch.setenv("AV1B200_WAVE_WARPS", warps)
+    w, h = 1920, 1080
+    rng = synth.SplitMix64(synth.SEED + 31)
+    planes = synth.make_planes(rng, w, h, "B")
+    cmd = synth.make_intra_frame(w, h, sb_log2=6, intra_frac=0.95, rect=True, sizes=(8, 16, 32, 64))
+    first = checks.run_wave(eng, w, h, planes, cmd)
+    for _ in range(7):
+        again = checks.run_wave(eng, w, h, planes, cmd)
+        for p in range(3):
+            assert np.array_equal(first[p], again[p]), f"wavefront not deterministic ({warps} warps, plane {p})"
+
+
 @pytest.mark.skipif(not oracle.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("w,h,kw", [(1920, 1080, dict(compound_frac=0.3)), (1920, 1080, dict(compound_frac=0.3, fast=False, max_mv=2048, seed=99)),
                                     (3840, 2160, dict(compound_frac=0.25, max_mv=1024)), (3840, 2160, dict(compound_frac=0.5, fast=False, seed=5))])
