@@ -293,7 +293,11 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
     // ---- phase 1: edge assembly (IntraPredict.cpp:579-611).  Every item gathers four bytes at
     // base + min(n - 1, i) * step; the three kinds of item (word of the row above, word of the
     // left column, corner) differ only in those operands, so the lanes do not diverge.
-    if (!direct) {
+    // Filter-intra with every edge sample there reads the tile as well: the row above and the
+    // column to the left of a 4x2 sub-block are then the same expression whether they are the
+    // block's edge or samples predicted a step earlier.
+    const bool fi_inplace = SMEM && kind == K_FILTER_INTRA && ha && hl && o.P == o.blk && p.above_n() >= w && p.left_n() >= h;
+    if (!direct && !fi_inplace) {
         const int an = p.above_n(), ln = p.left_n();
         const int nw4 = (w + h) >> 2;
         const bool none = !ha && !hl;
@@ -334,16 +338,24 @@ AV1B_DEV void run(const Packed& p, const Io& o, Scratch& S, int tid, int nt_rt)
                 int j4 = j_lo + (e >> 3), i2 = d - j4, k = e & 7;
                 int i1 = k >> 2, j1 = k & 3;
                 int px[7];
-                AV1B_UNROLL
-                for (int i = 0; i < 5; i++) {
-                    if (!i2) px[i] = A[(j4 << 2) + i - 1];
-                    else if (!j4 && !i) px[i] = L[(i2 << 1) - 1];
-                    else px[i] = P[((i2 << 1) - 1) * pp + (j4 << 2) + i - 1];
-                }
-                AV1B_UNROLL
-                for (int i = 5; i < 7; i++) {
-                    if (!j4) px[i] = L[(i2 << 1) + i - 5];
-                    else px[i] = P[((i2 << 1) + i - 5) * pp + (j4 << 2) - 1];
+                if (fi_inplace) {
+                    const uint8_t* t = P + ((i2 << 1) - 1) * pp + (j4 << 2) - 1; // above-left of the sub-block
+                    AV1B_UNROLL
+                    for (int i = 0; i < 5; i++) px[i] = t[i];
+                    px[5] = t[pp];
+                    px[6] = t[2 * pp];
+                } else {
+                    AV1B_UNROLL
+                    for (int i = 0; i < 5; i++) {
+                        if (!i2) px[i] = A[(j4 << 2) + i - 1];
+                        else if (!j4 && !i) px[i] = L[(i2 << 1) - 1];
+                        else px[i] = P[((i2 << 1) - 1) * pp + (j4 << 2) + i - 1];
+                    }
+                    AV1B_UNROLL
+                    for (int i = 5; i < 7; i++) {
+                        if (!j4) px[i] = L[(i2 << 1) + i - 5];
+                        else px[i] = P[((i2 << 1) + i - 5) * pp + (j4 << 2) - 1];
+                    }
                 }
                 int pr = 0;
                 AV1B_UNROLL
