@@ -10,7 +10,8 @@
 //                      block.
 //   wave_kernel        the dependent pass: intra prediction (+CfL, filter-intra, palette), inter-
 //                      intra blend and residual add on a shared-memory superblock tile, ops sorted by
-//                      dependency level, superblocks in wavefront order with the classic 2-SB lag.
+//                      dependency level, superblocks in wavefront order; neighbouring superblocks overlap
+//                      (per-superblock progress words, Av1bSb hints; all-zero hints = classic 2-SB lag).
 //   wave_kernel_global the same ops on global memory for frames with intrabc.
 //
 // Reference for the behaviour: decoder/TransformBlock.cpp:2376-2456 (TransformBlock::decode),
@@ -925,8 +926,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) wave_kernel(ReconCtx c)
     int16_t* const q1 = q0 + n0 * n0;
     int16_t* const q2 = q1 + n1 * n1;
     OpScratch* const scratch = (OpScratch*)(dyn + WAVE_TILE_BYTES(n0) + WAVE_RES_BYTES(n0)) + warp;
-    const int n_sb_rows = hdr->sb_rows;
-    (void)n_sb_rows;
     // progress[sb]: bit 0 = the upper half of superblock sb's right column is final and in the frame,
     // bit 1 = the left half of its bottom row, bit 2 = all of it
     auto poll = [&](int idx, int mask) {
