@@ -155,7 +155,13 @@ struct Decoder::Impl {
     }
 
     // ---- device side of one frame: serialise the parsed tree and hand it to the engine
-    bool submitFrame(const FramePtr& fr, TileGroup& ts, const std::shared_ptr<const SequenceHeader>& seq)
+    // Streaming emission (sync mode): a superblock is serialised right after it is parsed, while
+    // its block tree (37 KB per transform block) is still in the cache, and freed at once -- the
+    // tree of a whole frame (tens of MB even at CIF) is never built.  `streamed` = the emitter
+    // already holds this frame's superblocks when submitFrame runs.
+    bool streaming = false, streamed = false;
+
+    bool beginFrame(const FramePtr& fr, const std::shared_ptr<const SequenceHeader>& seq)
     {
         FrameHeader& h = *fr;
         if (!ensureCtx(*seq)) return false;
@@ -174,9 +180,19 @@ struct Decoder::Impl {
             if (!ensureCtx(*seq)) return false;
             if ((int)h.FrameWidth > ctx_w || (int)h.FrameHeight > ctx_h) return fail("frame larger than the sequence's maximum size");
         }
-        const double t0 = now();
         emitter.begin(h, *seq);
+        return true;
+    }
+
+    bool submitFrame(const FramePtr& fr, TileGroup& ts, const std::shared_ptr<const SequenceHeader>& seq)
+    {
+        FrameHeader& h = *fr;
+        const bool had = streamed;
+        streamed = false;
+        if (!had && !beginFrame(fr, seq)) return false;
+        const double t0 = now();
         for (auto& t : ts) {
+            if (had) break;
             const double ta = now();
             emitter.emitTile(*t);
             const double tb = now();
@@ -283,6 +299,64 @@ struct Decoder::Impl {
         if (worker.joinable()) worker.join();
     }
 
+    // Tile::parse (Tile.cpp:122-160) with the emitter called after every superblock; the
+    // superblock is dropped instead of being kept in Tile::m_sbs.
+    bool streamTile(Tile& t, const uint8_t* data, uint32_t size)
+    {
+        t.m_cdfs = *t.m_frame->m_cdfs;
+        t.m_entropy.reset(new EntropyDecoder(data, size, t.m_frame->disable_cdf_update, t.m_cdfs));
+        t.clear_above_context();
+        for (int i = 0; i < FRAME_LF_COUNT; i++) t.DeltaLF[i] = 0;
+        t.m_frame->m_loopRestoration.resetRefs(t.m_sequence->NumPlanes);
+        const BLOCK_SIZE sbSize = t.m_sequence->use_128x128_superblock ? BLOCK_128X128 : BLOCK_64X64;
+        const int sbSize4 = Num_4x4_Blocks_Wide[sbSize];
+        for (int r = t.MiRowStart; r < t.MiRowEnd; r += sbSize4) {
+            t.clear_left_context();
+            for (int c = t.MiColStart; c < t.MiColEnd; c += sbSize4) {
+                t.ReadDeltas = t.m_frame->m_deltaQ.delta_q_present;
+                const double ta = now();
+                SuperBlock sb(t, r, c, sbSize);
+                sb.parse();
+                const double tb = now();
+                emitter.emitSb(t, sb);
+                t_parse += tb - ta;
+                t_dbg[0] += now() - tb;
+            }
+        }
+        return true;
+    }
+
+    // Parser::parseTileGroup (Parser.cpp:474-524) over streamTile
+    bool streamTileGroup(BitReader& br, const FramePtr& fr, TileGroup& group)
+    {
+        bool tile_start_and_end_present_flag = false;
+        if (fr->NumTiles > 1 && !br.readT(tile_start_and_end_present_flag)) return false;
+        if (tile_start_and_end_present_flag) return fail("tile_start_and_end_present_flag is not supported (the reference asserts)");
+        parser->skipTrailingBits(br);
+        const uint8_t* data = br.getCurrent();
+        uint32_t size = (uint32_t)(br.getRemainingBitsCount() / 8);
+        const int tg_end = (int)fr->NumTiles - 1;
+        for (int TileNum = 0; TileNum <= tg_end; TileNum++) {
+            uint32_t tileSize;
+            if (TileNum == tg_end) tileSize = size;
+            else {
+                uint32_t tile_size_minus_1;
+                BitReader reader(data, size);
+                if (!reader.readLe(tile_size_minus_1, fr->TileSizeBytes)) return fail("read tile_size_minus_1 failed");
+                data += fr->TileSizeBytes;
+                size -= fr->TileSizeBytes;
+                tileSize = tile_size_minus_1 + 1;
+            }
+            if (tileSize > size) return fail("tile size exceeds the remaining data");
+            std::shared_ptr<Tile> tile(new Tile(parser->m_sequence, fr, TileNum));
+            if (!streamTile(*tile, data, tileSize)) return false;
+            data += tileSize;
+            size -= tileSize;
+            group.push_back(tile);
+        }
+        return true;
+    }
+
     bool decodeFrame(TileGroup& ts)
     {
         FrameHeader& h = *frame;
@@ -329,6 +403,8 @@ Decoder::Decoder()
     m_impl->parser.reset(new Parser);
     const char* dev = getenv("AV1B200_DEVICE");
     if (dev) m_impl->opt.device = atoi(dev);
+    const char* se = getenv("AV1B200_STREAM_EMIT");
+    m_impl->streaming = se ? atoi(se) != 0 : true;
 }
 
 Decoder::~Decoder()
@@ -366,7 +442,13 @@ bool Decoder::decode(uint8_t* data, size_t size)
         case OBU_TILE_GROUP: {
             if (!d.frame) return false;
             TileGroup group;
-            ok = parser.parseTileGroup(br, d.frame, group);
+            if (d.streaming && !d.async) {
+                if (d.tiles.empty() && !d.streamed) {
+                    ok = d.beginFrame(d.frame, parser.m_sequence);
+                    d.streamed = ok;
+                }
+                ok = ok && d.streamTileGroup(br, d.frame, group);
+            } else ok = parser.parseTileGroup(br, d.frame, group);
             if (ok) {
                 d.tiles.insert(d.tiles.end(), group.begin(), group.end());
                 if (d.tiles.size() == parser.m_frame->NumTiles) {
@@ -379,8 +461,22 @@ bool Decoder::decode(uint8_t* data, size_t size)
         case OBU_FRAME: {
             TileGroup group;
             const double tp = Impl::now();
-            d.frame = parser.parseFrame(br, group);
-            d.t_parse += Impl::now() - tp;
+            if (d.streaming && !d.async) {
+                // Parser::parseFrame (Parser.cpp:1761-1772) with the tile group streamed
+                d.frame = parser.parseFrameHeader(br);
+                d.t_parse += Impl::now() - tp;
+                if (d.frame) {
+                    parser.skipTrailingBits(br);
+                    d.streamed = d.beginFrame(d.frame, parser.m_sequence);
+                    if (!d.streamed || !d.streamTileGroup(br, d.frame, group)) {
+                        d.streamed = false;
+                        return false;
+                    }
+                }
+            } else {
+                d.frame = parser.parseFrame(br, group);
+                d.t_parse += Impl::now() - tp;
+            }
             ok = d.frame ? d.decodeFrame(group) : false;
             d.tiles.clear();
             break;

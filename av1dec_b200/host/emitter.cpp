@@ -106,19 +106,21 @@ static bool getenv_overlap()
 
 void FrameEmitter::emitTile(Tile& tile)
 {
+    for (auto& sbp : tile.m_sbs) emitSb(tile, *sbp);
+}
+
+void FrameEmitter::emitSb(Tile& tile, SuperBlock& sb)
+{
     const int sb4 = 1 << (m_hdr.sb_log2 - 2);
-    for (auto& sbp : tile.m_sbs) {
-        SuperBlock& sb = *sbp;
-        // SuperBlock::decode (SuperBlock.cpp:46-51)
-        tile.m_decoded.clear_block_decoded_flags(sb.m_r, sb.m_c, sb4);
-        const size_t idx = (size_t)(sb.m_r / sb4) * m_hdr.sb_cols + (sb.m_c / sb4);
-        const uint32_t first = (uint32_t)m_ops.size();
-        const size_t firstItx = m_itx.size();
-        walk(sb);
-        m_sbs[idx].first_op = first;
-        m_sbs[idx].n_ops = (uint32_t)m_ops.size() - first;
-        scheduleSb(first, firstItx, sb.m_c * MI_SIZE, sb.m_r * MI_SIZE);
-    }
+    // SuperBlock::decode (SuperBlock.cpp:46-51)
+    tile.m_decoded.clear_block_decoded_flags(sb.m_r, sb.m_c, sb4);
+    const size_t idx = (size_t)(sb.m_r / sb4) * m_hdr.sb_cols + (sb.m_c / sb4);
+    const uint32_t first = (uint32_t)m_ops.size();
+    const size_t firstItx = m_itx.size();
+    walk(sb);
+    m_sbs[idx].first_op = first;
+    m_sbs[idx].n_ops = (uint32_t)m_ops.size() - first;
+    scheduleSb(first, firstItx, sb.m_c * MI_SIZE, sb.m_r * MI_SIZE);
 }
 
 // Dependency levels inside one superblock.  Ops are emitted in bitstream order; two ops may run

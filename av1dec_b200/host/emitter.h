@@ -17,6 +17,7 @@ class TransformBlock;
 struct FrameHeader;
 struct SequenceHeader;
 class Partition;
+class SuperBlock;
 }
 
 namespace av1b200 {
@@ -25,6 +26,7 @@ class FrameEmitter {
 public:
     void begin(YamiAv1::FrameHeader& frame, const YamiAv1::SequenceHeader& seq);
     void emitTile(YamiAv1::Tile& tile);
+    void emitSb(YamiAv1::Tile& tile, YamiAv1::SuperBlock& sb); // one superblock of `tile` (emitTile = all of them, in order)
     void finish();
     size_t bytes() const { return m_total; }
     void write(uint8_t* dst) const;
