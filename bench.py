@@ -619,9 +619,9 @@ def run_ours(args, rank, world, local_rank):
             return px, len(yuv)
         t0 = time.perf_counter()
         # a stream of closed segments adds workers of its own and every context has driver threads:
-        # 3/4 of the cores as callers keeps the cores busy without thrashing (16 callers on 16
-        # cores: 270-480 ms per set and unstable; 12: a steady 240 ms; 8: 268 ms)
-        with cf.ThreadPoolExecutor(args.e2e_threads or max(1, host_threads * 3 // 4)) as ex:
+        # 7/8 of the cores as callers keeps the cores busy without thrashing (16 cores, host threads
+        # sleeping on fences, streaming emission: 12 callers 192-221 ms per set, 14: 186-196, 16: 191-216)
+        with cf.ThreadPoolExecutor(args.e2e_threads or max(1, host_threads * 7 // 8)) as ex:
             res = list(ex.map(one, sorted([s for _ in range(copies) for s in mine], key=lambda s: -len(s[1]))))
         return time.perf_counter() - t0, sum(p for p, _ in res)
     # untimed: fill the context / pinned / command-slot pools until a pass allocates nothing new
@@ -695,7 +695,7 @@ def run_ours(args, rank, world, local_rank):
                     "API with host buffers is e2e.value",
         "config": {"workload": WORKLOAD, "streams_per_gpu": len(mine), "distinct_streams_per_gpu": len({m[0] for m in mine}), "cuda_streams": len(side_streams), "lanes_per_context": args.lanes,
                    "replay": "submit API" if args.no_graphs else "one CUDA graph per stream (captured from the submit API, checked against it)",
-                   "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads * 3 // 4), "host_cores": cores,
+                   "host_threads_per_gpu": host_threads, "e2e_callers_per_gpu": args.e2e_threads or max(1, host_threads * 7 // 8), "host_cores": cores,
                    "l2": "stream leg: ~1.4 GB of command buffers + frames per step (larger than L2); roofline leg: 256 MiB L2 flush between iterations",
                    "stage_share_ms": share},
         "clocks": clocks,
