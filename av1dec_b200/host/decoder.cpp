@@ -435,6 +435,7 @@ bool Decoder::decode(uint8_t* data, size_t size)
         case OBU_SEQUENCE_HEADER: ok = parser.parseSequenceHeader(br); break;
         case OBU_TD: ok = parser.parseTemporalDelimiter(br); break;
         case OBU_FRAME_HEADER:
+            if (d.tiles.empty()) d.streamed = false; // (not a redundant copy between the tile groups of one frame)
             d.frame = parser.parseFrameHeader(br);
             ok = bool(d.frame);
             if (ok && d.frame->show_existing_frame) ok = d.showExisting();
@@ -448,6 +449,7 @@ bool Decoder::decode(uint8_t* data, size_t size)
                     d.streamed = ok;
                 }
                 ok = ok && d.streamTileGroup(br, d.frame, group);
+                if (!ok) d.streamed = false; // the emitter holds a partial frame: the next one starts afresh
             } else ok = parser.parseTileGroup(br, d.frame, group);
             if (ok) {
                 d.tiles.insert(d.tiles.end(), group.begin(), group.end());
