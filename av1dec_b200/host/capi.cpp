@@ -208,20 +208,22 @@ int av1b_decode_ivf(const uint8_t* ivf, size_t len, int device, uint32_t stages,
     std::vector<size_t> seg;
     if (!scan_ivf(ivf, len, tus, seg)) return -1;
     // The command emitter can run on a worker thread one frame behind the parser: lower latency
-    // for a lone stream, but ~35 % more CPU in total (the parsed tree crosses cores).  Once the
-    // process already keeps the cores busy with other decodes, emit inline instead.
+    // for a lone stream, but ~35 % more CPU in total (the tree of a whole frame is built and crosses
+    // cores; inline emission streams superblock by superblock, decoder.cpp).  With more than two
+    // decodes running in the process it is a throughput service: emit inline.  (The count is per
+    // process: a rule relative to the machine's cores picked the expensive mode in every rank of
+    // a multi-GPU job that saturated the box as a whole.)
     static std::atomic<int> active{ 0 };
     struct Busy {
         std::atomic<int>& n;
         explicit Busy(std::atomic<int>& a) : n(a) { n++; }
         ~Busy() { n--; }
     };
-    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     auto setup = [&](YamiAv1::Decoder& dec) {
         av1b200::decoderOptions(dec).device = device;
         av1b200::decoderOptions(dec).stages = stages;
         const char* e = getenv("AV1B200_SYNC_EMIT");
-        const bool async = e ? atoi(e) == 0 : 2 * active.load() <= hw;
+        const bool async = e ? atoi(e) == 0 : active.load() <= 2;
         av1b200::decoderSetAsync(dec, async);
     };
     unsigned workers = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
